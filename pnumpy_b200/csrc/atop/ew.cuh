@@ -1,0 +1,367 @@
+// Element-wise streaming kernels (the GPU form of the reference's SimpleMathOpFast /
+// UnaryOpFast / Compare* loop bodies: src/atop/ops_binary.cpp:398-793,
+// src/atop/ops_unary.cpp:327-376, src/atop/ops_compare.cpp:400-1255).
+//
+// Design (HBM-bound, no reuse, so no shared memory and no tensor cores):
+//   * the unit of work is a 16-byte "wide vector" of the WIDEST operand type; a lane
+//     moves one wide vector per operand per step with one 128-bit ld/st, the
+//     narrower operand (bool result of a compare, int32 input of an int->f64 divide)
+//     moves 16*narrow/wide bytes per lane with one narrower access.  Consecutive lanes
+//     touch consecutive vectors, so every warp-level access is fully coalesced.
+//   * each thread issues UNROLL independent vector loads per operand before the first
+//     use (memory-level parallelism), then computes, then stores.
+//   * persistent grid: SMs x ctas_per_sm CTAs walk the tiles grid-stride.
+//   * loads/stores use the streaming (.cs, evict-first) policy: nothing is re-read.
+//   * head/tail elements that do not fill an aligned wide vector are done by block 0
+//     in the same launch (no second kernel).
+//   * `out` may alias an input exactly (in-place): every element is read and written by
+//     the same thread, loads precede stores, and no pointer is declared __restrict__.
+#pragma once
+#include "common.cuh"
+
+namespace pncu {
+
+// ---- register image of one lane's share of a vector ---------------------------------------
+// N elements of T held in 32-bit words.  Elements are extracted / inserted with shifts on
+// compile-time indices so everything stays in registers (a union of byte arrays would be
+// demoted to local memory by the compiler for 1- and 2-byte types).
+template <int SIZE> struct Bits;
+template <> struct Bits<1> { typedef uint8_t type; };
+template <> struct Bits<2> { typedef uint16_t type; };
+template <> struct Bits<4> { typedef uint32_t type; };
+template <> struct Bits<8> { typedef uint64_t type; };
+
+template <class T> __device__ __forceinline__ typename Bits<sizeof(T)>::type to_bits(T v) {
+    union { T t; typename Bits<sizeof(T)>::type b; } c;
+    c.t = v;
+    return c.b;
+}
+template <class T> __device__ __forceinline__ T from_bits(typename Bits<sizeof(T)>::type b) {
+    union { T t; typename Bits<sizeof(T)>::type b; } c;
+    c.b = b;
+    return c.t;
+}
+
+template <class T, int N>
+struct Pack {
+    static constexpr int BYTES = (int)sizeof(T) * N;
+    static constexpr int WORDS = (BYTES + 3) / 4;
+    uint32_t w[WORDS];
+
+    __device__ __forceinline__ T get(int e) const {
+        if constexpr (sizeof(T) == 1) return from_bits<T>((uint8_t)(w[e >> 2] >> (8 * (e & 3))));
+        else if constexpr (sizeof(T) == 2) return from_bits<T>((uint16_t)(w[e >> 1] >> (16 * (e & 1))));
+        else if constexpr (sizeof(T) == 4) return from_bits<T>(w[e]);
+        else return from_bits<T>(((uint64_t)w[2 * e + 1] << 32) | (uint64_t)w[2 * e]);
+    }
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < WORDS; ++i) w[i] = 0u;
+    }
+    // insert element e; for sub-word T the pack must have been zero()ed first
+    __device__ __forceinline__ void set(int e, T v) {
+        if constexpr (sizeof(T) == 1) w[e >> 2] |= (uint32_t)to_bits<T>(v) << (8 * (e & 3));
+        else if constexpr (sizeof(T) == 2) w[e >> 1] |= (uint32_t)to_bits<T>(v) << (16 * (e & 1));
+        else if constexpr (sizeof(T) == 4) w[e] = to_bits<T>(v);
+        else {
+            const uint64_t b = to_bits<T>(v);
+            w[2 * e] = (uint32_t)b;
+            w[2 * e + 1] = (uint32_t)(b >> 32);
+        }
+    }
+};
+
+// streaming (evict-first) vector load / store of one lane's share
+template <class T, int N>
+__device__ __forceinline__ Pack<T, N> ld_stream(const T* p) {
+    Pack<T, N> r;
+    constexpr int B = Pack<T, N>::BYTES;
+    if constexpr (B == 16) { const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p)); r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w; }
+    else if constexpr (B == 8) { const uint2 q = __ldcs(reinterpret_cast<const uint2*>(p)); r.w[0] = q.x; r.w[1] = q.y; }
+    else if constexpr (B == 4) r.w[0] = __ldcs(reinterpret_cast<const unsigned int*>(p));
+    else if constexpr (B == 2) r.w[0] = __ldcs(reinterpret_cast<const unsigned short*>(p));
+    else r.w[0] = __ldcs(reinterpret_cast<const unsigned char*>(p));
+    return r;
+}
+template <class T, int N>
+__device__ __forceinline__ void st_stream(T* p, const Pack<T, N>& v) {
+    constexpr int B = Pack<T, N>::BYTES;
+    if constexpr (B == 16) __stcs(reinterpret_cast<uint4*>(p), make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]));
+    else if constexpr (B == 8) __stcs(reinterpret_cast<uint2*>(p), make_uint2(v.w[0], v.w[1]));
+    else if constexpr (B == 4) __stcs(reinterpret_cast<unsigned int*>(p), v.w[0]);
+    else if constexpr (B == 2) __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)v.w[0]);
+    else __stcs(reinterpret_cast<unsigned char*>(p), (unsigned char)v.w[0]);
+}
+
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+
+enum Layout { LAY_VV = 0, LAY_SV = 1, LAY_VS = 2 };
+
+constexpr int EW_BLOCK = 256;
+
+// ---- binary ----------------------------------------------------------------------
+// F: struct { typedef In; typedef Out; static __device__ Out apply(In, In); }
+template <class F, int LAYOUT, int UNROLL>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew2_vec_kernel(const typename F::In* a, const typename F::In* b, typename F::Out* o,
+               int64_t head, int64_t nvec, int64_t n) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
+    constexpr int64_t TILE = (int64_t)EW_BLOCK * UNROLL;
+
+    In sa = In(), sb = In();
+    if (LAYOUT == LAY_SV) sa = a[0];
+    if (LAYOUT == LAY_VS) sb = b[0];
+
+    const In* av = (LAYOUT == LAY_SV) ? a : a + head;
+    const In* bv = (LAYOUT == LAY_VS) ? b : b + head;
+    Out* ov = o + head;
+
+    const int64_t ntiles = (nvec + TILE - 1) / TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * TILE + threadIdx.x;
+        Pack<In, EPV> ra[UNROLL], rb[UNROLL];
+        if (base + (int64_t)(UNROLL - 1) * EW_BLOCK < nvec) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t v = base + (int64_t)u * EW_BLOCK;
+                if (LAYOUT != LAY_SV) ra[u] = ld_stream<In, EPV>(av + v * EPV);
+                if (LAYOUT != LAY_VS) rb[u] = ld_stream<In, EPV>(bv + v * EPV);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t v = base + (int64_t)u * EW_BLOCK;
+                Pack<Out, EPV> r;
+                r.zero();
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra[u].get(e),
+                                      LAYOUT == LAY_VS ? sb : rb[u].get(e)));
+                st_stream<Out, EPV>(ov + v * EPV, r);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t v = base + (int64_t)u * EW_BLOCK;
+                if (v < nvec) {
+                    if (LAYOUT != LAY_SV) ra[u] = ld_stream<In, EPV>(av + v * EPV);
+                    if (LAYOUT != LAY_VS) rb[u] = ld_stream<In, EPV>(bv + v * EPV);
+                    Pack<Out, EPV> r;
+                    r.zero();
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra[u].get(e),
+                                          LAYOUT == LAY_VS ? sb : rb[u].get(e)));
+                    st_stream<Out, EPV>(ov + v * EPV, r);
+                }
+            }
+        }
+    }
+    // head + tail scalars (fewer than 2*EPV elements... plus a misaligned head)
+    if (blockIdx.x == 0) {
+        const int64_t tail0 = head + nvec * EPV;
+        const int64_t nscalar = head + (n - tail0);
+        for (int64_t i = threadIdx.x; i < nscalar; i += EW_BLOCK) {
+            const int64_t idx = i < head ? i : tail0 + (i - head);
+            o[idx] = F::apply(LAYOUT == LAY_SV ? sa : a[idx], LAYOUT == LAY_VS ? sb : b[idx]);
+        }
+    }
+}
+
+// generic byte-strided fallback (any stride incl. 0 and negative); one element per lane
+template <class F>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew2_strided_kernel(const char* a, const char* b, char* o, int64_t n,
+                   int64_t s1, int64_t s2, int64_t so) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    const int64_t step = (int64_t)gridDim.x * EW_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += step) {
+        const In x = *reinterpret_cast<const In*>(a + i * s1);
+        const In y = *reinterpret_cast<const In*>(b + i * s2);
+        *reinterpret_cast<Out*>(o + i * so) = F::apply(x, y);
+    }
+}
+
+// ---- unary -------------------------------------------------------------------------
+// F: struct { typedef In; typedef Out; static __device__ Out apply(In); }
+template <class F, int UNROLL>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
+    constexpr int64_t TILE = (int64_t)EW_BLOCK * UNROLL;
+    const In* av = a + head;
+    Out* ov = o + head;
+    const int64_t ntiles = (nvec + TILE - 1) / TILE;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * TILE + threadIdx.x;
+        Pack<In, EPV> ra[UNROLL];
+        if (base + (int64_t)(UNROLL - 1) * EW_BLOCK < nvec) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+                ra[u] = ld_stream<In, EPV>(av + (base + (int64_t)u * EW_BLOCK) * EPV);
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                Pack<Out, EPV> r;
+                r.zero();
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra[u].get(e)));
+                st_stream<Out, EPV>(ov + (base + (int64_t)u * EW_BLOCK) * EPV, r);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int64_t v = base + (int64_t)u * EW_BLOCK;
+                if (v < nvec) {
+                    ra[u] = ld_stream<In, EPV>(av + v * EPV);
+                    Pack<Out, EPV> r;
+                    r.zero();
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra[u].get(e)));
+                    st_stream<Out, EPV>(ov + v * EPV, r);
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tail0 = head + nvec * EPV;
+        const int64_t nscalar = head + (n - tail0);
+        for (int64_t i = threadIdx.x; i < nscalar; i += EW_BLOCK) {
+            const int64_t idx = i < head ? i : tail0 + (i - head);
+            o[idx] = F::apply(a[idx]);
+        }
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew1_strided_kernel(const char* a, char* o, int64_t n, int64_t s1, int64_t so) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    const int64_t step = (int64_t)gridDim.x * EW_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += step) {
+        const In x = *reinterpret_cast<const In*>(a + i * s1);
+        *reinterpret_cast<Out*>(o + i * so) = F::apply(x);
+    }
+}
+
+// ---- host side: layout classification + launch -------------------------------------------
+
+inline bool ranges_overlap(const char* p, int64_t pbytes, const char* q, int64_t qbytes) {
+    return p < q + qbytes && q < p + pbytes;
+}
+// byte extent [lo, hi) of `len` elements of `size` bytes at byte stride `s`
+inline void extent(const void* p, int64_t len, int64_t s, int64_t size, const char** lo, int64_t* bytes) {
+    const char* c = (const char*)p;
+    int64_t span = (len - 1) * s;
+    if (span >= 0) { *lo = c; *bytes = span + size; }
+    else { *lo = c + span; *bytes = -span + size; }
+}
+
+// 0 ok, PNCU_ERR_OVERLAP if `out` overlaps `in` other than exact element-wise aliasing
+inline int check_alias(const void* in, int64_t sin, int64_t insize, const void* out, int64_t sout,
+                       int64_t outsize, int64_t len) {
+    const char *ilo, *olo;
+    int64_t ib, ob;
+    extent(in, len, sin, insize, &ilo, &ib);
+    extent(out, len, sout, outsize, &olo, &ob);
+    if (!ranges_overlap(ilo, ib, olo, ob)) return 0;
+    if (in == out && sin == sout && insize == outsize) return 0;
+    set_error("output overlaps an input without aliasing it exactly (in=%p stride %lld, out=%p stride %lld, len %lld)",
+              in, (long long)sin, out, (long long)sout, (long long)len);
+    return PNCU_ERR_OVERLAP;
+}
+
+constexpr int EW_UNROLL = 4;
+
+template <class F>
+int launch_binary(const void* in1, const void* in2, void* out, int64_t len, int64_t s1, int64_t s2,
+                  int64_t so, pncu_stream_t stream) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    if (len <= 0) return 0;
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!in1 || !in2 || !out) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
+    if (((uintptr_t)in1 | (uintptr_t)in2 | (uint64_t)s1 | (uint64_t)s2) % sizeof(In) ||
+        ((uintptr_t)out | (uint64_t)so) % sizeof(Out)) {
+        set_error("operand pointer or stride is not a multiple of the item size");
+        return PNCU_ERR_UNSUPPORTED;
+    }
+    if ((rc = check_alias(in1, s1, sizeof(In), out, so, sizeof(Out), len))) return rc;
+    if ((rc = check_alias(in2, s2, sizeof(In), out, so, sizeof(Out), len))) return rc;
+    cudaStream_t st = as_stream(stream);
+
+    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
+    constexpr int IN_VB = EPV * (int)sizeof(In);    // bytes one lane moves per input vector
+    constexpr int OUT_VB = EPV * (int)sizeof(Out);
+    const bool c1 = s1 == (int64_t)sizeof(In), c2 = s2 == (int64_t)sizeof(In);
+    const bool z1 = s1 == 0, z2 = s2 == 0;
+    if (so == (int64_t)sizeof(Out) && ((c1 && c2) || (z1 && c2) || (c1 && z2))) {
+        // elements to peel so that `out` reaches its vector alignment; inputs must agree
+        int64_t head = ((OUT_VB - (int64_t)((uintptr_t)out % OUT_VB)) % OUT_VB) / (int64_t)sizeof(Out);
+        if (head > len) head = len;
+        const bool a_ok = z1 || ((uintptr_t)in1 + head * sizeof(In)) % IN_VB == 0;
+        const bool b_ok = z2 || ((uintptr_t)in2 + head * sizeof(In)) % IN_VB == 0;
+        if (a_ok && b_ok) {
+            const int64_t nvec = (len - head) / EPV;
+            const int64_t tiles = (nvec + (int64_t)EW_BLOCK * EW_UNROLL - 1) / ((int64_t)EW_BLOCK * EW_UNROLL);
+            const unsigned grid = grid_for(tiles, g_tune.ctas_per_sm);
+            const In* a = (const In*)in1;
+            const In* b = (const In*)in2;
+            Out* o = (Out*)out;
+            if (c1 && c2)
+                ew2_vec_kernel<F, LAY_VV, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+            else if (z1)
+                ew2_vec_kernel<F, LAY_SV, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+            else
+                ew2_vec_kernel<F, LAY_VS, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+            return after_launch("ew2_vec_kernel");
+        }
+    }
+    const int64_t tiles = (len + EW_BLOCK - 1) / EW_BLOCK;
+    const unsigned grid = grid_for(tiles, 8);
+    ew2_strided_kernel<F><<<grid, EW_BLOCK, 0, st>>>((const char*)in1, (const char*)in2, (char*)out,
+                                                      len, s1, s2, so);
+    return after_launch("ew2_strided_kernel");
+}
+
+template <class F>
+int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so, pncu_stream_t stream) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    if (len <= 0) return 0;
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!in || !out) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
+    if (((uintptr_t)in | (uint64_t)s1) % sizeof(In) || ((uintptr_t)out | (uint64_t)so) % sizeof(Out)) {
+        set_error("operand pointer or stride is not a multiple of the item size");
+        return PNCU_ERR_UNSUPPORTED;
+    }
+    if ((rc = check_alias(in, s1, sizeof(In), out, so, sizeof(Out), len))) return rc;
+    cudaStream_t st = as_stream(stream);
+
+    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
+    constexpr int IN_VB = EPV * (int)sizeof(In);
+    constexpr int OUT_VB = EPV * (int)sizeof(Out);
+    if (so == (int64_t)sizeof(Out) && s1 == (int64_t)sizeof(In)) {
+        int64_t head = ((OUT_VB - (int64_t)((uintptr_t)out % OUT_VB)) % OUT_VB) / (int64_t)sizeof(Out);
+        if (head > len) head = len;
+        if (((uintptr_t)in + head * sizeof(In)) % IN_VB == 0) {
+            const int64_t nvec = (len - head) / EPV;
+            const int64_t tiles = (nvec + (int64_t)EW_BLOCK * EW_UNROLL - 1) / ((int64_t)EW_BLOCK * EW_UNROLL);
+            const unsigned grid = grid_for(tiles, g_tune.ctas_per_sm);
+            ew1_vec_kernel<F, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
+            return after_launch("ew1_vec_kernel");
+        }
+    }
+    const int64_t tiles = (len + EW_BLOCK - 1) / EW_BLOCK;
+    const unsigned grid = grid_for(tiles, 8);
+    ew1_strided_kernel<F><<<grid, EW_BLOCK, 0, st>>>((const char*)in, (char*)out, len, s1, so);
+    return after_launch("ew1_strided_kernel");
+}
+
+}  // namespace pncu

@@ -1,0 +1,547 @@
+// Reductions and arg-reductions: pncu_GetReduceMathOpFast, pncu_GetArgMinMaxOpFast and the
+// two-pass building blocks pncu_reduce_partials / pncu_reduce_finish (+ argminmax forms).
+//
+// replaces: ReduceMathOpFast / ReduceMathOpFastUpcast / GetReduceMathOpFast
+// (src/atop/ops_binary.cpp:186-344, 1060-1127), the reduce branch of the dispatcher with its
+// per-16K-chunk partials and second pass on the caller (src/pnumpy/_pnumpy.cpp:646-731,
+// 359-444) and the arg-reduction pass-through (src/pnumpy/_pnumpy.cpp:1105-1118).
+//
+// Scheme.  [0, n) is cut into fixed LOGICAL BLOCKS of RED_BLOCK_ELEMS elements.
+//   pass 1: a persistent grid walks the logical blocks; one CTA folds one block: every thread
+//           keeps RED_UNROLL independent accumulators over 128-bit coalesced streaming loads,
+//           folds them in index order, then a shuffle-down tree per warp, then warp leaders
+//           through shared memory folded by thread 0 in warp order -> partial[k] in slot k.
+//   pass 2: ONE CTA folds the partials: thread t takes slots t, t+1024, ... in order, then the
+//           same warp/shared tree, then applies the start value and writes the result.
+// Every choice above is a function of (n, type) only -- not of the grid, the SM count or the
+// arrival order of CTAs -- so results are bit-reproducible run to run, and a multi-GPU split
+// at multiples of RED_BLOCK_ELEMS that gathers all partials before pass 2 is bit-identical to
+// the single-GPU result.  No atomics anywhere.
+//
+// Semantics (8c):
+//   sum/prod of float32 accumulate in float64 (the reference's intent, ops_binary.cpp:1069-70),
+//   rounded to float32 once at the end; float64 in float64; integers wrap modulo 2^k; bool sum
+//   is logical OR and bool prod logical AND (ops_binary.cpp:1066,1082).
+//   min/max follow NumPy: any NaN -> NaN (the reference has no float body and runs NumPy's
+//   loop per chunk, ops_binary.cpp:1096-1098).
+//   argmax/argmin follow NumPy: first occurrence of the extreme; for floats the first NaN wins.
+#include <float.h>
+#include "ew.cuh"
+#include "functors.cuh"
+
+using namespace pncu;
+
+namespace {
+
+constexpr int64_t RED_BLOCK_ELEMS = 65536;
+constexpr int RED_THREADS = 256;
+constexpr int RED_UNROLL = 8;
+constexpr int FIN_THREADS = 1024;
+
+// ---- reducer policies ------------------------------------------------------------------------
+// In: element type; Acc: accumulator == partial type;
+// first(x): accumulator seeded from an element; step(acc, x, idx); combine(a, b) with `a` the
+// earlier operand; start(x): accumulator from the caller's start value; result(acc) -> In.
+
+template <class T, class A>
+struct SumR {
+    typedef T In; typedef A Acc;
+    static constexpr bool kHasIdentity = true;
+    static __device__ __forceinline__ A identity() { return (A)0; }
+    static __device__ __forceinline__ A first(T x, int64_t) { return (A)x; }
+    static __device__ __forceinline__ A step(A acc, T x, int64_t) { return acc + (A)x; }
+    static __device__ __forceinline__ A combine(A a, A b) { return a + b; }
+    static __device__ __forceinline__ A start(T x) { return (A)x; }
+    static __device__ __forceinline__ T result(A a) { return (T)a; }
+};
+template <class T, class A>
+struct ProdR {
+    typedef T In; typedef A Acc;
+    static constexpr bool kHasIdentity = true;
+    static __device__ __forceinline__ A identity() { return (A)1; }
+    static __device__ __forceinline__ A first(T x, int64_t) { return (A)x; }
+    static __device__ __forceinline__ A step(A acc, T x, int64_t) { return acc * (A)x; }
+    static __device__ __forceinline__ A combine(A a, A b) { return a * b; }
+    static __device__ __forceinline__ A start(T x) { return (A)x; }
+    static __device__ __forceinline__ T result(A a) { return (T)a; }
+};
+struct AnyR {  // bool sum
+    typedef bool8 In; typedef unsigned Acc;
+    static constexpr bool kHasIdentity = true;
+    static __device__ __forceinline__ unsigned identity() { return 0u; }
+    static __device__ __forceinline__ unsigned first(bool8 x, int64_t) { return x != 0; }
+    static __device__ __forceinline__ unsigned step(unsigned acc, bool8 x, int64_t) { return acc | (unsigned)(x != 0); }
+    static __device__ __forceinline__ unsigned combine(unsigned a, unsigned b) { return a | b; }
+    static __device__ __forceinline__ unsigned start(bool8 x) { return x != 0; }
+    static __device__ __forceinline__ bool8 result(unsigned a) { return (bool8)(a != 0); }
+};
+struct AllR {  // bool prod
+    typedef bool8 In; typedef unsigned Acc;
+    static constexpr bool kHasIdentity = true;
+    static __device__ __forceinline__ unsigned identity() { return 1u; }
+    static __device__ __forceinline__ unsigned first(bool8 x, int64_t) { return x != 0; }
+    static __device__ __forceinline__ unsigned step(unsigned acc, bool8 x, int64_t) { return acc & (unsigned)(x != 0); }
+    static __device__ __forceinline__ unsigned combine(unsigned a, unsigned b) { return a & b; }
+    static __device__ __forceinline__ unsigned start(bool8 x) { return x != 0; }
+    static __device__ __forceinline__ bool8 result(unsigned a) { return (bool8)(a != 0); }
+};
+// sub-word integers are folded in a 32-bit register (byte/short accumulator arrays would
+// otherwise be demoted to local memory)
+template <class T> struct Widen { typedef T type; };
+template <> struct Widen<int8_t> { typedef int type; };
+template <> struct Widen<int16_t> { typedef int type; };
+template <> struct Widen<uint8_t> { typedef unsigned type; };
+template <> struct Widen<uint16_t> { typedef unsigned type; };
+
+template <class T>
+struct MinR {
+    typedef T In; typedef typename Widen<T>::type Acc;
+    static constexpr bool kHasIdentity = false;
+    static __device__ __forceinline__ Acc identity() { return Acc(); }
+    static __device__ __forceinline__ Acc first(T x, int64_t) { return (Acc)x; }
+    static __device__ __forceinline__ Acc step(Acc acc, T x, int64_t) { return op_min<Acc>(acc, (Acc)x); }
+    static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return op_min<Acc>(a, b); }
+    static __device__ __forceinline__ Acc start(T x) { return (Acc)x; }
+    static __device__ __forceinline__ T result(Acc a) { return (T)a; }
+};
+template <class T>
+struct MaxR {
+    typedef T In; typedef typename Widen<T>::type Acc;
+    static constexpr bool kHasIdentity = false;
+    static __device__ __forceinline__ Acc identity() { return Acc(); }
+    static __device__ __forceinline__ Acc first(T x, int64_t) { return (Acc)x; }
+    static __device__ __forceinline__ Acc step(Acc acc, T x, int64_t) { return op_max<Acc>(acc, (Acc)x); }
+    static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return op_max<Acc>(a, b); }
+    static __device__ __forceinline__ Acc start(T x) { return (Acc)x; }
+    static __device__ __forceinline__ T result(Acc a) { return (T)a; }
+};
+
+// (value, index) pair of an arg-reduction.  16 bytes for every T: value at 0, index at 8.
+template <class T>
+struct alignas(16) ArgPair {
+    T v;
+    int64_t idx;
+};
+template <class T, bool IS_MAX>
+struct ArgR {
+    typedef T In; typedef ArgPair<T> Acc;
+    static constexpr bool kHasIdentity = false;
+    static __device__ __forceinline__ Acc identity() { Acc a; a.v = T(); a.idx = 0; return a; }
+    static __device__ __forceinline__ Acc first(T x, int64_t idx) { Acc a; a.v = x; a.idx = idx; return a; }
+    // strictly better than the incumbent; a NaN beats any non-NaN, nothing beats a NaN
+    static __device__ __forceinline__ bool better(T x, T cur) {
+        if constexpr (is_fp<T>::value) {
+            return (IS_MAX ? x > cur : x < cur) || (x != x && cur == cur);
+        } else {
+            return IS_MAX ? x > cur : x < cur;
+        }
+    }
+    static __device__ __forceinline__ Acc step(Acc acc, T x, int64_t idx) {
+        // a thread visits indices in increasing order, so a strict test keeps the first hit
+        if (better(x, acc.v)) { acc.v = x; acc.idx = idx; }
+        return acc;
+    }
+    static __device__ __forceinline__ Acc combine(Acc a, Acc b) {
+        if (better(b.v, a.v)) return b;
+        if (better(a.v, b.v)) return a;
+        return a.idx <= b.idx ? a : b;  // equal (or both NaN): smaller index
+    }
+};
+
+// ---- shuffles for every accumulator type ---------------------------------------------------------
+template <class A> __device__ __forceinline__ A shfl_down_any(A a, int o) { return __shfl_down_sync(0xffffffffu, a, o); }
+template <> __device__ __forceinline__ int8_t shfl_down_any(int8_t a, int o) { return (int8_t)__shfl_down_sync(0xffffffffu, (int)a, o); }
+template <> __device__ __forceinline__ uint8_t shfl_down_any(uint8_t a, int o) { return (uint8_t)__shfl_down_sync(0xffffffffu, (unsigned)a, o); }
+template <> __device__ __forceinline__ int16_t shfl_down_any(int16_t a, int o) { return (int16_t)__shfl_down_sync(0xffffffffu, (int)a, o); }
+template <> __device__ __forceinline__ uint16_t shfl_down_any(uint16_t a, int o) { return (uint16_t)__shfl_down_sync(0xffffffffu, (unsigned)a, o); }
+template <> __device__ __forceinline__ int64_t shfl_down_any(int64_t a, int o) { return (int64_t)__shfl_down_sync(0xffffffffu, (long long)a, o); }
+template <> __device__ __forceinline__ uint64_t shfl_down_any(uint64_t a, int o) { return (uint64_t)__shfl_down_sync(0xffffffffu, (unsigned long long)a, o); }
+template <class T> __device__ __forceinline__ ArgPair<T> shfl_down_pair(ArgPair<T> a, int o) {
+    ArgPair<T> r;
+    r.v = shfl_down_any<T>(a.v, o);
+    r.idx = shfl_down_any<int64_t>(a.idx, o);
+    return r;
+}
+template <class A> struct Shfl { static __device__ __forceinline__ A down(A a, int o) { return shfl_down_any<A>(a, o); } };
+template <class T> struct Shfl<ArgPair<T>> { static __device__ __forceinline__ ArgPair<T> down(ArgPair<T> a, int o) { return shfl_down_pair<T>(a, o); } };
+
+// fold one accumulator per thread across the CTA; result valid in thread 0
+template <class R, int THREADS>
+__device__ __forceinline__ typename R::Acc block_fold(typename R::Acc a, typename R::Acc* smem) {
+    typedef typename R::Acc Acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = R::combine(a, Shfl<Acc>::down(a, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = smem[0];
+        for (int w = 1; w < THREADS / 32; ++w) a = R::combine(a, smem[w]);
+    }
+    return a;
+}
+
+template <class R>
+__device__ __forceinline__ void write_result(typename R::Acc total, typename R::In* out, const typename R::In* startVal) {
+    typename R::Acc t = total;
+    if (startVal) t = R::combine(R::start(*startVal), total);
+    *out = R::result(t);
+}
+
+// ---- pass 1 --------------------------------------------------------------------------------------
+template <class R, bool VEC>
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_base,
+                     typename R::Acc* partials, int64_t nblocks) {
+    typedef typename R::In In;
+    typedef typename R::Acc Acc;
+    constexpr int EPV = VEC ? 16 / (int)sizeof(In) : 1;
+    __shared__ Acc smem[RED_THREADS / 32];
+
+    for (int64_t k = blockIdx.x; k < nblocks; k += gridDim.x) {
+        const int64_t start = k * RED_BLOCK_ELEMS;
+        const int64_t cnt = (n - start) < RED_BLOCK_ELEMS ? (n - start) : RED_BLOCK_ELEMS;
+        const char* base = in + start * stride;
+        const int64_t gidx0 = start + index_base;
+
+        Acc acc[RED_UNROLL];
+        if (R::kHasIdentity) {
+#pragma unroll
+            for (int u = 0; u < RED_UNROLL; ++u) acc[u] = R::identity();
+        } else {
+            // idempotent ops (min/max/arg): seed every accumulator with the block's first element
+            const Acc seed = R::first(*reinterpret_cast<const In*>(base), gidx0);
+#pragma unroll
+            for (int u = 0; u < RED_UNROLL; ++u) acc[u] = seed;
+        }
+
+        if (VEC) {
+            const In* p = reinterpret_cast<const In*>(base);
+            const int64_t nvec = cnt / EPV;
+            int64_t v = threadIdx.x;
+            for (; v + (int64_t)(RED_UNROLL - 1) * RED_THREADS < nvec; v += (int64_t)RED_UNROLL * RED_THREADS) {
+                Pack<In, EPV> r[RED_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RED_UNROLL; ++u) r[u] = ld_stream<In, EPV>(p + (v + (int64_t)u * RED_THREADS) * EPV);
+#pragma unroll
+                for (int u = 0; u < RED_UNROLL; ++u) {
+                    const int64_t e0 = gidx0 + (v + (int64_t)u * RED_THREADS) * EPV;
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e) acc[u] = R::step(acc[u], r[u].get(e), e0 + e);
+                }
+            }
+            for (; v < nvec; v += RED_THREADS) {  // ragged last group (fewer than RED_UNROLL vectors)
+                Pack<In, EPV> r = ld_stream<In, EPV>(p + v * EPV);
+                const int64_t e0 = gidx0 + v * EPV;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) acc[0] = R::step(acc[0], r.get(e), e0 + e);
+            }
+            const int64_t t0 = nvec * EPV + threadIdx.x;  // < EPV leftover elements
+            if (t0 < cnt) acc[0] = R::step(acc[0], p[t0], gidx0 + t0);
+        } else {
+            int64_t i = threadIdx.x;
+            for (; i + (int64_t)(RED_UNROLL - 1) * RED_THREADS < cnt; i += (int64_t)RED_UNROLL * RED_THREADS) {
+                In r[RED_UNROLL];
+#pragma unroll
+                for (int u = 0; u < RED_UNROLL; ++u)
+                    r[u] = *reinterpret_cast<const In*>(base + (i + (int64_t)u * RED_THREADS) * stride);
+#pragma unroll
+                for (int u = 0; u < RED_UNROLL; ++u) acc[u] = R::step(acc[u], r[u], gidx0 + i + (int64_t)u * RED_THREADS);
+            }
+            for (; i < cnt; i += RED_THREADS)
+                acc[0] = R::step(acc[0], *reinterpret_cast<const In*>(base + i * stride), gidx0 + i);
+        }
+
+        Acc a = acc[0];
+#pragma unroll
+        for (int u = 1; u < RED_UNROLL; ++u) a = R::combine(a, acc[u]);
+        a = block_fold<R, RED_THREADS>(a, smem);
+        if (threadIdx.x == 0) partials[k] = a;
+        __syncthreads();  // smem is reused by the next logical block
+    }
+}
+
+// ---- pass 2 --------------------------------------------------------------------------------------
+// VALUE: write R::result into `out` (reductions); else write the index (arg-reductions)
+template <class R, bool VALUE>
+__global__ void __launch_bounds__(FIN_THREADS)
+reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, const void* startVal) {
+    typedef typename R::Acc Acc;
+    __shared__ Acc smem[FIN_THREADS / 32];
+    // slots t, t+1024, ... in order; threads beyond `count` hold a copy of slot 0 (harmless for
+    // idempotent ops) or the identity
+    Acc a;
+    if (R::kHasIdentity) a = R::identity(); else a = partials[0];
+    for (int64_t k = threadIdx.x; k < count; k += FIN_THREADS) {
+        if (!R::kHasIdentity && k == threadIdx.x) a = partials[k];
+        else a = R::combine(a, partials[k]);
+    }
+    a = block_fold<R, FIN_THREADS>(a, smem);
+    if (threadIdx.x == 0) {
+        if constexpr (VALUE) {
+            write_result<R>(a, reinterpret_cast<typename R::In*>(out),
+                            reinterpret_cast<const typename R::In*>(startVal));
+        } else {
+            if constexpr (sizeof(Acc) == 16) *reinterpret_cast<int64_t*>(out) = a.idx;
+        }
+    }
+}
+
+// ---- host launchers ---------------------------------------------------------------------------------
+inline int64_t nblocks_for(int64_t len) { return (len + RED_BLOCK_ELEMS - 1) / RED_BLOCK_ELEMS; }
+
+template <class R>
+int launch_partials(const void* in, int64_t len, int64_t stride, int64_t index_base, void* partials,
+                    cudaStream_t st) {
+    typedef typename R::In In;
+    const int64_t nb = nblocks_for(len);
+    const unsigned grid = grid_for(nb, g_tune.reduce_ctas_per_sm);
+    const bool vec = stride == (int64_t)sizeof(In) && ((uintptr_t)in % 16) == 0;
+    if (vec)
+        reduce_blocks_kernel<R, true><<<grid, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
+                                                                  (typename R::Acc*)partials, nb);
+    else
+        reduce_blocks_kernel<R, false><<<grid, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
+                                                                   (typename R::Acc*)partials, nb);
+    return after_launch("reduce_blocks_kernel");
+}
+
+template <class R>
+int check_reduce_args(const void* in, int64_t stride) {
+    typedef typename R::In In;
+    if (!in) { set_error("null input"); return PNCU_ERR_ARGUMENT; }
+    if (stride == 0) { set_error("reduction over a stride-0 operand has no GPU body"); return PNCU_ERR_UNSUPPORTED; }
+    if (((uintptr_t)in | (uint64_t)stride) % sizeof(In)) {
+        set_error("operand pointer or stride is not a multiple of the item size");
+        return PNCU_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+// REDUCE_FUNC
+template <class R>
+int launch_reduce(const void* in, void* out, const void* startVal, int64_t len, int64_t stride,
+                  pncu_stream_t stream) {
+    typedef typename R::In In;
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (len <= 0) {
+        if (startVal && startVal != out) PNCU_CUDA(cudaMemcpyAsync(out, startVal, sizeof(In), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    if ((rc = check_reduce_args<R>(in, stride))) return rc;
+    const int64_t nb = nblocks_for(len);
+    void* ws = NULL;
+    if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
+    if ((rc = launch_partials<R>(in, len, stride, 0, ws, st))) return rc;
+    reduce_finish_kernel<R, true><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)ws, nb, out, startVal);
+    return after_launch("reduce_finish_kernel");
+}
+
+template <class R>
+int launch_argminmax(const void* in, int64_t len, int64_t* out_index, pncu_stream_t stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (!out_index) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (len <= 0) { set_error("arg-reduction of an empty sequence"); return PNCU_ERR_ARGUMENT; }
+    if ((rc = check_reduce_args<R>(in, sizeof(typename R::In)))) return rc;
+    const int64_t nb = nblocks_for(len);
+    void* ws = NULL;
+    if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
+    if ((rc = launch_partials<R>(in, len, sizeof(typename R::In), 0, ws, st))) return rc;
+    reduce_finish_kernel<R, false><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)ws, nb, out_index, NULL);
+    return after_launch("reduce_finish_kernel");
+}
+
+// type-erased entry for the two-pass building blocks
+struct ReduceOps {
+    int partial_bytes;
+    pncu_reduce_fn full;
+    int (*partials)(const void*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+    int (*finish)(const void*, int64_t, void*, const void*, cudaStream_t);
+};
+template <class R, bool VALUE>
+int finish_thunk(const void* partials, int64_t count, void* out, const void* startVal, cudaStream_t st) {
+    reduce_finish_kernel<R, VALUE><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)partials, count, out, startVal);
+    return after_launch("reduce_finish_kernel");
+}
+template <class R>
+ReduceOps make_ops() {
+    ReduceOps o;
+    o.partial_bytes = (int)sizeof(typename R::Acc);
+    o.full = launch_reduce<R>;
+    o.partials = launch_partials<R>;
+    o.finish = finish_thunk<R, true>;
+    return o;
+}
+template <class R>
+ReduceOps make_arg_ops() {
+    ReduceOps o;
+    o.partial_bytes = (int)sizeof(typename R::Acc);
+    o.full = NULL;
+    o.partials = launch_partials<R>;
+    o.finish = finish_thunk<R, false>;
+    return o;
+}
+
+bool lookup_reduce(int func, int t, ReduceOps* o) {
+    switch (func) {
+        case PNCU_ADD:
+            switch (t) {
+                case PNCU_BOOL: *o = make_ops<AnyR>(); return true;
+                case PNCU_INT8: *o = make_ops<SumR<int8_t, unsigned>>(); return true;
+                case PNCU_UINT8: *o = make_ops<SumR<uint8_t, unsigned>>(); return true;
+                case PNCU_INT16: *o = make_ops<SumR<int16_t, unsigned>>(); return true;
+                case PNCU_UINT16: *o = make_ops<SumR<uint16_t, unsigned>>(); return true;
+                case PNCU_INT32: *o = make_ops<SumR<int32_t, unsigned>>(); return true;
+                case PNCU_UINT32: *o = make_ops<SumR<uint32_t, unsigned>>(); return true;
+                case PNCU_INT64: *o = make_ops<SumR<int64_t, unsigned long long>>(); return true;
+                case PNCU_UINT64: *o = make_ops<SumR<uint64_t, unsigned long long>>(); return true;
+                case PNCU_FLOAT: *o = make_ops<SumR<float, double>>(); return true;
+                case PNCU_DOUBLE: *o = make_ops<SumR<double, double>>(); return true;
+            }
+            return false;
+        case PNCU_MUL:
+            switch (t) {
+                case PNCU_BOOL: *o = make_ops<AllR>(); return true;
+                case PNCU_INT8: *o = make_ops<ProdR<int8_t, unsigned>>(); return true;
+                case PNCU_UINT8: *o = make_ops<ProdR<uint8_t, unsigned>>(); return true;
+                case PNCU_INT16: *o = make_ops<ProdR<int16_t, unsigned>>(); return true;
+                case PNCU_UINT16: *o = make_ops<ProdR<uint16_t, unsigned>>(); return true;
+                case PNCU_INT32: *o = make_ops<ProdR<int32_t, unsigned>>(); return true;
+                case PNCU_UINT32: *o = make_ops<ProdR<uint32_t, unsigned>>(); return true;
+                case PNCU_INT64: *o = make_ops<ProdR<int64_t, unsigned long long>>(); return true;
+                case PNCU_UINT64: *o = make_ops<ProdR<uint64_t, unsigned long long>>(); return true;
+                case PNCU_FLOAT: *o = make_ops<ProdR<float, double>>(); return true;
+                case PNCU_DOUBLE: *o = make_ops<ProdR<double, double>>(); return true;
+            }
+            return false;
+#define PNCU_MINMAX_CASES(RR)                                                  \
+    switch (t) {                                                               \
+        case PNCU_BOOL: case PNCU_UINT8: *o = make_ops<RR<uint8_t>>(); return true; \
+        case PNCU_INT8: *o = make_ops<RR<int8_t>>(); return true;              \
+        case PNCU_INT16: *o = make_ops<RR<int16_t>>(); return true;            \
+        case PNCU_UINT16: *o = make_ops<RR<uint16_t>>(); return true;          \
+        case PNCU_INT32: *o = make_ops<RR<int32_t>>(); return true;            \
+        case PNCU_UINT32: *o = make_ops<RR<uint32_t>>(); return true;          \
+        case PNCU_INT64: *o = make_ops<RR<int64_t>>(); return true;            \
+        case PNCU_UINT64: *o = make_ops<RR<uint64_t>>(); return true;          \
+        case PNCU_FLOAT: *o = make_ops<RR<float>>(); return true;              \
+        case PNCU_DOUBLE: *o = make_ops<RR<double>>(); return true;            \
+    }                                                                          \
+    return false;
+        case PNCU_MIN: PNCU_MINMAX_CASES(MinR)
+        case PNCU_MAX: PNCU_MINMAX_CASES(MaxR)
+#undef PNCU_MINMAX_CASES
+    }
+    return false;
+}
+
+template <bool IS_MAX>
+bool lookup_arg_t(int t, ReduceOps* o) {
+    switch (t) {
+        case PNCU_BOOL: case PNCU_UINT8: *o = make_arg_ops<ArgR<uint8_t, IS_MAX>>(); return true;
+        case PNCU_INT8: *o = make_arg_ops<ArgR<int8_t, IS_MAX>>(); return true;
+        case PNCU_INT16: *o = make_arg_ops<ArgR<int16_t, IS_MAX>>(); return true;
+        case PNCU_UINT16: *o = make_arg_ops<ArgR<uint16_t, IS_MAX>>(); return true;
+        case PNCU_INT32: *o = make_arg_ops<ArgR<int32_t, IS_MAX>>(); return true;
+        case PNCU_UINT32: *o = make_arg_ops<ArgR<uint32_t, IS_MAX>>(); return true;
+        case PNCU_INT64: *o = make_arg_ops<ArgR<int64_t, IS_MAX>>(); return true;
+        case PNCU_UINT64: *o = make_arg_ops<ArgR<uint64_t, IS_MAX>>(); return true;
+        case PNCU_FLOAT: *o = make_arg_ops<ArgR<float, IS_MAX>>(); return true;
+        case PNCU_DOUBLE: *o = make_arg_ops<ArgR<double, IS_MAX>>(); return true;
+    }
+    return false;
+}
+bool lookup_arg(int kind, int t, ReduceOps* o) {
+    if (kind == PNCU_ARGMAX) return lookup_arg_t<true>(t, o);
+    if (kind == PNCU_ARGMIN) return lookup_arg_t<false>(t, o);
+    return false;
+}
+
+template <bool IS_MAX>
+pncu_argminmax_fn pick_arg(int t) {
+    switch (t) {
+        case PNCU_BOOL: case PNCU_UINT8: return launch_argminmax<ArgR<uint8_t, IS_MAX>>;
+        case PNCU_INT8: return launch_argminmax<ArgR<int8_t, IS_MAX>>;
+        case PNCU_INT16: return launch_argminmax<ArgR<int16_t, IS_MAX>>;
+        case PNCU_UINT16: return launch_argminmax<ArgR<uint16_t, IS_MAX>>;
+        case PNCU_INT32: return launch_argminmax<ArgR<int32_t, IS_MAX>>;
+        case PNCU_UINT32: return launch_argminmax<ArgR<uint32_t, IS_MAX>>;
+        case PNCU_INT64: return launch_argminmax<ArgR<int64_t, IS_MAX>>;
+        case PNCU_UINT64: return launch_argminmax<ArgR<uint64_t, IS_MAX>>;
+        case PNCU_FLOAT: return launch_argminmax<ArgR<float, IS_MAX>>;
+        case PNCU_DOUBLE: return launch_argminmax<ArgR<double, IS_MAX>>;
+    }
+    return NULL;
+}
+
+}  // namespace
+
+extern "C" pncu_reduce_fn pncu_GetReduceMathOpFast(int func, int t) {
+    ReduceOps o;
+    return lookup_reduce(func, t, &o) ? o.full : NULL;
+}
+
+extern "C" pncu_argminmax_fn pncu_GetArgMinMaxOpFast(int kind, int t) {
+    if (kind == PNCU_ARGMAX) return pick_arg<true>(t);
+    if (kind == PNCU_ARGMIN) return pick_arg<false>(t);
+    return NULL;
+}
+
+extern "C" int64_t pncu_reduce_block_elems(void) { return RED_BLOCK_ELEMS; }
+
+extern "C" int pncu_reduce_partial_bytes(int func, int t) {
+    ReduceOps o;
+    return lookup_reduce(func, t, &o) ? o.partial_bytes : 0;
+}
+
+extern "C" int pncu_reduce_partials(int func, int t, const void* in, int64_t len, void* partials,
+                                    pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_reduce(func, t, &o)) { set_error("no reduction kernel for func %d type %d", func, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (len <= 0) return 0;
+    if (!in || !partials) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
+    return o.partials(in, len, pncu_itemsize(t), 0, partials, as_stream(stream));
+}
+
+extern "C" int pncu_reduce_finish(int func, int t, const void* partials, int64_t count, void* out,
+                                  const void* startVal, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_reduce(func, t, &o)) { set_error("no reduction kernel for func %d type %d", func, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (count <= 0) {
+        if (startVal && startVal != out)
+            PNCU_CUDA(cudaMemcpyAsync(out, startVal, pncu_itemsize(t), cudaMemcpyDeviceToDevice, as_stream(stream)));
+        return 0;
+    }
+    return o.finish(partials, count, out, startVal, as_stream(stream));
+}
+
+extern "C" int pncu_argminmax_partials(int kind, int t, const void* in, int64_t len, int64_t index_base,
+                                       void* partials, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_arg(kind, t, &o)) { set_error("no arg-reduction kernel for kind %d type %d", kind, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (len <= 0) return 0;
+    if (!in || !partials) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
+    return o.partials(in, len, pncu_itemsize(t), index_base, partials, as_stream(stream));
+}
+
+extern "C" int pncu_argminmax_finish(int kind, int t, const void* partials, int64_t count,
+                                     int64_t* out_index, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_arg(kind, t, &o)) { set_error("no arg-reduction kernel for kind %d type %d", kind, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!out_index || count <= 0) { set_error("bad arguments"); return PNCU_ERR_ARGUMENT; }
+    return o.finish(partials, count, out_index, NULL, as_stream(stream));
+}

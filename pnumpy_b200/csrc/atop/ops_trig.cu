@@ -1,0 +1,205 @@
+// Transcendental getters: pncu_GetTrigOpFast  (sin, cos, log, exp on float32/float64).
+// replaces: GetTrigOpFast, src/atop/ops_trig.cpp:578-781, and the Cephes-derived bodies
+// log256_ps / exp256_ps / sin256_ps / cos256_ps, src/atop/avx_mathfun.h:177-248, 354-409,
+// 506-601, 604-673.
+//
+// float32: the kernels restate the Cephes operation SEQUENCE literally with round-to-nearest
+// mul/add/sub intrinsics (never contracted into FMA), so on the domain where the reference's
+// vector body is valid the results are bit-identical to it:
+//     log: every positive normal x;  exp: x in [-87.33, 88.376];  sin/cos: |x| <= 8192
+// (the range avx_mathfun.h:497-500 documents).  Outside that domain the reference is
+// defective (log(0)=nan, log(inf)=88.7, exp(>88.38) clamped, denormal
+// inputs/outputs flushed, garbage for huge sin arguments) and the kernels follow IEEE /
+// NumPy instead: log(+-0) = -inf, log(<0) = nan, log(inf) = inf, denormal inputs rescaled,
+// exp overflow -> inf, exp underflow through correctly rounded denormals, |x| > 8192 or
+// non-finite sin/cos through CUDA's full-range sinf/cosf.
+//
+// float64: the reference's pd bodies are wrong (exponent-bias typo avx_mathfun.h:107, float
+// clamp :326-327, float coefficients :472-481), so there is nothing to match; the kernels use
+// CUDA's double-precision sin/cos/log/exp (<= 2 ULP, documented by NVIDIA) and are checked
+// against correctly rounded values.
+#include <float.h>
+#include <math.h>
+#include "ew.cuh"
+#include "functors.cuh"
+
+using namespace pncu;
+
+namespace {
+
+// rn-only arithmetic helpers
+#define FM(a, b) __fmul_rn((a), (b))
+#define FA(a, b) __fadd_rn((a), (b))
+#define FS(a, b) __fsub_rn((a), (b))
+
+// ---- log ---------------------------------------------------------------------------------
+// avx_mathfun.h:177-248
+__device__ __forceinline__ float cephes_logf(float x) {
+    if (!(x > 0.0f)) return (x == 0.0f) ? -INFINITY : NAN;  // +-0 -> -inf; negative, NaN -> NaN
+    if (x == INFINITY) return INFINITY;
+    int eadj = 0;
+    if (x < FLT_MIN) {  // denormal: rescale exactly by 2^23 (the reference clamps to FLT_MIN)
+        x = FM(x, 8388608.0f);
+        eadj = -23;
+    }
+    const unsigned bits = __float_as_uint(x);
+    int imm0 = (int)(bits >> 23) - 0x7f + eadj;
+    x = __uint_as_float((bits & 0x807fffffu) | 0x3f000000u);  // mantissa in [0.5, 1)
+    float e = FA((float)imm0, 1.0f);
+    const bool lt = x < 0.707106781186547524f;  // cephes_SQRTHF
+    const float tmp0 = lt ? x : 0.0f;
+    x = FS(x, 1.0f);
+    e = FS(e, lt ? 1.0f : 0.0f);
+    x = FA(x, tmp0);
+    const float z = FM(x, x);
+    float y = 7.0376836292E-2f;
+    y = FM(y, x); y = FA(y, -1.1514610310E-1f);
+    y = FM(y, x); y = FA(y, 1.1676998740E-1f);
+    y = FM(y, x); y = FA(y, -1.2420140846E-1f);
+    y = FM(y, x); y = FA(y, +1.4249322787E-1f);
+    y = FM(y, x); y = FA(y, -1.6668057665E-1f);
+    y = FM(y, x); y = FA(y, +2.0000714765E-1f);
+    y = FM(y, x); y = FA(y, -2.4999993993E-1f);
+    y = FM(y, x); y = FA(y, +3.3333331174E-1f);
+    y = FM(y, x);
+    y = FM(y, z);
+    float tmp = FM(e, -2.12194440e-4f);  // cephes_log_q1
+    y = FA(y, tmp);
+    tmp = FM(z, 0.5f);
+    y = FS(y, tmp);
+    tmp = FM(e, 0.693359375f);  // cephes_log_q2
+    x = FA(x, y);
+    x = FA(x, tmp);
+    return x;
+}
+
+// ---- exp ---------------------------------------------------------------------------------
+// avx_mathfun.h:354-409
+__device__ __forceinline__ float cephes_expf(float x) {
+    if (x != x) return x;
+    if (x > 88.72283935546875f) return INFINITY;  // > log(FLT_MAX)
+    if (x < -103.98f) return 0.0f;                // < log(2^-150): rounds to +0
+    float fx = FM(x, 1.44269504088896341f);       // cephes_LOG2EF
+    fx = FA(fx, 0.5f);
+    fx = floorf(fx);
+    float tmp = FM(fx, 0.693359375f);             // cephes_exp_C1
+    float z = FM(fx, -2.12194440e-4f);            // cephes_exp_C2
+    x = FS(x, tmp);
+    x = FS(x, z);
+    z = FM(x, x);
+    float y = 1.9875691500E-4f;
+    y = FM(y, x); y = FA(y, 1.3981999507E-3f);
+    y = FM(y, x); y = FA(y, 8.3334519073E-3f);
+    y = FM(y, x); y = FA(y, 4.1665795894E-2f);
+    y = FM(y, x); y = FA(y, 1.6666665459E-1f);
+    y = FM(y, x); y = FA(y, 5.0000001201E-1f);
+    y = FM(y, z);
+    y = FA(y, x);
+    y = FA(y, 1.0f);
+    const int n = (int)fx;
+    if (n > 127) {  // the reference clamps x to 88.376 instead (avx_mathfun.h:360)
+        y = FM(y, __uint_as_float((unsigned)(n - 1 + 0x7f) << 23));
+        return FM(y, 2.0f);
+    }
+    if (n < -126) {  // denormal result: scale in two exact/once-rounded steps
+        y = FM(y, __uint_as_float((unsigned)(n + 24 + 0x7f) << 23));
+        return FM(y, 5.9604644775390625e-08f);  // 2^-24
+    }
+    return FM(y, __uint_as_float((unsigned)(n + 0x7f) << 23));
+}
+
+// ---- sin / cos -----------------------------------------------------------------------------
+// shared tail of avx_mathfun.h:558-600 and :632-672
+__device__ __forceinline__ float cephes_sincos_tail(float x, float y, bool sin_poly, unsigned sign) {
+    // extended precision modular arithmetic: x = ((x - y*DP1) - y*DP2) - y*DP3
+    const float x1 = FM(y, -0.78515625f);
+    const float x2 = FM(y, -2.4187564849853515625e-4f);
+    const float x3 = FM(y, -3.77489497744594108e-8f);
+    x = FA(x, x1);
+    x = FA(x, x2);
+    x = FA(x, x3);
+    const float z = FM(x, x);
+    float c = 2.443315711809948E-005f;  // coscof
+    c = FM(c, z); c = FA(c, -1.388731625493765E-003f);
+    c = FM(c, z); c = FA(c, 4.166664568298827E-002f);
+    c = FM(c, z);
+    c = FM(c, z);
+    c = FS(c, FM(z, 0.5f));
+    c = FA(c, 1.0f);
+    float s = -1.9515295891E-4f;  // sincof
+    s = FM(s, z); s = FA(s, 8.3321608736E-3f);
+    s = FM(s, z); s = FA(s, -1.6666654611E-1f);
+    s = FM(s, z);
+    s = FM(s, x);
+    s = FA(s, x);
+    // and / andnot / add select of the reference: the unselected operand contributes +0.0
+    const float r = sin_poly ? FA(0.0f, s) : FA(c, 0.0f);
+    return __uint_as_float(__float_as_uint(r) ^ sign);
+}
+
+__device__ __forceinline__ float cephes_sinf(float xin) {
+    const float x = fabsf(xin);
+    if (!(x <= 8192.0f)) return sinf(xin);  // outside the documented Cephes range, inf, NaN
+    unsigned sign = __float_as_uint(xin) & 0x80000000u;
+    float y = FM(x, 1.27323954473516f);  // 4/pi
+    int j = (int)y;                      // cvttps
+    j = (j + 1) & ~1;
+    y = (float)j;
+    sign ^= ((unsigned)(j & 4)) << 29;
+    const bool sin_poly = (j & 2) == 0;
+    return cephes_sincos_tail(x, y, sin_poly, sign);
+}
+
+__device__ __forceinline__ float cephes_cosf(float xin) {
+    const float x = fabsf(xin);
+    if (!(x <= 8192.0f)) return cosf(xin);
+    float y = FM(x, 1.27323954473516f);
+    int j = (int)y;
+    j = (j + 1) & ~1;
+    y = (float)j;
+    j -= 2;
+    const unsigned sign = ((unsigned)(~j & 4)) << 29;
+    const bool sin_poly = (j & 2) == 0;
+    return cephes_sincos_tail(x, y, sin_poly, sign);
+}
+
+#undef FM
+#undef FA
+#undef FS
+
+struct SinF32 { typedef float In; typedef float Out; static __device__ __forceinline__ float apply(float a) { return cephes_sinf(a); } };
+struct CosF32 { typedef float In; typedef float Out; static __device__ __forceinline__ float apply(float a) { return cephes_cosf(a); } };
+struct LogF32 { typedef float In; typedef float Out; static __device__ __forceinline__ float apply(float a) { return cephes_logf(a); } };
+struct ExpF32 { typedef float In; typedef float Out; static __device__ __forceinline__ float apply(float a) { return cephes_expf(a); } };
+struct SinF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return sin(a); } };
+struct CosF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return cos(a); } };
+struct LogF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return log(a); } };
+struct ExpF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return exp(a); } };
+
+}  // namespace
+
+extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType) {
+    if (!wantedOutType || func <= PNCU_TRIG_INVALID || func >= PNCU_TRIG_LAST) return NULL;
+    // ops_trig.cpp:584-777: every op sets the out-type to the in-type, body or not -- the hook
+    // layer registers all 20 names for f32/f64 (src/pnumpy/_pnumpy.cpp:1492-1547).
+    *wantedOutType = t;
+    switch (func) {
+        case PNCU_SIN:
+            if (t == PNCU_FLOAT) return launch_unary<SinF32>;
+            if (t == PNCU_DOUBLE) return launch_unary<SinF64>;
+            break;
+        case PNCU_COS:
+            if (t == PNCU_FLOAT) return launch_unary<CosF32>;
+            if (t == PNCU_DOUBLE) return launch_unary<CosF64>;
+            break;
+        case PNCU_LOG:
+            if (t == PNCU_FLOAT) return launch_unary<LogF32>;
+            if (t == PNCU_DOUBLE) return launch_unary<LogF64>;
+            break;
+        case PNCU_EXP:
+            if (t == PNCU_FLOAT) return launch_unary<ExpF32>;
+            if (t == PNCU_DOUBLE) return launch_unary<ExpF64>;
+            break;
+    }
+    return NULL;
+}

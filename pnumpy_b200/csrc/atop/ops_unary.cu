@@ -1,0 +1,222 @@
+// Unary getters: pncu_GetUnaryOpFast (the reference's Fast-then-Slow lookup folded into one).
+// replaces: GetUnaryOpFast / GetUnaryOpSlow, src/atop/ops_unary.cpp:1250-1774, and the loop
+// bodies UnaryOpFast (:327-376), UnaryNanFast* (:435-928) and the scalar fallbacks (:934-1204).
+//
+// Semantics follow NumPy's loops (which the reference equals on these ops, SURVEY.md
+// App. C.1) with the one documented exception of float `negative`: the reference computes
+// 0 - x (src/atop/ops_unary.cpp:295-305) so -(+0.0) = +0.0; NumPy flips the sign bit, as here.
+#include "ew.cuh"
+#include "functors.cuh"
+
+using namespace pncu;
+
+namespace {
+
+#define PNCU_UNARY_FUNCTOR(NAME, OUT_T, EXPR)                              \
+    template <class T> struct NAME {                                       \
+        typedef T In;                                                      \
+        typedef OUT_T Out;                                                 \
+        static __device__ __forceinline__ OUT_T apply(T a) { return EXPR; } \
+    };
+
+template <class T> __device__ __forceinline__ T u_abs(T a) {
+    typedef typename std::make_unsigned<T>::type U;
+    if constexpr (std::is_signed<T>::value) return a < 0 ? (T)(U)((U)0 - (U)a) : a;  // INT_MIN stays INT_MIN
+    else return a;
+}
+template <> __device__ __forceinline__ float u_abs<float>(float a) { return fabsf(a); }
+template <> __device__ __forceinline__ double u_abs<double>(double a) { return fabs(a); }
+
+template <class T> __device__ __forceinline__ T u_neg(T a) {
+    typedef typename std::make_unsigned<T>::type U;
+    return (T)(U)((U)0 - (U)a);
+}
+template <> __device__ __forceinline__ float u_neg<float>(float a) { return -a; }
+template <> __device__ __forceinline__ double u_neg<double>(double a) { return -a; }
+
+// NumPy sign: x>0 -> 1, x<0 -> -1, x==0 -> +0, NaN -> NaN
+template <class T> __device__ __forceinline__ T u_sign(T a) {
+    return a > 0 ? (T)1 : (a < 0 ? (T)-1 : (a == 0 ? (T)0 : a));
+}
+
+__device__ __forceinline__ float u_floor(float a) { return floorf(a); }
+__device__ __forceinline__ double u_floor(double a) { return floor(a); }
+__device__ __forceinline__ float u_ceil(float a) { return ceilf(a); }
+__device__ __forceinline__ double u_ceil(double a) { return ceil(a); }
+__device__ __forceinline__ float u_trunc(float a) { return truncf(a); }
+__device__ __forceinline__ double u_trunc(double a) { return trunc(a); }
+__device__ __forceinline__ float u_rint(float a) { return rintf(a); }  // half-to-even
+__device__ __forceinline__ double u_rint(double a) { return rint(a); }
+__device__ __forceinline__ float u_sqrt(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double u_sqrt(double a) { return __dsqrt_rn(a); }
+
+template <class T> __device__ __forceinline__ bool u_isnan(T a) {
+    if constexpr (is_fp<T>::value) return a != a;
+    else return false;
+}
+template <class T> __device__ __forceinline__ bool u_isinf(T a) {
+    if constexpr (is_fp<T>::value) return u_abs<T>(a) == (T)INFINITY;
+    else return false;
+}
+template <class T> __device__ __forceinline__ bool u_isfinite(T a) {
+    if constexpr (is_fp<T>::value) return u_abs<T>(a) < (T)INFINITY;  // false for inf and NaN
+    else return true;
+}
+__device__ __forceinline__ bool u_signbit(float a) { return (__float_as_uint(a) >> 31) != 0; }
+__device__ __forceinline__ bool u_signbit(double a) { return (__double_as_longlong(a) < 0); }
+__device__ __forceinline__ bool u_isnormal(float a) {
+    const unsigned e = (__float_as_uint(a) >> 23) & 0xffu;
+    return e != 0 && e != 0xffu;
+}
+__device__ __forceinline__ bool u_isnormal(double a) {
+    const unsigned e = (unsigned)((unsigned long long)__double_as_longlong(a) >> 52) & 0x7ffu;
+    return e != 0 && e != 0x7ffu;
+}
+template <class T> __device__ __forceinline__ bool u_isnormal(T a) { return a != 0; }
+
+PNCU_UNARY_FUNCTOR(AbsF, T, u_abs<T>(a))
+PNCU_UNARY_FUNCTOR(IdentF, T, a)
+PNCU_UNARY_FUNCTOR(NegF, T, u_neg<T>(a))
+PNCU_UNARY_FUNCTOR(SignF, T, u_sign<T>(a))
+PNCU_UNARY_FUNCTOR(InvertF, T, (T)~a)
+PNCU_UNARY_FUNCTOR(FloorF, T, u_floor(a))
+PNCU_UNARY_FUNCTOR(CeilF, T, u_ceil(a))
+PNCU_UNARY_FUNCTOR(TruncF, T, u_trunc(a))
+PNCU_UNARY_FUNCTOR(RintF, T, u_rint(a))
+PNCU_UNARY_FUNCTOR(SqrtF, T, u_sqrt(a))
+PNCU_UNARY_FUNCTOR(LogicalNotF, bool8, (bool8)(a == 0))
+PNCU_UNARY_FUNCTOR(IsNanF, bool8, (bool8)u_isnan<T>(a))
+PNCU_UNARY_FUNCTOR(IsNotNanF, bool8, (bool8)!u_isnan<T>(a))
+PNCU_UNARY_FUNCTOR(IsInfF, bool8, (bool8)u_isinf<T>(a))
+PNCU_UNARY_FUNCTOR(IsNotInfF, bool8, (bool8)!u_isinf<T>(a))
+PNCU_UNARY_FUNCTOR(IsFiniteF, bool8, (bool8)u_isfinite<T>(a))
+PNCU_UNARY_FUNCTOR(IsNotFiniteF, bool8, (bool8)!u_isfinite<T>(a))
+PNCU_UNARY_FUNCTOR(IsNormalF, bool8, (bool8)u_isnormal(a))
+PNCU_UNARY_FUNCTOR(IsNotNormalF, bool8, (bool8)!u_isnormal(a))
+PNCU_UNARY_FUNCTOR(IsNanOrZeroF, bool8, (bool8)(u_isnan<T>(a) || a == 0))
+PNCU_UNARY_FUNCTOR(SignBitF, bool8, (bool8)u_signbit(a))
+
+struct BoolNotF { typedef bool8 In; typedef bool8 Out; static __device__ __forceinline__ bool8 apply(bool8 a) { return (bool8)(a == 0); } };
+
+template <template <class> class F>
+pncu_unary_fn pick_all(int t) {
+    switch (t) {
+        case PNCU_BOOL: case PNCU_UINT8: return launch_unary<F<uint8_t>>;
+        case PNCU_INT8: return launch_unary<F<int8_t>>;
+        case PNCU_INT16: return launch_unary<F<int16_t>>;
+        case PNCU_UINT16: return launch_unary<F<uint16_t>>;
+        case PNCU_INT32: return launch_unary<F<int32_t>>;
+        case PNCU_UINT32: return launch_unary<F<uint32_t>>;
+        case PNCU_INT64: return launch_unary<F<int64_t>>;
+        case PNCU_UINT64: return launch_unary<F<uint64_t>>;
+        case PNCU_FLOAT: return launch_unary<F<float>>;
+        case PNCU_DOUBLE: return launch_unary<F<double>>;
+    }
+    return NULL;
+}
+template <template <class> class F>
+pncu_unary_fn pick_signed_fp(int t) {
+    switch (t) {
+        case PNCU_INT8: return launch_unary<F<int8_t>>;
+        case PNCU_INT16: return launch_unary<F<int16_t>>;
+        case PNCU_INT32: return launch_unary<F<int32_t>>;
+        case PNCU_INT64: return launch_unary<F<int64_t>>;
+        case PNCU_FLOAT: return launch_unary<F<float>>;
+        case PNCU_DOUBLE: return launch_unary<F<double>>;
+    }
+    return NULL;
+}
+template <template <class> class F>
+pncu_unary_fn pick_fp(int t) {
+    switch (t) {
+        case PNCU_FLOAT: return launch_unary<F<float>>;
+        case PNCU_DOUBLE: return launch_unary<F<double>>;
+    }
+    return NULL;
+}
+template <template <class> class F>
+pncu_unary_fn pick_uint_width(int t) {
+    switch (t) {
+        case PNCU_INT8: case PNCU_UINT8: return launch_unary<F<uint8_t>>;
+        case PNCU_INT16: case PNCU_UINT16: return launch_unary<F<uint16_t>>;
+        case PNCU_INT32: case PNCU_UINT32: return launch_unary<F<uint32_t>>;
+        case PNCU_INT64: case PNCU_UINT64: return launch_unary<F<uint64_t>>;
+    }
+    return NULL;
+}
+inline bool is_num(int t) { return (t >= PNCU_BOOL && t <= PNCU_UINT64) || t == PNCU_FLOAT || t == PNCU_DOUBLE || t == PNCU_LONGDOUBLE; }
+
+}  // namespace
+
+extern "C" pncu_unary_fn pncu_GetUnaryOpFast(int func, int t, int* wantedOutType) {
+    if (!wantedOutType) return NULL;
+    switch (func) {
+        case PNCU_ABS:  // ops_unary.cpp:1636-1644, 1266-1278: every type hooked
+            *wantedOutType = t;
+            switch (t) {
+                case PNCU_BOOL: case PNCU_UINT8: case PNCU_UINT16: case PNCU_UINT32: case PNCU_UINT64:
+                    return pick_uint_width<IdentF>(t == PNCU_BOOL ? PNCU_UINT8 : t);
+            }
+            return pick_signed_fp<AbsF>(t);
+        case PNCU_SIGNBIT:  // ops_unary.cpp:1612-1619
+            if (t == PNCU_FLOAT || t == PNCU_DOUBLE || t == PNCU_LONGDOUBLE) {
+                *wantedOutType = PNCU_BOOL;
+                return pick_fp<SignBitF>(t);
+            }
+            return NULL;
+        case PNCU_INVERT:
+        case PNCU_BITWISE_NOT:  // ops_unary.cpp:1709-1715, 1328-1345
+            if (t > PNCU_UINT64) return NULL;
+            *wantedOutType = t;
+            if (t == PNCU_BOOL) return launch_unary<BoolNotF>;
+            return pick_uint_width<InvertF>(t);
+        case PNCU_FLOOR:  // ops_unary.cpp:1716-1725
+            if (t < PNCU_FLOAT) return NULL;
+            *wantedOutType = t;
+            return pick_fp<FloorF>(t);
+        case PNCU_CEIL:
+            if (t < PNCU_FLOAT) return NULL;
+            *wantedOutType = t;
+            return pick_fp<CeilF>(t);
+        case PNCU_TRUNC:
+            if (t < PNCU_FLOAT) return NULL;
+            *wantedOutType = t;
+            return pick_fp<TruncF>(t);
+        case PNCU_ROUND:  // np.rint (src/pnumpy/_pnumpy.cpp:126); ops_unary.cpp:1746-1756
+            if (t < PNCU_FLOAT) return NULL;
+            *wantedOutType = t;
+            return pick_fp<RintF>(t);
+        case PNCU_NEGATIVE:  // ops_unary.cpp:1695-1708 (not on bool)
+            if (t <= PNCU_BOOL) return NULL;
+            *wantedOutType = t;
+            if (t == PNCU_FLOAT || t == PNCU_DOUBLE) return pick_fp<NegF>(t);
+            return pick_uint_width<NegF>(t);
+        case PNCU_SIGN:  // ops_unary.cpp:1280-1292 (signed ints and floats)
+            switch (t) {
+                case PNCU_INT8: case PNCU_INT16: case PNCU_INT32: case PNCU_INT64:
+                case PNCU_FLOAT: case PNCU_DOUBLE: case PNCU_LONGDOUBLE:
+                    *wantedOutType = t;
+                    return pick_signed_fp<SignF>(t);
+            }
+            return NULL;
+        case PNCU_SQRT:  // ops_unary.cpp:1757-1770
+            if (t < PNCU_FLOAT) return NULL;
+            *wantedOutType = (t == PNCU_FLOAT) ? PNCU_FLOAT : PNCU_DOUBLE;
+            return pick_fp<SqrtF>(t);
+        case PNCU_LOGICAL_NOT:  // ops_unary.cpp:1308-1326
+            *wantedOutType = PNCU_BOOL;
+            return pick_all<LogicalNotF>(t);
+        // classifiers: ops_unary.cpp:1646-1694 (fast) and 1347-1562 (slow); always -> bool
+        case PNCU_ISNAN: *wantedOutType = PNCU_BOOL; return pick_all<IsNanF>(t);
+        case PNCU_ISNOTNAN: *wantedOutType = PNCU_BOOL; return pick_all<IsNotNanF>(t);
+        case PNCU_ISINF: *wantedOutType = PNCU_BOOL; return pick_all<IsInfF>(t);
+        case PNCU_ISNOTINF: *wantedOutType = PNCU_BOOL; return pick_all<IsNotInfF>(t);
+        case PNCU_ISFINITE: *wantedOutType = PNCU_BOOL; return pick_all<IsFiniteF>(t);
+        case PNCU_ISNOTFINITE: *wantedOutType = PNCU_BOOL; return pick_all<IsNotFiniteF>(t);
+        case PNCU_ISNORMAL: *wantedOutType = PNCU_BOOL; return pick_all<IsNormalF>(t);
+        case PNCU_ISNOTNORMAL: *wantedOutType = PNCU_BOOL; return pick_all<IsNotNormalF>(t);
+        case PNCU_ISNANORZERO: *wantedOutType = PNCU_BOOL; return pick_all<IsNanOrZeroF>(t);
+    }
+    (void)is_num;
+    return NULL;
+}
