@@ -1,0 +1,547 @@
+#!/usr/bin/env python
+"""bench.py -- the atop ufunc hot path on B200, measured the way BASELINE.json asks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]        # this repo's CUDA path
+    python bench.py --impl reference [...]                     # the reference's threaded CPU path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+One STEP = one pass of BASELINE.json configs[1]: the binary ufunc sweep add / multiply / divide /
+greater over int32, int64, float32, float64 on 2^28-element device-resident arrays (16 kernel
+launches, 272 algorithmic bytes per element).  With N GPUs every rank runs the sweep
+on its own 2^28-element shard (weak scaling; element-wise work needs no exchange).
+`value` is the whole-job algorithmic GB/s with inputs resident in HBM; `e2e` is the same sweep
+through the NumPy ufunc hooks on pinned HOST ndarrays (PCIe copies inside the timed region).
+`detail` (outside the timed steps) adds the other covered ufuncs -- sin/log/exp/sqrt (configs[2]),
+sum/min/max/argmin/argmax (configs[3], with the cross-rank partial combine when N > 1) and the
+a*b+c -> sum chain (configs[4]) -- each with GB/s and the fraction of both HBM peaks.
+Every timing is CUDA events on the launching stream, after warm-up; inputs (>= 1 GiB per operand)
+are far larger than the 126 MB L2, so no separate flush is needed.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("PNUMPY_B200_AUTOINIT", "0")
+
+METRIC = "atop_ufunc_sweep_throughput"
+UNIT = "GB/s"
+N_ELEMS = 1 << 28
+SWEEP_DTYPES = ("int32", "int64", "float32", "float64")
+SWEEP_OPS = ("add", "multiply", "divide", "greater")
+ALIGN = 65536  # pncu_reduce_block_elems(): shard boundaries
+
+
+def bytes_per_elem(op, dt):
+    """Algorithmic bytes per element."""
+    s = np.dtype(dt).itemsize
+    if op in ("add", "multiply", "subtract"):
+        return 3 * s
+    if op == "divide":
+        return 3 * s if np.dtype(dt).kind == "f" else 2 * s + 8
+    if op == "greater":
+        return 2 * s + 1
+    if op in ("sin", "cos", "log", "exp", "sqrt", "abs"):
+        return 2 * s
+    if op == "isnan":
+        return s + 1
+    if op in ("sum", "min", "max", "argmin", "argmax"):
+        return s
+    raise KeyError(op)
+
+
+SWEEP_BYTES_PER_ELEM = sum(bytes_per_elem(op, dt) for dt in SWEEP_DTYPES for op in SWEEP_OPS)  # 272
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: binary ufunc sweep add/multiply/divide/greater x int32/int64/float32/float64, "
+                        "2^28 elements per GPU, device-resident",
+            "elements_per_gpu": N_ELEMS, "launches_per_step": 16, "algorithmic_bytes_per_element": SWEEP_BYTES_PER_ELEM,
+            "l2_policy": "inputs (1-2 GiB per operand) exceed the 126 MB L2; no flush needed",
+            "parallelism": f"{n_gpus} x independent shards (no data-path collective)"}
+
+
+# ---- multi-rank host logic (also exercised on CPU over gloo by tests/test_host_logic.py) ---------------
+def shard_bounds(n, rank, world):
+    """Contiguous even split of [0, n) at multiples of ALIGN elements."""
+    units = -(-n // ALIGN)
+    per = -(-units // world)
+    return min(n, rank * per * ALIGN), min(n, (rank + 1) * per * ALIGN)
+
+
+def partial_counts(n, itemsize, world):
+    """Block-partial slots each rank produces (one per 64 KiB logical block of its shard)."""
+    be = 65536 // itemsize
+    out = []
+    for r in range(world):
+        lo, hi = shard_bounds(n, r, world)
+        out.append(-(-(hi - lo) // be) if hi > lo else 0)
+    return out
+
+
+def gather_partials(t, counts):
+    """ONE all_gather of every rank's block partials (padded to the longest), compacted into the
+    global slot order.  `t`: 1-D tensor of this rank's partials on the backend's device."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return t
+    m = max(counts)
+    pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+    pad[: t.numel()] = t
+    allp = torch.empty(world * m, dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(allp, pad)
+    return torch.cat([allp[r * m: r * m + counts[r]] for r in range(world)])
+
+
+def fold_in_order(partials):
+    """Fixed-order fold of float64 partials (host stand-in for pncu_reduce_finish)."""
+    acc = 0.0
+    for v in np.asarray(partials, dtype=np.float64):
+        acc = acc + float(v)
+    return acc
+
+
+def combine_argminmax_host(kind, pairs, gather=False):
+    """(value, global index) pairs -> NumPy's answer: first NaN wins, else the extreme with the
+    smallest index.  kind 0 = argmax, 1 = argmin."""
+    if gather:
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            box = [None] * dist.get_world_size()
+            dist.all_gather_object(box, pairs)
+            pairs = [p for ps in box for p in ps]
+    nans = [p for p in pairs if p[0] != p[0]]
+    if nans:
+        return min(nans, key=lambda p: p[1])
+    best = max(p[0] for p in pairs) if kind == 0 else min(p[0] for p in pairs)
+    return min((p for p in pairs if p[0] == best), key=lambda p: p[1])
+
+
+# ---- helpers ----------------------------------------------------------------------------------------------
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the CUDA arm -----------------------------------------------------------------------------------------
+def run_cuda(args):
+    from pnumpy_b200 import cabi, device as dev
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cabi.init()
+    lib = cabi.load()
+    cabi.check(lib.pncu_set_device(local), "pncu_set_device")
+    stream = ctypes.c_void_p()
+    cabi.check(lib.pncu_stream_create(ctypes.byref(stream)), "stream")
+    peak, peak_kind = measured_peak()
+    n = N_ELEMS
+    rng = np.random.default_rng(1234 + rank)
+
+    def filled(dt, lo=1, hi=254):
+        """device array of n elements tiled from a 4 Mi-element random piece (reference benchmark
+        range arange % 253 + 1, src/pnumpy/benchmark.py:56-66)"""
+        d = dev.empty(n, dt)
+        piece = 1 << 22
+        host = rng.uniform(lo, hi, piece).astype(dt) if np.dtype(dt).kind == "f" else rng.integers(lo, hi, piece).astype(dt)
+        p = dev.to_device(host)
+        isz = np.dtype(dt).itemsize
+        for off in range(0, n, piece):
+            cabi.check(lib.pncu_memcpy_d2d(d.ptr + off * isz, p.ptr, min(piece, n - off) * isz, None), "fill")
+        dev.sync()
+        p.free()
+        return d
+
+    # ---- operands of the sweep (about 21 GiB) ---------------------------------------------------------
+    ops = []  # (name, dtype, bytes_per_elem, thunk)
+    keep = []
+    for dt in SWEEP_DTYPES:
+        a, b = filled(dt), filled(dt)
+        o = dev.empty(n, dt)
+        ob = dev.empty(n, np.bool_)
+        of = o if np.dtype(dt).kind == "f" else dev.empty(n, np.float64)
+        keep += [a, b, o, ob, of]
+        isf = np.dtype(dt).kind == "f"
+        ops.append(("add", dt, lambda a=a, b=b, o=o: dev.binary("ADD", a, b, out=o, stream=stream)))
+        ops.append(("multiply", dt, lambda a=a, b=b, o=o: dev.binary("MUL", a, b, out=o, stream=stream)))
+        if isf:
+            ops.append(("divide", dt, lambda a=a, b=b, o=o: dev.binary("DIV", a, b, out=o, stream=stream)))
+        else:
+            ops.append(("divide", dt, lambda a=a, b=b, of=of: dev.int_true_divide(a, b, out=of, stream=stream)))
+        ops.append(("greater", dt, lambda a=a, b=b, ob=ob: dev.compare("GT", a, b, out=ob, stream=stream)))
+
+    def barrier():
+        cabi.check(lib.pncu_device_sync(), "sync")
+        if dist:
+            dist.barrier()
+            cabi.check(lib.pncu_device_sync(), "sync")
+
+    def step():
+        for _, _, fn in ops:
+            fn()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # per-launch events inside the timed region (cheap; give the per-kernel table and the roofline)
+    ev = [[dev.Timer() for _ in ops] for _ in range(args.steps)]
+    whole = dev.Timer()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.pncu_launch_count()
+    whole.start(stream)
+    for k in range(args.steps):
+        for i, (_, _, fn) in enumerate(ops):
+            ev[k][i].start(stream)
+            fn()
+            ev[k][i].stop(stream)
+    whole.stop(stream)
+    ms_total = whole.ms()
+    barrier()
+    launches = lib.pncu_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    if dist:
+        import torch
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = SWEEP_BYTES_PER_ELEM * n * world / (ms_per_step * 1e-3) / 1e9
+
+    per_kernel = []
+    for i, (name, dt, _) in enumerate(ops):
+        ms = float(np.mean([ev[k][i].ms() for k in range(args.steps)]))
+        g = bytes_per_elem(name, dt) * n / (ms * 1e-3) / 1e9
+        per_kernel.append({"op": name, "dtype": dt, "ms": round(ms, 4), "gbs": round(g, 1),
+                           "frac_of_measured_peak": round(g / peak, 4), "frac_of_8tbs": round(g / 8000.0, 4)})
+    # dominant kernel: the 8-byte binary element-wise instantiations (add/multiply/divide on f64, i64)
+    dom = [k for k in per_kernel if k["dtype"] in ("int64", "float64") and k["op"] != "greater"]
+    dom_ms = float(np.mean([k["ms"] for k in dom]))
+    dom_bytes = 24.0 * n
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["ew2_vec_kernel_8byte_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "ew2_vec_kernel<op, 8-byte type, LAY_VV> (add/multiply/divide on float64, int64)",
+                "achieved": round(achieved, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "frac_of_8tbs": round(achieved / 8000.0, 4),
+                "algorithmic_bytes_per_launch": dom_bytes, "share_of_step": round(sum(k["ms"] for k in dom) / ms_per_step, 4),
+                "traffic": traffic}
+
+    detail = {}
+    if not args.no_detail:
+        detail = run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist)
+    for x in keep:
+        x.free()
+
+    line = None
+    if rank == 0:
+        e2e = run_e2e(args) if not args.no_e2e else None
+        cpu = run_cpu_baseline(sample_lg=args.cpu_lg) if (world == 1 and not args.no_cpu) else None
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64/f32/f64 (native width, FMA contraction off)",
+                "data": "synthetic", "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
+                "frac_of_measured_peak": round(value / world / peak, 4), "frac_of_8tbs": round(value / world / 8000.0, 4),
+                "roofline": roofline, "per_kernel": per_kernel, "detail": detail}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
+    """Untimed-by-the-contract extras: configs[2] and configs[3] kernels, device-resident."""
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        t = dev.Timer()
+        ms = []
+        for _ in range(reps):
+            t.start(stream)
+            fn()
+            t.stop(stream)
+            ms.append(t.ms())
+        return float(np.mean(ms))
+
+    out = {}
+    byname = {}
+    # keep = [a, b, o, ob, of] per dtype in SWEEP_DTYPES order
+    for i, dt in enumerate(SWEEP_DTYPES):
+        byname[dt] = keep[5 * i: 5 * i + 5]
+    rows = []
+    for dt in ("float32", "float64"):
+        a, b, o, ob, _ = byname[dt]
+        for name, op in (("sin", "SIN"), ("log", "LOG"), ("exp", "EXP"), ("sqrt", "SQRT")):
+            src = a  # values in [1, 254): in range for every function
+            ms = timeit(lambda: dev.unary(op, src, out=o, stream=stream))
+            rows.append((name, dt, ms))
+        ms = timeit(lambda: dev.unary("ISNAN", a, out=ob, stream=stream))
+        rows.append(("isnan", dt, ms))
+    for dt in SWEEP_DTYPES:
+        a = byname[dt][0]
+        r1, ri = dev.empty(1, dt), dev.empty(1, np.int64)
+        for name, fn in (("sum", lambda: dev.reduce("ADD", a, out=r1, stream=stream)),
+                         ("min", lambda: dev.reduce("MIN", a, out=r1, stream=stream)),
+                         ("max", lambda: dev.reduce("MAX", a, out=r1, stream=stream)),
+                         ("argmax", lambda: dev.argminmax(0, a, out=ri, stream=stream)),
+                         ("argmin", lambda: dev.argminmax(1, a, out=ri, stream=stream))):
+            rows.append((name, dt, timeit(fn)))
+    out["per_gpu_kernels"] = [
+        {"op": name, "dtype": dt, "ms": round(ms, 4), "gbs": round(bytes_per_elem(name, dt) * n / (ms * 1e-3) / 1e9, 1),
+         "frac_of_measured_peak": round(bytes_per_elem(name, dt) * n / (ms * 1e-3) / 1e9 / peak, 4),
+         "frac_of_8tbs": round(bytes_per_elem(name, dt) * n / (ms * 1e-3) / 1e9 / 8000.0, 4),
+         "melem_per_s": round(n / (ms * 1e-3) / 1e6, 0)} for name, dt, ms in rows]
+
+    # configs[3]: float32 sum over the WHOLE job (world x 2^28 elements) with the cross-rank combine:
+    # pass 1 on every rank's shard, ONE NCCL all_gather of the block partials, one finish kernel.
+    a = byname["float32"][0]
+    f, t = cabi.BINARY_OPS["ADD"], cabi.atop_of(np.float32)
+    pb = lib.pncu_reduce_partial_bytes(f, t)
+    cnt = lib.pncu_reduce_partial_count(t, n)
+    res = dev.empty(1, np.float32)
+    if world == 1:
+        parts = dev.empty(cnt * pb, np.uint8)
+
+        def sharded_sum():
+            cabi.check(lib.pncu_reduce_partials(f, t, a.ptr, n, parts.ptr, stream), "partials")
+            cabi.check(lib.pncu_reduce_finish(f, t, parts.ptr, cnt, res.ptr, None, stream), "finish")
+    else:
+        import torch
+        mine = torch.empty(cnt, dtype=torch.float64, device="cuda")
+        allp = torch.empty(world * cnt, dtype=torch.float64, device="cuda")
+
+        def sharded_sum():
+            cabi.check(lib.pncu_reduce_partials(f, t, a.ptr, n, mine.data_ptr(), stream), "partials")
+            cabi.check(lib.pncu_stream_sync(stream), "sync")
+            dist.all_gather_into_tensor(allp, mine)
+            torch.cuda.current_stream().synchronize()
+            cabi.check(lib.pncu_reduce_finish(f, t, allp.data_ptr(), world * cnt, res.ptr, None, stream), "finish")
+    for _ in range(3):
+        sharded_sum()
+    cabi.check(lib.pncu_device_sync(), "sync")
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    reps = 10
+    for _ in range(reps):
+        sharded_sum()
+    cabi.check(lib.pncu_device_sync(), "sync")
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    if dist:
+        import torch
+        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    out["sharded_sum_f32"] = {"elements_total": n * world, "ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1),
+                              "collective": "none (1 GPU)" if world == 1 else "one NCCL all_gather of float64 block partials",
+                              "result": float(res.to_host()[0])}
+    return out
+
+
+# ---- end to end through the NumPy hooks --------------------------------------------------------------------
+def run_e2e(args):
+    """The same sweep through the reference-facing API: np.add / np.multiply / np.true_divide /
+    np.greater on pinned HOST ndarrays with pnumpy_b200 enabled.  H2D and D2H copies are inside the
+    timed region (nte stages 8 MiB slabs through 3-deep rings on separate copy/compute streams)."""
+    import pnumpy_b200 as pn
+    try:
+        pn.init()
+    except ImportError as e:
+        return {"error": str(e)}
+    pn.enable()
+    n = 1 << args.e2e_lg
+    rng = np.random.default_rng(99)
+    arrs = {}
+    for dt in SWEEP_DTYPES:
+        a, b = pn.pinned_empty(n, dt), pn.pinned_empty(n, dt)
+        piece = rng.uniform(1, 254, 1 << 20).astype(dt)
+        for off in range(0, n, piece.size):
+            a[off: off + piece.size] = piece[: min(piece.size, n - off)]
+            b[off: off + piece.size] = piece[::-1][: min(piece.size, n - off)]
+        arrs[dt] = (a, b, pn.pinned_empty(n, dt), pn.pinned_empty(n, np.bool_),
+                    pn.pinned_empty(n, np.float64) if np.dtype(dt).kind != "f" else None)
+
+    def sweep():
+        for dt in SWEEP_DTYPES:
+            a, b, o, ob, of = arrs[dt]
+            np.add(a, b, out=o)
+            np.multiply(a, b, out=o)
+            np.true_divide(a, b, out=o if of is None else of)
+            np.greater(a, b, out=ob)
+
+    sweep()  # warm-up: lane resources, slab allocation
+    pn.cuda_reset_stats()
+    reps = max(1, args.e2e_steps)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sweep()
+    dt_s = (time.perf_counter() - t0) / reps
+    info = pn.cuda_info()
+    pn.disable()
+    return {"value": round(SWEEP_BYTES_PER_ELEM * n / dt_s / 1e9, 2), "unit": UNIT, "elements": n, "steps": reps,
+            "ms_per_step": round(dt_s * 1e3, 2), "h2d_bytes_per_step": int(info["h2d_bytes"] // reps),
+            "d2h_bytes_per_step": int(info["d2h_bytes"] // reps), "gpu_calls_per_step": int(info["calls"] // reps),
+            "staged_bytes_per_step": int(info["staged_bytes"] // reps), "lanes": int(info["lanes_last"]),
+            "api": "numpy ufunc call -> hooked loop -> nte dispatcher (pinned host ndarrays)",
+            "note": "int32/int64 true_divide reaches the hook as NumPy's buffered dd->d loop on its own pageable cast buffers"}
+
+
+# ---- the reference's threaded CPU path -----------------------------------------------------------------------
+REF_SNIPPET = r'''
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+lg, reps, maxthreads = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+import pnumpy_ref as pn
+pn.initialize()
+pn.atop_enable(); pn.thread_enable()
+cores = len(os.sched_getaffinity(0))
+if maxthreads:
+    pn.thread_setworkers(min(15, max(1, cores - 1)))
+n = 1 << lg
+rng = np.random.default_rng(99)
+ops = (("add", np.add), ("multiply", np.multiply), ("true_divide", np.true_divide), ("greater", np.greater))
+dts = ("int32", "int64", "float32", "float64")
+if maxthreads:
+    for name, _ in ops:
+        for dt in dts + ("float64",):
+            pn.atop_setworkers(name, np.dtype(dt).num, 15)
+arrs = {}
+for dt in dts:
+    a = rng.uniform(1, 254, n).astype(dt); b = a[::-1].copy()
+    arrs[dt] = (a, b, np.empty(n, dt), np.empty(n, np.bool_), np.empty(n, np.float64))
+def sweep():
+    for dt in dts:
+        a, b, o, ob, of = arrs[dt]
+        np.add(a, b, out=o); np.multiply(a, b, out=o)
+        np.true_divide(a, b, out=o if a.dtype.kind == "f" else of)
+        np.greater(a, b, out=ob)
+sweep()
+ts = []
+for _ in range(reps):
+    t0 = time.perf_counter(); sweep(); ts.append(time.perf_counter() - t0)
+print(json.dumps({"seconds": ts, "cores": cores, "workers": pn.thread_getworkers(), "n": n, "cpustring": pn.cpustring()}))
+'''
+
+
+def run_cpu_baseline(sample_lg=25, reps=3, maxthreads=1):
+    """The reference's own threaded CPU path (its extension built by oracle/build_ref_ext.sh), in a
+    subprocess because it patches NumPy's loop tables, on a bounded sample of the same sweep."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "pnumpy_ref", ".built")):
+        return {"value": None, "unit": UNIT, "kind": "reference", "cores": 0,
+                "sample": "oracle/_ref/pnumpy_ref is not built (make -C oracle)"}
+    try:
+        r = subprocess.run([sys.executable, "-c", REF_SNIPPET, ref_dir, str(sample_lg), str(reps), str(maxthreads)],
+                           capture_output=True, text=True, timeout=600)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "kind": "reference", "cores": 0, "sample": f"failed: {e}"}
+    best = min(d["seconds"])
+    threads = min(16, d["workers"] + 1)
+    return {"value": round(SWEEP_BYTES_PER_ELEM * d["n"] / best / 1e9, 2), "unit": UNIT, "cores": threads,
+            "host_logical_cpus": d["cores"], "kind": "reference",
+            "sample": f"same 16-op sweep on 2^{sample_lg} elements per operand, best of {reps} passes, pnumpy reference "
+                      f"extension (oracle/_ref) enabled with thread_setworkers({d['workers']}) and atop_setworkers(.., 15): "
+                      f"up to {threads} threads",
+            "ms_per_pass": round(best * 1e3, 1), "cpu": d.get("cpustring")}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cpu = run_cpu_baseline(sample_lg=args.cpu_lg, reps=max(1, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i32/i64/f32/f64", "data": "synthetic", "config": workload_config(world),
+            "ms_per_step": cpu.get("ms_per_pass"), "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-detail", action="store_true")
+    ap.add_argument("--e2e-lg", type=int, default=28, help="log2 elements per operand of the end-to-end sweep")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-lg", type=int, default=25, help="log2 elements per operand of the CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

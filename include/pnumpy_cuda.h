@@ -207,19 +207,22 @@ PNCU_API int pncu_itemsize(int atype);
 /* ---------------------------------------------------------------------------
  * Reduction building blocks for the multi-GPU dispatcher (pnumpy_nte.h).
  *
- * A reduction over [0, n) is defined on fixed LOGICAL BLOCKS of
- * pncu_reduce_block_elems() elements: block k covers
- * [k*B, min((k+1)*B, n)) and is folded in a fixed tree; the block partials are then
- * folded in index order by ONE thread block.  Because B does not depend on the
- * device, the grid or the number of shards, a shard boundary that is a multiple of
- * B gives bit-identical results on 1, 2, 4 or 8 GPUs.  This is the GPU form of the
- * reference's per-16K-chunk partials + second pass on the caller
+ * A reduction over [0, n) of a type with `itemsize` bytes is defined on fixed LOGICAL BLOCKS of
+ * 64 KiB, i.e. 65536 / itemsize elements: block k covers [k*B, min((k+1)*B, n)) and is folded in
+ * a fixed tree into partial slot k; the block partials are then folded in index order by ONE
+ * thread block.  Because B depends on the type only -- not on the device, the grid or the number
+ * of shards -- a shard boundary that is a multiple of pncu_reduce_block_elems() (= 65536, a
+ * multiple of every type's B) gives bit-identical results on 1, 2, 4 or 8 GPUs.  This is the GPU
+ * form of the reference's per-16K-chunk partials + second pass on the caller
  * (src/pnumpy/_pnumpy.cpp:666-700).
  * ------------------------------------------------------------------------- */
+/* alignment (in elements) that shard boundaries must have */
 PNCU_API int64_t pncu_reduce_block_elems(void);
+/* number of partial slots pass 1 writes for `len` elements of `atype` (= ceil(len / B)) */
+PNCU_API int64_t pncu_reduce_partial_count(int atype, int64_t len);
 /* bytes of one block partial for (func, type); 0 if no kernel */
 PNCU_API int pncu_reduce_partial_bytes(int func, int atype);
-/* pass 1: partials[k] for k in [0, ceil(len/B)) ; `in` contiguous */
+/* pass 1: partials[k] for k in [0, pncu_reduce_partial_count(atype, len)) ; `in` contiguous */
 PNCU_API int pncu_reduce_partials(int func, int atype, const void* in, int64_t len,
                                   void* partials, pncu_stream_t stream);
 /* pass 2: *out = fold(partials[0..count)) op *startVal (startVal may be NULL / alias out) */

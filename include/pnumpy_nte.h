@@ -1,0 +1,113 @@
+/*
+ * pnumpy_nte.h -- C ABI of the nte dispatcher inside libpnumpy_cuda: the per-GPU stream and
+ * shard dispatcher that replaces pnumpy's worker-thread 16K-chunk scheduler.
+ *
+ * What this replaces
+ * ------------------
+ * `CMathWorker` and friends, src/atop/threads.h:645-1171 + src/atop/threads.cpp:72-191, as the
+ * hook layer uses them (src/pnumpy/_pnumpy.cpp:638-996):
+ *     THREADER->GetWorkItem(n)            -> nte_* returns NTE_DECLINED below the size threshold,
+ *                                            for re-entrant calls and for layouts it cannot stage
+ *     THREADER->WorkMain(item, n, maxthr) -> the nte_binary / nte_unary / nte_reduce / nte_argminmax
+ *                                            calls below (synchronous: they return when the result
+ *                                            is in the caller's buffers, like WorkMain's spin-wait,
+ *                                            threads.h:1148-1152)
+ *     SetFutexWakeup/GetFutexWakeup/NoThreading -> nte_set_workers / nte_get_workers /
+ *                                            nte_set_threading  (same clamping and return values,
+ *                                            threads.h:852-872)
+ * The reference splits [0, n) into 16384-element chunks dealt round-robin to <= 16 threads.  Here
+ * [0, n) is split into `lanes` contiguous shards (boundaries at multiples of the 65536-element
+ * reduction block); lane l drives GPU l % G with its own three streams (H2D, compute, D2H) and a
+ * ring of pinned staging slabs, so the copy engines and the SMs of every GPU overlap.  Element-wise
+ * work needs no exchange between lanes; reductions gather every lane's block partials on GPU 0
+ * (peer copies over NVLink) and fold them there in fixed order -- the "second pass" of
+ * src/pnumpy/_pnumpy.cpp:697-699 -- so the result is independent of the number of lanes and GPUs.
+ *
+ * Operands are HOST pointers as NumPy hands them to a ufunc inner loop (pageable, or pinned when
+ * they came from nte_alloc_pinned / the recycler), or device / managed pointers, which are used in
+ * place with no PCIe traffic.  Strides are in bytes; 0 broadcasts a scalar.
+ */
+#ifndef PNUMPY_NTE_H
+#define PNUMPY_NTE_H
+
+#include "pnumpy_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* returned by the nte_* ops when the caller should run its previous (NumPy) loop instead:
+ * fewer elements than the threshold, dispatcher disabled or busy on another thread, or a layout
+ * that cannot be staged (non-contiguous host operand, partial overlap).  Never a failure. */
+#define NTE_DECLINED 1
+
+/* Bring up the dispatcher: pncu_init + per-GPU lane state on first use.  Returns 0, or
+ * PNCU_ERR_NO_DEVICE (there is no CPU mode).  Idempotent.   replaces: atop_init()'s
+ * `new CMathWorker` + StartWorkerThreads (src/atop/atop.cpp:96-101). */
+PNCU_API int nte_init(void);
+PNCU_API int nte_shutdown(void);
+PNCU_API int nte_device_count(void);
+
+/* thread_* controls.  `workers` is the number of EXTRA lanes beside the caller's, exactly like the
+ * reference's futex wake count: a call uses min(op_max_workers, workers) + 1 lanes.
+ * nte_set_workers clamps to [1, nte_max_workers()] and returns the PREVIOUS value
+ * (src/atop/threads.h:852-872). */
+PNCU_API int nte_set_workers(int workers);
+PNCU_API int nte_get_workers(void);
+PNCU_API int nte_max_workers(void);
+/* NoThreading flag (src/atop/threads.h:1058): when threading is off a call uses one lane on GPU 0 */
+PNCU_API void nte_set_threading(int enabled);
+PNCU_API int nte_get_threading(void);
+
+/* Size policy.  The reference threads a call iff n >= 65536 (src/atop/threads.h:199,1058); the
+ * analogue here is "worth a PCIe round trip".  Returns the previous value. */
+PNCU_API int64_t nte_set_min_elems(int64_t n);
+PNCU_API int64_t nte_get_min_elems(void);
+/* bytes of one staging slab (rounded to a multiple of 65536 * 8); returns the previous value */
+PNCU_API int64_t nte_set_slab_bytes(int64_t bytes);
+
+/* ---- the four dispatch entry points (one per hook-layer dispatcher) --------------------------------
+ * `launcher` is what pncu_Get*OpFast returned; item sizes are of one input / output element.
+ * max_workers is the per-(ufunc, dtype) MaxThreads of the hook layer (3 or 7,
+ * src/pnumpy/_pnumpy.cpp:1373,1544).  Return 0 (done), NTE_DECLINED, or a pncu_status / cudaError. */
+
+/* AtopBinaryMathFunction element-wise branch + AtopCompareMathFunction
+ * (src/pnumpy/_pnumpy.cpp:732-791, 805-866) */
+PNCU_API int nte_binary(pncu_any_two_fn launcher, int in_itemsize, int out_itemsize,
+                        const void* in1, const void* in2, void* out, int64_t len,
+                        int64_t stride1, int64_t stride2, int64_t strideOut, int max_workers);
+/* AtopUnaryMathFunction + AtopTrigMathFunction (src/pnumpy/_pnumpy.cpp:874-996) */
+PNCU_API int nte_unary(pncu_unary_fn launcher, int in_itemsize, int out_itemsize,
+                       const void* in, void* out, int64_t len, int64_t strideIn, int64_t strideOut,
+                       int max_workers);
+/* reduce branch of AtopBinaryMathFunction (src/pnumpy/_pnumpy.cpp:646-731): *out = fold(in) op *out
+ * when use_out_as_start, else fold(in) alone.  `out` is a HOST pointer to one element. */
+PNCU_API int nte_reduce(int func, int atype, const void* in, void* out, int use_out_as_start,
+                        int64_t len, int64_t strideIn, int max_workers);
+/* AtopArgMinMaxMathFunction (src/pnumpy/_pnumpy.cpp:1105-1118); `in` contiguous */
+PNCU_API int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out_index,
+                           int max_workers);
+
+/* ---- pinned host memory for ndarrays (the recycler's allocator) ---------------------
+ * Pinned + portable + mapped; operands that live in it are DMA'd in place, with no staging copy. */
+PNCU_API void* nte_alloc_pinned(size_t bytes);
+PNCU_API void nte_free_pinned(void* ptr);
+
+/* ---- accounting (feeds atop_info()/ledger and the tests) ------------------------------------------- */
+typedef struct nte_stats {
+    int64_t calls;          /* dispatches that ran on the GPU */
+    int64_t declined;       /* dispatches handed back to the caller */
+    int64_t launches;       /* kernels launched on behalf of those calls */
+    int64_t h2d_bytes;      /* bytes copied host -> device */
+    int64_t d2h_bytes;      /* bytes copied device -> host */
+    int64_t staged_bytes;   /* bytes memcpy'd through pinned staging slabs (pageable operands) */
+    int64_t lanes_last;     /* lanes used by the last call */
+    int64_t gpus_last;      /* distinct GPUs used by the last call */
+} nte_stats;
+PNCU_API void nte_get_stats(nte_stats* out);
+PNCU_API void nte_reset_stats(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNUMPY_NTE_H */

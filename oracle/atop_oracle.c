@@ -28,7 +28,7 @@
 #include <string.h>
 
 enum { T_BOOL = 0, T_I8, T_U8, T_I16, T_U16, T_I32, T_U32, T_I64, T_U64, T_F32 = 12, T_F64 = 13 };
-enum { B_ADD = 1, B_SUB = 2, B_MUL = 3, B_MIN = 5, B_MAX = 6, B_DIV = 13, B_LAND = 16, B_LOR = 18,
+enum { B_ADD = 1, B_SUB = 2, B_MUL = 3, B_MIN = 5, B_MAX = 6, B_FLOORDIV = 9, B_DIV = 13, B_LAND = 16, B_LOR = 18,
        B_LSHIFT = 19, B_RSHIFT = 20, B_AND = 21, B_XOR = 22, B_OR = 23 };
 enum { C_EQ = 0, C_NE, C_LT, C_GT, C_LE, C_GE };
 enum { U_ABS = 1, U_SIGNBIT = 2, U_INVERT = 4, U_FLOOR = 5, U_CEIL = 6, U_TRUNC = 7, U_ROUND = 8,
@@ -78,8 +78,29 @@ int oracle_itemsize(int t) {
     }                                                                          \
     return -1;
 
+/* NumPy's npy_floor_divide / npy_divmod (numpy/_core/src/npymath/npy_math_internal.h.src).
+ * The reference's scalar body is floor(x / y) (src/atop/ops_binary.cpp:80-82); they differ by
+ * one where x / y rounds up to an integer, and NumPy's value is the drop-in contract. */
+#define FLOORDIV_FN(NAME, T, SFX)                                              \
+    static T NAME(T a, T b) {                                                  \
+        if (b == 0) return a / b;                                              \
+        const T mod = fmod##SFX(a, b);                                         \
+        T div = (a - mod) / b;                                                 \
+        if (mod != 0 && ((b < 0) != (mod < 0))) div -= 1;                      \
+        if (div != 0) {                                                        \
+            T fl = floor##SFX(div);                                            \
+            if (div - fl > (T)0.5) fl += 1;                                    \
+            return fl;                                                         \
+        }                                                                      \
+        return copysign##SFX(0, a / b);                                        \
+    }
+FLOORDIV_FN(floordiv_f32, float, f)
+FLOORDIV_FN(floordiv_f64, double, )
+#define FLOORDIV(a, b) _Generic((a), float: floordiv_f32, double: floordiv_f64)(a, b)
+
 #define FP_BIN(T)                                                              \
     switch (op) {                                                              \
+        case B_FLOORDIV: BIN_LOOP(T, FLOORDIV(a, b))                           \
         case B_ADD: BIN_LOOP(T, a + b)                                         \
         case B_SUB: BIN_LOOP(T, a - b)                                         \
         case B_MUL: BIN_LOOP(T, a * b)                                         \
@@ -189,7 +210,7 @@ int oracle_compare(int op, int t, const void* in1, const void* in2, void* out, i
  * ---------------------------------------------------------------------------------------- */
 #define UN_LOOP(T, TO, EXPR)                                                   \
     for (int64_t i = 0; i < n; ++i) {                                          \
-        const T a = AT(T, in, i, s1);                                          \
+        const T a = AT(T, in, i, s1); (void)a;                                 \
         OUT(TO, out, i, so) = (TO)(EXPR);                                      \
     }                                                                          \
     return 0;

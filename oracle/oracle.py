@@ -18,7 +18,7 @@ REF_EXT_DIR = os.path.join(HERE, "_ref")
 
 _ATOP = {"bool": 0, "int8": 1, "uint8": 2, "int16": 3, "uint16": 4, "int32": 5, "uint32": 6,
          "int64": 7, "uint64": 8, "float32": 12, "float64": 13}
-BINARY = dict(ADD=1, SUB=2, MUL=3, MIN=5, MAX=6, DIV=13, LOGICAL_AND=16, LOGICAL_OR=18,
+BINARY = dict(ADD=1, SUB=2, MUL=3, MIN=5, MAX=6, FLOORDIV=9, DIV=13, LOGICAL_AND=16, LOGICAL_OR=18,
               BITWISE_LSHIFT=19, BITWISE_RSHIFT=20, BITWISE_AND=21, BITWISE_XOR=22, BITWISE_OR=23)
 COMPARE = dict(EQ=0, NE=1, LT=2, GT=3, LTE=4, GTE=5)
 UNARY = dict(ABS=1, SIGNBIT=2, INVERT=4, FLOOR=5, CEIL=6, TRUNC=7, ROUND=8, NEGATIVE=9, SIGN=11,

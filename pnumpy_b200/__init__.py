@@ -1,1 +1,88 @@
-"""placeholder (replaced below)"""
+"""
+pnumpy_b200 -- pnumpy's atop ufunc hot path on NVIDIA B200 GPUs, behind pnumpy's own hooks.
+
+Like pnumpy (reference: ``src/pnumpy/__init__.py``), importing the package calls ``init`` to set
+it up: NumPy's ufunc inner loops (add/subtract/multiply/divide, the comparisons, abs/isnan/sqrt/...,
+sin/cos/log/exp and the add/min/max reductions, argmin/argmax) are replaced with wrapped versions
+through ``PyUFunc_ReplaceLoopBySignature``.  You can then enable/disable the subsystems:
+
+  - atop
+        The fast inner loops.  Here they are hand-written sm_100a CUDA kernels in
+        ``libpnumpy_cuda`` (``include/pnumpy_cuda.h``); ``atop_disable()`` routes every call to
+        NumPy's original loop, as in the reference.
+
+  - threading
+        The reference splits a loop into 16K-element chunks over worker threads.  Here the ``nte``
+        dispatcher (``include/pnumpy_nte.h``) splits a call into contiguous shards over *lanes*:
+        lane ``l`` drives GPU ``l % G`` through its own H2D / compute / D2H streams and pinned
+        staging ring.  ``thread_setworkers(n)`` sets the number of extra lanes (the reference's
+        extra threads); ``thread_disable()`` pins every call to one lane on GPU 0.
+
+  - ledger
+        Per-category call counters (GPU loop vs NumPy loop) while enabled.
+
+  - recycler
+        A NEP-49 allocator: large ndarrays are born in recycled *pinned* host memory, so the
+        dispatcher can DMA them in place instead of staging them.
+
+There is no CPU fallback inside the GPU library: importing this package on a machine without a
+B200 raises ImportError (the reference raises on a CPU without AVX2).  Set
+``PNUMPY_B200_AUTOINIT=0`` to import without initialising (tools, CPU-side tests).
+"""
+import os as _os
+
+__version__ = "0.1.0"
+
+__all__ = [
+    'initialize', 'atop_enable', 'atop_disable', 'atop_isenabled', 'atop_info', 'atop_setworkers', 'cpustring',
+    'thread_enable', 'thread_disable', 'thread_isenabled', 'thread_getworkers', 'thread_setworkers', 'thread_zigzag',
+    'ledger_enable', 'ledger_disable', 'ledger_isenabled', 'ledger_info',
+    'recycler_enable', 'recycler_disable', 'recycler_isenabled', 'recycler_info',
+    'timer_gettsc', 'timer_getutc', 'benchmark', 'benchmark_func', 'init', 'enable', 'disable', 'cpu_count_linux',
+    'argmin', 'argmax',
+    # additions of this build (nothing above changes meaning)
+    'cuda_info', 'cuda_reset_stats', 'cuda_setthreshold', 'cuda_getthreshold', 'cuda_setslab',
+    'pinned_empty', 'pinned_array',
+]
+
+import numpy as np  # noqa: E402
+
+try:
+    from . import _pnumpy
+except ImportError as _e:  # the extension is the product: no Python fallback
+    raise ImportError(
+        "pnumpy_b200._pnumpy (the CUDA hook extension) is not built: run "
+        "`python -c 'import __graft_entry__ as g; g.build()'` or `make -C pnumpy_b200/csrc`") from _e
+
+from ._pnumpy import atop_enable, atop_disable, atop_isenabled, atop_info, atop_setworkers, cpustring  # noqa: E402
+from ._pnumpy import thread_enable, thread_disable, thread_isenabled, thread_getworkers, thread_setworkers, thread_zigzag  # noqa: E402
+from ._pnumpy import timer_gettsc, timer_getutc  # noqa: E402
+from ._pnumpy import ledger_enable, ledger_disable, ledger_isenabled, ledger_info  # noqa: E402
+from ._pnumpy import recycler_enable, recycler_disable, recycler_isenabled, recycler_info  # noqa: E402
+from ._pnumpy import cuda_info, cuda_reset_stats, cuda_setthreshold, cuda_getthreshold, cuda_setslab  # noqa: E402
+
+from .cpu import cpu_count_linux, init, enable, disable  # noqa: E402
+from .benchmark import benchmark, benchmark_func  # noqa: E402
+from .pinned import pinned_empty, pinned_array  # noqa: E402
+
+
+def initialize():
+    """Kept for compatibility with pnumpy (``src/pnumpy/__init__.py:70-72``): same as ``init()``."""
+    init()
+
+
+def argmax(a, axis=None, out=None):
+    """Indices of the maximum values along an axis (``ndarray.argmax``; first occurrence, first NaN
+    wins).  reference: ``src/pnumpy/sort.py:410-483`` -- a thin forward to NumPy, whose per-dtype
+    ``argmax`` slot this package has replaced with the GPU arg-reduction."""
+    return np.asanyarray(a).argmax(axis=axis, out=out)
+
+
+def argmin(a, axis=None, out=None):
+    """Indices of the minimum values along an axis.  reference: ``src/pnumpy/sort.py:486-563``."""
+    return np.asanyarray(a).argmin(axis=axis, out=out)
+
+
+# start the engine by default (reference: src/pnumpy/__init__.py:74-76)
+if _os.environ.get("PNUMPY_B200_AUTOINIT", "1") != "0":
+    init()

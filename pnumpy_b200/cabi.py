@@ -79,6 +79,7 @@ SIGNATURES = {
     "pncu_GetIntTrueDivide": (_vp, [ctypes.c_int]),
     "pncu_itemsize": (ctypes.c_int, [ctypes.c_int]),
     "pncu_reduce_block_elems": (_c_i64, []),
+    "pncu_reduce_partial_count": (_c_i64, [ctypes.c_int, _c_i64]),
     "pncu_reduce_partial_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "pncu_reduce_partials": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _vp, _vp]),
     "pncu_reduce_finish": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _vp, _vp, _vp]),

@@ -2,29 +2,25 @@
 // UnaryOpFast / Compare* loop bodies: src/atop/ops_binary.cpp:398-793,
 // src/atop/ops_unary.cpp:327-376, src/atop/ops_compare.cpp:400-1255).
 //
-// Design (HBM-bound, no reuse, so no shared memory and no tensor cores):
-//   * the unit of work is a 16-byte "wide vector" of the WIDEST operand type; a lane
-//     moves one wide vector per operand per step with one 128-bit ld/st, the
-//     narrower operand (bool result of a compare, int32 input of an int->f64 divide)
-//     moves 16*narrow/wide bytes per lane with one narrower access.  Consecutive lanes
-//     touch consecutive vectors, so every warp-level access is fully coalesced.
-//   * each thread issues UNROLL independent vector loads per operand before the first
-//     use (memory-level parallelism), then computes, then stores.
-//   * persistent grid: SMs x ctas_per_sm CTAs walk the tiles grid-stride.
-//   * loads/stores use the streaming (.cs, evict-first) policy: nothing is re-read.
-//   * head/tail elements that do not fill an aligned wide vector are done by block 0
-//     in the same launch (no second kernel).
-//   * `out` may alias an input exactly (in-place): every element is read and written by
-//     the same thread, loads precede stores, and no pointer is declared __restrict__.
+// Design (HBM-bound, no reuse, so no shared memory and no tensor cores).  The shape was chosen
+// from the sweep in tools/stream_tune.cu on a B200 (profiles/r01_stream_tune.md): for a 2R+1W
+// stream, 256-bit accesses, one vector per thread, 256-thread CTAs and a FULL grid (one tile per
+// CTA, no grid-stride loop) reached 7.1 TB/s, against 6.2 TB/s for a persistent SMs x k grid.
+//   * the unit of work is a 32-byte "wide vector" of the WIDEST operand type; a lane moves one
+//     wide vector per operand with one 256-bit ld.global.v8 / st.global.v8 (sm_100 only); the
+//     narrower operand (bool result of a compare, int32 input of an int->f64 divide) moves
+//     32*narrow/wide bytes per lane with one narrower access.  Consecutive lanes touch
+//     consecutive vectors, so every warp-level access is fully coalesced.
+//   * one CTA = one tile of EW_BLOCK vectors; the hardware CTA scheduler balances the tail.
+//   * head/tail elements that do not fill an aligned wide vector are done by block 0 in the same
+//     launch (no second kernel).
+//   * `out` may alias an input exactly (in-place): every element is read and written by the same
+//     thread, loads precede stores (volatile asm keeps program order), nothing is __restrict__.
 #pragma once
 #include "common.cuh"
 
 namespace pncu {
 
-// ---- register image of one lane's share of a vector ---------------------------------------
-// N elements of T held in 32-bit words.  Elements are extracted / inserted with shifts on
-// compile-time indices so everything stays in registers (a union of byte arrays would be
-// demoted to local memory by the compiler for 1- and 2-byte types).
 template <int SIZE> struct Bits;
 template <> struct Bits<1> { typedef uint8_t type; };
 template <> struct Bits<2> { typedef uint16_t type; };
@@ -42,6 +38,10 @@ template <class T> __device__ __forceinline__ T from_bits(typename Bits<sizeof(T
     return c.t;
 }
 
+// ---- register image of one lane's share of a vector ---------------------------------------
+// N elements of T held in 32-bit words.  Elements are extracted / inserted with shifts on
+// compile-time indices so everything stays in registers (a union of byte arrays would be
+// demoted to local memory by the compiler for 1- and 2-byte types).
 template <class T, int N>
 struct Pack {
     static constexpr int BYTES = (int)sizeof(T) * N;
@@ -71,94 +71,91 @@ struct Pack {
     }
 };
 
-// streaming (evict-first) vector load / store of one lane's share
+// one global access of BYTES in {1,2,4,8,16,32}; volatile asm keeps loads before stores
+template <int BYTES>
+__device__ __forceinline__ void ld_words(const void* p, uint32_t* w) {
+    if constexpr (BYTES == 32)
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(p) : "memory");
+    else if constexpr (BYTES == 16)
+        asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("ld.global.v2.b32 {%0,%1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(p) : "memory");
+    else if constexpr (BYTES == 4)
+        asm volatile("ld.global.b32 %0, [%1];" : "=r"(w[0]) : "l"(p) : "memory");
+    else if constexpr (BYTES == 2)
+        asm volatile("{ .reg .b16 t; ld.global.b16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(w[0]) : "l"(p) : "memory");
+    else
+        asm volatile("ld.global.u8 %0, [%1];" : "=r"(w[0]) : "l"(p) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void st_words(void* p, const uint32_t* w) {
+    if constexpr (BYTES == 32)
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    else if constexpr (BYTES == 16)
+        asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("st.global.v2.b32 [%0], {%1,%2};" :: "l"(p), "r"(w[0]), "r"(w[1]) : "memory");
+    else if constexpr (BYTES == 4)
+        asm volatile("st.global.b32 [%0], %1;" :: "l"(p), "r"(w[0]) : "memory");
+    else if constexpr (BYTES == 2)
+        asm volatile("{ .reg .b16 t; cvt.u16.u32 t, %1; st.global.b16 [%0], t; }" :: "l"(p), "r"(w[0]) : "memory");
+    else
+        asm volatile("st.global.u8 [%0], %1;" :: "l"(p), "r"(w[0]) : "memory");
+}
+
 template <class T, int N>
-__device__ __forceinline__ Pack<T, N> ld_stream(const T* p) {
+__device__ __forceinline__ Pack<T, N> ld_pack(const T* p) {
     Pack<T, N> r;
-    constexpr int B = Pack<T, N>::BYTES;
-    if constexpr (B == 16) { const uint4 q = __ldcs(reinterpret_cast<const uint4*>(p)); r.w[0] = q.x; r.w[1] = q.y; r.w[2] = q.z; r.w[3] = q.w; }
-    else if constexpr (B == 8) { const uint2 q = __ldcs(reinterpret_cast<const uint2*>(p)); r.w[0] = q.x; r.w[1] = q.y; }
-    else if constexpr (B == 4) r.w[0] = __ldcs(reinterpret_cast<const unsigned int*>(p));
-    else if constexpr (B == 2) r.w[0] = __ldcs(reinterpret_cast<const unsigned short*>(p));
-    else r.w[0] = __ldcs(reinterpret_cast<const unsigned char*>(p));
+    ld_words<Pack<T, N>::BYTES>(p, r.w);
     return r;
 }
 template <class T, int N>
-__device__ __forceinline__ void st_stream(T* p, const Pack<T, N>& v) {
-    constexpr int B = Pack<T, N>::BYTES;
-    if constexpr (B == 16) __stcs(reinterpret_cast<uint4*>(p), make_uint4(v.w[0], v.w[1], v.w[2], v.w[3]));
-    else if constexpr (B == 8) __stcs(reinterpret_cast<uint2*>(p), make_uint2(v.w[0], v.w[1]));
-    else if constexpr (B == 4) __stcs(reinterpret_cast<unsigned int*>(p), v.w[0]);
-    else if constexpr (B == 2) __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)v.w[0]);
-    else __stcs(reinterpret_cast<unsigned char*>(p), (unsigned char)v.w[0]);
+__device__ __forceinline__ void st_pack(T* p, const Pack<T, N>& v) {
+    st_words<Pack<T, N>::BYTES>(p, v.w);
 }
 
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 enum Layout { LAY_VV = 0, LAY_SV = 1, LAY_VS = 2 };
 
-constexpr int EW_BLOCK = 256;
+constexpr int EW_BLOCK = 256;   // threads per CTA == vectors per tile
+constexpr int EW_VEC_BYTES = 32;
+
+// elements per wide vector for an (In, Out) pair
+template <class In, class Out>
+struct Epv { static constexpr int value = EW_VEC_BYTES / cmax((int)sizeof(In), (int)sizeof(Out)); };
 
 // ---- binary ----------------------------------------------------------------------
 // F: struct { typedef In; typedef Out; static __device__ Out apply(In, In); }
-template <class F, int LAYOUT, int UNROLL>
+template <class F, int LAYOUT>
 __global__ void __launch_bounds__(EW_BLOCK)
 ew2_vec_kernel(const typename F::In* a, const typename F::In* b, typename F::Out* o,
                int64_t head, int64_t nvec, int64_t n) {
     typedef typename F::In In;
     typedef typename F::Out Out;
-    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
-    constexpr int64_t TILE = (int64_t)EW_BLOCK * UNROLL;
+    constexpr int EPV = Epv<In, Out>::value;
 
     In sa = In(), sb = In();
     if (LAYOUT == LAY_SV) sa = a[0];
     if (LAYOUT == LAY_VS) sb = b[0];
 
-    const In* av = (LAYOUT == LAY_SV) ? a : a + head;
-    const In* bv = (LAYOUT == LAY_VS) ? b : b + head;
-    Out* ov = o + head;
-
-    const int64_t ntiles = (nvec + TILE - 1) / TILE;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t base = t * TILE + threadIdx.x;
-        Pack<In, EPV> ra[UNROLL], rb[UNROLL];
-        if (base + (int64_t)(UNROLL - 1) * EW_BLOCK < nvec) {
+    const int64_t v = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x;
+    if (v < nvec) {
+        const int64_t e0 = head + v * EPV;
+        Pack<In, EPV> ra, rb;
+        if (LAYOUT != LAY_SV) ra = ld_pack<In, EPV>(a + e0);
+        if (LAYOUT != LAY_VS) rb = ld_pack<In, EPV>(b + e0);
+        Pack<Out, EPV> r;
+        r.zero();
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t v = base + (int64_t)u * EW_BLOCK;
-                if (LAYOUT != LAY_SV) ra[u] = ld_stream<In, EPV>(av + v * EPV);
-                if (LAYOUT != LAY_VS) rb[u] = ld_stream<In, EPV>(bv + v * EPV);
-            }
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t v = base + (int64_t)u * EW_BLOCK;
-                Pack<Out, EPV> r;
-                r.zero();
-#pragma unroll
-                for (int e = 0; e < EPV; ++e)
-                    r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra[u].get(e),
-                                      LAYOUT == LAY_VS ? sb : rb[u].get(e)));
-                st_stream<Out, EPV>(ov + v * EPV, r);
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t v = base + (int64_t)u * EW_BLOCK;
-                if (v < nvec) {
-                    if (LAYOUT != LAY_SV) ra[u] = ld_stream<In, EPV>(av + v * EPV);
-                    if (LAYOUT != LAY_VS) rb[u] = ld_stream<In, EPV>(bv + v * EPV);
-                    Pack<Out, EPV> r;
-                    r.zero();
-#pragma unroll
-                    for (int e = 0; e < EPV; ++e)
-                        r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra[u].get(e),
-                                          LAYOUT == LAY_VS ? sb : rb[u].get(e)));
-                    st_stream<Out, EPV>(ov + v * EPV, r);
-                }
-            }
-        }
+        for (int e = 0; e < EPV; ++e)
+            r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra.get(e), LAYOUT == LAY_VS ? sb : rb.get(e)));
+        st_pack<Out, EPV>(o + e0, r);
     }
-    // head + tail scalars (fewer than 2*EPV elements... plus a misaligned head)
+    // head + tail scalars: elements before the first / after the last aligned wide vector
     if (blockIdx.x == 0) {
         const int64_t tail0 = head + nvec * EPV;
         const int64_t nscalar = head + (n - tail0);
@@ -176,8 +173,8 @@ ew2_strided_kernel(const char* a, const char* b, char* o, int64_t n,
                    int64_t s1, int64_t s2, int64_t so) {
     typedef typename F::In In;
     typedef typename F::Out Out;
-    const int64_t step = (int64_t)gridDim.x * EW_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += step) {
+    const int64_t i = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x;
+    if (i < n) {
         const In x = *reinterpret_cast<const In*>(a + i * s1);
         const In y = *reinterpret_cast<const In*>(b + i * s2);
         *reinterpret_cast<Out*>(o + i * so) = F::apply(x, y);
@@ -186,45 +183,21 @@ ew2_strided_kernel(const char* a, const char* b, char* o, int64_t n,
 
 // ---- unary -------------------------------------------------------------------------
 // F: struct { typedef In; typedef Out; static __device__ Out apply(In); }
-template <class F, int UNROLL>
+template <class F>
 __global__ void __launch_bounds__(EW_BLOCK)
 ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n) {
     typedef typename F::In In;
     typedef typename F::Out Out;
-    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
-    constexpr int64_t TILE = (int64_t)EW_BLOCK * UNROLL;
-    const In* av = a + head;
-    Out* ov = o + head;
-    const int64_t ntiles = (nvec + TILE - 1) / TILE;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t base = t * TILE + threadIdx.x;
-        Pack<In, EPV> ra[UNROLL];
-        if (base + (int64_t)(UNROLL - 1) * EW_BLOCK < nvec) {
+    constexpr int EPV = Epv<In, Out>::value;
+    const int64_t v = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x;
+    if (v < nvec) {
+        const int64_t e0 = head + v * EPV;
+        const Pack<In, EPV> ra = ld_pack<In, EPV>(a + e0);
+        Pack<Out, EPV> r;
+        r.zero();
 #pragma unroll
-            for (int u = 0; u < UNROLL; ++u)
-                ra[u] = ld_stream<In, EPV>(av + (base + (int64_t)u * EW_BLOCK) * EPV);
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                Pack<Out, EPV> r;
-                r.zero();
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra[u].get(e)));
-                st_stream<Out, EPV>(ov + (base + (int64_t)u * EW_BLOCK) * EPV, r);
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                const int64_t v = base + (int64_t)u * EW_BLOCK;
-                if (v < nvec) {
-                    ra[u] = ld_stream<In, EPV>(av + v * EPV);
-                    Pack<Out, EPV> r;
-                    r.zero();
-#pragma unroll
-                    for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra[u].get(e)));
-                    st_stream<Out, EPV>(ov + v * EPV, r);
-                }
-            }
-        }
+        for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
+        st_pack<Out, EPV>(o + e0, r);
     }
     if (blockIdx.x == 0) {
         const int64_t tail0 = head + nvec * EPV;
@@ -241,8 +214,8 @@ __global__ void __launch_bounds__(EW_BLOCK)
 ew1_strided_kernel(const char* a, char* o, int64_t n, int64_t s1, int64_t so) {
     typedef typename F::In In;
     typedef typename F::Out Out;
-    const int64_t step = (int64_t)gridDim.x * EW_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x; i < n; i += step) {
+    const int64_t i = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x;
+    if (i < n) {
         const In x = *reinterpret_cast<const In*>(a + i * s1);
         *reinterpret_cast<Out*>(o + i * so) = F::apply(x);
     }
@@ -253,7 +226,7 @@ ew1_strided_kernel(const char* a, char* o, int64_t n, int64_t s1, int64_t so) {
 inline bool ranges_overlap(const char* p, int64_t pbytes, const char* q, int64_t qbytes) {
     return p < q + qbytes && q < p + pbytes;
 }
-// byte extent [lo, hi) of `len` elements of `size` bytes at byte stride `s`
+// byte extent [lo, lo+bytes) of `len` elements of `size` bytes at byte stride `s`
 inline void extent(const void* p, int64_t len, int64_t s, int64_t size, const char** lo, int64_t* bytes) {
     const char* c = (const char*)p;
     int64_t span = (len - 1) * s;
@@ -262,6 +235,8 @@ inline void extent(const void* p, int64_t len, int64_t s, int64_t size, const ch
 }
 
 // 0 ok, PNCU_ERR_OVERLAP if `out` overlaps `in` other than exact element-wise aliasing
+// (the reference drops to its scalar loop for near overlaps, src/pnumpy/_pnumpy.cpp:743-745;
+// a parallel kernel cannot honour sequential semantics, so the hook layer is told to decline)
 inline int check_alias(const void* in, int64_t sin, int64_t insize, const void* out, int64_t sout,
                        int64_t outsize, int64_t len) {
     const char *ilo, *olo;
@@ -275,7 +250,10 @@ inline int check_alias(const void* in, int64_t sin, int64_t insize, const void* 
     return PNCU_ERR_OVERLAP;
 }
 
-constexpr int EW_UNROLL = 4;
+inline unsigned full_grid(int64_t items, int per_cta) {
+    int64_t g = (items + per_cta - 1) / per_cta;
+    return (unsigned)(g < 1 ? 1 : g);
+}
 
 template <class F>
 int launch_binary(const void* in1, const void* in2, void* out, int64_t len, int64_t s1, int64_t s2,
@@ -291,11 +269,12 @@ int launch_binary(const void* in1, const void* in2, void* out, int64_t len, int6
         set_error("operand pointer or stride is not a multiple of the item size");
         return PNCU_ERR_UNSUPPORTED;
     }
+    if (len > ((int64_t)1 << 38)) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
     if ((rc = check_alias(in1, s1, sizeof(In), out, so, sizeof(Out), len))) return rc;
     if ((rc = check_alias(in2, s2, sizeof(In), out, so, sizeof(Out), len))) return rc;
     cudaStream_t st = as_stream(stream);
 
-    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
+    constexpr int EPV = Epv<In, Out>::value;
     constexpr int IN_VB = EPV * (int)sizeof(In);    // bytes one lane moves per input vector
     constexpr int OUT_VB = EPV * (int)sizeof(Out);
     const bool c1 = s1 == (int64_t)sizeof(In), c2 = s2 == (int64_t)sizeof(In);
@@ -308,24 +287,21 @@ int launch_binary(const void* in1, const void* in2, void* out, int64_t len, int6
         const bool b_ok = z2 || ((uintptr_t)in2 + head * sizeof(In)) % IN_VB == 0;
         if (a_ok && b_ok) {
             const int64_t nvec = (len - head) / EPV;
-            const int64_t tiles = (nvec + (int64_t)EW_BLOCK * EW_UNROLL - 1) / ((int64_t)EW_BLOCK * EW_UNROLL);
-            const unsigned grid = grid_for(tiles, g_tune.ctas_per_sm);
+            const unsigned grid = full_grid(nvec, EW_BLOCK);
             const In* a = (const In*)in1;
             const In* b = (const In*)in2;
             Out* o = (Out*)out;
             if (c1 && c2)
-                ew2_vec_kernel<F, LAY_VV, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+                ew2_vec_kernel<F, LAY_VV><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
             else if (z1)
-                ew2_vec_kernel<F, LAY_SV, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+                ew2_vec_kernel<F, LAY_SV><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
             else
-                ew2_vec_kernel<F, LAY_VS, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+                ew2_vec_kernel<F, LAY_VS><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
             return after_launch("ew2_vec_kernel");
         }
     }
-    const int64_t tiles = (len + EW_BLOCK - 1) / EW_BLOCK;
-    const unsigned grid = grid_for(tiles, 8);
-    ew2_strided_kernel<F><<<grid, EW_BLOCK, 0, st>>>((const char*)in1, (const char*)in2, (char*)out,
-                                                      len, s1, s2, so);
+    ew2_strided_kernel<F><<<full_grid(len, EW_BLOCK), EW_BLOCK, 0, st>>>((const char*)in1, (const char*)in2,
+                                                                         (char*)out, len, s1, s2, so);
     return after_launch("ew2_strided_kernel");
 }
 
@@ -341,10 +317,11 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
         set_error("operand pointer or stride is not a multiple of the item size");
         return PNCU_ERR_UNSUPPORTED;
     }
+    if (len > ((int64_t)1 << 38)) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
     if ((rc = check_alias(in, s1, sizeof(In), out, so, sizeof(Out), len))) return rc;
     cudaStream_t st = as_stream(stream);
 
-    constexpr int EPV = 16 / cmax((int)sizeof(In), (int)sizeof(Out));
+    constexpr int EPV = Epv<In, Out>::value;
     constexpr int IN_VB = EPV * (int)sizeof(In);
     constexpr int OUT_VB = EPV * (int)sizeof(Out);
     if (so == (int64_t)sizeof(Out) && s1 == (int64_t)sizeof(In)) {
@@ -352,15 +329,11 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
         if (head > len) head = len;
         if (((uintptr_t)in + head * sizeof(In)) % IN_VB == 0) {
             const int64_t nvec = (len - head) / EPV;
-            const int64_t tiles = (nvec + (int64_t)EW_BLOCK * EW_UNROLL - 1) / ((int64_t)EW_BLOCK * EW_UNROLL);
-            const unsigned grid = grid_for(tiles, g_tune.ctas_per_sm);
-            ew1_vec_kernel<F, EW_UNROLL><<<grid, EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
+            ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
             return after_launch("ew1_vec_kernel");
         }
     }
-    const int64_t tiles = (len + EW_BLOCK - 1) / EW_BLOCK;
-    const unsigned grid = grid_for(tiles, 8);
-    ew1_strided_kernel<F><<<grid, EW_BLOCK, 0, st>>>((const char*)in, (char*)out, len, s1, so);
+    ew1_strided_kernel<F><<<full_grid(len, EW_BLOCK), EW_BLOCK, 0, st>>>((const char*)in, (char*)out, len, s1, so);
     return after_launch("ew1_strided_kernel");
 }
 

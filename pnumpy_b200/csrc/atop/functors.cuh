@@ -43,6 +43,31 @@ template <> __device__ __forceinline__ double op_mul<double>(double a, double b)
 __device__ __forceinline__ float op_div(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ double op_div(double a, double b) { return __ddiv_rn(a, b); }
 
+// NumPy floor_divide for floats (npy_floor_divide -> npy_divmod, numpy/_core/src/npymath/
+// npy_math_internal.h.src): quotient from an exact fmod, Python sign convention, snapped to the
+// nearest integer.  The reference's scalar body is floor(x / y) (src/atop/ops_binary.cpp:80-82),
+// which differs from NumPy by one when x / y rounds up to an integer; NumPy semantics are used.
+__device__ __forceinline__ float fp_fmod(float a, float b) { return fmodf(a, b); }
+__device__ __forceinline__ double fp_fmod(double a, double b) { return fmod(a, b); }
+__device__ __forceinline__ float fp_floor(float a) { return floorf(a); }
+__device__ __forceinline__ double fp_floor(double a) { return floor(a); }
+__device__ __forceinline__ float fp_copysign(float a, float b) { return copysignf(a, b); }
+__device__ __forceinline__ double fp_copysign(double a, double b) { return copysign(a, b); }
+template <class T> __device__ __forceinline__ T op_floordiv(T a, T b) {
+    if (b == (T)0) return op_div(a, b);
+    const T mod = fp_fmod(a, b);
+    T div = op_div(op_sub<T>(a, mod), b);
+    if (mod != (T)0) {
+        if ((b < (T)0) != (mod < (T)0)) div = op_sub<T>(div, (T)1);
+    }
+    if (div != (T)0) {
+        T fl = fp_floor(div);
+        if (op_sub<T>(div, fl) > (T)0.5) fl = op_add<T>(fl, (T)1);
+        return fl;
+    }
+    return fp_copysign((T)0, op_div(a, b));
+}
+
 // NumPy minimum/maximum: NaN-propagating, and for equal operands (incl. +0/-0) the
 // SECOND operand is returned -- `(a < b || isnan(a)) ? a : b`.  The reference's float
 // body is _mm256_min_ps (src/atop/ops_binary.cpp:146-147) which drops a NaN in the
@@ -80,6 +105,7 @@ PNCU_BINARY_FUNCTOR(AddF, op_add<T>(a, b))
 PNCU_BINARY_FUNCTOR(SubF, op_sub<T>(a, b))
 PNCU_BINARY_FUNCTOR(MulF, op_mul<T>(a, b))
 PNCU_BINARY_FUNCTOR(DivF, op_div(a, b))
+PNCU_BINARY_FUNCTOR(FloorDivF, op_floordiv<T>(a, b))
 PNCU_BINARY_FUNCTOR(MinF, op_min<T>(a, b))
 PNCU_BINARY_FUNCTOR(MaxF, op_max<T>(a, b))
 PNCU_BINARY_FUNCTOR(AndF, (T)(a & b))

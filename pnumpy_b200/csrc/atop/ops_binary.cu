@@ -3,7 +3,7 @@
 //
 // Out-type rules are the reference's verbatim (they decide which NumPy loops get hooked,
 // src/pnumpy/_pnumpy.cpp:1349); kernel coverage is a superset of the reference's fast
-// pointers: every (op, type) the reference hooks has a GPU body except FLOORDIV.
+// pointers: every (op, type) the reference hooks has a GPU body.
 #include "ew.cuh"
 #include "functors.cuh"
 
@@ -71,11 +71,13 @@ extern "C" pncu_any_two_fn pncu_GetSimpleMathOpFast(int func, int t1, int t2, in
             if (t == PNCU_FLOAT) return launch_binary<DivF<float>>;
             if (t == PNCU_DOUBLE) return launch_binary<DivF<double>>;
             return NULL;
-        case PNCU_FLOORDIV:  // ops_binary.cpp:940-952: hooked for floats, no GPU body yet
+        case PNCU_FLOORDIV:  // ops_binary.cpp:940-952: floats only
             if (t <= PNCU_UINT64) return NULL;
             *wantedOutType = PNCU_DOUBLE;
             if (t == PNCU_FLOAT) *wantedOutType = PNCU_FLOAT;
             if (t == PNCU_LONGDOUBLE) *wantedOutType = PNCU_LONGDOUBLE;
+            if (t == PNCU_FLOAT) return launch_binary<FloorDivF<float>>;
+            if (t == PNCU_DOUBLE) return launch_binary<FloorDivF<double>>;
             return NULL;
         case PNCU_MIN:  // ops_binary.cpp:954-963
             *wantedOutType = t;

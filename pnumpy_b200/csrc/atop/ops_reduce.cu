@@ -6,16 +6,21 @@
 // per-16K-chunk partials and second pass on the caller (src/pnumpy/_pnumpy.cpp:646-731,
 // 359-444) and the arg-reduction pass-through (src/pnumpy/_pnumpy.cpp:1105-1118).
 //
-// Scheme.  [0, n) is cut into fixed LOGICAL BLOCKS of RED_BLOCK_ELEMS elements.
-//   pass 1: a persistent grid walks the logical blocks; one CTA folds one block: every thread
-//           keeps RED_UNROLL independent accumulators over 128-bit coalesced streaming loads,
-//           folds them in index order, then a shuffle-down tree per warp, then warp leaders
-//           through shared memory folded by thread 0 in warp order -> partial[k] in slot k.
+// Scheme.  [0, n) is cut into fixed LOGICAL BLOCKS of 64 KiB (65536 / itemsize elements).
+//   pass 1: FULL grid, one 256-thread CTA per logical block (the sweep in tools/stream_tune.cu
+//           showed a full grid of small CTAs beats a persistent grid by ~10% on B200: the
+//           hardware CTA scheduler absorbs the tail).  A thread issues its eight 256-bit loads
+//           (256 B in flight per thread) before the first use, folds them into four independent
+//           accumulators in a fixed order, then a shuffle-down tree per warp, then the warp
+//           leaders through shared memory folded by thread 0 in warp order -> partial[k] in slot k.
+//           Arg-reductions keep the block in registers: phase A finds the block extreme
+//           (NaN-propagating), phase B scans the registers for its first occurrence; HBM is read
+//           once and there is no per-element index arithmetic.
 //   pass 2: ONE CTA folds the partials: thread t takes slots t, t+1024, ... in order, then the
 //           same warp/shared tree, then applies the start value and writes the result.
 // Every choice above is a function of (n, type) only -- not of the grid, the SM count or the
 // arrival order of CTAs -- so results are bit-reproducible run to run, and a multi-GPU split
-// at multiples of RED_BLOCK_ELEMS that gathers all partials before pass 2 is bit-identical to
+// at multiples of 65536 elements that gathers all partials before pass 2 is bit-identical to
 // the single-GPU result.  No atomics anywhere.
 //
 // Semantics (8c):
@@ -33,10 +38,13 @@ using namespace pncu;
 
 namespace {
 
-constexpr int64_t RED_BLOCK_ELEMS = 65536;
+constexpr int RED_BLOCK_BYTES = 65536;   // one logical block
+constexpr int64_t RED_ALIGN_ELEMS = 65536;  // shard boundaries: a multiple of every type's block
 constexpr int RED_THREADS = 256;
-constexpr int RED_UNROLL = 8;
+constexpr int RED_NV = RED_BLOCK_BYTES / (RED_THREADS * 32);  // 256-bit vectors per thread (8)
+constexpr int RED_CHAINS = 4;            // independent accumulators per thread
 constexpr int FIN_THREADS = 1024;
+template <class In> __host__ __device__ constexpr int64_t block_elems() { return RED_BLOCK_BYTES / (int64_t)sizeof(In); }
 
 // ---- reducer policies ------------------------------------------------------------------------
 // In: element type; Acc: accumulator == partial type;
@@ -126,6 +134,7 @@ template <class T, bool IS_MAX>
 struct ArgR {
     typedef T In; typedef ArgPair<T> Acc;
     static constexpr bool kHasIdentity = false;
+    static constexpr bool kIsMax = IS_MAX;
     static __device__ __forceinline__ Acc identity() { Acc a; a.v = T(); a.idx = 0; return a; }
     static __device__ __forceinline__ Acc first(T x, int64_t idx) { Acc a; a.v = x; a.idx = idx; return a; }
     // strictly better than the incumbent; a NaN beats any non-NaN, nothing beats a NaN
@@ -192,72 +201,137 @@ __device__ __forceinline__ void write_result(typename R::Acc total, typename R::
 template <class R, bool VEC>
 __global__ void __launch_bounds__(RED_THREADS)
 reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_base,
-                     typename R::Acc* partials, int64_t nblocks) {
+                     typename R::Acc* partials) {
     typedef typename R::In In;
     typedef typename R::Acc Acc;
-    constexpr int EPV = VEC ? 16 / (int)sizeof(In) : 1;
+    constexpr int64_t BE = block_elems<In>();
+    constexpr int EPV = 32 / (int)sizeof(In);
     __shared__ Acc smem[RED_THREADS / 32];
 
-    for (int64_t k = blockIdx.x; k < nblocks; k += gridDim.x) {
-        const int64_t start = k * RED_BLOCK_ELEMS;
-        const int64_t cnt = (n - start) < RED_BLOCK_ELEMS ? (n - start) : RED_BLOCK_ELEMS;
-        const char* base = in + start * stride;
-        const int64_t gidx0 = start + index_base;
+    const int64_t k = blockIdx.x;
+    const int64_t start = k * BE;
+    const int64_t cnt = (n - start) < BE ? (n - start) : BE;
+    const char* base = in + start * stride;
+    const int64_t gidx0 = start + index_base;
 
-        Acc acc[RED_UNROLL];
-        if (R::kHasIdentity) {
+    Acc acc[RED_CHAINS];
+    if (R::kHasIdentity) {
 #pragma unroll
-            for (int u = 0; u < RED_UNROLL; ++u) acc[u] = R::identity();
-        } else {
-            // idempotent ops (min/max/arg): seed every accumulator with the block's first element
-            const Acc seed = R::first(*reinterpret_cast<const In*>(base), gidx0);
+        for (int c = 0; c < RED_CHAINS; ++c) acc[c] = R::identity();
+    } else {
+        // idempotent ops (min/max): seed every accumulator with the block's first element
+        const Acc seed = R::first(*reinterpret_cast<const In*>(base), gidx0);
 #pragma unroll
-            for (int u = 0; u < RED_UNROLL; ++u) acc[u] = seed;
+        for (int c = 0; c < RED_CHAINS; ++c) acc[c] = seed;
+    }
+
+    if (VEC && cnt == BE) {
+        const In* p = reinterpret_cast<const In*>(base);
+        Pack<In, EPV> r[RED_NV];
+#pragma unroll
+        for (int j = 0; j < RED_NV; ++j) r[j] = ld_pack<In, EPV>(p + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
+#pragma unroll
+        for (int j = 0; j < RED_NV; ++j) {
+            const int64_t e0 = gidx0 + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) acc[j % RED_CHAINS] = R::step(acc[j % RED_CHAINS], r[j].get(e), e0 + e);
         }
+    } else {
+        // ragged last block, strided or misaligned input: element loads, same fixed order
+        for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS)
+            acc[0] = R::step(acc[0], *reinterpret_cast<const In*>(base + i * stride), gidx0 + i);
+    }
 
-        if (VEC) {
-            const In* p = reinterpret_cast<const In*>(base);
-            const int64_t nvec = cnt / EPV;
-            int64_t v = threadIdx.x;
-            for (; v + (int64_t)(RED_UNROLL - 1) * RED_THREADS < nvec; v += (int64_t)RED_UNROLL * RED_THREADS) {
-                Pack<In, EPV> r[RED_UNROLL];
+    Acc a = acc[0];
 #pragma unroll
-                for (int u = 0; u < RED_UNROLL; ++u) r[u] = ld_stream<In, EPV>(p + (v + (int64_t)u * RED_THREADS) * EPV);
+    for (int c = 1; c < RED_CHAINS; ++c) a = R::combine(a, acc[c]);
+    a = block_fold<R, RED_THREADS>(a, smem);
+    if (threadIdx.x == 0) partials[k] = a;
+}
+
+// NaN-propagating extreme for phase A of the arg kernels
+template <class T, bool IS_MAX> __device__ __forceinline__ T ext_nan(T a, T b) {
+    if constexpr (std::is_same<T, float>::value) {
+        float r;
+        if (IS_MAX) asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+        else asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+        return r;
+    } else if constexpr (is_fp<T>::value) {
+        return (b != b) ? b : ((IS_MAX ? b > a : b < a) ? b : a);  // a NaN in `a` stays
+    } else {
+        return IS_MAX ? (b > a ? b : a) : (b < a ? b : a);
+    }
+}
+template <class T, bool IS_MAX> struct ExtR {  // block fold of phase A
+    typedef T In; typedef typename Widen<T>::type Acc;
+    static __device__ __forceinline__ Acc combine(Acc a, Acc b) { return (Acc)ext_nan<Acc, IS_MAX>(a, b); }
+};
+struct IdxMinR {  // block fold of phase B
+    typedef int In; typedef int Acc;
+    static __device__ __forceinline__ int combine(int a, int b) { return a < b ? a : b; }
+};
+
+// arg-reduction pass 1: partial[k] = {extreme of block k, global index of its first occurrence}
+template <class T, bool IS_MAX, bool VEC>
+__global__ void __launch_bounds__(RED_THREADS)
+arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partials) {
+    typedef typename Widen<T>::type W;
+    constexpr int64_t BE = block_elems<T>();
+    constexpr int EPV = 32 / (int)sizeof(T);
+    constexpr int NONE = 0x7fffffff;
+    __shared__ W smem_v[RED_THREADS / 32];
+    __shared__ int smem_i[RED_THREADS / 32];
+    __shared__ W bcast;
+
+    const int64_t k = blockIdx.x;
+    const int64_t start = k * BE;
+    const int64_t cnt = (n - start) < BE ? (n - start) : BE;
+    const T* p = in + start;
+    const bool full = VEC && cnt == BE;
+
+    Pack<T, EPV> r[RED_NV];
+    W m = (W)p[0];
+    if (full) {
 #pragma unroll
-                for (int u = 0; u < RED_UNROLL; ++u) {
-                    const int64_t e0 = gidx0 + (v + (int64_t)u * RED_THREADS) * EPV;
+        for (int j = 0; j < RED_NV; ++j) r[j] = ld_pack<T, EPV>(p + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e) acc[u] = R::step(acc[u], r[u].get(e), e0 + e);
-                }
+        for (int j = 0; j < RED_NV; ++j)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) m = ext_nan<W, IS_MAX>(m, (W)r[j].get(e));
+    } else {
+        for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) m = ext_nan<W, IS_MAX>(m, (W)p[i]);
+    }
+    m = block_fold<ExtR<T, IS_MAX>, RED_THREADS>(m, smem_v);
+    if (threadIdx.x == 0) bcast = m;
+    __syncthreads();
+    const W mb = bcast;
+    const bool want_nan = is_fp<T>::value && (mb != mb);
+
+    int local = NONE;
+    if (full) {
+        int c = NONE;  // scan downwards so the smallest matching position survives
+#pragma unroll
+        for (int j = RED_NV - 1; j >= 0; --j)
+#pragma unroll
+            for (int e = EPV - 1; e >= 0; --e) {
+                const W x = (W)r[j].get(e);
+                const bool hit = want_nan ? (x != x) : (x == mb);
+                c = hit ? (j * RED_THREADS * EPV + e) : c;
             }
-            for (; v < nvec; v += RED_THREADS) {  // ragged last group (fewer than RED_UNROLL vectors)
-                Pack<In, EPV> r = ld_stream<In, EPV>(p + v * EPV);
-                const int64_t e0 = gidx0 + v * EPV;
-#pragma unroll
-                for (int e = 0; e < EPV; ++e) acc[0] = R::step(acc[0], r.get(e), e0 + e);
-            }
-            const int64_t t0 = nvec * EPV + threadIdx.x;  // < EPV leftover elements
-            if (t0 < cnt) acc[0] = R::step(acc[0], p[t0], gidx0 + t0);
-        } else {
-            int64_t i = threadIdx.x;
-            for (; i + (int64_t)(RED_UNROLL - 1) * RED_THREADS < cnt; i += (int64_t)RED_UNROLL * RED_THREADS) {
-                In r[RED_UNROLL];
-#pragma unroll
-                for (int u = 0; u < RED_UNROLL; ++u)
-                    r[u] = *reinterpret_cast<const In*>(base + (i + (int64_t)u * RED_THREADS) * stride);
-#pragma unroll
-                for (int u = 0; u < RED_UNROLL; ++u) acc[u] = R::step(acc[u], r[u], gidx0 + i + (int64_t)u * RED_THREADS);
-            }
-            for (; i < cnt; i += RED_THREADS)
-                acc[0] = R::step(acc[0], *reinterpret_cast<const In*>(base + i * stride), gidx0 + i);
+        if (c != NONE) local = c + (int)threadIdx.x * EPV;
+    } else {
+        for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) {
+            const W x = (W)p[i];
+            const bool hit = want_nan ? (x != x) : (x == mb);
+            if (hit && (int)i < local) local = (int)i;
         }
-
-        Acc a = acc[0];
-#pragma unroll
-        for (int u = 1; u < RED_UNROLL; ++u) a = R::combine(a, acc[u]);
-        a = block_fold<R, RED_THREADS>(a, smem);
-        if (threadIdx.x == 0) partials[k] = a;
-        __syncthreads();  // smem is reused by the next logical block
+    }
+    local = block_fold<IdxMinR, RED_THREADS>(local, smem_i);
+    if (threadIdx.x == 0) {
+        ArgPair<T> out;
+        out.v = (T)mb;
+        out.idx = start + index_base + local;
+        partials[k] = out;
     }
 }
 
@@ -288,22 +362,34 @@ reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, 
 }
 
 // ---- host launchers ---------------------------------------------------------------------------------
-inline int64_t nblocks_for(int64_t len) { return (len + RED_BLOCK_ELEMS - 1) / RED_BLOCK_ELEMS; }
+template <class In> inline int64_t nblocks_for(int64_t len) { return (len + block_elems<In>() - 1) / block_elems<In>(); }
 
 template <class R>
 int launch_partials(const void* in, int64_t len, int64_t stride, int64_t index_base, void* partials,
                     cudaStream_t st) {
     typedef typename R::In In;
-    const int64_t nb = nblocks_for(len);
-    const unsigned grid = grid_for(nb, g_tune.reduce_ctas_per_sm);
-    const bool vec = stride == (int64_t)sizeof(In) && ((uintptr_t)in % 16) == 0;
+    const int64_t nb = nblocks_for<In>(len);
+    if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
+    const bool vec = stride == (int64_t)sizeof(In) && ((uintptr_t)in % 32) == 0;
     if (vec)
-        reduce_blocks_kernel<R, true><<<grid, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
-                                                                  (typename R::Acc*)partials, nb);
+        reduce_blocks_kernel<R, true><<<(unsigned)nb, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
+                                                                          (typename R::Acc*)partials);
     else
-        reduce_blocks_kernel<R, false><<<grid, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
-                                                                   (typename R::Acc*)partials, nb);
+        reduce_blocks_kernel<R, false><<<(unsigned)nb, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
+                                                                           (typename R::Acc*)partials);
     return after_launch("reduce_blocks_kernel");
+}
+
+template <class T, bool IS_MAX>
+int launch_arg_partials(const void* in, int64_t len, int64_t /*stride*/, int64_t index_base, void* partials,
+                        cudaStream_t st) {
+    const int64_t nb = nblocks_for<T>(len);
+    if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
+    if (((uintptr_t)in % 32) == 0)
+        arg_blocks_kernel<T, IS_MAX, true><<<(unsigned)nb, RED_THREADS, 0, st>>>((const T*)in, len, index_base, (ArgPair<T>*)partials);
+    else
+        arg_blocks_kernel<T, IS_MAX, false><<<(unsigned)nb, RED_THREADS, 0, st>>>((const T*)in, len, index_base, (ArgPair<T>*)partials);
+    return after_launch("arg_blocks_kernel");
 }
 
 template <class R>
@@ -332,7 +418,7 @@ int launch_reduce(const void* in, void* out, const void* startVal, int64_t len, 
         return 0;
     }
     if ((rc = check_reduce_args<R>(in, stride))) return rc;
-    const int64_t nb = nblocks_for(len);
+    const int64_t nb = nblocks_for<In>(len);
     void* ws = NULL;
     if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
     if ((rc = launch_partials<R>(in, len, stride, 0, ws, st))) return rc;
@@ -348,10 +434,10 @@ int launch_argminmax(const void* in, int64_t len, int64_t* out_index, pncu_strea
     if (!out_index) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
     if (len <= 0) { set_error("arg-reduction of an empty sequence"); return PNCU_ERR_ARGUMENT; }
     if ((rc = check_reduce_args<R>(in, sizeof(typename R::In)))) return rc;
-    const int64_t nb = nblocks_for(len);
+    const int64_t nb = nblocks_for<typename R::In>(len);
     void* ws = NULL;
     if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
-    if ((rc = launch_partials<R>(in, len, sizeof(typename R::In), 0, ws, st))) return rc;
+    if ((rc = launch_arg_partials<typename R::In, R::kIsMax>(in, len, sizeof(typename R::In), 0, ws, st))) return rc;
     reduce_finish_kernel<R, false><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)ws, nb, out_index, NULL);
     return after_launch("reduce_finish_kernel");
 }
@@ -382,7 +468,7 @@ ReduceOps make_arg_ops() {
     ReduceOps o;
     o.partial_bytes = (int)sizeof(typename R::Acc);
     o.full = NULL;
-    o.partials = launch_partials<R>;
+    o.partials = launch_arg_partials<typename R::In, R::kIsMax>;
     o.finish = finish_thunk<R, false>;
     return o;
 }
@@ -492,7 +578,14 @@ extern "C" pncu_argminmax_fn pncu_GetArgMinMaxOpFast(int kind, int t) {
     return NULL;
 }
 
-extern "C" int64_t pncu_reduce_block_elems(void) { return RED_BLOCK_ELEMS; }
+extern "C" int64_t pncu_reduce_block_elems(void) { return RED_ALIGN_ELEMS; }
+
+extern "C" int64_t pncu_reduce_partial_count(int t, int64_t len) {
+    const int isz = pncu_itemsize(t);
+    if (!isz || len <= 0) return 0;
+    const int64_t be = RED_BLOCK_BYTES / isz;
+    return (len + be - 1) / be;
+}
 
 extern "C" int pncu_reduce_partial_bytes(int func, int t) {
     ReduceOps o;

@@ -1,0 +1,712 @@
+// nte -- the per-GPU stream and shard dispatcher (see include/pnumpy_nte.h).
+//
+// replaces: CMathWorker / stMATH_WORKER_ITEM / stWorkerRing / WorkerThreadFunction
+// (src/atop/threads.h:165-1171, src/atop/threads.cpp:72-191) as driven by the four hook-layer
+// dispatchers (src/pnumpy/_pnumpy.cpp:638-996, 1105-1118).
+//
+// Reference                                   | here
+// --------------------------------------------+---------------------------------------------------
+// 16384-element chunks dealt round-robin to   | [0, n) cut into `lanes` contiguous shards at
+// per-core channels (threads.h:319-389)       | multiples of 65536 elements; lane l -> GPU l % G
+// futex-woken worker threads (threads.cpp:164)| persistent host threads, one per extra lane, woken
+//                                             | by a condition variable; the caller runs lane 0
+//                                             | (threads.h:1143: "main thread works as core 0")
+// loop body on the chunk, in cache            | per lane: pinned staging ring -> H2D stream ->
+//                                             | compute stream (libpnumpy_cuda launcher) -> D2H
+//                                             | stream, slabs pipelined through 3 ring slots
+// partials[chunk] then the same reduce on the | block partials gathered on GPU 0 (peer copies over
+// caller thread (_pnumpy.cpp:666-700)         | NVLink), ONE finish kernel in fixed order
+// spin until BlocksCompleted (threads.h:1148) | join lanes; stream-synchronize; return
+// re-entrant call -> unthreaded (:1064-1073)  | try_lock fails -> NTE_DECLINED (caller's old loop)
+#include <string.h>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include "../../../include/pnumpy_nte.h"
+#include "../atop/common.cuh"
+
+using namespace pncu;
+
+namespace {
+
+constexpr int kRing = 3;          // staging slots per lane
+constexpr int kMaxLanes = 16;     // the reference's hard maximum: 15 workers + caller (threads.h:56-66)
+constexpr int64_t kAlign = 65536; // == pncu_reduce_block_elems()
+
+struct Stats {
+    std::atomic<int64_t> calls{0}, declined{0}, launches{0}, h2d{0}, d2h{0}, staged{0}, lanes_last{0}, gpus_last{0};
+};
+Stats g_stats;
+
+struct Lane {
+    int device = -1;
+    bool ready = false;
+    cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[kRing], ev_k[kRing], ev_d2h[kRing];
+    char* d_buf[kRing][3];   // device slabs: in1, in2, out
+    char* h_buf[kRing][3];   // pinned staging slabs
+    size_t slab_bytes = 0;
+    char* d_scalar = nullptr;   // 2 x 16 B for broadcast scalars
+    char* d_partials = nullptr; // reduction block partials of this lane's shard
+    size_t partials_bytes = 0;
+    char* h_small = nullptr;    // pinned scratch for scalars / results (64 B)
+};
+
+struct Job;
+typedef void (*LaneFn)(Lane&, Job&, int lane_index);
+
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    LaneFn fn = nullptr;
+    Job* job = nullptr;
+    int lane_index = 0;
+    bool has_work = false, done = false, quit = false;
+};
+
+struct State {
+    std::mutex api_mu;            // one dispatch at a time (re-entrant callers are declined)
+    bool inited = false;
+    int ndev = 0;
+    int workers = 3;              // extra lanes beside the caller's (reference default futex wake count is
+                                  // min(11, cores-1), threads.h:67,891-894; per-op MaxThreads caps it at 3 or 7)
+    bool threading = true;
+    int64_t min_elems = 1 << 20;  // below this a PCIe round trip cannot win; the caller's loop runs
+    size_t slab_bytes = 8u << 20;
+    Lane lanes[kMaxLanes];
+    Worker* pool[kMaxLanes] = {nullptr};
+};
+State g;
+
+// ---- per-call job ---------------------------------------------------------------------------------
+enum JobKind { JOB_BINARY, JOB_UNARY, JOB_REDUCE, JOB_ARG };
+enum PtrKind { PK_PAGEABLE = 0, PK_PINNED = 1, PK_DEVICE = 2, PK_MANAGED = 3 };
+
+struct Job {
+    JobKind kind;
+    pncu_any_two_fn fn2 = nullptr;
+    pncu_unary_fn fn1 = nullptr;
+    int func = 0, atype = 0, argkind = 0;
+    int isz_in = 0, isz_out = 0;
+    const char* in1 = nullptr;
+    const char* in2 = nullptr;
+    char* out = nullptr;
+    int64_t len = 0;
+    int64_t s1 = 0, s2 = 0;     // 0 (scalar) or the item size
+    int pk_in1 = 0, pk_in2 = 0, pk_out = 0;
+    int nlanes = 1;
+    int64_t shard[kMaxLanes + 1];  // element boundaries
+    int rc[kMaxLanes];
+    char err[kMaxLanes][256];
+    // reductions
+    int partial_bytes = 0;
+    int64_t slot0[kMaxLanes + 1];  // first partial slot of each lane
+};
+
+int fail(Job& j, int lane, int rc) {
+    j.rc[lane] = rc;
+    snprintf(j.err[lane], sizeof(j.err[lane]), "%s", pncu_last_error());
+    return rc;
+}
+#define LCUDA(call)                                                             \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) { cuda_fail(_e, #call, __FILE__, __LINE__); fail(j, li, (int)_e); return; } \
+    } while (0)
+
+int classify(const void* p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return PK_PAGEABLE; }
+    switch (at.type) {
+        case cudaMemoryTypeHost: return PK_PINNED;
+        case cudaMemoryTypeDevice: return PK_DEVICE;
+        case cudaMemoryTypeManaged: return PK_MANAGED;
+        default: return PK_PAGEABLE;
+    }
+}
+
+// ---- lane resources -----------------------------------------------------------------------------------
+int ensure_lane(int li) {
+    Lane& L = g.lanes[li];
+    const int dev = li % g.ndev;
+    if (L.ready && L.slab_bytes == g.slab_bytes) return 0;
+    PNCU_CUDA(cudaSetDevice(dev));
+    if (!L.ready) {
+        L.device = dev;
+        PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_h2d, cudaStreamNonBlocking));
+        PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_k, cudaStreamNonBlocking));
+        PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_d2h, cudaStreamNonBlocking));
+        for (int r = 0; r < kRing; ++r) {
+            PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_h2d[r], cudaEventDisableTiming));
+            PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_k[r], cudaEventDisableTiming));
+            PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_d2h[r], cudaEventDisableTiming));
+            for (int k = 0; k < 3; ++k) { L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr; }
+        }
+        PNCU_CUDA(cudaMalloc((void**)&L.d_scalar, 64));
+        PNCU_CUDA(cudaHostAlloc((void**)&L.h_small, 64, cudaHostAllocPortable));
+    } else {
+        for (int r = 0; r < kRing; ++r)
+            for (int k = 0; k < 3; ++k) {
+                if (L.d_buf[r][k]) cudaFree(L.d_buf[r][k]);
+                if (L.h_buf[r][k]) cudaFreeHost(L.h_buf[r][k]);
+                L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr;
+            }
+    }
+    // device slabs now; pinned slabs lazily (only pageable operands need them)
+    for (int r = 0; r < kRing; ++r)
+        for (int k = 0; k < 3; ++k) PNCU_CUDA(cudaMalloc((void**)&L.d_buf[r][k], g.slab_bytes));
+    L.slab_bytes = g.slab_bytes;
+    L.ready = true;
+    return 0;
+}
+
+int ensure_pinned_slab(Lane& L, int r, int k) {
+    if (L.h_buf[r][k]) return 0;
+    PNCU_CUDA(cudaHostAlloc((void**)&L.h_buf[r][k], L.slab_bytes, cudaHostAllocPortable));
+    return 0;
+}
+
+int ensure_partials(Lane& L, size_t bytes) {
+    if (L.partials_bytes >= bytes) return 0;
+    if (L.d_partials) cudaFree(L.d_partials);
+    L.d_partials = nullptr;
+    L.partials_bytes = 0;
+    size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+    PNCU_CUDA(cudaMalloc((void**)&L.d_partials, want));
+    L.partials_bytes = want;
+    return 0;
+}
+
+// ---- one lane of an element-wise job: slabs through the H2D -> kernel -> D2H pipeline --------------------
+void lane_elementwise(Lane& L, Job& j, int li) {
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
+    if (e0 >= e1) return;
+    const bool binary = j.kind == JOB_BINARY;
+    const int64_t wide = j.isz_in > j.isz_out ? j.isz_in : j.isz_out;
+    const int64_t slab_elems = ((int64_t)(L.slab_bytes / wide) / kAlign) * kAlign;
+    const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
+    const bool vec1 = j.s1 != 0, vec2 = binary && j.s2 != 0;
+
+    // broadcast scalars: one tiny copy per call
+    const char* d_s1 = nullptr;
+    const char* d_s2 = nullptr;
+    if (!vec1) {
+        memcpy(L.h_small, j.in1, j.isz_in);
+        LCUDA(cudaMemcpyAsync(L.d_scalar, L.h_small, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
+        d_s1 = L.d_scalar;
+    }
+    if (binary && !vec2) {
+        memcpy(L.h_small + 16, j.in2, j.isz_in);
+        LCUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
+        d_s2 = L.d_scalar + 16;
+    }
+
+    auto slab_range = [&](int64_t i, int64_t* off, int64_t* cnt) {
+        *off = e0 + i * slab_elems;
+        *cnt = (e1 - *off) < slab_elems ? (e1 - *off) : slab_elems;
+    };
+    auto retire = [&](int64_t i) -> int {  // slab i's result is on the host once ev_d2h fires
+        const int r = (int)(i % kRing);
+        cudaError_t e = cudaEventSynchronize(L.ev_d2h[r]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(d2h)", __FILE__, __LINE__);
+        if (j.pk_out == PK_PAGEABLE) {
+            int64_t off, cnt;
+            slab_range(i, &off, &cnt);
+            memcpy(j.out + off * j.isz_out, L.h_buf[r][2], (size_t)(cnt * j.isz_out));
+            g_stats.staged += cnt * j.isz_out;
+        }
+        return 0;
+    };
+
+    for (int64_t i = 0; i < nslabs; ++i) {
+        const int r = (int)(i % kRing);
+        int rc;
+        if (i >= kRing && (rc = retire(i - kRing))) { fail(j, li, rc); return; }
+        int64_t off, cnt;
+        slab_range(i, &off, &cnt);
+        const size_t in_bytes = (size_t)(cnt * j.isz_in), out_bytes = (size_t)(cnt * j.isz_out);
+        // ---- inputs -> device slab
+        for (int k = 0; k < 2; ++k) {
+            if (k == 0 ? !vec1 : !vec2) continue;
+            const char* src = (k == 0 ? j.in1 : j.in2) + off * j.isz_in;
+            const int pk = k == 0 ? j.pk_in1 : j.pk_in2;
+            if (pk == PK_PAGEABLE) {
+                if ((rc = ensure_pinned_slab(L, r, k))) { fail(j, li, rc); return; }
+                memcpy(L.h_buf[r][k], src, in_bytes);
+                g_stats.staged += in_bytes;
+                src = L.h_buf[r][k];
+            }
+            LCUDA(cudaMemcpyAsync(L.d_buf[r][k], src, in_bytes, cudaMemcpyHostToDevice, L.s_h2d));
+            g_stats.h2d += in_bytes;
+        }
+        LCUDA(cudaEventRecord(L.ev_h2d[r], L.s_h2d));
+        LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_h2d[r], 0));
+        // ---- kernel
+        if (binary)
+            rc = j.fn2(vec1 ? L.d_buf[r][0] : d_s1, vec2 ? L.d_buf[r][1] : d_s2, L.d_buf[r][2], cnt,
+                       vec1 ? j.isz_in : 0, vec2 ? j.isz_in : 0, j.isz_out, (pncu_stream_t)L.s_k);
+        else
+            rc = j.fn1(L.d_buf[r][0], L.d_buf[r][2], cnt, j.isz_in, j.isz_out, (pncu_stream_t)L.s_k);
+        if (rc) { fail(j, li, rc); return; }
+        g_stats.launches += 1;
+        LCUDA(cudaEventRecord(L.ev_k[r], L.s_k));
+        LCUDA(cudaStreamWaitEvent(L.s_d2h, L.ev_k[r], 0));
+        // the next H2D into this slot must not overtake this kernel's reads
+        LCUDA(cudaStreamWaitEvent(L.s_h2d, L.ev_k[r], 0));
+        // ---- result -> host
+        char* dst = j.out + off * j.isz_out;
+        if (j.pk_out == PK_PAGEABLE) {
+            if ((rc = ensure_pinned_slab(L, r, 2))) { fail(j, li, rc); return; }
+            dst = L.h_buf[r][2];
+        }
+        LCUDA(cudaMemcpyAsync(dst, L.d_buf[r][2], out_bytes, cudaMemcpyDeviceToHost, L.s_d2h));
+        g_stats.d2h += out_bytes;
+        LCUDA(cudaEventRecord(L.ev_d2h[r], L.s_d2h));
+        // the next kernel writing this slot's out slab must wait for this D2H
+        LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_d2h[r], 0));
+    }
+    for (int64_t i = nslabs > kRing ? nslabs - kRing : 0; i < nslabs; ++i) {
+        int rc = retire(i);
+        if (rc) { fail(j, li, rc); return; }
+    }
+}
+
+// ---- one lane of a reduction / arg-reduction: slabs H2D -> pass-1 partials on this lane's GPU ------------
+void lane_reduce(Lane& L, Job& j, int li) {
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
+    if (e0 >= e1) return;
+    const int64_t nslots = j.slot0[li + 1] - j.slot0[li];
+    int rc;
+    if ((rc = ensure_partials(L, (size_t)nslots * j.partial_bytes))) { fail(j, li, rc); return; }
+    const int64_t slab_elems = ((int64_t)(L.slab_bytes / j.isz_in) / kAlign) * kAlign;
+    const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
+    for (int64_t i = 0; i < nslabs; ++i) {
+        const int r = (int)(i % kRing);
+        const int64_t off = e0 + i * slab_elems;
+        const int64_t cnt = (e1 - off) < slab_elems ? (e1 - off) : slab_elems;
+        const size_t in_bytes = (size_t)(cnt * j.isz_in);
+        const char* src = j.in1 + off * j.isz_in;
+        if (i >= kRing) {  // slot reuse: the kernel that read it must be done before we overwrite staging
+            cudaError_t e = cudaEventSynchronize(L.ev_k[r]);
+            if (e != cudaSuccess) { cuda_fail(e, "cudaEventSynchronize(k)", __FILE__, __LINE__); fail(j, li, (int)e); return; }
+        }
+        if (j.pk_in1 == PK_PAGEABLE) {
+            if ((rc = ensure_pinned_slab(L, r, 0))) { fail(j, li, rc); return; }
+            memcpy(L.h_buf[r][0], src, in_bytes);
+            g_stats.staged += in_bytes;
+            src = L.h_buf[r][0];
+        }
+        LCUDA(cudaMemcpyAsync(L.d_buf[r][0], src, in_bytes, cudaMemcpyHostToDevice, L.s_h2d));
+        g_stats.h2d += in_bytes;
+        LCUDA(cudaEventRecord(L.ev_h2d[r], L.s_h2d));
+        LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_h2d[r], 0));
+        const int64_t slot = pncu_reduce_partial_count(j.atype, off - e0);
+        char* parts = L.d_partials + slot * j.partial_bytes;
+        if (j.kind == JOB_REDUCE)
+            rc = pncu_reduce_partials(j.func, j.atype, L.d_buf[r][0], cnt, parts, (pncu_stream_t)L.s_k);
+        else
+            rc = pncu_argminmax_partials(j.argkind, j.atype, L.d_buf[r][0], cnt, off, parts, (pncu_stream_t)L.s_k);
+        if (rc) { fail(j, li, rc); return; }
+        g_stats.launches += 1;
+        LCUDA(cudaEventRecord(L.ev_k[r], L.s_k));
+        LCUDA(cudaStreamWaitEvent(L.s_h2d, L.ev_k[r], 0));
+    }
+    cudaError_t e = cudaStreamSynchronize(L.s_k);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); fail(j, li, (int)e); }
+}
+
+// ---- worker pool -----------------------------------------------------------------------------------------
+void worker_main(Worker* w) {
+    std::unique_lock<std::mutex> lk(w->mu);
+    for (;;) {
+        w->cv.wait(lk, [&] { return w->has_work || w->quit; });
+        if (w->quit) return;
+        w->has_work = false;
+        lk.unlock();
+        w->fn(g.lanes[w->lane_index], *w->job, w->lane_index);
+        lk.lock();
+        w->done = true;
+        w->cv.notify_all();
+    }
+}
+
+void run_lanes(Job& j, LaneFn fn) {
+    for (int li = 1; li < j.nlanes; ++li) {
+        Worker*& w = g.pool[li];
+        if (!w) {
+            w = new Worker();
+            w->th = std::thread(worker_main, w);
+        }
+        std::lock_guard<std::mutex> lk(w->mu);
+        w->fn = fn; w->job = &j; w->lane_index = li; w->done = false; w->has_work = true;
+        w->cv.notify_all();
+    }
+    fn(g.lanes[0], j, 0);  // the caller is lane 0
+    for (int li = 1; li < j.nlanes; ++li) {
+        Worker* w = g.pool[li];
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->cv.wait(lk, [&] { return w->done; });
+    }
+}
+
+// lanes for a call: min(op_max_workers, workers) + 1, never more than one per 65536-element unit
+int plan(Job& j, int max_workers) {
+    int lanes = 1;
+    if (g.threading) {
+        int extra = max_workers < g.workers ? max_workers : g.workers;
+        if (extra < 0) extra = 0;
+        lanes = extra + 1;
+    }
+    if (lanes > kMaxLanes) lanes = kMaxLanes;
+    const int64_t units = (j.len + kAlign - 1) / kAlign;
+    if (lanes > units) lanes = (int)units;
+    if (lanes < 1) lanes = 1;
+    j.nlanes = lanes;
+    const int64_t per = (units + lanes - 1) / lanes;
+    for (int l = 0; l <= lanes; ++l) {
+        int64_t e = (int64_t)l * per * kAlign;
+        j.shard[l] = e < j.len ? e : j.len;
+    }
+    for (int l = 0; l < lanes; ++l) { j.rc[l] = 0; j.err[l][0] = 0; }
+    int gpus = lanes < g.ndev ? lanes : g.ndev;
+    g_stats.lanes_last = lanes;
+    g_stats.gpus_last = gpus;
+    for (int l = 0; l < lanes; ++l) {
+        int rc = ensure_lane(l);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int first_error(Job& j) {
+    for (int l = 0; l < j.nlanes; ++l)
+        if (j.rc[l]) { set_error("lane %d (GPU %d): %s", l, g.lanes[l].device, j.err[l]); return j.rc[l]; }
+    return 0;
+}
+
+int decline() { g_stats.declined += 1; return NTE_DECLINED; }
+
+bool host_kind(int pk) { return pk == PK_PAGEABLE || pk == PK_PINNED; }
+
+// operands that already live in device / managed memory: run in place on that GPU, no PCIe
+int run_resident(Job& j) {
+    int dev = 0;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, j.out) == cudaSuccess && at.device >= 0) dev = at.device; else cudaGetLastError();
+    int rc = ensure_lane(dev % g.ndev);
+    if (rc) return rc;
+    Lane& L = g.lanes[dev % g.ndev];
+    PNCU_CUDA(cudaSetDevice(L.device));
+    if (j.kind == JOB_BINARY)
+        rc = j.fn2(j.in1, j.in2, j.out, j.len, j.s1, j.s2, j.isz_out, (pncu_stream_t)L.s_k);
+    else
+        rc = j.fn1(j.in1, j.out, j.len, j.s1, j.isz_out, (pncu_stream_t)L.s_k);
+    if (rc) return rc;
+    g_stats.launches += 1;
+    PNCU_CUDA(cudaStreamSynchronize(L.s_k));
+    return 0;
+}
+
+}  // namespace
+
+// =======================================================================================================
+extern "C" {
+
+int nte_init(void) {
+    std::lock_guard<std::mutex> lk(g.api_mu);
+    if (g.inited) return 0;
+    int n = 0;
+    int rc = pncu_init(&n);
+    if (rc) return rc;
+    g.ndev = n > kMaxLanes ? kMaxLanes : n;
+    const char* env = getenv("PNUMPY_CUDA_MIN_ELEMS");
+    if (env && *env) g.min_elems = atoll(env);
+    env = getenv("PNUMPY_CUDA_SLAB_BYTES");
+    if (env && *env) g.slab_bytes = (size_t)atoll(env);
+    env = getenv("PNUMPY_CUDA_DEVICES");  // use only the first k devices
+    if (env && *env && atoi(env) > 0 && atoi(env) < g.ndev) g.ndev = atoi(env);
+    // peer access so that the reduction gather can go GPU -> GPU 0 over NVLink
+    for (int a = 0; a < g.ndev; ++a)
+        for (int b = 0; b < g.ndev; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
+                cudaSetDevice(a);
+                cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                if (e != cudaSuccess) cudaGetLastError();
+            } else {
+                cudaGetLastError();
+            }
+        }
+    cudaSetDevice(0);
+    g.inited = true;
+    return 0;
+}
+
+int nte_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g.api_mu);
+    for (int l = 1; l < kMaxLanes; ++l) {
+        Worker* w = g.pool[l];
+        if (!w) continue;
+        { std::lock_guard<std::mutex> wl(w->mu); w->quit = true; w->cv.notify_all(); }
+        w->th.join();
+        delete w;
+        g.pool[l] = nullptr;
+    }
+    for (int l = 0; l < kMaxLanes; ++l) {
+        Lane& L = g.lanes[l];
+        if (!L.ready) continue;
+        cudaSetDevice(L.device);
+        for (int r = 0; r < kRing; ++r) {
+            for (int k = 0; k < 3; ++k) {
+                if (L.d_buf[r][k]) cudaFree(L.d_buf[r][k]);
+                if (L.h_buf[r][k]) cudaFreeHost(L.h_buf[r][k]);
+            }
+            cudaEventDestroy(L.ev_h2d[r]); cudaEventDestroy(L.ev_k[r]); cudaEventDestroy(L.ev_d2h[r]);
+        }
+        if (L.d_scalar) cudaFree(L.d_scalar);
+        if (L.d_partials) cudaFree(L.d_partials);
+        if (L.h_small) cudaFreeHost(L.h_small);
+        cudaStreamDestroy(L.s_h2d); cudaStreamDestroy(L.s_k); cudaStreamDestroy(L.s_d2h);
+        L = Lane();
+    }
+    g.inited = false;
+    return 0;
+}
+
+int nte_device_count(void) { return g.inited ? g.ndev : 0; }
+
+int nte_max_workers(void) { return kMaxLanes - 1; }
+int nte_set_workers(int workers) {
+    // CMathWorker::SetFutexWakeup, src/atop/threads.h:852-872: clamp, return the previous value
+    int prev = g.workers;
+    if (workers < 1) workers = 1;
+    if (workers > nte_max_workers()) workers = nte_max_workers();
+    g.workers = workers;
+    return prev;
+}
+int nte_get_workers(void) { return g.workers; }
+void nte_set_threading(int enabled) { g.threading = enabled != 0; }
+int nte_get_threading(void) { return g.threading ? 1 : 0; }
+int64_t nte_set_min_elems(int64_t n) { int64_t p = g.min_elems; g.min_elems = n < 0 ? 0 : n; return p; }
+int64_t nte_get_min_elems(void) { return g.min_elems; }
+int64_t nte_set_slab_bytes(int64_t bytes) {
+    std::lock_guard<std::mutex> lk(g.api_mu);
+    int64_t p = (int64_t)g.slab_bytes;
+    const int64_t unit = kAlign * 8;
+    if (bytes < unit) bytes = unit;
+    g.slab_bytes = (size_t)((bytes / unit) * unit);
+    return p;
+}
+
+void* nte_alloc_pinned(size_t bytes) {
+    if (pncu_init(nullptr)) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void nte_free_pinned(void* ptr) {
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) cudaGetLastError();
+}
+
+void nte_get_stats(nte_stats* o) {
+    if (!o) return;
+    o->calls = g_stats.calls; o->declined = g_stats.declined; o->launches = g_stats.launches;
+    o->h2d_bytes = g_stats.h2d; o->d2h_bytes = g_stats.d2h; o->staged_bytes = g_stats.staged;
+    o->lanes_last = g_stats.lanes_last; o->gpus_last = g_stats.gpus_last;
+}
+void nte_reset_stats(void) {
+    g_stats.calls = 0; g_stats.declined = 0; g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0;
+    g_stats.staged = 0; g_stats.lanes_last = 0; g_stats.gpus_last = 0;
+}
+
+static int dispatch_elementwise(Job& j, int max_workers) {
+    if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
+    if (j.len < g.min_elems || j.len <= 0) return decline();
+    std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
+    if (!lk.owns_lock()) return decline();  // re-entrant / concurrent caller: run the old loop
+    const bool binary = j.kind == JOB_BINARY;
+    j.pk_in1 = classify(j.in1);
+    j.pk_in2 = binary ? classify(j.in2) : PK_PAGEABLE;
+    j.pk_out = classify(j.out);
+    const bool any_resident = !host_kind(j.pk_out) || (j.s1 != 0 && !host_kind(j.pk_in1)) ||
+                              (binary && j.s2 != 0 && !host_kind(j.pk_in2));
+    if (any_resident) {
+        const bool all_ok = !host_kind(j.pk_out) && (j.s1 == 0 ? j.pk_in1 != PK_PAGEABLE || true : !host_kind(j.pk_in1)) &&
+                            (!binary || j.s2 == 0 || !host_kind(j.pk_in2));
+        // a host scalar next to resident arrays is not dereferenceable by the kernel: decline
+        if (!all_ok || (j.s1 == 0 && host_kind(j.pk_in1) && j.pk_in1 != PK_PINNED) ||
+            (binary && j.s2 == 0 && host_kind(j.pk_in2) && j.pk_in2 != PK_PINNED))
+            return decline();
+        int rc = run_resident(j);
+        if (!rc) g_stats.calls += 1;
+        return rc;
+    }
+    // host operands must be contiguous (or scalar) to be staged
+    if (j.s1 != 0 && j.s1 != j.isz_in) return decline();
+    if (binary && j.s2 != 0 && j.s2 != j.isz_in) return decline();
+    if (j.s1 == 0 && (!binary || j.s2 == 0)) return decline();
+    // exact aliasing of out with an input is fine (staged); partial overlap is not
+    {
+        const char* olo = j.out; const int64_t ob = j.len * j.isz_out;
+        const char* ins[2] = {j.in1, binary ? j.in2 : nullptr};
+        const int64_t strides[2] = {j.s1, j.s2};
+        for (int k = 0; k < 2; ++k) {
+            if (!ins[k]) continue;
+            const int64_t ib = strides[k] ? j.len * j.isz_in : j.isz_in;
+            const bool overlap = ins[k] < olo + ob && olo < ins[k] + ib;
+            if (overlap && !(ins[k] == olo && strides[k] == j.isz_out && j.isz_in == j.isz_out)) return decline();
+        }
+    }
+    int rc = plan(j, max_workers);
+    if (rc) return rc;
+    run_lanes(j, lane_elementwise);
+    rc = first_error(j);
+    if (!rc) g_stats.calls += 1;
+    return rc;
+}
+
+int nte_binary(pncu_any_two_fn launcher, int in_itemsize, int out_itemsize, const void* in1,
+               const void* in2, void* out, int64_t len, int64_t s1, int64_t s2, int64_t so, int max_workers) {
+    if (!launcher) return decline();
+    if (so != out_itemsize) return decline();
+    Job j;
+    j.kind = JOB_BINARY; j.fn2 = launcher; j.isz_in = in_itemsize; j.isz_out = out_itemsize;
+    j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.out = (char*)out; j.len = len; j.s1 = s1; j.s2 = s2;
+    return dispatch_elementwise(j, max_workers);
+}
+
+int nte_unary(pncu_unary_fn launcher, int in_itemsize, int out_itemsize, const void* in, void* out,
+              int64_t len, int64_t s1, int64_t so, int max_workers) {
+    if (!launcher) return decline();
+    if (so != out_itemsize || s1 != in_itemsize) return decline();
+    Job j;
+    j.kind = JOB_UNARY; j.fn1 = launcher; j.isz_in = in_itemsize; j.isz_out = out_itemsize;
+    j.in1 = (const char*)in; j.out = (char*)out; j.len = len; j.s1 = s1;
+    return dispatch_elementwise(j, max_workers);
+}
+
+// gather every lane's partials on GPU 0, fold there in fixed order, bring the scalar back
+static int finish_on_gpu0(Job& j, void* host_out, int out_bytes, const void* host_start) {
+    Lane& L0 = g.lanes[0];
+    PNCU_CUDA(cudaSetDevice(L0.device));
+    const int64_t total = j.slot0[j.nlanes];
+    char* all = L0.d_partials;
+    if (j.nlanes > 1) {
+        // lane 0's buffer holds its own slots at [0, n0); append the others behind them
+        int rc = 0;
+        if ((size_t)total * j.partial_bytes > L0.partials_bytes) {
+            // grow, preserving lane 0's partials
+            char* bigger = nullptr;
+            PNCU_CUDA(cudaMalloc((void**)&bigger, (size_t)total * j.partial_bytes * 2));
+            PNCU_CUDA(cudaMemcpyAsync(bigger, L0.d_partials, (size_t)j.slot0[1] * j.partial_bytes, cudaMemcpyDeviceToDevice, L0.s_k));
+            PNCU_CUDA(cudaStreamSynchronize(L0.s_k));
+            cudaFree(L0.d_partials);
+            L0.d_partials = bigger;
+            L0.partials_bytes = (size_t)total * j.partial_bytes * 2;
+            all = bigger;
+        }
+        for (int l = 1; l < j.nlanes; ++l) {
+            const int64_t cnt = j.slot0[l + 1] - j.slot0[l];
+            if (cnt <= 0) continue;
+            Lane& L = g.lanes[l];
+            // peer copy (NVLink P2P when enabled, else staged by the driver); same-GPU lanes: plain D2D
+            PNCU_CUDA(cudaMemcpyPeerAsync(all + j.slot0[l] * j.partial_bytes, L0.device, L.d_partials, L.device,
+                                          (size_t)cnt * j.partial_bytes, L0.s_k));
+        }
+        (void)rc;
+    }
+    char* d_res = L0.d_scalar + 32;
+    int rc;
+    if (j.kind == JOB_REDUCE) {
+        const void* d_start = nullptr;
+        if (host_start) {
+            memcpy(L0.h_small, host_start, out_bytes);
+            PNCU_CUDA(cudaMemcpyAsync(L0.d_scalar, L0.h_small, out_bytes, cudaMemcpyHostToDevice, L0.s_k));
+            d_start = L0.d_scalar;
+        }
+        rc = pncu_reduce_finish(j.func, j.atype, all, total, d_res, d_start, (pncu_stream_t)L0.s_k);
+    } else {
+        rc = pncu_argminmax_finish(j.argkind, j.atype, all, total, (int64_t*)d_res, (pncu_stream_t)L0.s_k);
+    }
+    if (rc) return rc;
+    g_stats.launches += 1;
+    PNCU_CUDA(cudaMemcpyAsync(L0.h_small + 32, d_res, out_bytes, cudaMemcpyDeviceToHost, L0.s_k));
+    PNCU_CUDA(cudaStreamSynchronize(L0.s_k));
+    memcpy(host_out, L0.h_small + 32, out_bytes);
+    g_stats.d2h += out_bytes;
+    return 0;
+}
+
+static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* host_start, int max_workers) {
+    if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
+    if (j.len < g.min_elems || j.len <= 0) return decline();
+    std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
+    if (!lk.owns_lock()) return decline();
+    j.pk_in1 = classify(j.in1);
+    int rc;
+    if (!host_kind(j.pk_in1)) {
+        // resident input: both passes on its GPU
+        cudaPointerAttributes at;
+        int dev = 0;
+        if (cudaPointerGetAttributes(&at, j.in1) == cudaSuccess && at.device >= 0) dev = at.device; else cudaGetLastError();
+        if ((rc = ensure_lane(dev % g.ndev))) return rc;
+        Lane& L = g.lanes[dev % g.ndev];
+        PNCU_CUDA(cudaSetDevice(L.device));
+        const int64_t slots = pncu_reduce_partial_count(j.atype, j.len);
+        if ((rc = ensure_partials(L, (size_t)slots * j.partial_bytes))) return rc;
+        if (j.kind == JOB_REDUCE) rc = pncu_reduce_partials(j.func, j.atype, j.in1, j.len, L.d_partials, (pncu_stream_t)L.s_k);
+        else rc = pncu_argminmax_partials(j.argkind, j.atype, j.in1, j.len, 0, L.d_partials, (pncu_stream_t)L.s_k);
+        if (rc) return rc;
+        g_stats.launches += 1;
+        j.nlanes = 1; j.slot0[0] = 0; j.slot0[1] = slots;
+        // finish_on_gpu0 works on lanes[0]; alias it when the data lives elsewhere
+        if (&L != &g.lanes[0]) {
+            PNCU_CUDA(cudaStreamSynchronize(L.s_k));
+            if ((rc = ensure_lane(0))) return rc;
+            if ((rc = ensure_partials(g.lanes[0], (size_t)slots * j.partial_bytes))) return rc;
+            PNCU_CUDA(cudaMemcpyPeer(g.lanes[0].d_partials, g.lanes[0].device, L.d_partials, L.device, (size_t)slots * j.partial_bytes));
+        }
+        rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
+        if (!rc) g_stats.calls += 1;
+        return rc;
+    }
+    if ((rc = plan(j, max_workers))) return rc;
+    for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
+    run_lanes(j, lane_reduce);
+    if ((rc = first_error(j))) return rc;
+    rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
+    if (!rc) g_stats.calls += 1;
+    return rc;
+}
+
+int nte_reduce(int func, int atype, const void* in, void* out, int use_out_as_start, int64_t len,
+               int64_t strideIn, int max_workers) {
+    const int isz = pncu_itemsize(atype);
+    const int pb = pncu_reduce_partial_bytes(func, atype);
+    if (!isz || !pb || strideIn != isz) return decline();
+    Job j;
+    j.kind = JOB_REDUCE; j.func = func; j.atype = atype; j.isz_in = isz; j.isz_out = isz; j.partial_bytes = pb;
+    j.in1 = (const char*)in; j.len = len; j.s1 = isz;
+    return dispatch_reduce(j, out, isz, use_out_as_start ? out : nullptr, max_workers);
+}
+
+int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out_index, int max_workers) {
+    const int isz = pncu_itemsize(atype);
+    if (!isz || !pncu_GetArgMinMaxOpFast(kind, atype)) return decline();
+    Job j;
+    j.kind = JOB_ARG; j.argkind = kind; j.atype = atype; j.isz_in = isz; j.isz_out = 8; j.partial_bytes = 16;
+    j.in1 = (const char*)in; j.len = len; j.s1 = isz;
+    return dispatch_reduce(j, out_index, 8, nullptr, max_workers);
+}
+
+}  // extern "C"

@@ -1,0 +1,712 @@
+// _pnumpy -- the CPython extension that installs the B200 loops into NumPy.
+//
+// replaces: src/pnumpy/_pnumpy.cpp (hook registration `newinit` :1287-1676, the four per-call
+// dispatchers :638-996, the arg-reduction dispatcher :1105-1118, the control functions
+// :1766-1966) and src/pnumpy/module_init.cpp:60-124 (method table, module init).
+//
+// Same hooks, same tables, same Python surface.  What changed underneath:
+//   * the loop bodies come from libpnumpy_cuda's getters (pncu_Get*OpFast) instead of atop's,
+//   * a call is handed to the nte dispatcher (nte_binary / nte_unary / nte_reduce / nte_argminmax)
+//     instead of THREADER->WorkMain; nte stages host operands through pinned slabs, shards them over
+//     the GPUs and returns when the result is in the caller's buffers,
+//   * when nte declines (small n, odd strides, re-entrant call) or atop is disabled, the saved
+//     NumPy loop `pOldFunc` runs -- exactly where the reference runs it
+//     (src/pnumpy/_pnumpy.cpp:653-663, 748-759).
+// A CUDA failure is never papered over: it raises RuntimeError.
+#define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <numpy/arrayobject.h>
+#include <numpy/ufuncobject.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "pnumpy_nte.h"
+
+#include "stubs.h"
+
+// ---- dtype <-> atop tables (reference: src/pnumpy/_pnumpy.cpp:7-54; Linux LP64 column) ------------------
+static const int convert_dtype_to_atop[] = {
+    PNCU_BOOL,                              // NPY_BOOL = 0
+    PNCU_INT8, PNCU_UINT8,                  // NPY_BYTE, NPY_UBYTE
+    PNCU_INT16, PNCU_UINT16,                // NPY_SHORT, NPY_USHORT
+    PNCU_INT32, PNCU_UINT32,                // NPY_INT, NPY_UINT
+    PNCU_INT64, PNCU_UINT64,                // NPY_LONG, NPY_ULONG
+    PNCU_INT64, PNCU_UINT64,                // NPY_LONGLONG, NPY_ULONGLONG
+    PNCU_FLOAT, PNCU_DOUBLE, PNCU_LONGDOUBLE,
+    PNCU_CFLOAT, PNCU_CDOUBLE, PNCU_CLONGDOUBLE,
+    -1,                                     // NPY_OBJECT
+    PNCU_STRING, PNCU_UNICODE, PNCU_VOID,
+    -1, -1, PNCU_HALF_FLOAT                 // NPY_DATETIME, NPY_TIMEDELTA, NPY_HALF
+};
+static const int convert_atop_to_dtype[] = {
+    NPY_BOOL, NPY_INT8, NPY_UINT8, NPY_INT16, NPY_UINT16, NPY_INT32, NPY_UINT32, NPY_INT64, NPY_UINT64,
+    NPY_LONGLONG, NPY_ULONGLONG,  // "really INT128" in the reference
+    NPY_HALF, NPY_FLOAT, NPY_DOUBLE, NPY_LONGDOUBLE,
+    NPY_HALF, NPY_CFLOAT, NPY_CDOUBLE, NPY_CLONGDOUBLE,
+    NPY_STRING, NPY_UNICODE, NPY_VOID
+};
+
+struct stUFuncToAtop { const char* str_ufunc_name; int atop_op; };
+
+// reference: gBinaryMapping / gCompareMapping / gUnaryMapping / gTrigMapping, src/pnumpy/_pnumpy.cpp:90-170
+static const stUFuncToAtop gBinaryMapping[] = {
+    {"add", PNCU_ADD}, {"subtract", PNCU_SUB}, {"multiply", PNCU_MUL}, {"true_divide", PNCU_DIV},
+    {"floor_divide", PNCU_FLOORDIV}, {"minimum", PNCU_MIN}, {"maximum", PNCU_MAX}, {"power", PNCU_POWER},
+    {"remainder", PNCU_REMAINDER}, {"logical_and", PNCU_LOGICAL_AND}, {"logical_or", PNCU_LOGICAL_OR},
+    {"bitwise_and", PNCU_BITWISE_AND}, {"bitwise_or", PNCU_BITWISE_OR}, {"bitwise_xor", PNCU_BITWISE_XOR},
+    {"left_shift", PNCU_BITWISE_LSHIFT}, {"right_shift", PNCU_BITWISE_RSHIFT},
+};
+static const stUFuncToAtop gCompareMapping[] = {
+    {"equal", PNCU_CMP_EQ}, {"not_equal", PNCU_CMP_NE}, {"greater", PNCU_CMP_GT},
+    {"greater_equal", PNCU_CMP_GTE}, {"less", PNCU_CMP_LT}, {"less_equal", PNCU_CMP_LTE},
+};
+static const stUFuncToAtop gUnaryMapping[] = {
+    {"abs", PNCU_ABS}, {"signbit", PNCU_SIGNBIT}, {"fabs", PNCU_FABS}, {"invert", PNCU_INVERT},
+    {"floor", PNCU_FLOOR}, {"ceil", PNCU_CEIL}, {"trunc", PNCU_TRUNC}, {"rint", PNCU_ROUND},
+    {"negative", PNCU_NEGATIVE}, {"positive", PNCU_POSITIVE}, {"sign", PNCU_SIGN}, {"rint", PNCU_RINT},
+    {"sqrt", PNCU_SQRT}, {"square", PNCU_SQUARE}, {"reciprocal", PNCU_RECIPROCAL},
+    {"logical_not", PNCU_LOGICAL_NOT}, {"isinf", PNCU_ISINF}, {"isnan", PNCU_ISNAN},
+    {"isfinite", PNCU_ISFINITE}, {"bitwise_not", PNCU_BITWISE_NOT},
+};
+static const stUFuncToAtop gTrigMapping[] = {
+    {"sin", PNCU_SIN}, {"cos", PNCU_COS}, {"tan", PNCU_TAN}, {"arcsin", PNCU_ASIN}, {"arccos", PNCU_ACOS},
+    {"arctan", PNCU_ATAN}, {"sinh", PNCU_SINH}, {"cosh", PNCU_COSH}, {"tanh", PNCU_TANH},
+    {"arcsinh", PNCU_ASINH}, {"arccosh", PNCU_ACOSH}, {"arctanh", PNCU_ATANH}, {"cbrt", PNCU_CBRT},
+    {"exp", PNCU_EXP}, {"exp2", PNCU_EXP2}, {"expm1", PNCU_EXPM1}, {"log", PNCU_LOG}, {"log2", PNCU_LOG2},
+    {"log10", PNCU_LOG10}, {"log1p", PNCU_LOG1P},
+};
+#define COUNT_OF(a) ((int)(sizeof(a) / sizeof((a)[0])))
+
+// reference: stUFunc, src/pnumpy/_pnumpy.cpp:239-253 (same fields; pReduceFunc holds the launcher the
+// GPU library would use for a device-resident caller, the hook itself goes through nte_reduce)
+struct stUFunc {
+    union {
+        pncu_any_two_fn pBinaryFunc;
+        pncu_unary_fn pUnaryFunc;
+    };
+    PyUFuncGenericFunction pOldFunc;
+    pncu_reduce_fn pReduceFunc;
+    int32_t MaxThreads;
+    int32_t MinElementsToThread;
+    int32_t OutType;  // atop type of the output
+};
+struct stArgMinMaxFunc {
+    ArgMinMaxFunc pOldFunc;
+    pncu_argminmax_fn pFunc;
+    int32_t MaxThreads;
+    int32_t MinElementsToThread;
+};
+
+static stUFunc g_UFuncLUT[PNCU_BINARY_LAST][PNCU_ATYPE_LAST];
+static stUFunc g_CompFuncLUT[PNCU_CMP_LAST][PNCU_ATYPE_LAST];
+static stUFunc g_UnaryFuncLUT[PNCU_UNARY_LAST][PNCU_ATYPE_LAST];
+static stUFunc g_TrigFuncLUT[PNCU_TRIG_LAST][PNCU_ATYPE_LAST];
+static stArgMinMaxFunc g_ArgMinMaxFuncLUT[2][PNCU_ATYPE_LAST];
+
+// reference: stSettings, src/pnumpy/common.h:23-31, initial values src/pnumpy/_pnumpy.cpp:348
+struct stSettings {
+    int32_t AtopEnabled;
+    int32_t LedgerEnabled;
+    int32_t RecyclerEnabled;
+    int32_t ZigZag;
+    int32_t Initialized;
+};
+static stSettings g_Settings = {1, 0, 0, 0, 0};
+static PyObject* gpUnaryDict = NULL;  // {(ufunc_name, dtype_num): address of the stUFunc}
+static char g_DeviceString[512] = "";
+
+// ---- ledger: counts per category while enabled (reference: src/pnumpy/ledger.cpp:144-272 keeps a ring
+// of records and printf()s each one; the toggles are kept, the printf is not) ---------------------------
+struct LedgerCounters { int64_t gpu_calls, old_calls, elements; };
+static LedgerCounters g_Ledger[5];
+enum { CAT_BINARY, CAT_UNARY, CAT_COMPARE, CAT_TRIG, CAT_ARGMINMAX };
+static inline void ledger(int cat, bool gpu, int64_t n) {
+    if (!g_Settings.LedgerEnabled) return;
+    if (gpu) g_Ledger[cat].gpu_calls++; else g_Ledger[cat].old_calls++;
+    g_Ledger[cat].elements += n;
+}
+
+// A CUDA failure inside a loop: NumPy has dropped the GIL around large loops, so take it back first.
+static void raise_cuda_error(const char* where, int rc) {
+    PyGILState_STATE st = PyGILState_Ensure();
+    if (!PyErr_Occurred())
+        PyErr_Format(PyExc_RuntimeError, "pnumpy_b200: %s failed on the GPU (status %d): %s", where, rc, pncu_last_error());
+    PyGILState_Release(st);
+}
+
+#define IS_BINARY_REDUCE ((args[0] == args[2]) && (steps[0] == steps[2]) && (steps[0] == 0))
+
+// =======================================================================================================
+// dispatchers
+// reference: AtopBinaryMathFunction, src/pnumpy/_pnumpy.cpp:638-799
+static void AtopBinaryMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
+    stUFunc* p = &g_UFuncLUT[funcop][atype];
+    const npy_intp n = dimensions[0];
+    if (g_Settings.AtopEnabled) {
+        int rc = NTE_DECLINED;
+        if (IS_BINARY_REDUCE) {
+            // the middle array is the real input; the accumulator seeds the fold (:646-652)
+            if (p->pReduceFunc) rc = nte_reduce(funcop, atype, args[1], args[0], 1, (int64_t)n, (int64_t)steps[1], p->MaxThreads);
+        } else if (p->pBinaryFunc) {
+            rc = nte_binary(p->pBinaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], args[2],
+                            (int64_t)n, (int64_t)steps[0], (int64_t)steps[1], (int64_t)steps[2], p->MaxThreads);
+        }
+        if (rc == 0) { ledger(CAT_BINARY, true, n); return; }
+        if (rc != NTE_DECLINED) { raise_cuda_error("binary ufunc loop", rc); return; }
+    }
+    ledger(CAT_BINARY, false, n);
+    p->pOldFunc(args, dimensions, steps, innerloop);
+}
+
+// reference: AtopCompareMathFunction, src/pnumpy/_pnumpy.cpp:805-866
+static void AtopCompareMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
+    stUFunc* p = &g_CompFuncLUT[funcop][atype];
+    const npy_intp n = dimensions[0];
+    if (g_Settings.AtopEnabled && p->pBinaryFunc) {
+        int rc = nte_binary(p->pBinaryFunc, pncu_itemsize(atype), 1, args[0], args[1], args[2], (int64_t)n,
+                            (int64_t)steps[0], (int64_t)steps[1], (int64_t)steps[2], p->MaxThreads);
+        if (rc == 0) { ledger(CAT_COMPARE, true, n); return; }
+        if (rc != NTE_DECLINED) { raise_cuda_error("comparison ufunc loop", rc); return; }
+    }
+    ledger(CAT_COMPARE, false, n);
+    p->pOldFunc(args, dimensions, steps, innerloop);
+}
+
+static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int atype) {
+    const npy_intp n = dimensions[0];
+    // the reference drops the fast pointer when the output stride is 0 (:882-884, 946-948)
+    if (g_Settings.AtopEnabled && p->pUnaryFunc && steps[1] != 0) {
+        int rc = nte_unary(p->pUnaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], (int64_t)n,
+                           (int64_t)steps[0], (int64_t)steps[1], p->MaxThreads);
+        if (rc == 0) { ledger(cat, true, n); return; }
+        if (rc != NTE_DECLINED) { raise_cuda_error("unary ufunc loop", rc); return; }
+    }
+    ledger(cat, false, n);
+    p->pOldFunc(args, dimensions, steps, innerloop);
+}
+// reference: AtopUnaryMathFunction, src/pnumpy/_pnumpy.cpp:874-932
+static void AtopUnaryMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
+    unary_common(&g_UnaryFuncLUT[funcop][atype], CAT_UNARY, args, dimensions, steps, innerloop, atype);
+}
+// reference: AtopTrigMathFunction, src/pnumpy/_pnumpy.cpp:938-996
+static void AtopTrigMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
+    unary_common(&g_TrigFuncLUT[funcop][atype], CAT_TRIG, args, dimensions, steps, innerloop, atype);
+}
+
+// reference: AtopArgMinMaxMathFunction, src/pnumpy/_pnumpy.cpp:1105-1118 (an empty `if (AtopEnabled) {}`
+// followed by the old function: the reference never accelerated it; this build does)
+static int AtopArgMinMaxMathFunction(void* data, npy_intp n, npy_intp* out_index, void* arr, int kind, int atype) {
+    stArgMinMaxFunc* p = &g_ArgMinMaxFuncLUT[kind][atype];
+    if (g_Settings.AtopEnabled && p->pFunc) {
+        int64_t idx = 0;
+        int rc = nte_argminmax(kind, atype, data, (int64_t)n, &idx, p->MaxThreads);
+        if (rc == 0) { *out_index = (npy_intp)idx; ledger(CAT_ARGMINMAX, true, n); return 0; }
+        if (rc != NTE_DECLINED) { raise_cuda_error("arg-reduction", rc); return -1; }
+    }
+    ledger(CAT_ARGMINMAX, false, n);
+    return p->pOldFunc(data, n, out_index, arr);
+}
+
+// =======================================================================================================
+// registration.  reference: newinit, src/pnumpy/_pnumpy.cpp:1287-1676
+static void AddToDict(const char* ufunc_name, int dtype, void* pstUFunc) {
+    PyObject* key = Py_BuildValue("(si)", ufunc_name, dtype);
+    PyObject* val = PyLong_FromLongLong((long long)(intptr_t)pstUFunc);
+    PyDict_SetItem(gpUnaryDict, key, val);
+    Py_DECREF(key);
+    Py_DECREF(val);
+}
+static stUFunc* GetFromDict(const char* ufunc_name, int dtype) {
+    if (!gpUnaryDict) return NULL;
+    PyObject* key = Py_BuildValue("(si)", ufunc_name, dtype);
+    PyObject* val = PyDict_GetItem(gpUnaryDict, key);  // borrowed
+    Py_DECREF(key);
+    return val ? (stUFunc*)(intptr_t)PyLong_AsLongLong(val) : NULL;
+}
+
+// "Check for problem with two int32 depending on OS" (:1357-1362): keep the input's own type number
+static int fix_out_dtype(int in_dtype, int out_atype) {
+    int out_dtype = convert_atop_to_dtype[out_atype];
+    if (in_dtype >= 5 && in_dtype <= 10 && out_dtype >= 5 && out_dtype <= 10) out_dtype = in_dtype;
+    return out_dtype;
+}
+
+static PyObject* newinit(PyObject* self, PyObject* args, PyObject* kwargs) {
+    // NPY_BOOL .. NPY_USHORT, NPY_INT, NPY_UINT, NPY_LONG, NPY_ULONG, NPY_LONGLONG, NPY_ULONGLONG, NPY_FLOAT, NPY_DOUBLE
+    static const int dtypes[] = {NPY_BOOL, NPY_INT8, NPY_UINT8, NPY_INT16, NPY_UINT16, 5, 6, 7, 8, 9, 10, 11, 12};
+    if (g_Settings.Initialized) Py_RETURN_NONE;  // idempotent (:1294)
+
+    // the analogue of the reference's AVX2 gate (src/pnumpy/__init__.py:48-53): no sm_100 GPU, no pnumpy
+    int rc = nte_init();
+    if (rc != 0)
+        return PyErr_Format(PyExc_ImportError, "pnumpy_b200 requires an NVIDIA B200 (sm_100) GPU: %s", pncu_last_error());
+    {
+        char one[256];
+        int n = nte_device_count(), off = 0;
+        for (int d = 0; d < n && off < (int)sizeof(g_DeviceString) - 1; ++d) {
+            if (pncu_device_info(d, one, sizeof(one)) != 0) continue;
+            off += snprintf(g_DeviceString + off, sizeof(g_DeviceString) - off, "%s[%d] %s", d ? "; " : "**GPU: ", d, one);
+        }
+    }
+
+    memset(g_UFuncLUT, 0, sizeof(g_UFuncLUT));
+    memset(g_CompFuncLUT, 0, sizeof(g_CompFuncLUT));
+    memset(g_UnaryFuncLUT, 0, sizeof(g_UnaryFuncLUT));
+    memset(g_TrigFuncLUT, 0, sizeof(g_TrigFuncLUT));
+    memset(g_ArgMinMaxFuncLUT, 0, sizeof(g_ArgMinMaxFuncLUT));
+
+    PyObject* numpy_module = PyImport_ImportModule("numpy");
+    if (!numpy_module) return NULL;
+
+    // np.setbufsize(8192*1024): casting / buffered calls then deliver <= 8Mi-element loops (:1306-1314)
+    PyObject* r = PyObject_CallMethod(numpy_module, "setbufsize", "L", (long long)8192 * 1024);
+    if (!r) PyErr_Clear();
+    Py_XDECREF(r);
+
+    gpUnaryDict = PyDict_New();
+    const int num_dtypes = COUNT_OF(dtypes);
+
+    // ---- binary (:1320-1380)
+    for (int i = 0; i < COUNT_OF(gBinaryMapping); i++) {
+        const char* name = gBinaryMapping[i].str_ufunc_name;
+        const int atop = gBinaryMapping[i].atop_op;
+        PyObject* ufunc = PyObject_GetAttrString(numpy_module, name);
+        if (!ufunc) return PyErr_Format(PyExc_TypeError, "func %s must be the name of a ufunc", name);
+        for (int jx = 0; jx < num_dtypes; jx++) {
+            const int dtype = dtypes[jx];
+            const int atype = convert_dtype_to_atop[dtype];
+            int out_atype = -1;
+            pncu_any_two_fn fn = pncu_GetSimpleMathOpFast(atop, atype, atype, &out_atype);
+            pncu_reduce_fn red = pncu_GetReduceMathOpFast(atop, atype);
+            if (out_atype == -1) continue;  // the pair is not hooked at all (:1349)
+            int signature[3] = {dtype, dtype, fix_out_dtype(dtype, out_atype)};
+            PyUFuncGenericFunction oldFunc;
+            int ret = PyUFunc_ReplaceLoopBySignature((PyUFuncObject*)ufunc, g_UFuncGenericLUT[atop][atype], signature, &oldFunc);
+            if (ret < 0)
+                return PyErr_Format(PyExc_TypeError, "Binary failed with %d. func %s must be the name of a ufunc.  atop:%d   atype:%d  sigs:%d, %d, %d",
+                                    ret, name, atop, atype, signature[0], signature[1], signature[2]);
+            stUFunc* p = &g_UFuncLUT[atop][atype];
+            p->pOldFunc = oldFunc;
+            p->pBinaryFunc = fn;
+            p->pReduceFunc = red;
+            p->MaxThreads = 3;
+            p->OutType = out_atype;
+            AddToDict(name, dtype, p);
+        }
+        Py_DECREF(ufunc);
+    }
+    // ---- compare (:1383-1432): always hooked, out is bool
+    for (int i = 0; i < COUNT_OF(gCompareMapping); i++) {
+        const char* name = gCompareMapping[i].str_ufunc_name;
+        const int atop = gCompareMapping[i].atop_op;
+        PyObject* ufunc = PyObject_GetAttrString(numpy_module, name);
+        if (!ufunc) return PyErr_Format(PyExc_TypeError, "func %s must be the name of a ufunc", name);
+        for (int jx = 0; jx < num_dtypes; jx++) {
+            const int dtype = dtypes[jx];
+            const int atype = convert_dtype_to_atop[dtype];
+            int out_atype = PNCU_BOOL;
+            pncu_any_two_fn fn = pncu_GetComparisonOpFast(atop, atype, atype, &out_atype);
+            int signature[3] = {dtype, dtype, fix_out_dtype(dtype, out_atype)};
+            PyUFuncGenericFunction oldFunc;
+            int ret = PyUFunc_ReplaceLoopBySignature((PyUFuncObject*)ufunc, g_UFuncCompareLUT[atop][atype], signature, &oldFunc);
+            if (ret < 0)
+                return PyErr_Format(PyExc_TypeError, "Comparison failed with %d. func %s must be the name of a ufunc.  atop:%d   atype:%d  sigs:%d, %d, %d",
+                                    ret, name, atop, atype, signature[0], signature[1], signature[2]);
+            stUFunc* p = &g_CompFuncLUT[atop][atype];
+            p->pOldFunc = oldFunc;
+            p->pBinaryFunc = fn;
+            p->MaxThreads = 3;
+            p->OutType = PNCU_BOOL;
+            AddToDict(name, dtype, p);
+        }
+        Py_DECREF(ufunc);
+    }
+    // ---- unary (:1435-1488)
+    for (int i = 0; i < COUNT_OF(gUnaryMapping); i++) {
+        const char* name = gUnaryMapping[i].str_ufunc_name;
+        const int atop = gUnaryMapping[i].atop_op;
+        PyObject* ufunc = PyObject_GetAttrString(numpy_module, name);
+        if (!ufunc) return PyErr_Format(PyExc_TypeError, "func %s must be the name of a ufunc", name);
+        for (int jx = 0; jx < num_dtypes; jx++) {
+            const int dtype = dtypes[jx];
+            const int atype = convert_dtype_to_atop[dtype];
+            int out_atype = -1;
+            pncu_unary_fn fn = pncu_GetUnaryOpFast(atop, atype, &out_atype);
+            if (out_atype == -1) continue;
+            int signature[3] = {dtype, fix_out_dtype(dtype, out_atype), dtype};
+            PyUFuncGenericFunction oldFunc;
+            int ret = PyUFunc_ReplaceLoopBySignature((PyUFuncObject*)ufunc, g_UFuncUnaryLUT[atop][atype], signature, &oldFunc);
+            if (ret < 0)
+                return PyErr_Format(PyExc_TypeError, "Unary failed with %d. func %s must be the name of a ufunc.  atop:%d   atype:%d  sigs:%d, %d, %d",
+                                    ret, name, atop, atype, signature[0], signature[1], signature[2]);
+            stUFunc* p = &g_UnaryFuncLUT[atop][atype];
+            p->pOldFunc = oldFunc;
+            p->pUnaryFunc = fn;
+            p->MaxThreads = 3;
+            p->OutType = out_atype;
+            AddToDict(name, dtype, p);
+        }
+        Py_DECREF(ufunc);
+    }
+    // ---- trig / log / exp (:1492-1547): float32 and float64, hooked even without a body, MaxThreads 7
+    static const int trig_dtypes[] = {NPY_FLOAT32, NPY_FLOAT64};
+    for (int i = 0; i < COUNT_OF(gTrigMapping); i++) {
+        const char* name = gTrigMapping[i].str_ufunc_name;
+        const int atop = gTrigMapping[i].atop_op;
+        PyObject* ufunc = PyObject_GetAttrString(numpy_module, name);
+        if (!ufunc) return PyErr_Format(PyExc_TypeError, "func %s must be the name of a ufunc", name);
+        for (int jx = 0; jx < COUNT_OF(trig_dtypes); jx++) {
+            const int dtype = trig_dtypes[jx];
+            const int atype = convert_dtype_to_atop[dtype];
+            int out_atype = atype;
+            pncu_unary_fn fn = pncu_GetTrigOpFast(atop, atype, &out_atype);
+            int signature[3] = {dtype, convert_atop_to_dtype[out_atype], dtype};
+            PyUFuncGenericFunction oldFunc;
+            int ret = PyUFunc_ReplaceLoopBySignature((PyUFuncObject*)ufunc, g_UFuncTrigLUT[atop][atype], signature, &oldFunc);
+            if (ret < 0)
+                return PyErr_Format(PyExc_TypeError, "Trig failed with %d. func %s must be the name of a ufunc.  atop:%d   atype:%d  sigs:%d, %d, %d",
+                                    ret, name, atop, atype, signature[0], signature[1], signature[2]);
+            stUFunc* p = &g_TrigFuncLUT[atop][atype];
+            p->pOldFunc = oldFunc;
+            p->pUnaryFunc = fn;  // NULL allowed: the old loop runs
+            p->MaxThreads = 7;
+            p->OutType = out_atype;
+            AddToDict(name, dtype, p);
+        }
+        Py_DECREF(ufunc);
+    }
+    // ---- PyArray_ArrFuncs: argmax / argmin (:1600-1614).  sort, argsort and fill are out of scope
+    //  and are left to NumPy.
+    for (int jx = 0; jx < num_dtypes; jx++) {
+        const int dtype = dtypes[jx];
+        const int atype = convert_dtype_to_atop[dtype];
+        PyArray_Descr* descr = PyArray_DescrFromType(dtype);
+        if (!descr) { PyErr_Clear(); continue; }
+        PyArray_ArrFuncs* f = PyDataType_GetArrFuncs(descr);
+        if (f) {
+            stArgMinMaxFunc* p = &g_ArgMinMaxFuncLUT[0][atype];
+            if (f->argmax && f->argmax != (PyArray_ArgFunc*)g_UFuncArgMinMaxLUT[0][atype]) {
+                p->pOldFunc = (ArgMinMaxFunc)f->argmax;
+                p->pFunc = pncu_GetArgMinMaxOpFast(PNCU_ARGMAX, atype);
+                p->MaxThreads = 3;
+                f->argmax = (PyArray_ArgFunc*)g_UFuncArgMinMaxLUT[0][atype];
+            }
+            p = &g_ArgMinMaxFuncLUT[1][atype];
+            if (f->argmin && f->argmin != (PyArray_ArgFunc*)g_UFuncArgMinMaxLUT[1][atype]) {
+                p->pOldFunc = (ArgMinMaxFunc)f->argmin;
+                p->pFunc = pncu_GetArgMinMaxOpFast(PNCU_ARGMIN, atype);
+                p->MaxThreads = 3;
+                f->argmin = (PyArray_ArgFunc*)g_UFuncArgMinMaxLUT[1][atype];
+            }
+        }
+        Py_DECREF(descr);
+    }
+    Py_DECREF(numpy_module);
+    g_Settings.Initialized = 1;
+    Py_RETURN_NONE;
+}
+
+// =======================================================================================================
+// control surface.  reference: src/pnumpy/_pnumpy.cpp:1766-1966
+static PyObject* atop_enable(PyObject*, PyObject*) { g_Settings.AtopEnabled = 1; Py_RETURN_NONE; }
+static PyObject* atop_disable(PyObject*, PyObject*) { g_Settings.AtopEnabled = 0; Py_RETURN_NONE; }
+static PyObject* atop_isenabled(PyObject*, PyObject*) { return PyBool_FromLong(g_Settings.AtopEnabled); }
+
+// atop_info() -> the live dict; atop_info(name, dtype_num) -> per-entry dict or False (:1791-1818)
+static PyObject* atop_info(PyObject*, PyObject* args) {
+    if (!g_Settings.Initialized) Py_RETURN_FALSE;
+    if (PyTuple_Size(args) == 0) {
+        Py_INCREF(gpUnaryDict);
+        return gpUnaryDict;
+    }
+    const char* uname = NULL;
+    int dtype = 0;
+    if (!PyArg_ParseTuple(args, "si:atop_info", &uname, &dtype)) return NULL;
+    stUFunc* p = GetFromDict(uname, dtype);
+    if (!p) Py_RETURN_FALSE;
+    // a compare / binary entry keeps its launcher in the pBinaryFunc/pUnaryFunc union, as in the reference
+    return Py_BuildValue("{s:i,s:i,s:L,s:L,s:L,s:L}", "MaxThreads", (int)p->MaxThreads, "MinElementsToThread",
+                         (int)p->MinElementsToThread, "pBinaryFunc", (long long)(intptr_t)p->pBinaryFunc, "pOldFunc",
+                         (long long)(intptr_t)p->pOldFunc, "pReduceFunc", (long long)(intptr_t)p->pReduceFunc,
+                         "pUnaryFunc", (long long)(intptr_t)p->pUnaryFunc);
+}
+
+// atop_setworkers(name, dtype_num, n): 0 <= n < 64, returns the previous value or False, only while
+// atop is enabled (:1825-1846)
+static PyObject* atop_setworkers(PyObject*, PyObject* args) {
+    if (g_Settings.AtopEnabled) {
+        const char* uname = NULL;
+        int dtype = 0, workers = 0;
+        if (!PyArg_ParseTuple(args, "sii:atop_setworkers", &uname, &dtype, &workers)) return NULL;
+        stUFunc* p = GetFromDict(uname, dtype);
+        if (p && workers >= 0 && workers < 64) {
+            int32_t prev = p->MaxThreads;
+            p->MaxThreads = workers;
+            return PyLong_FromLong(prev);
+        }
+    }
+    Py_RETURN_FALSE;
+}
+
+static PyObject* thread_enable(PyObject*, PyObject*) { nte_set_threading(1); Py_RETURN_NONE; }
+static PyObject* thread_disable(PyObject*, PyObject*) { nte_set_threading(0); Py_RETURN_NONE; }
+static PyObject* thread_isenabled(PyObject*, PyObject*) { return PyBool_FromLong(nte_get_threading()); }
+static PyObject* thread_setworkers(PyObject*, PyObject* args) {
+    int workers = 0;
+    if (!PyArg_ParseTuple(args, "i:thread_setworkers", &workers)) return NULL;
+    return PyLong_FromLong(nte_set_workers(workers));  // clamps, returns the previous value
+}
+static PyObject* thread_getworkers(PyObject*, PyObject*) { return PyLong_FromLong(nte_get_workers()); }
+static PyObject* thread_zigzag(PyObject*, PyObject*) {
+    // toggles 0 <-> 3 and reports the new state (:1953-1966); the value has no effect on a GPU
+    g_Settings.ZigZag = g_Settings.ZigZag ? 0 : 3;
+    return PyBool_FromLong(g_Settings.ZigZag != 0);
+}
+
+static PyObject* cpustring(PyObject*, PyObject*) {
+    // the reference returns CMathWorker::CPUString ("**CPU: <brand> AVX2:1 ..."); here the devices
+    if (!g_DeviceString[0]) Py_RETURN_NONE;
+    return PyUnicode_FromString(g_DeviceString);
+}
+
+static PyObject* ledger_enable(PyObject*, PyObject*) { g_Settings.LedgerEnabled = 1; Py_RETURN_NONE; }
+static PyObject* ledger_disable(PyObject*, PyObject*) { g_Settings.LedgerEnabled = 0; Py_RETURN_NONE; }
+static PyObject* ledger_isenabled(PyObject*, PyObject*) { return PyBool_FromLong(g_Settings.LedgerEnabled); }
+static PyObject* ledger_info(PyObject*, PyObject*) {
+    static const char* names[5] = {"Binary", "Unary", "Compare", "TrigLog", "ArgMinMax"};
+    PyObject* d = PyDict_New();
+    for (int c = 0; c < 5; ++c) {
+        PyObject* v = Py_BuildValue("{s:L,s:L,s:L}", "gpu_calls", (long long)g_Ledger[c].gpu_calls, "numpy_calls",
+                                    (long long)g_Ledger[c].old_calls, "elements", (long long)g_Ledger[c].elements);
+        PyDict_SetItemString(d, names[c], v);
+        Py_DECREF(v);
+    }
+    return d;
+}
+
+// ---- recycler: NEP-49 data allocator that hands out PINNED host memory for large ndarrays and recycles
+// freed blocks (the reference's roadmap for its placeholder recycler, src/pnumpy/__init__.py:18-21,
+// src/pnumpy/recycler.cpp).  Operands that live in pinned memory are DMA'd in place by nte. ---------------
+static const size_t kPinnedThreshold = (size_t)1 << 20;
+static std::mutex g_PoolMu;
+static std::multimap<size_t, void*> g_Pool;
+static size_t g_PoolBytes = 0, g_PoolCap = (size_t)8 << 30;
+static int64_t g_PoolHits = 0, g_PoolMisses = 0, g_PinnedLive = 0;
+
+static std::map<void*, size_t> g_Live;  // pinned blocks currently owned by ndarrays -> their size
+
+static void* pool_get(size_t size) {
+    void* p = NULL;
+    {
+        std::lock_guard<std::mutex> lk(g_PoolMu);
+        auto it = g_Pool.find(size);
+        if (it != g_Pool.end()) {
+            p = it->second;
+            g_Pool.erase(it);
+            g_PoolBytes -= size;
+            g_PoolHits++;
+        } else {
+            g_PoolMisses++;
+        }
+    }
+    if (!p) p = nte_alloc_pinned(size);
+    if (p) {
+        std::lock_guard<std::mutex> lk(g_PoolMu);
+        g_Live[p] = size;
+        g_PinnedLive++;
+    }
+    return p;
+}
+// true (and the block is retired) if `p` is one of ours
+static bool pool_put(void* p) {
+    size_t size = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_PoolMu);
+        auto it = g_Live.find(p);
+        if (it == g_Live.end()) return false;
+        size = it->second;
+        g_Live.erase(it);
+        g_PinnedLive--;
+        if (g_PoolBytes + size <= g_PoolCap) {
+            g_Pool.insert(std::make_pair(size, p));
+            g_PoolBytes += size;
+            return true;
+        }
+    }
+    nte_free_pinned(p);
+    return true;
+}
+static size_t pinned_size_of(void* p) {
+    std::lock_guard<std::mutex> lk(g_PoolMu);
+    auto it = g_Live.find(p);
+    return it == g_Live.end() ? 0 : it->second;
+}
+static void* rc_malloc(void*, size_t size) {
+    if (size >= kPinnedThreshold) { void* p = pool_get(size); if (p) return p; }
+    return malloc(size ? size : 1);
+}
+static void* rc_calloc(void*, size_t nelem, size_t elsize) {
+    const size_t size = nelem * elsize;
+    if (size >= kPinnedThreshold) { void* p = pool_get(size); if (p) { memset(p, 0, size); return p; } }
+    return calloc(nelem ? nelem : 1, elsize ? elsize : 1);
+}
+static void rc_free(void*, void* ptr, size_t) {
+    if (!ptr) return;
+    if (!pool_put(ptr)) free(ptr);
+}
+static void* rc_realloc(void* ctx, void* ptr, size_t new_size) {
+    if (!ptr) return rc_malloc(ctx, new_size);
+    const size_t old_pinned = pinned_size_of(ptr);
+    if (!old_pinned && new_size < kPinnedThreshold) return realloc(ptr, new_size ? new_size : 1);
+    if (!old_pinned) {
+        // growing a malloc'd block past the threshold: plain realloc keeps the data valid; it simply
+        // stays pageable (staged through nte's slabs like any other host array)
+        return realloc(ptr, new_size);
+    }
+    void* q = rc_malloc(ctx, new_size);
+    if (!q) return NULL;
+    memcpy(q, ptr, old_pinned < new_size ? old_pinned : new_size);
+    pool_put(ptr);
+    return q;
+}
+static PyDataMem_Handler g_RecyclerHandler = {"pnumpy_b200_pinned_recycler", 1, {NULL, rc_malloc, rc_calloc, rc_realloc, rc_free}};
+static PyObject* g_OldHandler = NULL;
+
+static PyObject* recycler_enable(PyObject*, PyObject*) {
+    if (!g_Settings.RecyclerEnabled) {
+        if (!g_Settings.Initialized) { PyErr_SetString(PyExc_RuntimeError, "call initialize() first"); return NULL; }
+        PyObject* cap = PyCapsule_New(&g_RecyclerHandler, "mem_handler", NULL);
+        if (!cap) return NULL;
+        PyObject* old = PyDataMem_SetHandler(cap);
+        Py_DECREF(cap);
+        if (!old) return NULL;
+        Py_XDECREF(g_OldHandler);
+        g_OldHandler = old;
+        g_Settings.RecyclerEnabled = 1;
+    }
+    Py_RETURN_NONE;
+}
+static PyObject* recycler_disable(PyObject*, PyObject*) {
+    if (g_Settings.RecyclerEnabled) {
+        PyObject* old = PyDataMem_SetHandler(g_OldHandler);  // arrays keep the handler they were born with
+        Py_XDECREF(old);
+        Py_CLEAR(g_OldHandler);
+        g_Settings.RecyclerEnabled = 0;
+    }
+    Py_RETURN_NONE;
+}
+static PyObject* recycler_isenabled(PyObject*, PyObject*) { return PyBool_FromLong(g_Settings.RecyclerEnabled); }
+static PyObject* recycler_info(PyObject*, PyObject*) {
+    std::lock_guard<std::mutex> lk(g_PoolMu);
+    return Py_BuildValue("{s:L,s:L,s:L,s:L,s:L,s:L}", "pooled_blocks", (long long)g_Pool.size(), "pooled_bytes",
+                         (long long)g_PoolBytes, "hits", (long long)g_PoolHits, "misses", (long long)g_PoolMisses,
+                         "live_pinned_blocks", (long long)g_PinnedLive, "threshold_bytes", (long long)kPinnedThreshold);
+}
+
+// ---- timers.  reference: src/pnumpy/ledger.cpp:91-114 ---------------------------------------------------
+static inline uint64_t rdtsc_now(void) {
+#if defined(__x86_64__) || defined(__i386__)
+    unsigned hi, lo;
+    __asm__ __volatile__("rdtsc" : "=a"(lo), "=d"(hi));
+    return ((uint64_t)lo) | (((uint64_t)hi) << 32);
+#else
+    struct timespec x;
+    clock_gettime(CLOCK_MONOTONIC, &x);
+    return (uint64_t)x.tv_sec * 1000000000ull + (uint64_t)x.tv_nsec;
+#endif
+}
+static PyObject* timer_gettsc(PyObject*, PyObject*) { return PyLong_FromUnsignedLongLong(rdtsc_now()); }
+static PyObject* timer_getutc(PyObject*, PyObject*) {
+    struct timespec x;
+    clock_gettime(CLOCK_REALTIME, &x);
+    return PyLong_FromLongLong((long long)x.tv_sec * 1000000000LL + x.tv_nsec);
+}
+
+// ---- additions (new keys only; nothing above changes meaning) ----------------------------------------------
+static PyObject* cuda_info(PyObject*, PyObject*) {
+    nte_stats s;
+    nte_get_stats(&s);
+    return Py_BuildValue("{s:i,s:s,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:i,s:i}", "devices", nte_device_count(), "device_string",
+                         g_DeviceString, "min_elems", (long long)nte_get_min_elems(), "calls", (long long)s.calls, "declined",
+                         (long long)s.declined, "launches", (long long)s.launches, "library_launches", (long long)pncu_launch_count(),
+                         "h2d_bytes", (long long)s.h2d_bytes, "d2h_bytes", (long long)s.d2h_bytes, "staged_bytes",
+                         (long long)s.staged_bytes, "lanes_last", (long long)s.lanes_last, "gpus_last", (long long)s.gpus_last,
+                         "workers", nte_get_workers(), "threading", nte_get_threading());
+}
+static PyObject* cuda_reset_stats(PyObject*, PyObject*) { nte_reset_stats(); Py_RETURN_NONE; }
+static PyObject* cuda_setthreshold(PyObject*, PyObject* args) {
+    long long n = 0;
+    if (!PyArg_ParseTuple(args, "L:cuda_setthreshold", &n)) return NULL;
+    return PyLong_FromLongLong(nte_set_min_elems(n));
+}
+static PyObject* cuda_getthreshold(PyObject*, PyObject*) { return PyLong_FromLongLong(nte_get_min_elems()); }
+static PyObject* cuda_setslab(PyObject*, PyObject* args) {
+    long long n = 0;
+    if (!PyArg_ParseTuple(args, "L:cuda_setslab", &n)) return NULL;
+    return PyLong_FromLongLong(nte_set_slab_bytes(n));
+}
+
+// pinned_empty(nbytes) -> a writable buffer object over pinned host memory (freed with the object)
+static void pinned_capsule_free(PyObject* cap) { nte_free_pinned(PyCapsule_GetPointer(cap, "pnumpy_b200.pinned")); }
+static PyObject* pinned_alloc(PyObject*, PyObject* args) {
+    long long nbytes = 0;
+    if (!PyArg_ParseTuple(args, "L:pinned_alloc", &nbytes)) return NULL;
+    if (nbytes < 0) { PyErr_SetString(PyExc_ValueError, "negative size"); return NULL; }
+    void* p = nte_alloc_pinned((size_t)nbytes);
+    if (!p) return PyErr_Format(PyExc_MemoryError, "cudaHostAlloc(%lld) failed: %s", nbytes, pncu_last_error());
+    PyObject* cap = PyCapsule_New(p, "pnumpy_b200.pinned", pinned_capsule_free);
+    if (!cap) { nte_free_pinned(p); return NULL; }
+    return Py_BuildValue("(NL)", cap, (long long)(intptr_t)p);
+}
+
+static PyMethodDef module_functions[] = {
+    {"initialize", (PyCFunction)(void (*)(void))newinit, METH_VARARGS | METH_KEYWORDS,
+     "Initialize the module. Replaces the ufunc inner loops with wrapped versions using "
+     "PyUFunc_ReplaceLoopBySignature and calls numpy.setbufsize(8192 * 1024)."},
+    {"atop_enable", atop_enable, METH_VARARGS, "enable the atop (GPU) inner loop implementations."},
+    {"atop_disable", atop_disable, METH_VARARGS, "disable the atop (GPU) inner loop implementations."},
+    {"atop_isenabled", atop_isenabled, METH_VARARGS, "returns True if atop is enabled"},
+    {"atop_info", atop_info, METH_VARARGS, "return dict"},
+    {"atop_setworkers", atop_setworkers, METH_VARARGS, "set workers for a func"},
+    {"thread_enable", thread_enable, METH_VARARGS, "enable sharding a call over several lanes / GPUs"},
+    {"thread_disable", thread_disable, METH_VARARGS, "run every call on one lane of GPU 0"},
+    {"thread_isenabled", thread_isenabled, METH_VARARGS, "returns True if threading is enabled"},
+    {"thread_getworkers", thread_getworkers, METH_VARARGS, "number of extra lanes a call may use"},
+    {"thread_setworkers", thread_setworkers, METH_VARARGS, "set the number of extra lanes; returns the previous value"},
+    {"thread_zigzag", thread_zigzag, METH_VARARGS, "toggle zigzag mode"},
+    {"timer_gettsc", timer_gettsc, METH_VARARGS, "time stamp counter"},
+    {"timer_getutc", timer_getutc, METH_VARARGS, "nanoseconds since the unix epoch"},
+    {"ledger_enable", ledger_enable, METH_VARARGS, "enable the ledger"},
+    {"ledger_disable", ledger_disable, METH_VARARGS, "disable the ledger"},
+    {"ledger_isenabled", ledger_isenabled, METH_VARARGS, "returns True if the ledger is enabled"},
+    {"ledger_info", ledger_info, METH_VARARGS, "per-category call counts recorded while the ledger was enabled"},
+    {"recycler_enable", recycler_enable, METH_VARARGS, "large ndarrays are born in recycled pinned host memory"},
+    {"recycler_disable", recycler_disable, METH_VARARGS, "restore NumPy's default data allocator"},
+    {"recycler_isenabled", recycler_isenabled, METH_VARARGS, "returns True if the recycler is enabled"},
+    {"recycler_info", recycler_info, METH_VARARGS, "pinned-block pool statistics"},
+    {"cpustring", cpustring, METH_VARARGS, "device identification string"},
+    {"cuda_info", cuda_info, METH_VARARGS, "devices, thresholds and dispatch counters"},
+    {"cuda_reset_stats", cuda_reset_stats, METH_VARARGS, "zero the dispatch counters"},
+    {"cuda_setthreshold", cuda_setthreshold, METH_VARARGS, "minimum elements for a GPU dispatch; returns the previous value"},
+    {"cuda_getthreshold", cuda_getthreshold, METH_VARARGS, "minimum elements for a GPU dispatch"},
+    {"cuda_setslab", cuda_setslab, METH_VARARGS, "bytes per staging slab; returns the previous value"},
+    {"pinned_alloc", pinned_alloc, METH_VARARGS, "(capsule, address) of a pinned host block"},
+    {NULL, NULL, 0, NULL}};
+
+static PyModuleDef moduledef = {PyModuleDef_HEAD_INIT, "pnumpy_b200._pnumpy",
+                                "B200 loops for NumPy ufuncs behind pnumpy's hooks", -1, module_functions,
+                                NULL, NULL, NULL, NULL};
+
+PyMODINIT_FUNC PyInit__pnumpy(void) {
+    PyObject* module = PyModule_Create(&moduledef);
+    if (!module) return NULL;
+    import_array();
+    import_umath();
+    return module;
+}

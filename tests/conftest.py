@@ -4,6 +4,9 @@ import sys
 import numpy as np
 import pytest
 
+# importing pnumpy_b200 must not try to grab a GPU in the CPU-only runs; GPU tests call pn.init()
+os.environ.setdefault("PNUMPY_B200_AUTOINIT", "0")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))

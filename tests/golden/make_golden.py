@@ -122,5 +122,22 @@ def main():
     print("wrote", len(g), "arrays;", os.path.getsize(os.path.join(HERE, "golden.npz")) // 1024, "KiB")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--hook-keys" not in sys.argv:
     main()
+
+
+def hook_keys():
+    """(ufunc name, dtype num) pairs the reference hooks at initialize() -- its atop_info() keys --
+    taken from the reference's own extension built by oracle/build_ref_ext.sh.  Run in a fresh
+    process (python tests/golden/make_golden.py --hook-keys): it patches NumPy's loop tables."""
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle", "_ref"))
+    import pnumpy_ref
+    pnumpy_ref.initialize()
+    keys = sorted([k[0], int(k[1])] for k in pnumpy_ref.atop_info().keys())
+    with open(os.path.join(HERE, "hook_keys.json"), "w") as f:
+        json.dump(keys, f)
+    print("wrote", len(keys), "hook keys")
+
+
+if __name__ == "__main__" and "--hook-keys" in sys.argv:
+    hook_keys()

@@ -1,0 +1,299 @@
+"""GPU tests of the drop-in path: NumPy ufunc call -> hooked loop stub -> nte dispatcher (pinned
+staging, lanes) -> libpnumpy_cuda kernels -> result in the caller's ndarray.  The checker is NumPy's
+own loop reached through the very same hooks with ``pn.disable()`` (what the reference's
+tests/test_ufuncs.py:59-88 does with threading on/off), plus the CPU oracle where the reference
+and NumPy differ.  Every test asserts that the GPU path really ran (dispatch counters)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from inputs import fill_random
+from util import DTYPES, FP_DTYPES, assert_bits_equal, ulp_error
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pn():
+    import pnumpy_b200 as pn
+    pn.init()  # raises ImportError without a B200
+    pn.enable()
+    old = pn.cuda_setthreshold(0)  # every call goes to the GPU, however small
+    yield pn
+    pn.cuda_setthreshold(old)
+    pn.disable()  # later test modules use NumPy as a reference: leave its own loops in charge
+
+
+def _both(pn, fn):
+    """(GPU result, NumPy-loop result, GPU calls made)"""
+    pn.enable()
+    c0 = pn.cuda_info()["calls"]
+    with np.errstate(all="ignore"):
+        got = fn()
+    calls = pn.cuda_info()["calls"] - c0
+    pn.disable()
+    try:
+        with np.errstate(all="ignore"):
+            want = fn()
+    finally:
+        pn.enable()
+    return got, want, calls
+
+
+def test_hook_table_matches_reference(pn):
+    """atop_info() lists exactly the (ufunc, dtype) pairs the reference hooks (359 on NumPy 2.3)."""
+    want = {(k, d) for k, d in json.load(open(os.path.join(ROOT, "tests", "golden", "hook_keys.json")))}
+    got = set(pn.atop_info().keys())
+    assert got == want, (sorted(got - want)[:5], sorted(want - got)[:5])
+    info = pn.atop_info("add", np.dtype(np.float32).num)
+    assert set(info) == {"MaxThreads", "MinElementsToThread", "pBinaryFunc", "pOldFunc", "pReduceFunc", "pUnaryFunc"}
+    assert info["MaxThreads"] == 3 and info["pBinaryFunc"] and info["pOldFunc"] and info["pReduceFunc"]
+    assert pn.atop_info("sin", np.dtype(np.float64).num)["MaxThreads"] == 7
+    assert pn.atop_info("nosuchufunc", 11) is False
+    assert "B200" in pn.cpustring()
+
+
+def test_enable_disable_roundtrip(pn):
+    """reference: tests/test_pnumpy.py:10-25"""
+    old = pn.atop_isenabled()
+    pn.atop_enable()
+    assert pn.atop_isenabled() is True
+    pn.atop_disable()
+    assert pn.atop_isenabled() is False
+    a = np.ones(1 << 16, np.float32)
+    c0 = pn.cuda_info()["calls"]
+    assert np.all(a + a == 2)  # hooks stay installed, the NumPy loop runs
+    assert pn.cuda_info()["calls"] == c0
+    pn.atop_enable() if old else pn.atop_disable()
+    assert pn.atop_isenabled() == old
+    prev = pn.atop_setworkers("add", np.dtype(np.float32).num, 5)
+    assert prev == 3 and pn.atop_setworkers("add", np.dtype(np.float32).num, prev) == 5
+    assert pn.atop_setworkers("add", np.dtype(np.float32).num, 64) is False
+
+
+def test_small_result(pn, rng):
+    """reference: tests/test_pnumpy.py:28-48"""
+    m = rng.integers(100, size=(10, 10), dtype=np.int32)
+    o = np.empty_like(m)
+    for i in range(m.shape[0]):
+        for j in range(m.shape[1]):
+            o[i, j] = m[i, j] + m[i, j]
+    assert np.all(np.add(m, m) == o)
+
+
+BIN = ["add", "subtract", "multiply", "true_divide", "floor_divide", "minimum", "maximum", "bitwise_and",
+       "bitwise_or", "bitwise_xor", "left_shift", "right_shift", "logical_and", "logical_or"]
+CMP = ["equal", "not_equal", "greater", "greater_equal", "less", "less_equal"]
+UNA = ["abs", "negative", "sign", "floor", "ceil", "trunc", "rint", "sqrt", "isnan", "isinf", "isfinite",
+       "logical_not", "invert", "signbit"]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_ufuncs_gpu_vs_numpy_loops(pn, rng, dt):
+    """The reference's sweep (1024x1024 random bit patterns, tests/test_ufuncs.py:59-88) restricted to
+    the hooked ufuncs, comparing the GPU loop with NumPy's loop bit for bit."""
+    shape = (1024, 1024)
+    a = fill_random(shape[0] * shape[1], dt, rng).reshape(shape)
+    b = fill_random(shape[0] * shape[1], dt, rng).reshape(shape)
+    ran = 0
+    for name in BIN + CMP:
+        uf = getattr(np, name)
+        sig = np.dtype(dt).char * 2
+        if not any(t.startswith(sig + "->") for t in uf.types):
+            continue
+        if (name, np.dtype(dt).num) not in pn.atop_info():
+            continue
+        bb = b
+        if "shift" in name:
+            bb = (b.astype(np.int64) % 70 - 3).astype(dt)
+        for rhs in (bb, bb[3, 5]):
+            got, want, calls = _both(pn, lambda: uf(a, rhs))
+            assert_bits_equal(got, want, f"{name} {dt}")
+            ran += calls
+    for name in UNA:
+        uf = getattr(np, name)
+        if not any(t.startswith(np.dtype(dt).char + "->") for t in uf.types):
+            continue
+        if (name, np.dtype(dt).num) not in pn.atop_info():
+            continue
+        got, want, calls = _both(pn, lambda: uf(a))
+        assert_bits_equal(got, want, f"{name} {dt}")
+        ran += calls
+    assert ran >= 10, "the GPU path did not run"
+
+
+@pytest.mark.parametrize("dt", FP_DTYPES)
+def test_transcendentals_through_hooks(pn, rng, dt):
+    n = 1 << 20
+    x = {"sin": rng.uniform(-8192, 8192, n), "cos": rng.uniform(-3.14, 3.14, n),
+         "log": np.exp(rng.uniform(-80, 80, n)), "exp": rng.uniform(-80, 80, n)}
+    from oracle import oracle as O
+    for name, v in x.items():
+        v = v.astype(dt)
+        got, want, calls = _both(pn, lambda: getattr(np, name)(v))
+        assert calls >= 1
+        if dt == "float32":
+            assert_bits_equal(got, O.unary(name.upper(), v), name)  # == the reference's vector body
+            if name != "sin":  # sin near zeros inside +-8192: absolute, not relative, accuracy (App. C.2)
+                assert ulp_error(got, getattr(np, name)(v.astype(np.float64))).max() <= 2.0
+        else:
+            truth = getattr(np, name)(v.astype(np.longdouble))
+            sp = np.spacing(np.abs(truth).astype(np.float64))
+            assert (np.abs(got.astype(np.longdouble) - truth) / sp).max() <= 2.0
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_reductions_through_hooks(pn, rng, dt):
+    n = (1 << 20) + 77
+    a = fill_random(n, dt, rng)
+    if dt in FP_DTYPES:
+        a = rng.normal(0, 100, n).astype(dt)
+    for fn in (lambda: a.min(), lambda: a.max(), lambda: a.argmax(), lambda: a.argmin(),
+               lambda: np.add.reduce(a, dtype=a.dtype) if dt != "bool" else a.any(), lambda: a.all() if dt == "bool" else a.max()):
+        got, want, calls = _both(pn, fn)
+        assert calls >= 1, "GPU reduction did not run"
+        if dt in FP_DTYPES and np.asarray(got).dtype.kind == "f":
+            tol = 2.0 ** -22 * abs(float(want)) + 2.0 ** -45 * float(np.abs(a.astype(np.float64)).sum())
+            assert abs(float(got) - float(want)) <= tol, (got, want)
+        else:
+            assert got == want, (got, want)
+    if dt in FP_DTYPES:
+        for pos in ([0], [n - 1], [70000, 500000]):
+            b = a.copy()
+            b[pos] = np.nan
+            for fn in (lambda: b.min(), lambda: b.max(), lambda: b.argmax(), lambda: b.argmin()):
+                got, want, calls = _both(pn, fn)
+                assert calls >= 1
+                assert (np.isnan(got) and np.isnan(want)) or got == want, (pos, got, want)
+        # float32 sum: GPU accumulates in float64 (the reference's intent), within SURVEY 8c tolerance
+        got, _, _ = _both(pn, lambda: a.sum())
+        ref = float(np.sum(a.astype(np.float64)))
+        eps = 2.0 ** -23 if dt == "float32" else 2.0 ** -52
+        assert abs(float(got) - ref) <= eps * abs(ref) + 2.0 ** -45 * float(np.abs(a.astype(np.float64)).sum())
+
+
+def test_layouts_inplace_and_declines(pn, rng):
+    n = 1 << 18
+    a = rng.normal(size=n).astype(np.float32)
+    b = rng.normal(size=n).astype(np.float32)
+    want = a + b
+    c = a.copy()
+    c0 = pn.cuda_info()["calls"]
+    c += b                       # in place: out aliases in1
+    assert pn.cuda_info()["calls"] == c0 + 1
+    assert_bits_equal(c, want, "in-place")
+    out = np.empty_like(a)
+    np.add(a, b, out=out)
+    assert_bits_equal(out, want, "out=")
+    # non-contiguous operands are declined by nte and computed by NumPy's loop, correctly
+    d0 = pn.cuda_info()["declined"]
+    s = a[::2] + b[::2]
+    assert pn.cuda_info()["declined"] > d0
+    assert_bits_equal(s, want[::2].copy(), "strided")
+    # 2-D reduction along axis 1: many short reduce calls, all correct
+    m = rng.normal(size=(512, 2048)).astype(np.float64)
+    got, wantm, _ = _both(pn, lambda: m.max(axis=1))
+    assert_bits_equal(got, wantm, "axis reduce")
+    # below the size threshold the old loop runs
+    old = pn.cuda_setthreshold(1 << 30)
+    c1 = pn.cuda_info()["calls"]
+    assert_bits_equal(a + b, want, "below threshold")
+    assert pn.cuda_info()["calls"] == c1
+    pn.cuda_setthreshold(old)
+
+
+def test_lanes_do_not_change_results(pn, rng):
+    """thread on/off and worker counts (the reference's tests/test_ufuncs.py protocol): the number of
+    lanes must not change a single bit -- reductions included."""
+    n = (1 << 22) + 4099
+    a = rng.normal(0, 100, n).astype(np.float32)
+    b = rng.normal(0, 100, n).astype(np.float32)
+    results = []
+    oldw = pn.thread_getworkers()
+    for threading, workers in ((False, 1), (True, 1), (True, 3), (True, 7)):
+        pn.thread_enable() if threading else pn.thread_disable()
+        pn.thread_setworkers(workers)
+        pn.atop_setworkers("sin", np.dtype(np.float32).num, 7)
+        r = (np.add(a, b), np.sin(a), np.greater(a, b), a.sum(), a.min(), a.argmax(), np.float64(a.astype(np.float64).sum()))
+        info = pn.cuda_info()
+        if not threading:
+            assert info["lanes_last"] == 1
+        results.append(r)
+    pn.thread_enable()
+    pn.thread_setworkers(oldw)
+    for r in results[1:]:
+        for x, y in zip(results[0], r):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+    assert pn.thread_isenabled()
+
+
+def test_pinned_operands_are_not_staged(pn, rng):
+    n = 1 << 22
+    a, b, c = pn.pinned_empty(n, np.float32), pn.pinned_empty(n, np.float32), pn.pinned_empty(n, np.float32)
+    a[:] = rng.normal(size=n)
+    b[:] = rng.normal(size=n)
+    pn.cuda_reset_stats()
+    np.multiply(a, b, out=c)
+    info = pn.cuda_info()
+    assert info["calls"] == 1 and info["staged_bytes"] == 0
+    assert info["h2d_bytes"] == 2 * 4 * n and info["d2h_bytes"] == 4 * n
+    pn.disable()
+    want = a * b
+    pn.enable()
+    assert_bits_equal(np.asarray(c), want, "pinned")
+    s = float(c.sum())
+    assert abs(s - float(np.sum(want.astype(np.float64)))) <= 1e-6 * n
+
+
+def test_recycler_gives_pinned_arrays(pn, rng):
+    assert pn.recycler_isenabled() is False
+    pn.recycler_enable()
+    try:
+        assert pn.recycler_isenabled() is True
+        n = 1 << 21
+        a = np.ones(n, np.float32)       # born pinned
+        b = np.full(n, 2.0, np.float32)
+        pn.cuda_reset_stats()
+        c = a + b                        # output allocated by NumPy through the recycler too
+        info = pn.cuda_info()
+        assert info["calls"] == 1 and info["staged_bytes"] == 0
+        assert np.all(c == 3)
+        del c
+        d = a * b                        # same size: the freed block is recycled
+        assert pn.recycler_info()["hits"] >= 1 and np.all(d == 2)
+        small = np.ones(10)              # small arrays stay on malloc
+        assert small.sum() == 10
+    finally:
+        pn.recycler_disable()
+    assert pn.recycler_isenabled() is False
+    assert np.all(np.ones(1 << 21, np.float32) + 1 == 2)
+
+
+def test_ledger_counts(pn):
+    pn.ledger_enable()
+    try:
+        assert pn.ledger_isenabled()
+        before = pn.ledger_info()["Binary"]["gpu_calls"]
+        a = np.ones(1 << 16)
+        a + a
+        assert pn.ledger_info()["Binary"]["gpu_calls"] == before + 1
+    finally:
+        pn.ledger_disable()
+    assert not pn.ledger_isenabled()
+
+
+def test_benchmark_plumbing(pn, capsys):
+    """config 1 of BASELINE.json: pn.benchmark plumbing on 1 000 000 float32 elements."""
+    old = pn.cuda_setthreshold(1 << 16)
+    try:
+        r = pn.benchmark_func(np.add, ctypes=[np.float32], sizes=[1_000_000], loop_size=5)
+        assert r.shape == (1,) and np.isfinite(r[0]) and r[0] > 0
+        assert pn.atop_isenabled() and pn.thread_isenabled()
+        pn.benchmark(ctypes=[np.float32], sizes=[1 << 17], loop_size=3)
+        out = capsys.readouterr().out
+        assert out.startswith("131072 rows,float32,") and "a+b," in out and "sum," in out and "min," in out
+    finally:
+        pn.cuda_setthreshold(old)

@@ -1,0 +1,414 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (ctypes on
+libpnumpy_cuda.so, device pointers), against the CPU oracle on the same seeded inputs, against
+the golden fixtures, and -- at the BASELINE.json sizes -- through size-independent properties.
+
+Bar (BASELINE.json north_star): bit-exact for integer / bool / comparison / min / max / arg* and
+IEEE float add, sub, mul, div, sqrt; float32 sin/cos/log/exp bit-exact with the oracle's Cephes
+restatement (hence 0 ULP from the reference's vector body on its valid domain) and <= 2 ULP of the
+correctly rounded value elsewhere; float64 sin/cos/log/exp <= 2 ULP; float sums within
+    |gpu - S64| <= 2^-23 |S64| + 2^-50 sum|x|      (float32)
+    |gpu - S|   <= (log2(n) + 2) 2^-53 sum|x|      (float64)
+"""
+import math
+import zlib
+
+import numpy as np
+import pytest
+
+from inputs import fill_random, nan_case_input, reduction_input
+from util import DTYPES, FP_DTYPES, INT_DTYPES, assert_bits_equal, ulp_error
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from pnumpy_b200 import cabi, device
+    cabi.init()  # raises without a B200: the tests must not pass on a fallback
+    return device
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def _ops_for(dt):
+    ops = ["ADD", "MUL", "MIN", "MAX"]
+    if dt != "bool":
+        ops.append("SUB")
+    if dt in FP_DTYPES:
+        ops += ["DIV", "FLOORDIV"]
+    else:
+        ops += ["BITWISE_AND", "BITWISE_OR", "BITWISE_XOR"]
+    if dt in INT_DTYPES:
+        ops += ["BITWISE_LSHIFT", "BITWISE_RSHIFT"]
+    if dt == "bool":
+        ops += ["LOGICAL_AND", "LOGICAL_OR"]
+    return ops
+
+
+N_SMALL = (1 << 16) + 13  # not a multiple of any vector width: exercises head/tail code
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_binary_vs_oracle(dev, O, rng, dt):
+    launches0 = _launches()
+    a, b = fill_random(N_SMALL, dt, rng), fill_random(N_SMALL, dt, rng)
+    if dt in INT_DTYPES:
+        b_shift = (b.astype(np.int64) % 70 - 3).astype(dt)  # shift counts around the width
+    da, db = dev.to_device(a), dev.to_device(b)
+    for op in _ops_for(dt):
+        bb, dbb = (b_shift, dev.to_device(b_shift)) if "SHIFT" in op else (b, db)
+        with np.errstate(all="ignore"):
+            want = O.binary(op, a, bb)
+        assert_bits_equal(dev.binary(op, da, dbb).to_host(), want, f"{op} {dt} vv")
+        # scalar second operand and scalar first operand (stride 0)
+        s = bb[7:8].copy()
+        ds = dev.to_device(s)
+        with np.errstate(all="ignore"):
+            assert_bits_equal(dev.binary(op, da, ds, b_scalar=True).to_host(),
+                              O.binary(op, a, np.broadcast_to(s, (1,))[0]), f"{op} {dt} vs")
+            s1 = a[3:4].copy()
+            assert_bits_equal(dev.binary(op, dev.to_device(s1), dbb, a_scalar=True).to_host(),
+                              O.binary(op, np.broadcast_to(s1, (1,))[0], bb), f"{op} {dt} sv")
+    assert _launches() > launches0  # the CUDA kernels really ran
+
+
+def _launches():
+    from pnumpy_b200 import cabi
+    return cabi.load().pncu_launch_count()
+
+
+@pytest.mark.parametrize("dt", ["int8", "int32", "float32", "float64"])
+def test_binary_layouts(dev, O, rng, dt):
+    """in-place, misaligned heads, ragged tiny sizes, byte strides (incl. negative)."""
+    from pnumpy_b200 import cabi
+    for n in (0, 1, 2, 3, 5, 15, 17, 31, 33, 255, 1023, 1025, 4099):
+        a, b = fill_random(n, dt, rng), fill_random(n, dt, rng)
+        with np.errstate(all="ignore"):
+            want = O.binary("ADD", a, b) if n else np.empty(0, dt)
+        got = dev.binary("ADD", dev.to_device(a), dev.to_device(b)).to_host() if n else want
+        assert_bits_equal(got, want, f"n={n}")
+    n = 50021
+    a, b = fill_random(n + 8, dt, rng), fill_random(n + 8, dt, rng)
+    da, db, dout = dev.to_device(a), dev.to_device(b), dev.empty(n + 8, dt)
+    with np.errstate(all="ignore"):
+        for off in (1, 2, 3, 5):  # same misalignment on all three: peeled head
+            got = dev.binary("MUL", da.view(off, n), db.view(off, n), out=dout.view(off, n)).to_host()
+            assert_bits_equal(got, O.binary("MUL", a[off:off + n], b[off:off + n]), f"off={off}")
+        # different misalignment per operand: element-wise fallback kernel
+        got = dev.binary("SUB", da.view(1, n), db.view(2, n), out=dout.view(3, n)).to_host()
+        assert_bits_equal(got, O.binary("SUB", a[1:1 + n], b[2:2 + n]), "mixed misalignment")
+        # in place: out aliases in1 exactly
+        want = O.binary("ADD", a, b)
+        dev.binary("ADD", da, db, out=da)
+        assert_bits_equal(da.to_host(), want, "in-place")
+    # arbitrary byte strides through the raw launcher, incl. a negative one
+    fn, _ = cabi.get_binary(cabi.BINARY_OPS["ADD"], cabi.atop_of(dt))
+    a, b = fill_random(3 * 4000, dt, rng), fill_random(2 * 4000, dt, rng)
+    da, db, dout = dev.to_device(a), dev.to_device(b), dev.empty(4000, dt)
+    isz = np.dtype(dt).itemsize
+    cabi.check(fn(da.ptr, db.ptr + (2 * 4000 - 1) * isz, dout.ptr, 4000, 3 * isz, -2 * isz, isz, None), "strided")
+    with np.errstate(all="ignore"):
+        assert_bits_equal(dout.to_host(), O.binary("ADD", a[::3], b[::-2][:4000].copy()), "strided")
+    # partial overlap is refused, never computed wrongly
+    rc = fn(da.ptr, db.ptr, da.ptr + isz, 1000, isz, isz, isz, None)
+    assert rc == -3 and b"overlaps" in cabi.load().pncu_last_error()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_compare_vs_oracle(dev, O, rng, dt):
+    a, b = fill_random(N_SMALL, dt, rng), fill_random(N_SMALL, dt, rng)
+    b[::3] = a[::3]  # plenty of equal pairs
+    da, db = dev.to_device(a), dev.to_device(b)
+    for op in ("EQ", "NE", "LT", "GT", "LTE", "GTE"):
+        assert_bits_equal(dev.compare(op, da, db).to_host(), O.compare(op, a, b), f"{op} {dt}")
+        s = b[5:6].copy()
+        assert_bits_equal(dev.compare(op, da, dev.to_device(s), b_scalar=True).to_host(),
+                          O.compare(op, a, np.broadcast_to(s, (1,))[0]), f"{op} {dt} scalar")
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_unary_vs_oracle(dev, O, rng, dt):
+    a = fill_random(N_SMALL, dt, rng)
+    da = dev.to_device(a)
+    ops = ["ABS", "LOGICAL_NOT", "ISNAN", "ISINF", "ISFINITE"]
+    if dt in FP_DTYPES:
+        ops += ["NEGATIVE", "SIGN", "FLOOR", "CEIL", "TRUNC", "ROUND", "SQRT", "SIGNBIT"]
+    else:
+        ops += ["INVERT"]
+        if dt != "bool":
+            ops += ["NEGATIVE"]
+        if dt in ("int8", "int16", "int32", "int64"):
+            ops += ["SIGN"]
+    for op in ops:
+        with np.errstate(all="ignore"):
+            want = O.unary(op, a)
+        got = dev.unary(op, da).to_host()
+        assert_bits_equal(got, want.view(got.dtype), f"{op} {dt}")
+
+
+@pytest.mark.parametrize("dt", INT_DTYPES)
+def test_int_true_divide(dev, O, rng, dt):
+    a, b = fill_random(N_SMALL, dt, rng), fill_random(N_SMALL, dt, rng)
+    b[::5] = 0
+    with np.errstate(all="ignore"):
+        want = O.int_true_divide(a, b)
+        assert_bits_equal(want, np.true_divide(a.astype(np.float64), b.astype(np.float64)), "oracle==numpy")
+    assert_bits_equal(dev.int_true_divide(dev.to_device(a), dev.to_device(b)).to_host(), want, dt)
+
+
+# ---- transcendental ---------------------------------------------------------------------------
+TRIG_RANGES = {"SIN": (-8192, 8192), "COS": (-8192, 8192), "LOG": (0, 1e6), "EXP": (-80, 80)}
+
+
+@pytest.mark.parametrize("op", ["SIN", "COS", "LOG", "EXP"])
+def test_trig_f32_bit_exact_vs_oracle(dev, O, rng, golden, op):
+    lo, hi = TRIG_RANGES[op]
+    x = rng.uniform(lo, hi, 1 << 18).astype(np.float32)
+    with np.errstate(all="ignore"):
+        assert_bits_equal(dev.unary(op, dev.to_device(x)).to_host(), O.unary(op, x), f"{op} range")
+        # every bit pattern class: NaN, inf, denormals, huge
+        y = fill_random(1 << 18, "float32", rng)
+        got, want = dev.unary(op, dev.to_device(y)).to_host(), O.unary(op, y)
+        if op in ("SIN", "COS"):
+            m = np.abs(y) <= 8192  # Cephes restatement: bit-exact; beyond: CUDA vs glibc libm
+            assert_bits_equal(got[m], want[m], f"{op} bits in-range")
+            err = ulp_error(got[~m], (np.sin if op == "SIN" else np.cos)(y[~m].astype(np.float64)))
+            assert np.all(err <= 2.0), err.max()
+        else:
+            assert_bits_equal(got, want, f"{op} bits")
+    # the reference's own vector-body outputs (golden, valid Cephes domain)
+    xin = golden[f"in_{op}_float32"]
+    assert_bits_equal(dev.unary(op, dev.to_device(xin)).to_host(), golden[f"ref_{op}_float32"], f"{op} golden")
+    # edge cases follow IEEE / NumPy
+    e = golden["in_edge_float32"]
+    got = dev.unary(op, dev.to_device(e)).to_host()
+    err = ulp_error(got, golden[f"np64_{op}_edge"])
+    m = np.ones(e.size, bool) if op in ("LOG", "EXP") else ((np.abs(e) <= 3.2) | ~(np.abs(e) <= 8192))
+    assert np.all(err[m] <= 2.0), (e[m][err[m] > 2], got[m][err[m] > 2])
+
+
+@pytest.mark.parametrize("op,lo,hi", [("SIN", -20, 20), ("SIN", -1e5, 1e5), ("COS", -20, 20),
+                                      ("LOG", 1e-300, 1e300), ("EXP", -700, 700)])
+def test_trig_f64_within_2ulp(dev, rng, op, lo, hi):
+    if op == "LOG":
+        x = np.exp(rng.uniform(np.log(lo), np.log(hi), 1 << 17))
+    else:
+        x = rng.uniform(lo, hi, 1 << 17)
+    x = np.concatenate([x, [0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 5e-324, 1e-310]])
+    fn = {"SIN": np.sin, "COS": np.cos, "LOG": np.log, "EXP": np.exp}[op]
+    with np.errstate(all="ignore"):
+        truth = fn(x.astype(np.longdouble))
+    got = dev.unary(op, dev.to_device(x)).to_host()
+    with np.errstate(all="ignore"):
+        g = got.astype(np.longdouble)
+        fin = np.isfinite(truth) & np.isfinite(g)
+        sp = np.maximum(np.spacing(np.abs(truth[fin]).astype(np.float64)), 5e-324)
+        err = np.abs(g[fin] - truth[fin]) / sp
+    assert err.max() <= 2.0, err.max()
+    assert np.array_equal(np.isnan(got[~fin]), np.isnan(truth[~fin].astype(np.float64)))
+    nn = ~fin & ~np.isnan(got)
+    assert np.array_equal(got[nn], truth[nn].astype(np.float64))
+
+
+# ---- reductions ---------------------------------------------------------------------------------
+def _sum_tol(a):
+    s = np.abs(a.astype(np.float64)).sum()
+    if a.dtype == np.float32:
+        return lambda ref: 2.0 ** -23 * abs(ref) + 2.0 ** -50 * s
+    return lambda ref: (math.log2(max(a.size, 2)) + 2) * 2.0 ** -53 * s
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_reductions_vs_oracle_and_golden(dev, O, golden, dt):
+    a = reduction_input(dt)
+    assert zlib.crc32(a.tobytes()) == int(golden[f"red_crc_{dt}"])
+    da = dev.to_device(a)
+    zero = dev.to_device(np.zeros(1, a.dtype))
+    with np.errstate(all="ignore"):
+        got = dev.reduce("ADD", da, start=zero).to_host()[0]
+        if dt in FP_DTYPES:
+            ref = math.fsum(a.astype(np.float64))
+            assert abs(float(got) - ref) <= _sum_tol(a)(ref), (got, ref)
+            assert abs(float(got) - float(O.reduce("ADD", a, start=0))) <= 2 * _sum_tol(a)(ref)
+        else:
+            assert got == golden[f"red_SUM_{dt}"] == O.reduce("ADD", a, start=np.zeros(1, a.dtype)[0])
+        # NumPy's calling convention for min/max: accumulator pre-loaded with a[0], n-1 elements
+        first = dev.to_device(a[:1])
+        for op in ("MIN", "MAX"):
+            got = dev.reduce(op, da.view(1, a.size - 1), start=first).to_host()[0]
+            assert got == golden[f"red_{op}_{dt}"] == O.reduce(op, a[1:], start=a[0]), (op, got)
+            assert dev.reduce(op, da).to_host()[0] == golden[f"red_{op}_{dt}"]  # NULL start
+        if dt != "bool":
+            got = dev.reduce("MUL", da.view(0, 1000), start=dev.to_device(np.ones(1, a.dtype))).to_host()[0]
+            want = O.reduce("MUL", a[:1000], start=np.ones(1, a.dtype)[0])
+            if dt in FP_DTYPES:
+                assert (np.isnan(got) and np.isnan(want)) or got == want or abs(got - want) <= 1e-5 * abs(want)
+            else:
+                assert got == want
+        assert dev.argminmax(0, da).to_host()[0] == int(golden[f"red_ARGMAX_{dt}"]) == O.argminmax(0, a)
+        assert dev.argminmax(1, da).to_host()[0] == int(golden[f"red_ARGMIN_{dt}"]) == O.argminmax(1, a)
+
+
+@pytest.mark.parametrize("dt", FP_DTYPES)
+@pytest.mark.parametrize("tag", ["none", "first", "last", "mid"])
+def test_nan_reductions(dev, golden, dt, tag):
+    a = nan_case_input(dt, tag)
+    assert zlib.crc32(a.tobytes()) == int(golden[f"nan_crc_{tag}_{dt}"])
+    da = dev.to_device(a)
+    for op in ("MIN", "MAX"):
+        got = dev.reduce(op, da).to_host()[0]
+        want = golden[f"nan_{op}_{tag}_{dt}"]
+        assert (np.isnan(got) and np.isnan(want)) or got == want, (op, got, want)
+    assert dev.argminmax(0, da).to_host()[0] == int(golden[f"nan_ARGMAX_{tag}_{dt}"])
+    assert dev.argminmax(1, da).to_host()[0] == int(golden[f"nan_ARGMIN_{tag}_{dt}"])
+
+
+@pytest.mark.parametrize("dt", ["int16", "float32", "float64"])
+def test_reduction_edge_shapes(dev, O, rng, dt):
+    """empty, 1 element, ragged sizes around the 65536-element logical block, strided input,
+    first-occurrence ties, run-to-run determinism."""
+    from pnumpy_b200 import cabi
+    for n in (1, 2, 7, 255, 257, 65535, 65536, 65537, 131072 + 5):
+        a = reduction_input(dt, n=n, seed=n)
+        da = dev.to_device(a)
+        with np.errstate(all="ignore"):
+            got = dev.reduce("ADD", da).to_host()[0]
+            if dt == "int16":
+                assert got == np.add.reduce(a, dtype=a.dtype)
+            else:
+                ref = math.fsum(a.astype(np.float64))
+                assert abs(float(got) - ref) <= _sum_tol(a)(ref) + 1e-300
+            assert dev.reduce("MAX", da).to_host()[0] == a.max()
+            assert dev.argminmax(0, da).to_host()[0] == a.argmax()
+            assert dev.argminmax(1, da).to_host()[0] == a.argmin()
+    # empty with a start value: out = start
+    st = dev.to_device(np.array([42], dtype=dt))
+    assert dev.reduce("ADD", dev.empty(0, dt), start=st).to_host()[0] == 42
+    # ties: the extreme value repeated across block boundaries -> smallest index
+    a = np.zeros(200000, dtype=dt)
+    a[[70000, 65535, 65536, 199999]] = 9
+    a[[3, 150000]] = -9
+    da = dev.to_device(a)
+    assert dev.argminmax(0, da).to_host()[0] == 65535
+    assert dev.argminmax(1, da).to_host()[0] == 3
+    # strided input (every other element) through the raw launcher
+    a = reduction_input(dt, n=100001, seed=5)
+    da, out = dev.to_device(a), dev.empty(1, dt)
+    fn = cabi.get_reduce(cabi.BINARY_OPS["MAX"], cabi.atop_of(dt))
+    cabi.check(fn(da.ptr, out.ptr, None, 50000, 2 * a.dtype.itemsize, None), "strided reduce")
+    assert out.to_host()[0] == a[::2][:50000].max()
+    # bit-reproducible run to run
+    b = reduction_input(dt, n=(1 << 20) + 3, seed=77)
+    db = dev.to_device(b)
+    r = [dev.reduce("ADD", db).to_host().tobytes() for _ in range(5)]
+    assert len(set(r)) == 1
+
+
+def test_two_pass_building_blocks_are_shard_invariant(dev, rng):
+    """pncu_reduce_partials over shards cut at multiples of pncu_reduce_block_elems() + one
+    pncu_reduce_finish over the gathered partials == the single-call result, bit for bit
+    (the multi-GPU combine of the nte dispatcher and of bench.py --gpus N)."""
+    from pnumpy_b200 import cabi
+    lib = cabi.load()
+    A = lib.pncu_reduce_block_elems()
+    n = 11 * A + 1234
+    for dt, op in (("float32", "ADD"), ("float64", "ADD"), ("float32", "MIN"), ("int32", "ADD"), ("int8", "MAX")):
+        a = reduction_input(dt, n=n, seed=11)
+        if op == "MIN":
+            a[5 * A + 3] = np.nan
+        da = dev.to_device(a)
+        whole = dev.reduce(op, da).to_host()
+        t, f = cabi.atop_of(dt), cabi.BINARY_OPS[op]
+        pb = lib.pncu_reduce_partial_bytes(f, t)
+        nb = lib.pncu_reduce_partial_count(t, n)
+        assert nb == -(-n * a.dtype.itemsize // 65536)
+        parts = dev.empty(nb * pb, np.uint8)
+        units = -(-n // A)  # shardable units of A elements
+        for shards in (1, 2, 4, 8):
+            cabi.check(lib.pncu_memset(parts.ptr, 0xFF, nb * pb, None), "memset")
+            per = -(-units // shards)
+            for s_ in range(shards):
+                e0, e1 = min(n, s_ * per * A), min(n, (s_ + 1) * per * A)
+                if e0 >= e1:
+                    continue
+                slot0 = lib.pncu_reduce_partial_count(t, e0)
+                cabi.check(lib.pncu_reduce_partials(f, t, da.ptr + e0 * a.dtype.itemsize, e1 - e0,
+                                                    parts.ptr + slot0 * pb, None), "partials")
+            out = dev.empty(1, dt)
+            cabi.check(lib.pncu_reduce_finish(f, t, parts.ptr, nb, out.ptr, None, None), "finish")
+            assert out.to_host().tobytes() == whole.tobytes(), (dt, op, shards)
+    # arg-reduction with global index bases
+    a = reduction_input("float32", n=n, seed=12)
+    a[[7 * A + 5, 2 * A + 1]] = a.max() + 1
+    da = dev.to_device(a)
+    nb = lib.pncu_reduce_partial_count(12, n)
+    parts = dev.empty(nb * 16, np.uint8)
+    units = -(-n // A)
+    for shards in (1, 3, 8):
+        per = -(-units // shards)
+        for s_ in range(shards):
+            e0, e1 = min(n, s_ * per * A), min(n, (s_ + 1) * per * A)
+            if e0 >= e1:
+                continue
+            slot0 = lib.pncu_reduce_partial_count(12, e0)
+            cabi.check(lib.pncu_argminmax_partials(0, 12, da.ptr + e0 * 4, e1 - e0, e0,
+                                                   parts.ptr + slot0 * 16, None), "arg partials")
+        out = dev.empty(1, np.int64)
+        cabi.check(lib.pncu_argminmax_finish(0, 12, parts.ptr, nb, out.ptr, None), "arg finish")
+        assert out.to_host()[0] == 2 * A + 1 == a.argmax()
+
+
+# ---- BASELINE.json sizes: size-independent properties ----------------------------------------------
+@pytest.mark.parametrize("dt", ["int32", "int64", "float32", "float64"])
+def test_full_size_properties(dev, dt):
+    """2^28 elements (config 2/3): structured inputs whose results are known in closed form, so no
+    CPU pass over 2^28 elements is needed: a = i mod 253 + 1 (the reference's benchmark data,
+    src/pnumpy/benchmark.py:56-66), generated on the device from small pieces."""
+    n = 1 << 28
+    period = 253 * 4096  # multiple of 253; host builds one period, device tiles it by d2d copies
+    host = (np.arange(period, dtype=np.int64) % 253 + 1).astype(dt)
+    from pnumpy_b200 import cabi
+    lib = cabi.load()
+    da = dev.empty(n, dt)
+    isz = host.dtype.itemsize
+    dpiece = dev.to_device(host)
+    off = 0
+    while off < n:
+        m = min(period, n - off)
+        cabi.check(lib.pncu_memcpy_d2d(da.ptr + off * isz, dpiece.ptr, m * isz, None), "tile")
+        off += m
+    dev.sync()
+    # a + a == 2a, a * a, a > a == 0, a / a == 1: check by reductions on the device
+    two = dev.binary("ADD", da, da)
+    full, rem = divmod(n, 253)
+    s_period = sum(range(1, 254))
+    exact_sum = full * s_period + sum(range(1, rem + 1))
+    if dt in ("int32", "int64"):
+        got = int(dev.reduce("ADD", two).to_host()[0])
+        want = (2 * exact_sum) % (1 << (8 * isz))
+        assert got % (1 << (8 * isz)) == want
+    else:
+        got = float(dev.reduce("ADD", two).to_host()[0])
+        assert abs(got - 2 * exact_sum) <= 2.0 ** -22 * 2 * exact_sum
+    assert dev.reduce("MAX", two).to_host()[0] == 506 and dev.reduce("MIN", two).to_host()[0] == 2
+    gt = dev.compare("GT", two, da)            # 2a > a everywhere
+    assert dev.reduce("MIN", gt).to_host()[0] == 1
+    eq = dev.compare("GT", da, da)             # a > a nowhere
+    assert dev.reduce("MAX", eq).to_host()[0] == 0
+    sq = dev.binary("MUL", da, da)
+    assert dev.reduce("MAX", sq).to_host()[0] == 253 * 253
+    assert dev.argminmax(0, sq).to_host()[0] == 252     # first a == 253
+    assert dev.argminmax(1, sq).to_host()[0] == 0
+    if dt in ("float32", "float64"):
+        one = dev.binary("DIV", da, da)
+        assert dev.reduce("MIN", one).to_host()[0] == 1 and dev.reduce("MAX", one).to_host()[0] == 1
+        r = dev.unary("SQRT", sq)                        # sqrt(a*a) == a exactly
+        d = dev.binary("SUB", r, da)
+        assert dev.reduce("MAX", d).to_host()[0] == 0 and dev.reduce("MIN", d).to_host()[0] == 0
+    else:
+        q = dev.int_true_divide(two, da)
+        assert dev.reduce("MIN", q).to_host()[0] == 2.0 and dev.reduce("MAX", q).to_host()[0] == 2.0
