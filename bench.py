@@ -142,7 +142,7 @@ class ClockSampler:
     def __init__(self, index):
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                        "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -236,13 +236,17 @@ def run_cuda(args):
         for _, _, fn in ops:
             fn()
 
+    # clocks are sampled from before the warm-up to the end of the timed region (nvidia-smi needs a
+    # few hundred ms to start; the warm-up steps are the same load)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(0.5)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     # per-launch events inside the timed region (cheap; give the per-kernel table and the roofline)
     ev = [[dev.Timer() for _ in ops] for _ in range(args.steps)]
     whole = dev.Timer()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.pncu_launch_count()
     whole.start(stream)
     for k in range(args.steps):

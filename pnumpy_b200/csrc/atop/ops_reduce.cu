@@ -522,6 +522,14 @@ bool lookup_reduce(int func, int t, ReduceOps* o) {
         case PNCU_MIN: PNCU_MINMAX_CASES(MinR)
         case PNCU_MAX: PNCU_MINMAX_CASES(MaxR)
 #undef PNCU_MINMAX_CASES
+        // bool any()/all() arrive as logical_or / logical_and reductions (the reference has no fast
+        // body for them and threads NumPy's loop; the OR / AND folds above are the same thing)
+        case PNCU_LOGICAL_OR: case PNCU_BITWISE_OR:
+            if (t == PNCU_BOOL) { *o = make_ops<AnyR>(); return true; }
+            return false;
+        case PNCU_LOGICAL_AND: case PNCU_BITWISE_AND:
+            if (t == PNCU_BOOL) { *o = make_ops<AllR>(); return true; }
+            return false;
     }
     return false;
 }

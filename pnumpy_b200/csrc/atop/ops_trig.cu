@@ -32,24 +32,30 @@ namespace {
 #define FA(a, b) __fadd_rn((a), (b))
 #define FS(a, b) __fsub_rn((a), (b))
 
+// The kernels are instruction-issue bound, not HBM bound (about 45 issue slots per element in a
+// literal transcription, profiles/r01_sweep.md), so each function has a lean FAST path that is the
+// same arithmetic with the non-arithmetic glue made cheap, and a general path for the rare rest:
+//   * float<->int conversions (F2I/I2F/FRND issue at quarter rate) are replaced by exact
+//     "magic number" adds: for 0 <= v < 2^22, __fadd_rz(v, 2^23) = 2^23 + trunc(v) exactly, its low
+//     mantissa bits ARE the integer, and (2^23 + j) - 2^23 = (float)j exactly;
+//   * sin/cos evaluate ONE Horner chain with per-lane selected coefficients instead of both
+//     polynomials; every retained operation has the same operands in the same order as the
+//     reference's, so the rounded results are identical (the discarded polynomial never
+//     influenced the result);
+//   * all edge-case tests collapse into one range test that sends the lane to the general path.
+
 // ---- log ---------------------------------------------------------------------------------
-// avx_mathfun.h:177-248
-__device__ __forceinline__ float cephes_logf(float x) {
-    if (!(x > 0.0f)) return (x == 0.0f) ? -INFINITY : NAN;  // +-0 -> -inf; negative, NaN -> NaN
-    if (x == INFINITY) return INFINITY;
-    int eadj = 0;
-    if (x < FLT_MIN) {  // denormal: rescale exactly by 2^23 (the reference clamps to FLT_MIN)
-        x = FM(x, 8388608.0f);
-        eadj = -23;
-    }
+// avx_mathfun.h:177-248.  `x` positive, finite and normal on entry; eadj = 0, or -23 for a rescaled denormal.
+__device__ __forceinline__ float cephes_log_core(float x, float ebias) {
     const unsigned bits = __float_as_uint(x);
-    int imm0 = (int)(bits >> 23) - 0x7f + eadj;
+    // (float)((bits >> 23) - 127) + 1 and the later "- 1 if mantissa < sqrt(1/2)" are sums of small
+    // integers, exact in any order: fold them into one subtraction from the magic value 2^23 + E.
+    const float emagic = __uint_as_float(0x4B000000u | (bits >> 23));
     x = __uint_as_float((bits & 0x807fffffu) | 0x3f000000u);  // mantissa in [0.5, 1)
-    float e = FA((float)imm0, 1.0f);
-    const bool lt = x < 0.707106781186547524f;  // cephes_SQRTHF
+    const bool lt = x < 0.707106781186547524f;                // cephes_SQRTHF
+    const float e = FS(emagic, lt ? FA(8388735.0f, ebias) : FA(8388734.0f, ebias));
     const float tmp0 = lt ? x : 0.0f;
     x = FS(x, 1.0f);
-    e = FS(e, lt ? 1.0f : 0.0f);
     x = FA(x, tmp0);
     const float z = FM(x, x);
     float y = 7.0376836292E-2f;
@@ -72,16 +78,21 @@ __device__ __forceinline__ float cephes_logf(float x) {
     x = FA(x, tmp);
     return x;
 }
+__device__ __noinline__ float cephes_log_general(float x) {
+    if (!(x > 0.0f)) return (x == 0.0f) ? -INFINITY : NAN;  // +-0 -> -inf; negative, NaN -> NaN
+    if (x == INFINITY) return INFINITY;
+    // denormal: rescale exactly by 2^23 (the reference clamps to FLT_MIN instead)
+    return cephes_log_core(FM(x, 8388608.0f), 23.0f);
+}
+__device__ __forceinline__ float cephes_logf(float x) {
+    // positive normal finite <=> bits in [0x00800000, 0x7f800000)
+    if (__float_as_uint(x) - 0x00800000u >= 0x7f000000u) return cephes_log_general(x);
+    return cephes_log_core(x, 0.0f);
+}
 
 // ---- exp ---------------------------------------------------------------------------------
 // avx_mathfun.h:354-409
-__device__ __forceinline__ float cephes_expf(float x) {
-    if (x != x) return x;
-    if (x > 88.72283935546875f) return INFINITY;  // > log(FLT_MAX)
-    if (x < -103.98f) return 0.0f;                // < log(2^-150): rounds to +0
-    float fx = FM(x, 1.44269504088896341f);       // cephes_LOG2EF
-    fx = FA(fx, 0.5f);
-    fx = floorf(fx);
+__device__ __forceinline__ float cephes_exp_poly(float x, float fx) {
     float tmp = FM(fx, 0.693359375f);             // cephes_exp_C1
     float z = FM(fx, -2.12194440e-4f);            // cephes_exp_C2
     x = FS(x, tmp);
@@ -96,21 +107,45 @@ __device__ __forceinline__ float cephes_expf(float x) {
     y = FM(y, z);
     y = FA(y, x);
     y = FA(y, 1.0f);
+    return y;
+}
+__device__ __noinline__ float cephes_exp_general(float x) {
+    if (x != x) return x;
+    if (x > 88.72283935546875f) return INFINITY;  // > log(FLT_MAX)
+    if (x < -103.98f) return 0.0f;                // < log(2^-150): rounds to +0
+    float fx = FM(x, 1.44269504088896341f);       // cephes_LOG2EF
+    fx = FA(fx, 0.5f);
+    fx = floorf(fx);
+    float y = cephes_exp_poly(x, fx);
     const int n = (int)fx;
     if (n > 127) {  // the reference clamps x to 88.376 instead (avx_mathfun.h:360)
         y = FM(y, __uint_as_float((unsigned)(n - 1 + 0x7f) << 23));
         return FM(y, 2.0f);
     }
-    if (n < -126) {  // denormal result: scale in two exact/once-rounded steps
+    if (n < -126) {  // denormal result: scale in two exact / once-rounded steps
         y = FM(y, __uint_as_float((unsigned)(n + 24 + 0x7f) << 23));
         return FM(y, 5.9604644775390625e-08f);  // 2^-24
     }
     return FM(y, __uint_as_float((unsigned)(n + 0x7f) << 23));
 }
+__device__ __forceinline__ float cephes_expf(float x) {
+    if (!(fabsf(x) <= 87.0f)) return cephes_exp_general(x);  // n stays within [-126, 126]
+    float v = FM(x, 1.44269504088896341f);
+    v = FA(v, 0.5f);
+    // floor(v) by a round-down add of 1.5 * 2^23: t = 1.5*2^23 + floor(v) exactly, |v| < 2^22
+    const float t = __fadd_rd(v, 12582912.0f);
+    const float fx = FS(t, 12582912.0f);
+    const float y = cephes_exp_poly(x, fx);
+    // bits(t) = 0x4B400000 + floor(v)  ->  2^n = (n + 127) << 23
+    const unsigned pow2n = (__float_as_uint(t) - 0x4B400000u + 0x7fu) << 23;
+    return FM(y, __uint_as_float(pow2n));
+}
 
 // ---- sin / cos -----------------------------------------------------------------------------
-// shared tail of avx_mathfun.h:558-600 and :632-672
-__device__ __forceinline__ float cephes_sincos_tail(float x, float y, bool sin_poly, unsigned sign) {
+// avx_mathfun.h:506-601 (sin256_ps) and :604-673 (cos256_ps).
+// `jb` carries j in its low bits (the exponent bits of the magic float above them are harmless:
+// only bits 1 and 2 are ever tested).
+__device__ __forceinline__ float cephes_sincos_core(float x, float y, bool sin_poly, unsigned sign) {
     // extended precision modular arithmetic: x = ((x - y*DP1) - y*DP2) - y*DP3
     const float x1 = FM(y, -0.78515625f);
     const float x2 = FM(y, -2.4187564849853515625e-4f);
@@ -119,48 +154,42 @@ __device__ __forceinline__ float cephes_sincos_tail(float x, float y, bool sin_p
     x = FA(x, x2);
     x = FA(x, x3);
     const float z = FM(x, x);
-    float c = 2.443315711809948E-005f;  // coscof
-    c = FM(c, z); c = FA(c, -1.388731625493765E-003f);
-    c = FM(c, z); c = FA(c, 4.166664568298827E-002f);
-    c = FM(c, z);
-    c = FM(c, z);
-    c = FS(c, FM(z, 0.5f));
-    c = FA(c, 1.0f);
-    float s = -1.9515295891E-4f;  // sincof
-    s = FM(s, z); s = FA(s, 8.3321608736E-3f);
-    s = FM(s, z); s = FA(s, -1.6666654611E-1f);
-    s = FM(s, z);
-    s = FM(s, x);
-    s = FA(s, x);
-    // and / andnot / add select of the reference: the unselected operand contributes +0.0
-    const float r = sin_poly ? FA(0.0f, s) : FA(c, 0.0f);
-    return __uint_as_float(__float_as_uint(r) ^ sign);
+    // one Horner chain, coefficients of the polynomial this lane needs:
+    //   cos: ((c0 z + c1) z + c2) z * z - z/2 + 1      sin: ((s0 z + s1) z + s2) z * x + x
+    float t = sin_poly ? -1.9515295891E-4f : 2.443315711809948E-005f;
+    t = FM(t, z); t = FA(t, sin_poly ? 8.3321608736E-3f : -1.388731625493765E-003f);
+    t = FM(t, z); t = FA(t, sin_poly ? -1.6666654611E-1f : 4.166664568298827E-002f);
+    t = FM(t, z);
+    t = FM(t, sin_poly ? x : z);
+    // cos: t - z*0.5 == t + z*(-0.5) exactly;  the reference's and/andnot/add select then adds +0.0
+    // to the chosen polynomial: a no-op for cos (its value is >= 0.7), "+ 0.0" for sin
+    t = FA(t, sin_poly ? x : FM(z, -0.5f));
+    t = FA(t, sin_poly ? 0.0f : 1.0f);
+    return __uint_as_float(__float_as_uint(t) ^ sign);
 }
+__device__ __noinline__ float sin_general(float x) { return sinf(x); }
+__device__ __noinline__ float cos_general(float x) { return cosf(x); }
 
 __device__ __forceinline__ float cephes_sinf(float xin) {
     const float x = fabsf(xin);
-    if (!(x <= 8192.0f)) return sinf(xin);  // outside the documented Cephes range, inf, NaN
-    unsigned sign = __float_as_uint(xin) & 0x80000000u;
-    float y = FM(x, 1.27323954473516f);  // 4/pi
-    int j = (int)y;                      // cvttps
-    j = (j + 1) & ~1;
-    y = (float)j;
-    sign ^= ((unsigned)(j & 4)) << 29;
-    const bool sin_poly = (j & 2) == 0;
-    return cephes_sincos_tail(x, y, sin_poly, sign);
+    if (!(x <= 8192.0f)) return sin_general(xin);  // outside the documented Cephes range, inf, NaN
+    // j = ((int)y + 1) & ~1 ;  y = (float)j      (y < 2^14 here)
+    const float yt = __fadd_rz(FM(x, 1.27323954473516f), 8388608.0f);   // 2^23 + trunc(x * 4/pi)
+    const unsigned jb = (__float_as_uint(yt) + 1u) & ~1u;
+    const float y = FS(__uint_as_float(jb), 8388608.0f);
+    const unsigned sign = (__float_as_uint(xin) & 0x80000000u) ^ ((jb & 4u) << 29);
+    return cephes_sincos_core(x, y, (jb & 2u) == 0u, sign);
 }
 
 __device__ __forceinline__ float cephes_cosf(float xin) {
     const float x = fabsf(xin);
-    if (!(x <= 8192.0f)) return cosf(xin);
-    float y = FM(x, 1.27323954473516f);
-    int j = (int)y;
-    j = (j + 1) & ~1;
-    y = (float)j;
-    j -= 2;
-    const unsigned sign = ((unsigned)(~j & 4)) << 29;
-    const bool sin_poly = (j & 2) == 0;
-    return cephes_sincos_tail(x, y, sin_poly, sign);
+    if (!(x <= 8192.0f)) return cos_general(xin);
+    const float yt = __fadd_rz(FM(x, 1.27323954473516f), 8388608.0f);
+    unsigned jb = (__float_as_uint(yt) + 1u) & ~1u;
+    const float y = FS(__uint_as_float(jb), 8388608.0f);
+    jb -= 2u;  // low three bits behave exactly as two's-complement j - 2
+    const unsigned sign = (~jb & 4u) << 29;
+    return cephes_sincos_core(x, y, (jb & 2u) == 0u, sign);
 }
 
 #undef FM
