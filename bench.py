@@ -338,8 +338,19 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
     rows = []
     for dt in ("float32", "float64"):
         a, b, o, ob, _ = byname[dt]
+        # input ranges of SURVEY.md 8d: sin uniform in [-8192, 8192] (the documented Cephes range),
+        # log on (0, 1e6], exp on [-80, 80]; sqrt on the sweep's [1, 254) data.  `b` is refilled in place.
+        lo_hi = {"sin": (-8192.0, 8192.0), "log": (1e-6, 1e6), "exp": (-80.0, 80.0), "sqrt": None}
         for name, op in (("sin", "SIN"), ("log", "LOG"), ("exp", "EXP"), ("sqrt", "SQRT")):
-            src = a  # values in [1, 254): in range for every function
+            src = a
+            if lo_hi[name] is not None:
+                piece = np.random.default_rng(5).uniform(lo_hi[name][0], lo_hi[name][1], 1 << 22).astype(dt)
+                dp = dev.to_device(piece)
+                for off in range(0, n, piece.size):
+                    cabi.check(lib.pncu_memcpy_d2d(b.ptr + off * piece.itemsize, dp.ptr, piece.nbytes, None), "fill")
+                dev.sync()
+                dp.free()
+                src = b
             ms = timeit(lambda: dev.unary(op, src, out=o, stream=stream))
             rows.append((name, dt, ms))
         ms = timeit(lambda: dev.unary("ISNAN", a, out=ob, stream=stream))

@@ -121,6 +121,10 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 enum Layout { LAY_VV = 0, LAY_SV = 1, LAY_VS = 2 };
 
+// unary functors may offer a two-element form: static void apply2(In, In, Out&, Out&)
+template <class F, class = void> struct has_apply2 { static constexpr bool value = false; };
+template <class F> struct has_apply2<F, decltype((void)&F::apply2)> { static constexpr bool value = true; };
+
 constexpr int EW_BLOCK = 256;   // threads per CTA == vectors per tile
 constexpr int EW_VEC_BYTES = 32;
 
@@ -195,8 +199,19 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
         const Pack<In, EPV> ra = ld_pack<In, EPV>(a + e0);
         Pack<Out, EPV> r;
         r.zero();
+        if constexpr (has_apply2<F>::value) {
+            // two elements per instruction (packed f32x2 math, see ops_trig.cu)
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
+            for (int e = 0; e < EPV; e += 2) {
+                Out r0, r1;
+                F::apply2(ra.get(e), ra.get(e + 1), r0, r1);
+                r.set(e, r0);
+                r.set(e + 1, r1);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
+        }
         st_pack<Out, EPV>(o + e0, r);
     }
     if (blockIdx.x == 0) {

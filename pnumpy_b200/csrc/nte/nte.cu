@@ -75,7 +75,7 @@ struct State {
                                   // min(11, cores-1), threads.h:67,891-894; per-op MaxThreads caps it at 3 or 7)
     bool threading = true;
     int64_t min_elems = 1 << 20;  // below this a PCIe round trip cannot win; the caller's loop runs
-    size_t slab_bytes = 8u << 20;
+    size_t slab_bytes = 32u << 20;  // tools/e2e_probe.py on B200: 32 MiB slabs give 75 GB/s of PCIe traffic vs 73 at 8 MiB (pinned), 43 vs 31 (pageable, 4 lanes)
     Lane lanes[kMaxLanes];
     Worker* pool[kMaxLanes] = {nullptr};
 };
