@@ -187,32 +187,58 @@ ew2_strided_kernel(const char* a, const char* b, char* o, int64_t n,
 
 // ---- unary -------------------------------------------------------------------------
 // F: struct { typedef In; typedef Out; static __device__ Out apply(In); }
+// Compute-heavy functors (sin/log/exp: ~25-40 instructions per element) set kUnroll > 1: a thread
+// then issues kUnroll 256-bit loads before its first use.  With one load per thread the time a warp
+// spends computing is time it has nothing in flight, and 64 warps/SM x 32 B no longer cover the
+// HBM latency-bandwidth product (measured: sin at 5.8 TB/s with 1 vector per thread).
+template <class F, class = void> struct unroll_of { static constexpr int value = 1; };
+template <class F> struct unroll_of<F, decltype((void)F::kUnroll)> { static constexpr int value = F::kUnroll; };
+
+template <class F, int EPV>
+__device__ __forceinline__ Pack<typename F::Out, EPV> apply_pack(const Pack<typename F::In, EPV>& ra) {
+    typedef typename F::Out Out;
+    Pack<Out, EPV> r;
+    r.zero();
+    if constexpr (has_apply2<F>::value) {
+        // two elements per instruction (packed f32x2 math, see ops_trig.cu)
+#pragma unroll
+        for (int e = 0; e < EPV; e += 2) {
+            Out r0, r1;
+            F::apply2(ra.get(e), ra.get(e + 1), r0, r1);
+            r.set(e, r0);
+            r.set(e + 1, r1);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
+    }
+    return r;
+}
+
 template <class F>
 __global__ void __launch_bounds__(EW_BLOCK)
 ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n) {
     typedef typename F::In In;
     typedef typename F::Out Out;
     constexpr int EPV = Epv<In, Out>::value;
-    const int64_t v = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x;
-    if (v < nvec) {
-        const int64_t e0 = head + v * EPV;
-        const Pack<In, EPV> ra = ld_pack<In, EPV>(a + e0);
-        Pack<Out, EPV> r;
-        r.zero();
-        if constexpr (has_apply2<F>::value) {
-            // two elements per instruction (packed f32x2 math, see ops_trig.cu)
+    constexpr int U = unroll_of<F>::value;
+    const int64_t v0 = (int64_t)blockIdx.x * (EW_BLOCK * U) + threadIdx.x;
+    if (v0 + (int64_t)(U - 1) * EW_BLOCK < nvec) {
+        Pack<In, EPV> ra[U];
 #pragma unroll
-            for (int e = 0; e < EPV; e += 2) {
-                Out r0, r1;
-                F::apply2(ra.get(e), ra.get(e + 1), r0, r1);
-                r.set(e, r0);
-                r.set(e + 1, r1);
+        for (int u = 0; u < U; ++u) ra[u] = ld_pack<In, EPV>(a + head + (v0 + (int64_t)u * EW_BLOCK) * EPV);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
+    } else {
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+            const int64_t v = v0 + (int64_t)u * EW_BLOCK;
+            if (v < nvec) {
+                const Pack<In, EPV> ra = ld_pack<In, EPV>(a + head + v * EPV);
+                st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra));
             }
-        } else {
-#pragma unroll
-            for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
         }
-        st_pack<Out, EPV>(o + e0, r);
     }
     if (blockIdx.x == 0) {
         const int64_t tail0 = head + nvec * EPV;
@@ -344,7 +370,7 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
         if (head > len) head = len;
         if (((uintptr_t)in + head * sizeof(In)) % IN_VB == 0) {
             const int64_t nvec = (len - head) / EPV;
-            ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
+            ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
             return after_launch("ew1_vec_kernel");
         }
     }

@@ -194,22 +194,29 @@ __device__ __forceinline__ float cephes_cosf(float xin) {
 
 // ---- packed pairs ------------------------------------------------------------------------------
 // Blackwell's FP32 pipe retires a 3-register FMUL/FADD every other cycle per sub-partition but has
-// packed two-lane forms (PTX fma.rn.f32x2 -> SASS FMUL2 / FADD2 / FFMA2, sm_100 only).  The
-// kernels above are bound by that pipe, so the fast paths below process TWO elements per
-// instruction.  Exactness is kept by construction: a product is fma(a, b, -0.0) and a sum is
-// fma(a, 1.0, b), each a single correctly rounded IEEE operation per lane (x*1.0 and x + -0.0 are
-// exact), which ptxas may only rewrite into the equally exact FMUL2 / FADD2.  A difference a - b is
-// fma(b, -1.0, a).  Operation order and operands are those of the scalar functions above.
+// packed two-lane forms (PTX fma.rn.f32x2 -> SASS FFMA2, sm_100 only).  The kernels above are
+// bound by that pipe, so the fast paths below process TWO elements per instruction.
+// Exactness is kept by construction: a product is fma(a, b, -0.0), a sum is fma(a, 1.0, b) and a
+// difference a - b is fma(b, -1.0, a): each is ONE correctly rounded IEEE operation per lane
+// (x*1.0 and x + -0.0 are exact).  The three constants are read from __constant__ memory so that
+// ptxas sees them as unknown run-time values: when it knew them it folded the fma's back into
+// mul/add and then CONTRACTED neighbouring pairs into a single FFMA2 (it does so for the f32x2
+// forms even under -fmad=false and explicit .rn), which changes the rounding.  With opaque
+// multiplicands no such rewrite is possible.  Operation order and operands are those of the scalar
+// functions above.
 typedef unsigned long long f2;
+__constant__ f2 k_negzero2 = 0x8000000080000000ULL;  // (-0.0f, -0.0f)
+__constant__ f2 k_one2 = 0x3f8000003f800000ULL;      // ( 1.0f,  1.0f)
+__constant__ f2 k_minusone2 = 0xbf800000bf800000ULL; // (-1.0f, -1.0f)
 __device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void un2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f2 sp2(float c) { return mk2(c, c); }
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return fma2(a, b, sp2(-0.0f)); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return fma2(a, sp2(1.0f), b); }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return fma2(b, sp2(-1.0f), a); }
-__device__ __forceinline__ f2 add2_rz(f2 a, f2 b) { f2 r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(sp2(1.0f)), "l"(b)); return r; }
-__device__ __forceinline__ f2 add2_rm(f2 a, f2 b) { f2 r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(sp2(1.0f)), "l"(b)); return r; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return fma2(a, b, k_negzero2); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return fma2(a, k_one2, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return fma2(b, k_minusone2, a); }
+__device__ __forceinline__ f2 add2_rz(f2 a, f2 b) { f2 r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(k_one2), "l"(b)); return r; }
+__device__ __forceinline__ f2 add2_rm(f2 a, f2 b) { f2 r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(k_one2), "l"(b)); return r; }
 // y = y * x + c  as two rounded operations
 __device__ __forceinline__ f2 horner2(f2 y, f2 x, float c) { return add2(mul2(y, x), sp2(c)); }
 
@@ -326,28 +333,32 @@ __device__ __forceinline__ void exp2x(float a0, float a1, float& r0, float& r1) 
 
 struct SinF32 {
     typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4;
     static __device__ __forceinline__ float apply(float a) { return cephes_sinf(a); }
     static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { sincos2<true>(a0, a1, r0, r1); }
 };
 struct CosF32 {
     typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4;
     static __device__ __forceinline__ float apply(float a) { return cephes_cosf(a); }
     static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { sincos2<false>(a0, a1, r0, r1); }
 };
 struct LogF32 {
     typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4;
     static __device__ __forceinline__ float apply(float a) { return cephes_logf(a); }
     static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { log2x(a0, a1, r0, r1); }
 };
 struct ExpF32 {
     typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4;
     static __device__ __forceinline__ float apply(float a) { return cephes_expf(a); }
     static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { exp2x(a0, a1, r0, r1); }
 };
-struct SinF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return sin(a); } };
-struct CosF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return cos(a); } };
-struct LogF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return log(a); } };
-struct ExpF64 { typedef double In; typedef double Out; static __device__ __forceinline__ double apply(double a) { return exp(a); } };
+struct SinF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return sin(a); } };
+struct CosF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return cos(a); } };
+struct LogF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return log(a); } };
+struct ExpF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return exp(a); } };
 
 }  // namespace
 
