@@ -427,6 +427,13 @@ def run_e2e(args):
     except ImportError as e:
         return {"error": str(e)}
     pn.enable()
+    # one lane per GPU at least; 4 lanes on a single GPU (the reference's main + 3 workers)
+    ndev = pn.cuda_info()["devices"]
+    extra = max(3, ndev - 1)
+    pn.thread_setworkers(extra)
+    for name in ("add", "multiply", "true_divide", "greater"):
+        for dt in SWEEP_DTYPES:
+            pn.atop_setworkers(name, np.dtype(dt).num, extra)
     n = 1 << args.e2e_lg
     rng = np.random.default_rng(99)
     arrs = {}
@@ -460,6 +467,7 @@ def run_e2e(args):
             "ms_per_step": round(dt_s * 1e3, 2), "h2d_bytes_per_step": int(info["h2d_bytes"] // reps),
             "d2h_bytes_per_step": int(info["d2h_bytes"] // reps), "gpu_calls_per_step": int(info["calls"] // reps),
             "staged_bytes_per_step": int(info["staged_bytes"] // reps), "lanes": int(info["lanes_last"]),
+            "gpus": int(info["gpus_last"]),
             "api": "numpy ufunc call -> hooked loop -> nte dispatcher (pinned host ndarrays)",
             "note": "int32/int64 true_divide reaches the hook as NumPy's buffered dd->d loop on its own pageable cast buffers"}
 
@@ -550,7 +558,7 @@ def main():
     ap.add_argument("--no-detail", action="store_true")
     ap.add_argument("--e2e-lg", type=int, default=28, help="log2 elements per operand of the end-to-end sweep")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-lg", type=int, default=25, help="log2 elements per operand of the CPU sample")
+    ap.add_argument("--cpu-lg", type=int, default=27, help="log2 elements per operand of the CPU sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
