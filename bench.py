@@ -469,7 +469,8 @@ def run_e2e(args):
             "staged_bytes_per_step": int(info["staged_bytes"] // reps), "lanes": int(info["lanes_last"]),
             "gpus": int(info["gpus_last"]),
             "api": "numpy ufunc call -> hooked loop -> nte dispatcher (pinned host ndarrays)",
-            "note": "int32/int64 true_divide reaches the hook as NumPy's buffered dd->d loop on its own pageable cast buffers"}
+            "note": "bound by the H2D direction of PCIe (2 input operands per op); int32/int64 true_divide runs through the "
+                    "added (intN,intN)->float64 loops, operands uncast"}
 
 
 # ---- the reference's threaded CPU path -----------------------------------------------------------------------

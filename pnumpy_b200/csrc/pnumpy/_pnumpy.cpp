@@ -14,6 +14,7 @@
 //     (src/pnumpy/_pnumpy.cpp:653-663, 748-759).
 // A CUDA failure is never papered over: it raises RuntimeError.
 #define NPY_NO_DEPRECATED_API NPY_1_7_API_VERSION
+#define NPY_TARGET_VERSION NPY_2_0_API_VERSION  /* PyUFunc_AddLoopFromSpec, PyDataType_GetArrFuncs */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
 #include <numpy/arrayobject.h>
@@ -214,6 +215,97 @@ static int AtopArgMinMaxMathFunction(void* data, npy_intp n, npy_intp* out_index
 }
 
 // =======================================================================================================
+// int / int -> float64 true_divide without NumPy's casts (an ADDITION; the 359 reference hooks are
+// untouched and these loops are not listed in atop_info()).
+//
+// np.true_divide has no integer loops beyond 'bb->d': for int16..int64 operands NumPy casts both
+// inputs to float64 in 8 Mi-element buffers on one CPU thread and then runs 'dd->d' -- the only
+// thing a replace-loop hook (the reference's, src/atop/ops_binary.cpp:926, or ours) ever sees.  On a
+// GPU those casts cost 20x the divide itself.  NumPy 2's public PyUFunc_AddLoopFromSpec lets us add
+// exact (intN, intN) -> float64 loops, so the operands reach the dispatcher as they are and the
+// kernel (pncu_GetIntTrueDivide: cvt.rn.f64 of both operands, div.rn.f64) produces bit-for-bit what
+// NumPy's cast + divide produce.  When atop is disabled or nte declines, the loop does what NumPy
+// would have done, with NumPy's own code: PyArray_CastRawArrays into two small float64 buffers and
+// the saved 'dd->d' loop -- no arithmetic of ours runs on the CPU.
+static int g_ExtraLoops = 0;
+
+static int int_true_divide_loop(PyArrayMethod_Context* context, char* const* data, const npy_intp* dimensions,
+                                const npy_intp* strides, NpyAuxData*) {
+    const int type_num = context->descriptors[0]->type_num;
+    const int atype = convert_dtype_to_atop[type_num];
+    const npy_intp n = dimensions[0];
+    if (g_Settings.AtopEnabled) {
+        pncu_any_two_fn fn = pncu_GetIntTrueDivide(atype);
+        int rc = fn ? nte_binary(fn, pncu_itemsize(atype), 8, data[0], data[1], data[2], (int64_t)n, (int64_t)strides[0],
+                                 (int64_t)strides[1], (int64_t)strides[2], 3)
+                    : NTE_DECLINED;
+        if (rc == 0) { ledger(CAT_BINARY, true, n); return 0; }
+        if (rc != NTE_DECLINED) { raise_cuda_error("int true_divide loop", rc); return -1; }
+    }
+    ledger(CAT_BINARY, false, n);
+    // NumPy's own path, chunk by chunk: cast, cast (PyArray_CopyInto on 1-D views), DOUBLE_true_divide
+    PyUFuncGenericFunction dd = g_UFuncLUT[PNCU_DIV][PNCU_DOUBLE].pOldFunc;
+    const npy_intp CHUNK = 65536;
+    double* buf = (double*)malloc(2 * CHUNK * sizeof(double));
+    if (!buf) return -1;
+    PyGILState_STATE st = PyGILState_Ensure();  // creating array views needs the Python C-API
+    int ret = 0;
+    for (npy_intp off = 0; off < n && ret == 0; off += CHUNK) {
+        npy_intp cnt = (n - off) < CHUNK ? (n - off) : CHUNK;
+        for (int k = 0; k < 2 && ret == 0; ++k) {
+            PyArray_Descr* src_descr = (PyArray_Descr*)context->descriptors[k];
+            Py_INCREF(src_descr);  // NewFromDescr steals a reference
+            npy_intp sstride = strides[k];
+            PyObject* src = PyArray_NewFromDescr(&PyArray_Type, src_descr, 1, &cnt, &sstride, data[k] + off * strides[k], 0, NULL);
+            npy_intp dstride = 8;
+            PyObject* dst = PyArray_NewFromDescr(&PyArray_Type, PyArray_DescrFromType(NPY_DOUBLE), 1, &cnt, &dstride,
+                                                 buf + k * CHUNK, NPY_ARRAY_WRITEABLE, NULL);
+            if (!src || !dst || PyArray_CopyInto((PyArrayObject*)dst, (PyArrayObject*)src) < 0) ret = -1;
+            Py_XDECREF(src);
+            Py_XDECREF(dst);
+        }
+        if (ret == 0) {
+            char* a3[3] = {(char*)buf, (char*)(buf + CHUNK), data[2] + off * strides[2]};
+            const npy_intp dims[1] = {cnt};
+            const npy_intp steps[3] = {8, 8, strides[2]};
+            dd(a3, dims, steps, NULL);
+        }
+    }
+    PyGILState_Release(st);
+    free(buf);
+    return ret;
+}
+
+static int register_int_true_divide(PyObject* numpy_module) {
+    if (!g_UFuncLUT[PNCU_DIV][PNCU_DOUBLE].pOldFunc) return 0;
+    PyObject* ufunc = PyObject_GetAttrString(numpy_module, "true_divide");
+    if (!ufunc) return -1;
+    PyArray_DTypeMeta* ints[] = {&PyArray_UByteDType, &PyArray_ShortDType, &PyArray_UShortDType, &PyArray_IntDType,
+                                 &PyArray_UIntDType, &PyArray_LongDType, &PyArray_ULongDType, &PyArray_LongLongDType,
+                                 &PyArray_ULongLongDType};
+    for (PyArray_DTypeMeta* dt : ints) {
+        PyArray_DTypeMeta* dtypes[3] = {dt, dt, &PyArray_DoubleDType};
+        PyType_Slot slots[] = {{NPY_METH_strided_loop, (void*)int_true_divide_loop}, {0, NULL}};
+        PyArrayMethod_Spec spec;
+        memset(&spec, 0, sizeof(spec));
+        spec.name = "pnumpy_b200_int_true_divide";
+        spec.nin = 2;
+        spec.nout = 1;
+        spec.casting = NPY_NO_CASTING;
+        spec.flags = (NPY_ARRAYMETHOD_FLAGS)0;
+        spec.dtypes = dtypes;
+        spec.slots = slots;
+        if (PyUFunc_AddLoopFromSpec(ufunc, &spec) < 0) {
+            PyErr_Clear();  // e.g. a loop for this pair already exists: leave NumPy's behaviour alone
+            continue;
+        }
+        g_ExtraLoops++;
+    }
+    Py_DECREF(ufunc);
+    return 0;
+}
+
+// =======================================================================================================
 // registration.  reference: newinit, src/pnumpy/_pnumpy.cpp:1287-1676
 static void AddToDict(const char* ufunc_name, int dtype, void* pstUFunc) {
     PyObject* key = Py_BuildValue("(si)", ufunc_name, dtype);
@@ -407,6 +499,7 @@ static PyObject* newinit(PyObject* self, PyObject* args, PyObject* kwargs) {
         }
         Py_DECREF(descr);
     }
+    if (register_int_true_divide(numpy_module) < 0) return NULL;
     Py_DECREF(numpy_module);
     g_Settings.Initialized = 1;
     Py_RETURN_NONE;
@@ -632,12 +725,12 @@ static PyObject* timer_getutc(PyObject*, PyObject*) {
 static PyObject* cuda_info(PyObject*, PyObject*) {
     nte_stats s;
     nte_get_stats(&s);
-    return Py_BuildValue("{s:i,s:s,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:i,s:i}", "devices", nte_device_count(), "device_string",
+    return Py_BuildValue("{s:i,s:s,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:i,s:i,s:i}", "devices", nte_device_count(), "device_string",
                          g_DeviceString, "min_elems", (long long)nte_get_min_elems(), "calls", (long long)s.calls, "declined",
                          (long long)s.declined, "launches", (long long)s.launches, "library_launches", (long long)pncu_launch_count(),
                          "h2d_bytes", (long long)s.h2d_bytes, "d2h_bytes", (long long)s.d2h_bytes, "staged_bytes",
                          (long long)s.staged_bytes, "lanes_last", (long long)s.lanes_last, "gpus_last", (long long)s.gpus_last,
-                         "workers", nte_get_workers(), "threading", nte_get_threading());
+                         "workers", nte_get_workers(), "threading", nte_get_threading(), "extra_loops", g_ExtraLoops);
 }
 static PyObject* cuda_reset_stats(PyObject*, PyObject*) { nte_reset_stats(); Py_RETURN_NONE; }
 static PyObject* cuda_setthreshold(PyObject*, PyObject* args) {

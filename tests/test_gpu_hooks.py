@@ -289,6 +289,39 @@ def test_ledger_counts(pn):
     assert not pn.ledger_isenabled()
 
 
+@pytest.mark.parametrize("dt", ["uint8", "int16", "uint16", "int32", "uint32", "int64", "uint64"])
+def test_int_true_divide_loops(pn, rng, dt):
+    """The added (intN, intN) -> float64 true_divide loops: operands reach the GPU uncast; the result is
+    bit-for-bit NumPy's cast-then-divide, on the GPU path, on the NumPy path (atop disabled -> NumPy's own
+    casts + its dd->d loop) and for declined layouts."""
+    assert pn.cuda_info()["extra_loops"] == 9
+    n = (1 << 20) + 5
+    a, b = fill_random(n, dt, rng), fill_random(n, dt, rng)
+    b[::7] = 0
+    a[::21] = 0  # 0/0 -> nan as well as x/0 -> inf
+    with np.errstate(all="ignore"):
+        want = a.astype(np.float64) / b.astype(np.float64)
+        pn.cuda_reset_stats()
+        got = np.true_divide(a, b)
+        info = pn.cuda_info()
+        assert info["calls"] == 1 and info["h2d_bytes"] == 2 * a.nbytes, "operands must travel uncast"
+        assert_bits_equal(got, want, f"gpu {dt}")
+        assert_bits_equal(a / b[3], a.astype(np.float64) / np.float64(b[3]), "scalar divisor")
+        assert_bits_equal(a[::2] / b[::2], want[::2].copy(), "strided -> NumPy path")
+        out = np.empty(n, np.float64)
+        np.divide(a, b, out=out)
+        assert_bits_equal(out, want, "out=")
+        pn.disable()
+        try:
+            assert_bits_equal(np.true_divide(a, b), want, f"numpy path {dt}")
+            assert_bits_equal(np.true_divide(a[:1000:3], b[:1000:3]), want[:1000:3].copy(), "numpy path strided")
+        finally:
+            pn.enable()
+        # mixed widths still promote through NumPy and land on one of the added loops or dd->d
+        other = b.astype(np.int64 if np.dtype(dt).kind == "i" else np.uint64)
+        assert_bits_equal(np.true_divide(a, other), a.astype(np.float64) / other.astype(np.float64), "mixed")
+
+
 def test_benchmark_plumbing(pn, capsys):
     """config 1 of BASELINE.json: pn.benchmark plumbing on 1 000 000 float32 elements."""
     old = pn.cuda_setthreshold(1 << 16)
