@@ -413,6 +413,24 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
     out["sharded_sum_f32"] = {"elements_total": n * world, "ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1),
                               "collective": "none (1 GPU)" if world == 1 else "one NCCL all_gather of float64 block partials",
                               "result": float(res.to_host()[0])}
+
+    # configs[4], device-resident leg: t = a*b; u = t+c; r = u.sum() as three kernels (28 B/element)
+    a, b, o = byname["float32"][0], byname["float32"][1], byname["float32"][2]
+
+    def as_f32(x):  # reuse the int32 buffers (same size) as float32 scratch
+        v = x.view(0, n)
+        v.dtype = np.dtype(np.float32)
+        return v
+    c, tt = as_f32(byname["int32"][2]), as_f32(byname["int32"][0])
+
+    def chain():
+        dev.binary("MUL", a, b, out=tt, stream=stream)
+        dev.binary("ADD", tt, c, out=o, stream=stream)
+        dev.reduce("ADD", o, out=res, stream=stream)
+    ms = timeit(chain)
+    out["chain_device_resident"] = {"expr": "t=a*b; u=t+c; u.sum()  (float32, unfused: 3 kernels + finish)", "elements": n,
+                                    "ms": round(ms, 4), "gbs": round(28.0 * n / (ms * 1e-3) / 1e9, 1),
+                                    "frac_of_8tbs": round(28.0 * n / (ms * 1e-3) / 1e9 / 8000.0, 4)}
     return out
 
 
@@ -462,8 +480,59 @@ def run_e2e(args):
         sweep()
     dt_s = (time.perf_counter() - t0) / reps
     info = pn.cuda_info()
+    # configs[4]: a*b+c then sum on pinned float32 host ndarrays (intermediates materialised on the host,
+    # as NumPy semantics require): 28 algorithmic B/element, 20 B/element over PCIe H2D, 8 D2H
+    chain = None
+    try:
+        a, b, o = arrs["float32"][0], arrs["float32"][1], arrs["float32"][2]
+        c = arrs["int32"][2].view(np.float32)
+        t = arrs["int32"][0].view(np.float32)
+
+        def run_chain():
+            np.multiply(a, b, out=t)
+            np.add(t, c, out=o)
+            return o.sum()
+        run_chain()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = run_chain()
+        ch_s = (time.perf_counter() - t0) / reps
+        chain = {"expr": "t=a*b; u=t+c; u.sum() on pinned float32 host ndarrays", "elements": n,
+                 "ms": round(ch_s * 1e3, 2), "gbs": round(28.0 * n / ch_s / 1e9, 2), "result": float(r)}
+    except Exception as e:  # pragma: no cover
+        chain = {"error": str(e)}
+    # the same hooks on DEVICE-RESIDENT ndarrays (CUDA managed memory): no PCIe in steady state
+    resident = None
+    try:
+        m = 1 << 28
+        ma, mb, mo = pn.managed_empty(m, np.float32), pn.managed_empty(m, np.float32), pn.managed_empty(m, np.float32)
+        ma[:] = arrs["float32"][0][:m]
+        mb[:] = arrs["float32"][1][:m]
+        np.add(ma, mb, out=mo)  # first call migrates the pages to the GPU
+        np.add(ma, mb, out=mo)
+        pn.cuda_reset_stats()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            np.add(ma, mb, out=mo)
+        add_s = (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        for _ in range(10):
+            np.sin(ma, out=mo)
+        sin_s = (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ssum = ma.sum()
+        sum_s = (time.perf_counter() - t0) / 10
+        ri = pn.cuda_info()
+        resident = {"what": "np.add / np.sin / ndarray.sum on managed (device-resident) float32 ndarrays, wall clock per call",
+                    "elements": m, "add_gbs": round(12.0 * m / add_s / 1e9, 1), "sin_gbs": round(8.0 * m / sin_s / 1e9, 1),
+                    "sum_gbs": round(4.0 * m / sum_s / 1e9, 1), "h2d_bytes": int(ri["h2d_bytes"]), "gpu_calls": int(ri["calls"]),
+                    "sum": float(ssum)}
+        del ma, mb, mo
+    except Exception as e:  # pragma: no cover
+        resident = {"error": str(e)}
     pn.disable()
-    return {"value": round(SWEEP_BYTES_PER_ELEM * n / dt_s / 1e9, 2), "unit": UNIT, "elements": n, "steps": reps,
+    return {"value": round(SWEEP_BYTES_PER_ELEM * n / dt_s / 1e9, 2), "unit": UNIT, "elements": n, "steps": reps, "chain": chain, "resident": resident,
             "ms_per_step": round(dt_s * 1e3, 2), "h2d_bytes_per_step": int(info["h2d_bytes"] // reps),
             "d2h_bytes_per_step": int(info["d2h_bytes"] // reps), "gpu_calls_per_step": int(info["calls"] // reps),
             "staged_bytes_per_step": int(info["staged_bytes"] // reps), "lanes": int(info["lanes_last"]),
@@ -507,7 +576,15 @@ sweep()
 ts = []
 for _ in range(reps):
     t0 = time.perf_counter(); sweep(); ts.append(time.perf_counter() - t0)
-print(json.dumps({"seconds": ts, "cores": cores, "workers": pn.thread_getworkers(), "n": n, "cpustring": pn.cpustring()}))
+a, b, o = arrs["float32"][0], arrs["float32"][1], arrs["float32"][2]
+c = b[::-1].copy(); t = np.empty(n, np.float32)
+def chain():
+    np.multiply(a, b, out=t); np.add(t, c, out=o); return o.sum()
+chain()
+cs = []
+for _ in range(reps):
+    t0 = time.perf_counter(); chain(); cs.append(time.perf_counter() - t0)
+print(json.dumps({"seconds": ts, "chain_seconds": cs, "cores": cores, "workers": pn.thread_getworkers(), "n": n, "cpustring": pn.cpustring()}))
 '''
 
 
@@ -531,7 +608,8 @@ def run_cpu_baseline(sample_lg=25, reps=3, maxthreads=1):
             "sample": f"same 16-op sweep on 2^{sample_lg} elements per operand, best of {reps} passes, pnumpy reference "
                       f"extension (oracle/_ref) enabled with thread_setworkers({d['workers']}) and atop_setworkers(.., 15): "
                       f"up to {threads} threads",
-            "ms_per_pass": round(best * 1e3, 1), "cpu": d.get("cpustring")}
+            "ms_per_pass": round(best * 1e3, 1), "cpu": d.get("cpustring"),
+            "chain_gbs": round(28.0 * d["n"] / min(d["chain_seconds"]) / 1e9, 2) if d.get("chain_seconds") else None}
 
 
 def run_reference(args):

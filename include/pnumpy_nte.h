@@ -93,6 +93,14 @@ PNCU_API int nte_argminmax(int kind, int atype, const void* in, int64_t len, int
 PNCU_API void* nte_alloc_pinned(size_t bytes);
 PNCU_API void nte_free_pinned(void* ptr);
 
+/* ---- device-resident ndarrays: CUDA managed memory -------------------------------------------------
+ * Host code (NumPy) and kernels share one pointer; pages migrate on demand.  The dispatcher runs
+ * resident operands IN PLACE (no staging, no PCIe in steady state): it prefetches managed operands
+ * to the GPU before the launch, so a ufunc chain over managed arrays touches PCIe only when the
+ * host reads a result. */
+PNCU_API void* nte_alloc_managed(size_t bytes);
+PNCU_API void nte_free_managed(void* ptr);
+
 /* ---- accounting (feeds atop_info()/ledger and the tests) ------------------------------------------- */
 typedef struct nte_stats {
     int64_t calls;          /* dispatches that ran on the GPU */

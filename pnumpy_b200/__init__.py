@@ -42,7 +42,7 @@ __all__ = [
     'argmin', 'argmax',
     # additions of this build (nothing above changes meaning)
     'cuda_info', 'cuda_reset_stats', 'cuda_setthreshold', 'cuda_getthreshold', 'cuda_setslab',
-    'pinned_empty', 'pinned_array',
+    'pinned_empty', 'pinned_array', 'managed_empty', 'managed_array',
 ]
 
 import numpy as np  # noqa: E402
@@ -63,7 +63,7 @@ from ._pnumpy import cuda_info, cuda_reset_stats, cuda_setthreshold, cuda_getthr
 
 from .cpu import cpu_count_linux, init, enable, disable  # noqa: E402
 from .benchmark import benchmark, benchmark_func  # noqa: E402
-from .pinned import pinned_empty, pinned_array  # noqa: E402
+from .pinned import pinned_empty, pinned_array, managed_empty, managed_array  # noqa: E402
 
 
 def initialize():

@@ -11,7 +11,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpnumpy_cuda.so")
+LIB_PATH = os.environ.get("PNUMPY_CUDA_LIB") or os.path.join(_HERE, "lib", "libpnumpy_cuda.so")  # env: tuning builds only
 
 # ---- vocabulary (reference: src/atop/common_inc.h:236-372) -------------------------------------
 ATOP_BOOL, ATOP_INT8, ATOP_UINT8, ATOP_INT16, ATOP_UINT16 = 0, 1, 2, 3, 4

@@ -121,9 +121,6 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 enum Layout { LAY_VV = 0, LAY_SV = 1, LAY_VS = 2 };
 
-// unary functors may offer a two-element form: static void apply2(In, In, Out&, Out&)
-template <class F, class = void> struct has_apply2 { static constexpr bool value = false; };
-template <class F> struct has_apply2<F, decltype((void)&F::apply2)> { static constexpr bool value = true; };
 
 constexpr int EW_BLOCK = 256;   // threads per CTA == vectors per tile
 constexpr int EW_VEC_BYTES = 32;
@@ -199,19 +196,8 @@ __device__ __forceinline__ Pack<typename F::Out, EPV> apply_pack(const Pack<type
     typedef typename F::Out Out;
     Pack<Out, EPV> r;
     r.zero();
-    if constexpr (has_apply2<F>::value) {
-        // two elements per instruction (packed f32x2 math, see ops_trig.cu)
 #pragma unroll
-        for (int e = 0; e < EPV; e += 2) {
-            Out r0, r1;
-            F::apply2(ra.get(e), ra.get(e + 1), r0, r1);
-            r.set(e, r0);
-            r.set(e + 1, r1);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
-    }
+    for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
     return r;
 }
 

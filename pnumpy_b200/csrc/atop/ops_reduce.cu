@@ -281,7 +281,6 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
     constexpr int NONE = 0x7fffffff;
     __shared__ W smem_v[RED_THREADS / 32];
     __shared__ int smem_i[RED_THREADS / 32];
-    __shared__ W bcast;
 
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
@@ -301,29 +300,53 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
     } else {
         for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) m = ext_nan<W, IS_MAX>(m, (W)p[i]);
     }
-    m = block_fold<ExtR<T, IS_MAX>, RED_THREADS>(m, smem_v);
-    if (threadIdx.x == 0) bcast = m;
+    // block extreme with ONE barrier: shuffle tree per warp, leaders to shared memory, then every
+    // thread folds the eight warp values itself (same order everywhere -> same value everywhere)
+    const W m_thread = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = ext_nan<W, IS_MAX>(m, Shfl<W>::down(m, o));
+    if ((threadIdx.x & 31) == 0) smem_v[threadIdx.x >> 5] = m;
     __syncthreads();
-    const W mb = bcast;
-    const bool want_nan = is_fp<T>::value && (mb != mb);
+    W mb = smem_v[0];
+#pragma unroll
+    for (int w = 1; w < RED_THREADS / 32; ++w) mb = ext_nan<W, IS_MAX>(mb, smem_v[w]);
+    bool want_nan = false;
+    if constexpr (is_fp<T>::value) want_nan = mb != mb;
 
+    // phase B only in the threads whose own extreme IS the block extreme (usually one thread of one
+    // warp): they scan their registers for its first occurrence
     int local = NONE;
-    if (full) {
-        int c = NONE;  // scan downwards so the smallest matching position survives
+    bool mine = want_nan ? false : (m_thread == mb);
+    if constexpr (is_fp<T>::value) mine = want_nan ? (m_thread != m_thread) : mine;
+    if (mine) {
+        if (full) {
+            int c = NONE;  // scan downwards so the smallest matching position survives
+            if (want_nan) {
+                if constexpr (is_fp<T>::value) {
 #pragma unroll
-        for (int j = RED_NV - 1; j >= 0; --j)
+                    for (int j = RED_NV - 1; j >= 0; --j)
 #pragma unroll
-            for (int e = EPV - 1; e >= 0; --e) {
-                const W x = (W)r[j].get(e);
-                const bool hit = want_nan ? (x != x) : (x == mb);
-                c = hit ? (j * RED_THREADS * EPV + e) : c;
+                        for (int e = EPV - 1; e >= 0; --e) {
+                            const W x = (W)r[j].get(e);
+                            c = (x != x) ? (j * RED_THREADS * EPV + e) : c;
+                        }
+                }
+            } else {
+#pragma unroll
+                for (int j = RED_NV - 1; j >= 0; --j)
+#pragma unroll
+                    for (int e = EPV - 1; e >= 0; --e) {
+                        const W x = (W)r[j].get(e);
+                        c = (x == mb) ? (j * RED_THREADS * EPV + e) : c;
+                    }
             }
-        if (c != NONE) local = c + (int)threadIdx.x * EPV;
-    } else {
-        for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) {
-            const W x = (W)p[i];
-            const bool hit = want_nan ? (x != x) : (x == mb);
-            if (hit && (int)i < local) local = (int)i;
+            if (c != NONE) local = c + (int)threadIdx.x * EPV;
+        } else {
+            for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) {
+                const W x = (W)p[i];
+                const bool hit = want_nan ? (x != x) : (x == mb);
+                if (hit && (int)i < local) local = (int)i;
+            }
         }
     }
     local = block_fold<IdxMinR, RED_THREADS>(local, smem_i);

@@ -192,169 +192,23 @@ __device__ __forceinline__ float cephes_cosf(float xin) {
     return cephes_sincos_core(x, y, (jb & 2u) == 0u, sign);
 }
 
-// ---- packed pairs ------------------------------------------------------------------------------
-// Blackwell's FP32 pipe retires a 3-register FMUL/FADD every other cycle per sub-partition but has
-// packed two-lane forms (PTX fma.rn.f32x2 -> SASS FFMA2, sm_100 only).  The kernels above are
-// bound by that pipe, so the fast paths below process TWO elements per instruction.
-// Exactness is kept by construction: a product is fma(a, b, -0.0), a sum is fma(a, 1.0, b) and a
-// difference a - b is fma(b, -1.0, a): each is ONE correctly rounded IEEE operation per lane
-// (x*1.0 and x + -0.0 are exact).  The three constants are read from __constant__ memory so that
-// ptxas sees them as unknown run-time values: when it knew them it folded the fma's back into
-// mul/add and then CONTRACTED neighbouring pairs into a single FFMA2 (it does so for the f32x2
-// forms even under -fmad=false and explicit .rn), which changes the rounding.  With opaque
-// multiplicands no such rewrite is possible.  Operation order and operands are those of the scalar
-// functions above.
-typedef unsigned long long f2;
-__constant__ f2 k_negzero2 = 0x8000000080000000ULL;  // (-0.0f, -0.0f)
-__constant__ f2 k_one2 = 0x3f8000003f800000ULL;      // ( 1.0f,  1.0f)
-__constant__ f2 k_minusone2 = 0xbf800000bf800000ULL; // (-1.0f, -1.0f)
-__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void un2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f2 sp2(float c) { return mk2(c, c); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return fma2(a, b, k_negzero2); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return fma2(a, k_one2, b); }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return fma2(b, k_minusone2, a); }
-__device__ __forceinline__ f2 add2_rz(f2 a, f2 b) { f2 r; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(k_one2), "l"(b)); return r; }
-__device__ __forceinline__ f2 add2_rm(f2 a, f2 b) { f2 r; asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(k_one2), "l"(b)); return r; }
-// y = y * x + c  as two rounded operations
-__device__ __forceinline__ f2 horner2(f2 y, f2 x, float c) { return add2(mul2(y, x), sp2(c)); }
-
-template <bool IS_SIN>
-__device__ __forceinline__ void sincos2(float a0, float a1, float& r0, float& r1) {
-    const float x0 = fabsf(a0), x1 = fabsf(a1);
-    if (!(x0 <= 8192.0f && x1 <= 8192.0f)) {
-        r0 = IS_SIN ? cephes_sinf(a0) : cephes_cosf(a0);
-        r1 = IS_SIN ? cephes_sinf(a1) : cephes_cosf(a1);
-        return;
-    }
-    f2 x = mk2(x0, x1);
-    const f2 yt = add2_rz(mul2(x, sp2(1.27323954473516f)), sp2(8388608.0f));  // 2^23 + trunc(x * 4/pi)
-    float yt0, yt1;
-    un2(yt, yt0, yt1);
-    unsigned j0 = (__float_as_uint(yt0) + 1u) & ~1u, j1 = (__float_as_uint(yt1) + 1u) & ~1u;
-    const f2 y = sub2(mk2(__uint_as_float(j0), __uint_as_float(j1)), sp2(8388608.0f));
-    unsigned s0, s1;
-    if (IS_SIN) {
-        s0 = (__float_as_uint(a0) ^ (j0 << 29)) & 0x80000000u;  // sign(x) ^ (j & 4)
-        s1 = (__float_as_uint(a1) ^ (j1 << 29)) & 0x80000000u;
-    } else {
-        j0 -= 2u; j1 -= 2u;
-        s0 = (~j0 << 29) & 0x80000000u;
-        s1 = (~j1 << 29) & 0x80000000u;
-    }
-    const bool p0 = (j0 & 2u) == 0u, p1 = (j1 & 2u) == 0u;  // true: sine polynomial
-    x = add2(x, mul2(y, sp2(-0.78515625f)));
-    x = add2(x, mul2(y, sp2(-2.4187564849853515625e-4f)));
-    x = add2(x, mul2(y, sp2(-3.77489497744594108e-8f)));
-    const f2 z = mul2(x, x);
-    float xr0, xr1, z0, z1;
-    un2(x, xr0, xr1);
-    un2(z, z0, z1);
-    f2 t = mk2(p0 ? -1.9515295891E-4f : 2.443315711809948E-005f, p1 ? -1.9515295891E-4f : 2.443315711809948E-005f);
-    t = add2(mul2(t, z), mk2(p0 ? 8.3321608736E-3f : -1.388731625493765E-003f, p1 ? 8.3321608736E-3f : -1.388731625493765E-003f));
-    t = add2(mul2(t, z), mk2(p0 ? -1.6666654611E-1f : 4.166664568298827E-002f, p1 ? -1.6666654611E-1f : 4.166664568298827E-002f));
-    t = mul2(t, z);
-    t = mul2(t, mk2(p0 ? xr0 : z0, p1 ? xr1 : z1));
-    float h0, h1;
-    un2(mul2(z, sp2(-0.5f)), h0, h1);
-    t = add2(t, mk2(p0 ? xr0 : h0, p1 ? xr1 : h1));
-    t = add2(t, mk2(p0 ? 0.0f : 1.0f, p1 ? 0.0f : 1.0f));
-    float t0, t1;
-    un2(t, t0, t1);
-    r0 = __uint_as_float(__float_as_uint(t0) ^ s0);
-    r1 = __uint_as_float(__float_as_uint(t1) ^ s1);
-}
-
-__device__ __forceinline__ void log2x(float a0, float a1, float& r0, float& r1) {
-    const unsigned b0 = __float_as_uint(a0), b1 = __float_as_uint(a1);
-    if (b0 - 0x00800000u >= 0x7f000000u || b1 - 0x00800000u >= 0x7f000000u) {  // not both positive normal
-        r0 = cephes_logf(a0);
-        r1 = cephes_logf(a1);
-        return;
-    }
-    const float m0 = __uint_as_float((b0 & 0x807fffffu) | 0x3f000000u), m1 = __uint_as_float((b1 & 0x807fffffu) | 0x3f000000u);
-    const bool lt0 = m0 < 0.707106781186547524f, lt1 = m1 < 0.707106781186547524f;
-    const f2 e = sub2(mk2(__uint_as_float(0x4B000000u | (b0 >> 23)), __uint_as_float(0x4B000000u | (b1 >> 23))),
-                      mk2(lt0 ? 8388735.0f : 8388734.0f, lt1 ? 8388735.0f : 8388734.0f));
-    f2 x = sub2(mk2(m0, m1), sp2(1.0f));
-    x = add2(x, mk2(lt0 ? m0 : 0.0f, lt1 ? m1 : 0.0f));
-    const f2 z = mul2(x, x);
-    f2 y = sp2(7.0376836292E-2f);
-    y = horner2(y, x, -1.1514610310E-1f);
-    y = horner2(y, x, 1.1676998740E-1f);
-    y = horner2(y, x, -1.2420140846E-1f);
-    y = horner2(y, x, +1.4249322787E-1f);
-    y = horner2(y, x, -1.6668057665E-1f);
-    y = horner2(y, x, +2.0000714765E-1f);
-    y = horner2(y, x, -2.4999993993E-1f);
-    y = horner2(y, x, +3.3333331174E-1f);
-    y = mul2(y, x);
-    y = mul2(y, z);
-    y = add2(y, mul2(e, sp2(-2.12194440e-4f)));
-    y = sub2(y, mul2(z, sp2(0.5f)));
-    x = add2(x, y);
-    x = add2(x, mul2(e, sp2(0.693359375f)));
-    un2(x, r0, r1);
-}
-
-__device__ __forceinline__ void exp2x(float a0, float a1, float& r0, float& r1) {
-    if (!(fabsf(a0) <= 87.0f && fabsf(a1) <= 87.0f)) {
-        r0 = cephes_expf(a0);
-        r1 = cephes_expf(a1);
-        return;
-    }
-    f2 x = mk2(a0, a1);
-    const f2 v = add2(mul2(x, sp2(1.44269504088896341f)), sp2(0.5f));
-    const f2 t = add2_rm(v, sp2(12582912.0f));  // 1.5 * 2^23 + floor(v)
-    const f2 fx = sub2(t, sp2(12582912.0f));
-    x = sub2(x, mul2(fx, sp2(0.693359375f)));
-    x = sub2(x, mul2(fx, sp2(-2.12194440e-4f)));
-    const f2 z = mul2(x, x);
-    f2 y = sp2(1.9875691500E-4f);
-    y = horner2(y, x, 1.3981999507E-3f);
-    y = horner2(y, x, 8.3334519073E-3f);
-    y = horner2(y, x, 4.1665795894E-2f);
-    y = horner2(y, x, 1.6666665459E-1f);
-    y = horner2(y, x, 5.0000001201E-1f);
-    y = mul2(y, z);
-    y = add2(y, x);
-    y = add2(y, sp2(1.0f));
-    float t0, t1;
-    un2(t, t0, t1);
-    const unsigned p0 = (__float_as_uint(t0) - 0x4B400000u + 0x7fu) << 23, p1 = (__float_as_uint(t1) - 0x4B400000u + 0x7fu) << 23;
-    y = mul2(y, mk2(__uint_as_float(p0), __uint_as_float(p1)));
-    un2(y, r0, r1);
-}
-
 #undef FM
 #undef FA
 #undef FS
 
-struct SinF32 {
-    typedef float In; typedef float Out;
-    static constexpr int kUnroll = 4;
-    static __device__ __forceinline__ float apply(float a) { return cephes_sinf(a); }
-    static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { sincos2<true>(a0, a1, r0, r1); }
-};
-struct CosF32 {
-    typedef float In; typedef float Out;
-    static constexpr int kUnroll = 4;
-    static __device__ __forceinline__ float apply(float a) { return cephes_cosf(a); }
-    static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { sincos2<false>(a0, a1, r0, r1); }
-};
-struct LogF32 {
-    typedef float In; typedef float Out;
-    static constexpr int kUnroll = 4;
-    static __device__ __forceinline__ float apply(float a) { return cephes_logf(a); }
-    static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { log2x(a0, a1, r0, r1); }
-};
-struct ExpF32 {
-    typedef float In; typedef float Out;
-    static constexpr int kUnroll = 4;
-    static __device__ __forceinline__ float apply(float a) { return cephes_expf(a); }
-    static __device__ __forceinline__ void apply2(float a0, float a1, float& r0, float& r1) { exp2x(a0, a1, r0, r1); }
-};
+// Loads in flight per thread matter as much as the instruction count: with one 32-byte load per
+// thread a warp that is computing has nothing in flight, and 64 warps/SM x 32 B no longer cover the
+// HBM latency-bandwidth product (sin: 5.8 TB/s at kUnroll 1, 6.7 at 4, 5.8 again at 8 where the
+// registers cut occupancy).  Measured with tools/time_unary.py, 2^28 elements, B200:
+//   kUnroll 4: sin 6.72, cos 6.73, exp 6.66, log 6.42 TB/s.
+// A packed two-lane variant (PTX fma.rn.f32x2 -> FFMA2, products as fma(a,b,-0.0), sums as
+// fma(a,1.0,b) with the constants hidden in __constant__ memory so that ptxas cannot re-fold and
+// then CONTRACT the pairs -- it does, even under -fmad=false) was bit-exact but no faster: FFMA2
+// retires two lanes at the cost of two scalar instructions on this part.  It was removed.
+struct SinF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_sinf(a); } };
+struct CosF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_cosf(a); } };
+struct LogF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_logf(a); } };
+struct ExpF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_expf(a); } };
 struct SinF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return sin(a); } };
 struct CosF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return cos(a); } };
 struct LogF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return log(a); } };

@@ -395,18 +395,49 @@ int decline() { g_stats.declined += 1; return NTE_DECLINED; }
 bool host_kind(int pk) { return pk == PK_PAGEABLE || pk == PK_PINNED; }
 
 // operands that already live in device / managed memory: run in place on that GPU, no PCIe
-int run_resident(Job& j) {
-    int dev = 0;
+// the GPU a resident pointer belongs to (managed memory: wherever it was last prefetched, else GPU 0)
+int device_of(const void* p) {
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, j.out) == cudaSuccess && at.device >= 0) dev = at.device; else cudaGetLastError();
-    int rc = ensure_lane(dev % g.ndev);
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.device >= 0 && at.device < g.ndev) return at.device;
+    cudaGetLastError();
+    return 0;
+}
+
+// managed operands: make the pages resident on the GPU before the kernel touches them, otherwise the
+// kernel demand-faults them over PCIe at a fraction of the copy rate.  A no-op once they are there.
+int prefetch_managed(const void* p, int pk, size_t bytes, Lane& L) {
+    if (pk != PK_MANAGED || !bytes) return 0;
+    PNCU_CUDA(cudaMemPrefetchAsync(p, bytes, L.device, L.s_k));
+    return 0;
+}
+
+int run_resident(Job& j) {
+    const int dev = device_of(j.out);
+    int rc = ensure_lane(dev);
     if (rc) return rc;
-    Lane& L = g.lanes[dev % g.ndev];
+    Lane& L = g.lanes[dev];
     PNCU_CUDA(cudaSetDevice(L.device));
-    if (j.kind == JOB_BINARY)
-        rc = j.fn2(j.in1, j.in2, j.out, j.len, j.s1, j.s2, j.isz_out, (pncu_stream_t)L.s_k);
+    const bool binary = j.kind == JOB_BINARY;
+    const char* in1 = j.in1;
+    const char* in2 = j.in2;
+    // a host scalar (NumPy's `a + 5.0`) next to resident arrays: one 8-byte copy
+    if (j.s1 == 0 && host_kind(j.pk_in1)) {
+        memcpy(L.h_small, j.in1, j.isz_in);
+        PNCU_CUDA(cudaMemcpyAsync(L.d_scalar, L.h_small, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
+        in1 = L.d_scalar;
+    }
+    if (binary && j.s2 == 0 && host_kind(j.pk_in2)) {
+        memcpy(L.h_small + 16, j.in2, j.isz_in);
+        PNCU_CUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
+        in2 = L.d_scalar + 16;
+    }
+    if ((rc = prefetch_managed(j.in1, j.s1 ? j.pk_in1 : PK_PAGEABLE, (size_t)j.len * j.isz_in, L))) return rc;
+    if (binary && (rc = prefetch_managed(j.in2, j.s2 ? j.pk_in2 : PK_PAGEABLE, (size_t)j.len * j.isz_in, L))) return rc;
+    if ((rc = prefetch_managed(j.out, j.pk_out, (size_t)j.len * j.isz_out, L))) return rc;
+    if (binary)
+        rc = j.fn2(in1, in2, j.out, j.len, j.s1, j.s2, j.isz_out, (pncu_stream_t)L.s_k);
     else
-        rc = j.fn1(j.in1, j.out, j.len, j.s1, j.isz_out, (pncu_stream_t)L.s_k);
+        rc = j.fn1(in1, j.out, j.len, j.s1, j.isz_out, (pncu_stream_t)L.s_k);
     if (rc) return rc;
     g_stats.launches += 1;
     PNCU_CUDA(cudaStreamSynchronize(L.s_k));
@@ -518,6 +549,19 @@ void nte_free_pinned(void* ptr) {
     if (ptr && cudaFreeHost(ptr) != cudaSuccess) cudaGetLastError();
 }
 
+void* nte_alloc_managed(size_t bytes) {
+    if (pncu_init(nullptr)) return nullptr;
+    void* p = nullptr;
+    if (cudaMallocManaged(&p, bytes ? bytes : 1, cudaMemAttachGlobal) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void nte_free_managed(void* ptr) {
+    if (ptr && cudaFree(ptr) != cudaSuccess) cudaGetLastError();
+}
+
 void nte_get_stats(nte_stats* o) {
     if (!o) return;
     o->calls = g_stats.calls; o->declined = g_stats.declined; o->launches = g_stats.launches;
@@ -541,12 +585,11 @@ static int dispatch_elementwise(Job& j, int max_workers) {
     const bool any_resident = !host_kind(j.pk_out) || (j.s1 != 0 && !host_kind(j.pk_in1)) ||
                               (binary && j.s2 != 0 && !host_kind(j.pk_in2));
     if (any_resident) {
-        const bool all_ok = !host_kind(j.pk_out) && (j.s1 == 0 ? j.pk_in1 != PK_PAGEABLE || true : !host_kind(j.pk_in1)) &&
+        // every ARRAY operand must be resident (a host array next to a managed one goes to the caller's
+        // loop, which may read managed memory); host scalars are copied by run_resident
+        const bool all_ok = !host_kind(j.pk_out) && (j.s1 == 0 || !host_kind(j.pk_in1)) &&
                             (!binary || j.s2 == 0 || !host_kind(j.pk_in2));
-        // a host scalar next to resident arrays is not dereferenceable by the kernel: decline
-        if (!all_ok || (j.s1 == 0 && host_kind(j.pk_in1) && j.pk_in1 != PK_PINNED) ||
-            (binary && j.s2 == 0 && host_kind(j.pk_in2) && j.pk_in2 != PK_PINNED))
-            return decline();
+        if (!all_ok) return decline();
         int rc = run_resident(j);
         if (!rc) g_stats.calls += 1;
         return rc;
@@ -603,7 +646,6 @@ static int finish_on_gpu0(Job& j, void* host_out, int out_bytes, const void* hos
     char* all = L0.d_partials;
     if (j.nlanes > 1) {
         // lane 0's buffer holds its own slots at [0, n0); append the others behind them
-        int rc = 0;
         if ((size_t)total * j.partial_bytes > L0.partials_bytes) {
             // grow, preserving lane 0's partials
             char* bigger = nullptr;
@@ -623,7 +665,6 @@ static int finish_on_gpu0(Job& j, void* host_out, int out_bytes, const void* hos
             PNCU_CUDA(cudaMemcpyPeerAsync(all + j.slot0[l] * j.partial_bytes, L0.device, L.d_partials, L.device,
                                           (size_t)cnt * j.partial_bytes, L0.s_k));
         }
-        (void)rc;
     }
     char* d_res = L0.d_scalar + 32;
     int rc;
@@ -656,12 +697,11 @@ static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* ho
     int rc;
     if (!host_kind(j.pk_in1)) {
         // resident input: both passes on its GPU
-        cudaPointerAttributes at;
-        int dev = 0;
-        if (cudaPointerGetAttributes(&at, j.in1) == cudaSuccess && at.device >= 0) dev = at.device; else cudaGetLastError();
-        if ((rc = ensure_lane(dev % g.ndev))) return rc;
-        Lane& L = g.lanes[dev % g.ndev];
+        const int dev = device_of(j.in1);
+        if ((rc = ensure_lane(dev))) return rc;
+        Lane& L = g.lanes[dev];
         PNCU_CUDA(cudaSetDevice(L.device));
+        if ((rc = prefetch_managed(j.in1, j.pk_in1, (size_t)j.len * j.isz_in, L))) return rc;
         const int64_t slots = pncu_reduce_partial_count(j.atype, j.len);
         if ((rc = ensure_partials(L, (size_t)slots * j.partial_bytes))) return rc;
         if (j.kind == JOB_REDUCE) rc = pncu_reduce_partials(j.func, j.atype, j.in1, j.len, L.d_partials, (pncu_stream_t)L.s_k);

@@ -758,7 +758,21 @@ static PyObject* pinned_alloc(PyObject*, PyObject* args) {
     return Py_BuildValue("(NL)", cap, (long long)(intptr_t)p);
 }
 
+// managed_alloc(nbytes) -> (capsule, address) of a CUDA managed block: one pointer for NumPy and kernels
+static void managed_capsule_free(PyObject* cap) { nte_free_managed(PyCapsule_GetPointer(cap, "pnumpy_b200.managed")); }
+static PyObject* managed_alloc(PyObject*, PyObject* args) {
+    long long nbytes = 0;
+    if (!PyArg_ParseTuple(args, "L:managed_alloc", &nbytes)) return NULL;
+    if (nbytes < 0) { PyErr_SetString(PyExc_ValueError, "negative size"); return NULL; }
+    void* p = nte_alloc_managed((size_t)nbytes);
+    if (!p) return PyErr_Format(PyExc_MemoryError, "cudaMallocManaged(%lld) failed: %s", nbytes, pncu_last_error());
+    PyObject* cap = PyCapsule_New(p, "pnumpy_b200.managed", managed_capsule_free);
+    if (!cap) { nte_free_managed(p); return NULL; }
+    return Py_BuildValue("(NL)", cap, (long long)(intptr_t)p);
+}
+
 static PyMethodDef module_functions[] = {
+    {"managed_alloc", managed_alloc, METH_VARARGS, "(capsule, address) of a CUDA managed block"},
     {"initialize", (PyCFunction)(void (*)(void))newinit, METH_VARARGS | METH_KEYWORDS,
      "Initialize the module. Replaces the ufunc inner loops with wrapped versions using "
      "PyUFunc_ReplaceLoopBySignature and calls numpy.setbufsize(8192 * 1024)."},

@@ -252,6 +252,33 @@ def test_pinned_operands_are_not_staged(pn, rng):
     assert abs(s - float(np.sum(want.astype(np.float64)))) <= 1e-6 * n
 
 
+def test_managed_arrays_run_in_place(pn, rng):
+    """Device-resident ndarrays (CUDA managed memory): a ufunc chain over them runs in place on the GPU,
+    with no PCIe copies issued by the dispatcher, and the host reads the right answer afterwards."""
+    n = (1 << 21) + 3
+    ha, hb, hc = (rng.normal(size=n).astype(np.float32) for _ in range(3))
+    a, b, c = pn.managed_array(ha), pn.managed_array(hb), pn.managed_array(hc)
+    t, u = pn.managed_empty(n, np.float32), pn.managed_empty(n, np.float32)
+    pn.cuda_reset_stats()
+    np.multiply(a, b, out=t)
+    np.add(t, c, out=u)
+    s = u.sum()
+    m = u.max()
+    i = u.argmin()
+    np.add(u, np.float32(2.5), out=t)      # host scalar next to resident arrays
+    g = np.greater(t, c)                    # output allocated by NumPy (pageable) -> NumPy's loop reads managed memory
+    info = pn.cuda_info()
+    assert info["calls"] == 6 and info["h2d_bytes"] == 0 and info["staged_bytes"] == 0, info
+    assert info["d2h_bytes"] <= 64          # only the reduction scalars came back
+    want_u = ha * hb + hc
+    assert_bits_equal(np.asarray(u), want_u, "chain on managed arrays")
+    assert_bits_equal(np.asarray(t), want_u + np.float32(2.5), "scalar operand")
+    assert np.array_equal(g, (want_u + np.float32(2.5)) > hc)
+    assert m == want_u.max() and i == want_u.argmin()
+    ref = float(np.sum(want_u.astype(np.float64)))
+    assert abs(float(s) - ref) <= 2.0 ** -23 * abs(ref) + 2.0 ** -45 * float(np.abs(want_u).sum())
+
+
 def test_recycler_gives_pinned_arrays(pn, rng):
     assert pn.recycler_isenabled() is False
     pn.recycler_enable()
