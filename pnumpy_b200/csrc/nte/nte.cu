@@ -21,6 +21,7 @@
 #include <string.h>
 #include <atomic>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -405,10 +406,29 @@ int device_of(const void* p) {
 
 // managed operands: make the pages resident on the GPU before the kernel touches them, otherwise the
 // kernel demand-faults them over PCIe at a fraction of the copy rate.  A no-op once they are there.
+// Prefetching a range that is already resident still costs ~1 ms of driver time per GiB (page-table
+// walk), 5x the kernel it precedes.  So a range is prefetched the FIRST time it is seen on a GPU and
+// trusted afterwards; if host code touched some pages in between, the kernel demand-faults those back
+// (correct, slower, and then they are resident again).  Guarded by g.api_mu (held by every dispatch).
+std::map<const void*, size_t> g_prefetched[kMaxLanes];
+std::map<const void*, size_t> g_managed_allocs;  // blocks handed out by nte_alloc_managed
+
 int prefetch_managed(const void* p, int pk, size_t bytes, Lane& L) {
     if (pk != PK_MANAGED || !bytes) return 0;
+    std::map<const void*, size_t>& seen = g_prefetched[L.device];
+    auto it = seen.find(p);
+    if (it != seen.end() && it->second >= bytes) return 0;
     PNCU_CUDA(cudaMemPrefetchAsync(p, bytes, L.device, L.s_k));
+    if (seen.size() > 4096) seen.clear();
+    seen[p] = bytes;
     return 0;
+}
+
+void forget_prefetched(const void* lo, size_t bytes) {
+    for (int d = 0; d < kMaxLanes; ++d) {
+        std::map<const void*, size_t>& seen = g_prefetched[d];
+        for (auto it = seen.lower_bound(lo); it != seen.end() && (const char*)it->first < (const char*)lo + bytes;) it = seen.erase(it);
+    }
 }
 
 int run_resident(Job& j) {
@@ -556,10 +576,20 @@ void* nte_alloc_managed(size_t bytes) {
         cudaGetLastError();
         return nullptr;
     }
+    std::lock_guard<std::mutex> lk(g.api_mu);
+    g_managed_allocs[p] = bytes ? bytes : 1;
     return p;
 }
 void nte_free_managed(void* ptr) {
-    if (ptr && cudaFree(ptr) != cudaSuccess) cudaGetLastError();
+    if (!ptr) return;
+    {
+        std::lock_guard<std::mutex> lk(g.api_mu);
+        auto it = g_managed_allocs.find(ptr);
+        const size_t bytes = it != g_managed_allocs.end() ? it->second : 1;
+        if (it != g_managed_allocs.end()) g_managed_allocs.erase(it);
+        forget_prefetched(ptr, bytes);  // views into the block are remembered by their own base address
+    }
+    if (cudaFree(ptr) != cudaSuccess) cudaGetLastError();
 }
 
 void nte_get_stats(nte_stats* o) {
