@@ -192,7 +192,8 @@ def test_trig_f32_bit_exact_vs_oracle(dev, O, rng, golden, op):
 
 
 @pytest.mark.parametrize("op,lo,hi", [("SIN", -20, 20), ("SIN", -1e5, 1e5), ("COS", -20, 20),
-                                      ("LOG", 1e-300, 1e300), ("EXP", -700, 700)])
+                                      ("LOG", 1e-300, 1e300), ("LOG", 0.5, 2.0), ("LOG", 0.999, 1.001),
+                                      ("LOG", 1 - 1e-9, 1 + 1e-9), ("EXP", -700, 700), ("COS", -1e5, 1e5)])
 def test_trig_f64_within_2ulp(dev, rng, op, lo, hi):
     if op == "LOG":
         x = np.exp(rng.uniform(np.log(lo), np.log(hi), 1 << 17))
