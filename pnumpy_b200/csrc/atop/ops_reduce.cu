@@ -197,6 +197,85 @@ __device__ __forceinline__ void write_result(typename R::Acc total, typename R::
     *out = R::result(t);
 }
 
+// ---- word-at-a-time folds for the 1- and 2-byte types ----------------------------------------------
+// Extracting bytes one by one costs ~3 ALU instructions per element.  These fold a whole 32-bit word
+// per step with the integer dot-product unit (IDP.4A / IDP.2A: sum of the 4 or 2 packed lanes in one
+// instruction) and the packed 16x2 min/max (VIMNMX.S16x2 / .U16x2; bytes are widened to 16x2 by one
+// PRMT per pair).  Integer results are exact in any order, so this changes no value.  (Measured: it
+// does not change the 2^28-element timings either -- a 256 MiB int8 array takes 38 us to stream and
+// the two launches + the second pass add ~25 us; at equal BYTES the small types match the wide ones.)
+template <class R> struct WordOps { static constexpr bool enabled = false; };
+
+template <> struct WordOps<SumR<int8_t, unsigned>> {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static __device__ __forceinline__ W seed(int8_t) { return 0u; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) { return (unsigned)__dp4a((int)w, 0x01010101, (int)a); }
+    static __device__ __forceinline__ unsigned finish(W a) { return a; }
+};
+template <> struct WordOps<SumR<uint8_t, unsigned>> {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static __device__ __forceinline__ W seed(uint8_t) { return 0u; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) { return __dp4a((unsigned)w, 0x01010101u, a); }
+    static __device__ __forceinline__ unsigned finish(W a) { return a; }
+};
+template <> struct WordOps<SumR<int16_t, unsigned>> {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static __device__ __forceinline__ W seed(int16_t) { return 0u; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) { return (unsigned)__dp2a_lo((int)w, 0x00000101, (int)a); }
+    static __device__ __forceinline__ unsigned finish(W a) { return a; }
+};
+template <> struct WordOps<SumR<uint16_t, unsigned>> {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static __device__ __forceinline__ W seed(uint16_t) { return 0u; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) { return __dp2a_lo((unsigned)w, 0x00000101u, a); }
+    static __device__ __forceinline__ unsigned finish(W a) { return a; }
+};
+template <> struct WordOps<AnyR> {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static __device__ __forceinline__ W seed(bool8) { return 0u; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) { return a | w; }
+    static __device__ __forceinline__ unsigned finish(W a) { return a != 0u; }
+};
+template <> struct WordOps<AllR> {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static __device__ __forceinline__ W seed(bool8) { return 0xffffffffu; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) { return a & __vcmpne4(w, 0u); }  // 0xff per non-zero byte
+    static __device__ __forceinline__ unsigned finish(W a) { return a == 0xffffffffu; }
+};
+// packed 16x2 min / max
+template <bool IS_MAX, bool SIGNED> __device__ __forceinline__ unsigned mm16x2(unsigned a, unsigned b) {
+    if (SIGNED) return IS_MAX ? __vmaxs2(a, b) : __vmins2(a, b);
+    return IS_MAX ? __vmaxu2(a, b) : __vminu2(a, b);
+}
+template <class T, bool IS_MAX> struct MinMaxWord {
+    static constexpr bool enabled = true; typedef unsigned W;
+    static constexpr bool kSigned = std::is_signed<T>::value;
+    typedef typename Widen<T>::type A;
+    static __device__ __forceinline__ W seed(T first) { return ((unsigned)(uint16_t)(int16_t)(A)first) * 0x00010001u; }
+    static __device__ __forceinline__ W step(W a, uint32_t w) {
+        if constexpr (sizeof(T) == 2) {
+            return mm16x2<IS_MAX, kSigned>(a, w);
+        } else {  // bytes -> two 16x2 words (sign- or zero-extended) by PRMT
+            const unsigned lo = kSigned ? __byte_perm(w, 0u, 0x9180) : __byte_perm(w, 0u, 0x4140);
+            const unsigned hi = kSigned ? __byte_perm(w, 0u, 0xb3a2) : __byte_perm(w, 0u, 0x4342);
+            return mm16x2<IS_MAX, kSigned>(mm16x2<IS_MAX, kSigned>(a, lo), hi);
+        }
+    }
+    static __device__ __forceinline__ A finish(W a) {
+        const A x = kSigned ? (A)(int16_t)(a & 0xffffu) : (A)(a & 0xffffu);
+        const A y = kSigned ? (A)(int16_t)(a >> 16) : (A)(a >> 16);
+        return IS_MAX ? (x > y ? x : y) : (x < y ? x : y);
+    }
+};
+template <> struct WordOps<MinR<int8_t>> : MinMaxWord<int8_t, false> {};
+template <> struct WordOps<MinR<uint8_t>> : MinMaxWord<uint8_t, false> {};
+template <> struct WordOps<MinR<int16_t>> : MinMaxWord<int16_t, false> {};
+template <> struct WordOps<MinR<uint16_t>> : MinMaxWord<uint16_t, false> {};
+template <> struct WordOps<MaxR<int8_t>> : MinMaxWord<int8_t, true> {};
+template <> struct WordOps<MaxR<uint8_t>> : MinMaxWord<uint8_t, true> {};
+template <> struct WordOps<MaxR<int16_t>> : MinMaxWord<int16_t, true> {};
+template <> struct WordOps<MaxR<uint16_t>> : MinMaxWord<uint16_t, true> {};
+
 // ---- pass 1 --------------------------------------------------------------------------------------
 template <class R, bool VEC>
 __global__ void __launch_bounds__(RED_THREADS)
@@ -230,11 +309,24 @@ reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_ba
         Pack<In, EPV> r[RED_NV];
 #pragma unroll
         for (int j = 0; j < RED_NV; ++j) r[j] = ld_pack<In, EPV>(p + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
+        if constexpr (WordOps<R>::enabled) {
+            // 1- and 2-byte types: fold whole 32-bit words (4 or 2 elements per instruction)
+            typename WordOps<R>::W wacc[RED_CHAINS];
 #pragma unroll
-        for (int j = 0; j < RED_NV; ++j) {
-            const int64_t e0 = gidx0 + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV;
+            for (int c = 0; c < RED_CHAINS; ++c) wacc[c] = WordOps<R>::seed(*reinterpret_cast<const In*>(base));
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) acc[j % RED_CHAINS] = R::step(acc[j % RED_CHAINS], r[j].get(e), e0 + e);
+            for (int j = 0; j < RED_NV; ++j)
+#pragma unroll
+                for (int wi = 0; wi < 8; ++wi) wacc[j % RED_CHAINS] = WordOps<R>::step(wacc[j % RED_CHAINS], r[j].w[wi]);
+#pragma unroll
+            for (int c = 0; c < RED_CHAINS; ++c) acc[c] = R::combine(acc[c], WordOps<R>::finish(wacc[c]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < RED_NV; ++j) {
+                const int64_t e0 = gidx0 + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) acc[j % RED_CHAINS] = R::step(acc[j % RED_CHAINS], r[j].get(e), e0 + e);
+            }
         }
     } else {
         // ragged last block, strided or misaligned input: element loads, same fixed order
