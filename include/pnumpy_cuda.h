@@ -156,6 +156,20 @@ typedef int (*pncu_reduce_fn)(const void* in, void* out, const void* startVal, i
 typedef int (*pncu_argminmax_fn)(const void* in, int64_t len, int64_t* out_index,
                                  pncu_stream_t stream);
 
+/* Fused chain (the reference runs `a*b + c` as two ufunc calls through
+ * SimpleMathOpFast, src/atop/ops_binary.cpp:398-571, and `.sum()` as a third through
+ * ReduceMathOpFast, :186-254).  Three contiguous inputs of one type.
+ * pncu_any_three_fn:    out[i] = (in1[i] * in2[i]) + in3[i]; the product and the sum are rounded
+ *                       separately (no FMA), so the result is bit-identical to multiply-then-add.
+ * pncu_three_reduce_fn: *out = sum_i ((in1[i] * in2[i]) + in3[i]) with the block structure, fold
+ *                       order and accumulator type of the ADD reduction, so it is bit-identical to
+ *                       multiply, add, then sum (operands 32-byte aligned alike) while HBM is
+ *                       read once.  `out` is a device pointer to one element. */
+typedef int (*pncu_any_three_fn)(const void* in1, const void* in2, const void* in3, void* out,
+                                 int64_t len, pncu_stream_t stream);
+typedef int (*pncu_three_reduce_fn)(const void* in1, const void* in2, const void* in3, void* out,
+                                    int64_t len, pncu_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * Library lifetime.  replaces: atop_init() (src/atop/atop.cpp:68-104)
  * ------------------------------------------------------------------------- */
@@ -201,6 +215,9 @@ PNCU_API pncu_argminmax_fn pncu_GetArgMinMaxOpFast(int kind, int atopInType1);
  * hook it (src/atop/ops_binary.cpp:926); NumPy casts to the hooked dd->d loop.  Offered
  * for device-resident callers so the cast never touches HBM twice. */
 PNCU_API pncu_any_two_fn pncu_GetIntTrueDivide(int atopInType1);
+/* fused a*b+c and sum(a*b+c) for int32/uint32/int64/uint64/float32/float64; NULL otherwise */
+PNCU_API pncu_any_three_fn pncu_GetMulAddFast(int atopInType1);
+PNCU_API pncu_three_reduce_fn pncu_GetMulAddSumFast(int atopInType1);
 /* itemsize of an atop type, 0 if unsupported (src/pnumpy/_pnumpy.cpp:43-54) */
 PNCU_API int pncu_itemsize(int atype);
 
@@ -228,6 +245,10 @@ PNCU_API int pncu_reduce_partials(int func, int atype, const void* in, int64_t l
 /* pass 2: *out = fold(partials[0..count)) op *startVal (startVal may be NULL / alias out) */
 PNCU_API int pncu_reduce_finish(int func, int atype, const void* partials, int64_t count,
                                 void* out, const void* startVal, pncu_stream_t stream);
+/* pass 1 of sum(in1*in2 + in3); the partials have the layout of pncu_reduce_partials(PNCU_ADD,
+ * atype, ...) and are finished by pncu_reduce_finish(PNCU_ADD, atype, ...) */
+PNCU_API int pncu_muladd_sum_partials(int atype, const void* in1, const void* in2, const void* in3,
+                                      int64_t len, void* partials, pncu_stream_t stream);
 /* arg-reduction equivalents; a partial is {value bits (8 B), index (8 B)}.
  * `index_base` is added to every index (the shard's global offset). */
 PNCU_API int pncu_argminmax_partials(int kind, int atype, const void* in, int64_t len,

@@ -87,6 +87,15 @@ PNCU_API int nte_reduce(int func, int atype, const void* in, void* out, int use_
 /* AtopArgMinMaxMathFunction (src/pnumpy/_pnumpy.cpp:1105-1118); `in` contiguous */
 PNCU_API int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out_index,
                            int max_workers);
+/* Fused chain: out = in1*in2 + in3 and *out = sum(in1*in2 + in3) over three
+ * contiguous arrays of one type, bit-identical to the two / three hooked calls they replace
+ * (pnumpy_cuda.h: pncu_any_three_fn, pncu_three_reduce_fn) with 16 / 12 bytes per float32 element
+ * over PCIe or HBM instead of 24 / 28.  Same sharding, staging, residency and NTE_DECLINED rules as
+ * the calls above; for nte_muladd_sum `out` is a HOST pointer to one element. */
+PNCU_API int nte_muladd(int atype, const void* in1, const void* in2, const void* in3, void* out,
+                        int64_t len, int max_workers);
+PNCU_API int nte_muladd_sum(int atype, const void* in1, const void* in2, const void* in3, void* out,
+                            int64_t len, int max_workers);
 
 /* ---- pinned host memory for ndarrays (the recycler's allocator) ---------------------
  * Pinned + portable + mapped; operands that live in it are DMA'd in place, with no staging copy. */

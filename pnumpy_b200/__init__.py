@@ -42,7 +42,7 @@ __all__ = [
     'argmin', 'argmax',
     # additions of this build (nothing above changes meaning)
     'cuda_info', 'cuda_reset_stats', 'cuda_setthreshold', 'cuda_getthreshold', 'cuda_setslab',
-    'pinned_empty', 'pinned_array', 'managed_empty', 'managed_array',
+    'pinned_empty', 'pinned_array', 'managed_empty', 'managed_array', 'muladd', 'muladd_sum',
 ]
 
 import numpy as np  # noqa: E402
@@ -81,6 +81,38 @@ def argmax(a, axis=None, out=None):
 def argmin(a, axis=None, out=None):
     """Indices of the minimum values along an axis.  reference: ``src/pnumpy/sort.py:486-563``."""
     return np.asanyarray(a).argmin(axis=axis, out=out)
+
+
+def muladd(a, b, c, out=None):
+    """``a*b + c`` in one pass (the reference's "for longer equations: a=b*c+d" case).
+
+    Same values, bit for bit, as ``np.add(np.multiply(a, b), c, out=out)``: the product and the sum
+    are rounded separately, there is no FMA.  For equal-shape C-contiguous arrays of one dtype
+    (int32/uint32/int64/uint64/float32/float64) above the dispatch threshold the operands cross PCIe
+    / HBM once and no temporary is materialised; anything else runs the two hooked ufunc calls."""
+    a = np.asanyarray(a)
+    if out is None and isinstance(a, np.ndarray):
+        from .pinned import pinned_empty as _pe, managed_empty as _me
+        from ._pnumpy import pointer_kind as _kind
+        k = _kind(a.ctypes.data) if a.size else 0
+        res = _me(a.shape, a.dtype) if k >= 2 else (_pe(a.shape, a.dtype) if k == 1 else np.empty_like(a))
+    else:
+        res = out
+    if isinstance(res, np.ndarray) and _pnumpy.fused_muladd(a, b, c, res):
+        return res
+    return np.add(np.multiply(a, b), c, out=out)
+
+
+def muladd_sum(a, b, c):
+    """``(a*b + c).sum()`` in one pass: 12 bytes per float32 element instead of 28, no temporaries.
+
+    Bit-identical to ``np.add(np.multiply(a, b), c).sum()`` as this package computes it (same 64 KiB
+    blocks, same fold order, float32 accumulated in float64); falls back to exactly that chain when
+    the operands do not qualify (see ``muladd``)."""
+    r = _pnumpy.fused_muladd_sum(a, b, c)
+    if r is not None:
+        return r
+    return np.add(np.multiply(a, b), c).sum()
 
 
 # start the engine by default (reference: src/pnumpy/__init__.py:74-76)

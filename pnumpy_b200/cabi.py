@@ -59,6 +59,7 @@ UNARY_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _c_i64, _c_i64, _c_i64, _vp)
 ANY_TWO_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _vp, _c_i64, _c_i64, _c_i64, _c_i64, _vp)
 REDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _vp, _c_i64, _c_i64, _vp)
 ARGMINMAX_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _c_i64, _vp, _vp)
+ANY_THREE_FN = ctypes.CFUNCTYPE(ctypes.c_int, _vp, _vp, _vp, _vp, _c_i64, _vp)   # also pncu_three_reduce_fn
 
 # every symbol include/pnumpy_cuda.h declares: name -> (restype, argtypes)
 _P_INT = ctypes.POINTER(ctypes.c_int)
@@ -77,6 +78,9 @@ SIGNATURES = {
     "pncu_GetTrigOpFast": (_vp, [ctypes.c_int, ctypes.c_int, _P_INT]),
     "pncu_GetArgMinMaxOpFast": (_vp, [ctypes.c_int, ctypes.c_int]),
     "pncu_GetIntTrueDivide": (_vp, [ctypes.c_int]),
+    "pncu_GetMulAddFast": (_vp, [ctypes.c_int]),
+    "pncu_GetMulAddSumFast": (_vp, [ctypes.c_int]),
+    "pncu_muladd_sum_partials": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _c_i64, _vp, _vp]),
     "pncu_itemsize": (ctypes.c_int, [ctypes.c_int]),
     "pncu_reduce_block_elems": (_c_i64, []),
     "pncu_reduce_partial_count": (_c_i64, [ctypes.c_int, _c_i64]),
@@ -179,3 +183,11 @@ def get_argminmax(kind, atype):
 
 def get_int_true_divide(atype):
     return _getter("pncu_GetIntTrueDivide", ANY_TWO_FN, atype, with_out=False)
+
+
+def get_muladd(atype):
+    return _getter("pncu_GetMulAddFast", ANY_THREE_FN, atype, with_out=False)
+
+
+def get_muladd_sum(atype):
+    return _getter("pncu_GetMulAddSumFast", ANY_THREE_FN, atype, with_out=False)

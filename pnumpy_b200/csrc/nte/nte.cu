@@ -46,8 +46,8 @@ struct Lane {
     bool ready = false;
     cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[kRing], ev_k[kRing], ev_d2h[kRing];
-    char* d_buf[kRing][3];   // device slabs: in1, in2, out
-    char* h_buf[kRing][3];   // pinned staging slabs
+    char* d_buf[kRing][4];   // device slabs: in1, in2, out, in3 (in3: fused chain only, allocated lazily)
+    char* h_buf[kRing][4];   // pinned staging slabs (allocated lazily, pageable operands only)
     size_t slab_bytes = 0;
     char* d_scalar = nullptr;   // 2 x 16 B for broadcast scalars
     char* d_partials = nullptr; // reduction block partials of this lane's shard
@@ -83,21 +83,23 @@ struct State {
 State g;
 
 // ---- per-call job ---------------------------------------------------------------------------------
-enum JobKind { JOB_BINARY, JOB_UNARY, JOB_REDUCE, JOB_ARG };
+enum JobKind { JOB_BINARY, JOB_UNARY, JOB_REDUCE, JOB_ARG, JOB_MULADD, JOB_MULADD_SUM };
 enum PtrKind { PK_PAGEABLE = 0, PK_PINNED = 1, PK_DEVICE = 2, PK_MANAGED = 3 };
 
 struct Job {
     JobKind kind;
     pncu_any_two_fn fn2 = nullptr;
     pncu_unary_fn fn1 = nullptr;
+    pncu_any_three_fn fn3 = nullptr;
     int func = 0, atype = 0, argkind = 0;
     int isz_in = 0, isz_out = 0;
     const char* in1 = nullptr;
     const char* in2 = nullptr;
+    const char* in3 = nullptr;
     char* out = nullptr;
     int64_t len = 0;
     int64_t s1 = 0, s2 = 0;     // 0 (scalar) or the item size
-    int pk_in1 = 0, pk_in2 = 0, pk_out = 0;
+    int pk_in1 = 0, pk_in2 = 0, pk_in3 = 0, pk_out = 0;
     int nlanes = 1;
     int64_t shard[kMaxLanes + 1];  // element boundaries
     int rc[kMaxLanes];
@@ -145,13 +147,13 @@ int ensure_lane(int li) {
             PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_h2d[r], cudaEventDisableTiming));
             PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_k[r], cudaEventDisableTiming));
             PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_d2h[r], cudaEventDisableTiming));
-            for (int k = 0; k < 3; ++k) { L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr; }
+            for (int k = 0; k < 4; ++k) { L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr; }
         }
         PNCU_CUDA(cudaMalloc((void**)&L.d_scalar, 64));
         PNCU_CUDA(cudaHostAlloc((void**)&L.h_small, 64, cudaHostAllocPortable));
     } else {
         for (int r = 0; r < kRing; ++r)
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 if (L.d_buf[r][k]) cudaFree(L.d_buf[r][k]);
                 if (L.h_buf[r][k]) cudaFreeHost(L.h_buf[r][k]);
                 L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr;
@@ -168,6 +170,12 @@ int ensure_lane(int li) {
 int ensure_pinned_slab(Lane& L, int r, int k) {
     if (L.h_buf[r][k]) return 0;
     PNCU_CUDA(cudaHostAlloc((void**)&L.h_buf[r][k], L.slab_bytes, cudaHostAllocPortable));
+    return 0;
+}
+
+int ensure_third_input(Lane& L) {
+    for (int r = 0; r < kRing; ++r)
+        if (!L.d_buf[r][3]) PNCU_CUDA(cudaMalloc((void**)&L.d_buf[r][3], L.slab_bytes));
     return 0;
 }
 
@@ -320,6 +328,93 @@ void lane_reduce(Lane& L, Job& j, int li) {
     }
     cudaError_t e = cudaStreamSynchronize(L.s_k);
     if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); fail(j, li, (int)e); }
+}
+
+// ---- one lane of the fused chain: three input slabs -> a*b+c (-> D2H) or -> block partials of its sum ------
+void lane_fused(Lane& L, Job& j, int li) {
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
+    if (e0 >= e1) return;
+    const bool to_sum = j.kind == JOB_MULADD_SUM;
+    const int isz = j.isz_in;
+    int rc;
+    if ((rc = ensure_third_input(L))) { fail(j, li, rc); return; }
+    if (to_sum && (rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
+    const int64_t slab_elems = ((int64_t)(L.slab_bytes / isz) / kAlign) * kAlign;
+    const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
+    const char* ins[3] = {j.in1, j.in2, j.in3};
+    const int pks[3] = {j.pk_in1, j.pk_in2, j.pk_in3};
+    const int slot_of[3] = {0, 1, 3};  // d_buf / h_buf index of each input (2 is `out`)
+
+    auto slab_range = [&](int64_t i, int64_t* off, int64_t* cnt) {
+        *off = e0 + i * slab_elems;
+        *cnt = (e1 - *off) < slab_elems ? (e1 - *off) : slab_elems;
+    };
+    // slot reuse: a sum only needs the kernel that read the slot to be done; an element-wise job needs
+    // the slot's result on the host (and copies it out of staging for a pageable `out`)
+    auto retire = [&](int64_t i) -> int {
+        const int r = (int)(i % kRing);
+        cudaError_t e = cudaEventSynchronize(to_sum ? L.ev_k[r] : L.ev_d2h[r]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(fused)", __FILE__, __LINE__);
+        if (!to_sum && j.pk_out == PK_PAGEABLE) {
+            int64_t off, cnt;
+            slab_range(i, &off, &cnt);
+            memcpy(j.out + off * isz, L.h_buf[r][2], (size_t)(cnt * isz));
+            g_stats.staged += cnt * isz;
+        }
+        return 0;
+    };
+
+    for (int64_t i = 0; i < nslabs; ++i) {
+        const int r = (int)(i % kRing);
+        if (i >= kRing && (rc = retire(i - kRing))) { fail(j, li, rc); return; }
+        int64_t off, cnt;
+        slab_range(i, &off, &cnt);
+        const size_t bytes = (size_t)(cnt * isz);
+        for (int k = 0; k < 3; ++k) {
+            const char* src = ins[k] + off * isz;
+            if (pks[k] == PK_PAGEABLE) {
+                if ((rc = ensure_pinned_slab(L, r, slot_of[k]))) { fail(j, li, rc); return; }
+                memcpy(L.h_buf[r][slot_of[k]], src, bytes);
+                g_stats.staged += bytes;
+                src = L.h_buf[r][slot_of[k]];
+            }
+            LCUDA(cudaMemcpyAsync(L.d_buf[r][slot_of[k]], src, bytes, cudaMemcpyHostToDevice, L.s_h2d));
+            g_stats.h2d += bytes;
+        }
+        LCUDA(cudaEventRecord(L.ev_h2d[r], L.s_h2d));
+        LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_h2d[r], 0));
+        if (to_sum) {
+            const int64_t slot = pncu_reduce_partial_count(j.atype, off - e0);
+            rc = pncu_muladd_sum_partials(j.atype, L.d_buf[r][0], L.d_buf[r][1], L.d_buf[r][3], cnt,
+                                          L.d_partials + slot * j.partial_bytes, (pncu_stream_t)L.s_k);
+        } else {
+            rc = j.fn3(L.d_buf[r][0], L.d_buf[r][1], L.d_buf[r][3], L.d_buf[r][2], cnt, (pncu_stream_t)L.s_k);
+        }
+        if (rc) { fail(j, li, rc); return; }
+        g_stats.launches += 1;
+        LCUDA(cudaEventRecord(L.ev_k[r], L.s_k));
+        LCUDA(cudaStreamWaitEvent(L.s_h2d, L.ev_k[r], 0));
+        if (!to_sum) {
+            LCUDA(cudaStreamWaitEvent(L.s_d2h, L.ev_k[r], 0));
+            char* dst = j.out + off * isz;
+            if (j.pk_out == PK_PAGEABLE) {
+                if ((rc = ensure_pinned_slab(L, r, 2))) { fail(j, li, rc); return; }
+                dst = L.h_buf[r][2];
+            }
+            LCUDA(cudaMemcpyAsync(dst, L.d_buf[r][2], bytes, cudaMemcpyDeviceToHost, L.s_d2h));
+            g_stats.d2h += bytes;
+            LCUDA(cudaEventRecord(L.ev_d2h[r], L.s_d2h));
+            LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_d2h[r], 0));
+        }
+    }
+    if (to_sum) {
+        cudaError_t e = cudaStreamSynchronize(L.s_k);
+        if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); fail(j, li, (int)e); }
+    } else {
+        for (int64_t i = nslabs > kRing ? nslabs - kRing : 0; i < nslabs; ++i)
+            if ((rc = retire(i))) { fail(j, li, rc); return; }
+    }
 }
 
 // ---- worker pool -----------------------------------------------------------------------------------------
@@ -515,7 +610,7 @@ int nte_shutdown(void) {
         if (!L.ready) continue;
         cudaSetDevice(L.device);
         for (int r = 0; r < kRing; ++r) {
-            for (int k = 0; k < 3; ++k) {
+            for (int k = 0; k < 4; ++k) {
                 if (L.d_buf[r][k]) cudaFree(L.d_buf[r][k]);
                 if (L.h_buf[r][k]) cudaFreeHost(L.h_buf[r][k]);
             }
@@ -777,6 +872,91 @@ int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out
     j.kind = JOB_ARG; j.argkind = kind; j.atype = atype; j.isz_in = isz; j.isz_out = 8; j.partial_bytes = 16;
     j.in1 = (const char*)in; j.len = len; j.s1 = isz;
     return dispatch_reduce(j, out_index, 8, nullptr, max_workers);
+}
+
+// fused chain: element-wise (out != NULL) or summed (host_out)
+static int dispatch_fused(Job& j, void* host_out, int max_workers) {
+    if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
+    if (j.len < g.min_elems || j.len <= 0) return decline();
+    std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
+    if (!lk.owns_lock()) return decline();
+    const bool to_sum = j.kind == JOB_MULADD_SUM;
+    j.pk_in1 = classify(j.in1); j.pk_in2 = classify(j.in2); j.pk_in3 = classify(j.in3);
+    j.pk_out = to_sum ? j.pk_in1 : classify(j.out);
+    const int pks[4] = {j.pk_in1, j.pk_in2, j.pk_in3, j.pk_out};
+    int nhost = 0;
+    for (int k = 0; k < 4; ++k) nhost += host_kind(pks[k]);
+    if (nhost != 0 && nhost != 4) return decline();  // host and resident arrays mixed: the caller's loops
+    const size_t bytes = (size_t)j.len * j.isz_in;
+    int rc;
+    if (nhost == 0) {
+        // resident operands: in place on their GPU, no PCIe
+        const int dev = device_of(j.in1);
+        if ((rc = ensure_lane(dev))) return rc;
+        Lane& L = g.lanes[dev];
+        PNCU_CUDA(cudaSetDevice(L.device));
+        if ((rc = prefetch_managed(j.in1, j.pk_in1, bytes, L))) return rc;
+        if ((rc = prefetch_managed(j.in2, j.pk_in2, bytes, L))) return rc;
+        if ((rc = prefetch_managed(j.in3, j.pk_in3, bytes, L))) return rc;
+        if (!to_sum) {
+            if ((rc = prefetch_managed(j.out, j.pk_out, bytes, L))) return rc;
+            if ((rc = j.fn3(j.in1, j.in2, j.in3, j.out, j.len, (pncu_stream_t)L.s_k))) return rc;
+            g_stats.launches += 1;
+            PNCU_CUDA(cudaStreamSynchronize(L.s_k));
+        } else {
+            pncu_three_reduce_fn full = pncu_GetMulAddSumFast(j.atype);
+            char* d_res = L.d_scalar + 32;
+            if ((rc = full(j.in1, j.in2, j.in3, d_res, j.len, (pncu_stream_t)L.s_k))) return rc;
+            g_stats.launches += 2;
+            PNCU_CUDA(cudaMemcpyAsync(L.h_small + 32, d_res, j.isz_in, cudaMemcpyDeviceToHost, L.s_k));
+            PNCU_CUDA(cudaStreamSynchronize(L.s_k));
+            memcpy(host_out, L.h_small + 32, j.isz_in);
+            g_stats.d2h += j.isz_in;
+        }
+        g_stats.calls += 1;
+        return 0;
+    }
+    if (!to_sum) {
+        // `out` may alias an input exactly; partial overlap is declined
+        const char* ins[3] = {j.in1, j.in2, j.in3};
+        for (int k = 0; k < 3; ++k) {
+            const bool overlap = ins[k] < j.out + bytes && j.out < ins[k] + bytes;
+            if (overlap && ins[k] != j.out) return decline();
+        }
+    }
+    if ((rc = plan(j, max_workers))) return rc;
+    if (to_sum)
+        for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
+    run_lanes(j, lane_fused);
+    if ((rc = first_error(j))) return rc;
+    if (to_sum) {
+        j.kind = JOB_REDUCE;  // the partials are those of the ADD reduction: ordinary gather + finish
+        j.func = PNCU_ADD;
+        rc = finish_on_gpu0(j, host_out, j.isz_in, nullptr);
+        if (rc) return rc;
+    }
+    g_stats.calls += 1;
+    return 0;
+}
+
+int nte_muladd(int atype, const void* in1, const void* in2, const void* in3, void* out, int64_t len, int max_workers) {
+    pncu_any_three_fn fn = pncu_GetMulAddFast(atype);
+    if (!fn) return decline();
+    Job j;
+    j.kind = JOB_MULADD; j.fn3 = fn; j.atype = atype; j.isz_in = j.isz_out = pncu_itemsize(atype);
+    j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.in3 = (const char*)in3; j.out = (char*)out; j.len = len;
+    j.s1 = j.s2 = j.isz_in;
+    return dispatch_fused(j, nullptr, max_workers);
+}
+
+int nte_muladd_sum(int atype, const void* in1, const void* in2, const void* in3, void* out, int64_t len, int max_workers) {
+    if (!pncu_GetMulAddSumFast(atype)) return decline();
+    Job j;
+    j.kind = JOB_MULADD_SUM; j.atype = atype; j.isz_in = j.isz_out = pncu_itemsize(atype);
+    j.partial_bytes = pncu_reduce_partial_bytes(PNCU_ADD, atype);
+    j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.in3 = (const char*)in3; j.len = len;
+    j.s1 = j.s2 = j.isz_in;
+    return dispatch_fused(j, out, max_workers);
 }
 
 }  // extern "C"

@@ -771,7 +771,81 @@ static PyObject* managed_alloc(PyObject*, PyObject* args) {
     return Py_BuildValue("(NL)", cap, (long long)(intptr_t)p);
 }
 
+// =======================================================================================================
+// Fused chain (an ADDITION, the reference has nothing like it): a*b + c and
+// sum(a*b + c) in one pass over the operands.  The Python wrappers (pnumpy_b200.muladd / muladd_sum)
+// run the ordinary hooked ufunc chain whenever these return False / None, and the results are
+// bit-identical either way (include/pnumpy_cuda.h: pncu_any_three_fn, pncu_three_reduce_fn).
+static bool fused_operands(PyObject* const* objs, int count, int writable_index, PyArrayObject** arr, int* atype, npy_intp* n) {
+    for (int k = 0; k < count; ++k) {
+        if (!PyArray_Check(objs[k])) return false;
+        arr[k] = (PyArrayObject*)objs[k];
+        const int need = NPY_ARRAY_C_CONTIGUOUS | NPY_ARRAY_ALIGNED | (k == writable_index ? NPY_ARRAY_WRITEABLE : 0);
+        if ((PyArray_FLAGS(arr[k]) & need) != need) return false;
+        if (!PyArray_ISNOTSWAPPED(arr[k])) return false;
+        if (PyArray_TYPE(arr[k]) != PyArray_TYPE(arr[0])) return false;
+        if (PyArray_NDIM(arr[k]) != PyArray_NDIM(arr[0])) return false;
+        for (int d = 0; d < PyArray_NDIM(arr[0]); ++d)
+            if (PyArray_DIM(arr[k], d) != PyArray_DIM(arr[0], d)) return false;
+    }
+    const int dt = PyArray_TYPE(arr[0]);
+    if (dt < 0 || dt >= COUNT_OF(convert_dtype_to_atop)) return false;
+    *atype = convert_dtype_to_atop[dt];
+    *n = PyArray_SIZE(arr[0]);
+    return *atype >= 0;
+}
+
+static PyObject* fused_muladd(PyObject*, PyObject* args) {
+    PyObject* o[4];
+    if (!PyArg_ParseTuple(args, "OOOO:fused_muladd", &o[0], &o[1], &o[2], &o[3])) return NULL;
+    PyArrayObject* a[4];
+    int atype = -1;
+    npy_intp n = 0;
+    if (!g_Settings.AtopEnabled || !fused_operands(o, 4, 3, a, &atype, &n)) Py_RETURN_FALSE;
+    int rc;
+    Py_BEGIN_ALLOW_THREADS
+    rc = nte_muladd(atype, PyArray_DATA(a[0]), PyArray_DATA(a[1]), PyArray_DATA(a[2]), PyArray_DATA(a[3]), (int64_t)n, 3);
+    Py_END_ALLOW_THREADS
+    if (rc == NTE_DECLINED) Py_RETURN_FALSE;
+    if (rc) return PyErr_Format(PyExc_RuntimeError, "pnumpy_b200: fused multiply-add failed on the GPU (status %d): %s", rc, pncu_last_error());
+    ledger(CAT_BINARY, true, n);
+    Py_RETURN_TRUE;
+}
+
+static PyObject* fused_muladd_sum(PyObject*, PyObject* args) {
+    PyObject* o[3];
+    if (!PyArg_ParseTuple(args, "OOO:fused_muladd_sum", &o[0], &o[1], &o[2])) return NULL;
+    PyArrayObject* a[3];
+    int atype = -1;
+    npy_intp n = 0;
+    if (!g_Settings.AtopEnabled || !fused_operands(o, 3, -1, a, &atype, &n)) Py_RETURN_NONE;
+    // ndarray.sum() of a 4-byte integer array accumulates (and returns) int64 / uint64; the fused kernel sums
+    // in-type like np.add.reduce(dtype=int32) and ReduceMathOpFast do, so those dtypes take the ufunc chain
+    if (atype == PNCU_INT32 || atype == PNCU_UINT32) Py_RETURN_NONE;
+    alignas(16) char result[16] = {0};
+    int rc;
+    Py_BEGIN_ALLOW_THREADS
+    rc = nte_muladd_sum(atype, PyArray_DATA(a[0]), PyArray_DATA(a[1]), PyArray_DATA(a[2]), result, (int64_t)n, 3);
+    Py_END_ALLOW_THREADS
+    if (rc == NTE_DECLINED) Py_RETURN_NONE;
+    if (rc) return PyErr_Format(PyExc_RuntimeError, "pnumpy_b200: fused multiply-add-sum failed on the GPU (status %d): %s", rc, pncu_last_error());
+    ledger(CAT_BINARY, true, n);
+    PyArray_Descr* descr = PyArray_DESCR(a[0]);
+    return PyArray_Scalar(result, descr, NULL);
+}
+
+// pointer_kind(address) -> 0 pageable host, 1 pinned host, 2 device, 3 managed
+static PyObject* pointer_kind(PyObject*, PyObject* args) {
+    unsigned long long addr = 0;
+    if (!PyArg_ParseTuple(args, "K:pointer_kind", &addr)) return NULL;
+    int dev = -1;
+    return PyLong_FromLong(pncu_pointer_kind((const void*)(uintptr_t)addr, &dev));
+}
+
 static PyMethodDef module_functions[] = {
+    {"pointer_kind", pointer_kind, METH_VARARGS, "0 pageable host, 1 pinned host, 2 device, 3 managed"},
+    {"fused_muladd", fused_muladd, METH_VARARGS, "a*b+c into out in one GPU pass; False when the caller must run the ufunc chain"},
+    {"fused_muladd_sum", fused_muladd_sum, METH_VARARGS, "sum(a*b+c) in one GPU pass; None when the caller must run the ufunc chain"},
     {"managed_alloc", managed_alloc, METH_VARARGS, "(capsule, address) of a CUDA managed block"},
     {"initialize", (PyCFunction)(void (*)(void))newinit, METH_VARARGS | METH_KEYWORDS,
      "Initialize the module. Replaces the ufunc inner loops with wrapped versions using "

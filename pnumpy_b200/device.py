@@ -123,6 +123,28 @@ def int_true_divide(a, b, out=None, stream=None):
     return out
 
 
+def muladd(a, b, c, out=None, stream=None):
+    """out = a*b + c in one pass (two roundings; bit-identical to multiply then add)."""
+    fn = cabi.get_muladd(a.atype)
+    if fn is None:
+        raise cabi.PnumpyCudaError(f"no fused multiply-add kernel for {a.dtype}")
+    if out is None:
+        out = DeviceArray(a.size, a.dtype, a.device)
+    cabi.check(fn(a.ptr, b.ptr, c.ptr, out.ptr, a.size, stream), "muladd")
+    return out
+
+
+def muladd_sum(a, b, c, out=None, stream=None):
+    """one-element DeviceArray holding sum(a*b + c), bit-identical to the three-call chain."""
+    fn = cabi.get_muladd_sum(a.atype)
+    if fn is None:
+        raise cabi.PnumpyCudaError(f"no fused multiply-add-sum kernel for {a.dtype}")
+    if out is None:
+        out = DeviceArray(1, a.dtype, a.device)
+    cabi.check(fn(a.ptr, b.ptr, c.ptr, out.ptr, a.size, stream), "muladd_sum")
+    return out
+
+
 def compare(op, a, b, out=None, stream=None, a_scalar=False, b_scalar=False):
     fn, _ = cabi.get_compare(cabi.COMP_OPS[op], a.atype)
     if fn is None:

@@ -361,3 +361,75 @@ def test_benchmark_plumbing(pn, capsys):
         assert out.startswith("131072 rows,float32,") and "a+b," in out and "sum," in out and "min," in out
     finally:
         pn.cuda_setthreshold(old)
+
+
+# ---- fused chain: pn.muladd / pn.muladd_sum ---------------------------------------------
+@pytest.mark.parametrize("dt", ["float32", "float64", "int32", "int64"])
+def test_fused_chain_equals_the_hooked_chain(pn, rng, dt):
+    """pn.muladd / pn.muladd_sum == np.add(np.multiply(a, b), c) [.sum()] bit for bit -- against NumPy's own
+    loops element-wise, against the three hooked GPU calls for the sum -- with 3 operands in, 1 (or none) out
+    over PCIe, for pageable and pinned arrays and any number of lanes."""
+    n = (1 << 22) + 4099
+    if np.dtype(dt).kind == "f":
+        ha, hb, hc = (rng.normal(0, 100, n).astype(dt) for _ in range(3))
+    else:
+        ha, hb, hc = (fill_random(n, dt, rng) for _ in range(3))
+    isz = np.dtype(dt).itemsize
+    pn.disable()
+    want = np.add(np.multiply(ha, hb), hc)
+    pn.enable()
+    chain_sum = np.add(np.multiply(ha, hb), hc).sum()    # three hooked calls on the GPU
+    oldw = pn.thread_getworkers()
+    try:
+        for workers in (1, 3, 7):
+            pn.thread_setworkers(workers)
+            pn.cuda_reset_stats()
+            got = pn.muladd(ha, hb, hc)
+            info = pn.cuda_info()
+            assert info["calls"] == 1 and info["h2d_bytes"] == 3 * n * isz and info["d2h_bytes"] == n * isz, info
+            assert_bits_equal(got, want, f"pn.muladd {dt} workers={workers}")
+            pn.cuda_reset_stats()
+            s = pn.muladd_sum(ha, hb, hc)
+            info = pn.cuda_info()
+            if dt == "int32":   # ndarray.sum() widens int32 to int64: pn.muladd_sum runs the three hooked calls
+                assert info["calls"] == 3, info
+            else:
+                assert info["calls"] == 1 and info["h2d_bytes"] == 3 * n * isz and info["d2h_bytes"] <= 64, info
+            assert type(s) is type(chain_sum) and s.tobytes() == chain_sum.tobytes(), (dt, workers, s, chain_sum)
+    finally:
+        pn.thread_setworkers(oldw)
+    # pinned operands: DMA'd in place, nothing staged; out= honoured and may alias an input
+    pa, pb, pc = pn.pinned_array(ha), pn.pinned_array(hb), pn.pinned_array(hc)
+    pn.cuda_reset_stats()
+    r = pn.muladd(pa, pb, pc, out=pc)
+    assert r is pc and pn.cuda_info()["staged_bytes"] == 0 and pn.cuda_info()["calls"] == 1
+    assert_bits_equal(np.asarray(pc), want, f"pn.muladd {dt} pinned, in place")
+
+
+def test_fused_chain_on_resident_arrays_and_fallbacks(pn, rng):
+    n = (1 << 21) + 3
+    ha, hb, hc = (rng.normal(size=n).astype(np.float32) for _ in range(3))
+    want = ha * hb + hc
+    a, b, c = pn.managed_array(ha), pn.managed_array(hb), pn.managed_array(hc)
+    pn.cuda_reset_stats()
+    u = pn.muladd(a, b, c)                   # result allocated in managed memory too
+    s = pn.muladd_sum(a, b, c)
+    info = pn.cuda_info()
+    assert info["calls"] == 2 and info["h2d_bytes"] == 0 and info["staged_bytes"] == 0 and info["d2h_bytes"] <= 64, info
+    assert_bits_equal(np.asarray(u), want, "muladd on managed arrays")
+    assert s.tobytes() == np.add(np.multiply(a, b), c).sum().tobytes()
+    # operands that do not qualify run the ordinary ufunc chain: same values, NumPy's broadcasting and casting
+    pn.cuda_reset_stats()
+    r = pn.muladd(ha[::2], hb[::2], hc[::2])                      # non-contiguous
+    assert_bits_equal(r, want[::2], "strided fallback")
+    r = pn.muladd(ha, np.float32(3.0), hc)                        # scalar operand
+    assert_bits_equal(r, ha * np.float32(3.0) + hc, "scalar fallback")
+    r = pn.muladd(ha, hb.astype(np.float64), hc)                  # mixed dtypes
+    assert r.dtype == np.float64 and np.array_equal(r, ha * hb.astype(np.float64) + hc)
+    assert pn.muladd_sum(ha[::2], hb[::2], hc[::2]).tobytes() == np.add(np.multiply(ha[::2], hb[::2]), hc[::2]).sum().tobytes()
+    assert pn.muladd_sum([1.0, 2.0], [3.0, 4.0], [5.0, 6.0]) == 22.0
+    pn.disable()
+    try:
+        assert_bits_equal(pn.muladd(ha, hb, hc), want, "atop disabled -> NumPy chain")
+    finally:
+        pn.enable()

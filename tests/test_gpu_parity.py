@@ -413,3 +413,103 @@ def test_full_size_properties(dev, dt):
     else:
         q = dev.int_true_divide(two, da)
         assert dev.reduce("MIN", q).to_host()[0] == 2.0 and dev.reduce("MAX", q).to_host()[0] == 2.0
+
+
+# ---- fused chain a*b + c and sum(a*b + c) -------------------------------------------
+FUSED_DTYPES = ["int32", "uint32", "int64", "uint64", "float32", "float64"]
+
+
+@pytest.mark.parametrize("dt", FUSED_DTYPES)
+def test_muladd_vs_oracle(dev, O, rng, dt):
+    """out = a*b + c in one kernel == the oracle's MUL body then its ADD body (two roundings, no FMA),
+    on raw bit patterns, for aligned, misaligned and in-place operands."""
+    launches0 = _launches()
+    n = N_SMALL
+    a, b, c = (fill_random(n + 8, dt, rng) for _ in range(3))
+    with np.errstate(all="ignore"):
+        want = O.binary("ADD", O.binary("MUL", a, b), c)
+        assert_bits_equal(want, a * b + c, f"oracle vs numpy muladd {dt}")
+    da, db, dc = dev.to_device(a), dev.to_device(b), dev.to_device(c)
+    got = dev.muladd(da, db, dc).to_host()
+    assert_bits_equal(got, want, f"muladd {dt}")
+    # operands whose 32-byte alignments disagree (element kernel) and agree-but-offset (head/tail path)
+    for oa, ob, oc in ((1, 2, 3), (3, 3, 3)):
+        out = dev.empty(n, dt)
+        dev.muladd(da.view(oa, n), db.view(ob, n), dc.view(oc, n), out=out)
+        with np.errstate(all="ignore"):
+            w = O.binary("ADD", O.binary("MUL", a[oa:oa + n], b[ob:ob + n]), c[oc:oc + n])
+        assert_bits_equal(out.to_host(), w, f"muladd {dt} offsets {(oa, ob, oc)}")
+    dev.muladd(da, db, dc, out=dc)  # in place over the addend
+    assert_bits_equal(dc.to_host(), want, f"muladd {dt} in place")
+    assert _launches() - launches0 >= 4
+
+
+@pytest.mark.parametrize("dt", FUSED_DTYPES)
+def test_muladd_sum_is_the_three_call_chain(dev, O, dt):
+    """sum(a*b + c) fused == multiply, add, sum as three kernels, BIT FOR BIT (same logical blocks, same
+    fold order, same accumulator), and within the stated sum tolerance of a float64 reference."""
+    from pnumpy_b200 import cabi
+    A = cabi.load().pncu_reduce_block_elems()
+    for n in (1, 777, A // 4 + 5, 3 * A + 1234):
+        a, b, c = (reduction_input(dt, n=n, seed=s) for s in (21, 22, 23))
+        da, db, dc = dev.to_device(a), dev.to_device(b), dev.to_device(c)
+        chain = dev.reduce("ADD", dev.binary("ADD", dev.binary("MUL", da, db), dc)).to_host()
+        fused = dev.muladd_sum(da, db, dc).to_host()
+        assert fused.tobytes() == chain.tobytes(), (dt, n, fused, chain)
+        with np.errstate(all="ignore"):
+            u = a * b + c
+        if dt in FP_DTYPES:
+            ref = math.fsum(u.astype(np.float64))
+            mag = float(np.abs(u.astype(np.float64)).sum())
+            tol = (2.0 ** -23 * abs(ref) + 2.0 ** -50 * mag) if dt == "float32" else (math.log2(max(n, 2)) + 2) * 2.0 ** -53 * mag
+            assert abs(float(fused[0]) - ref) <= tol, (dt, n, fused, ref)
+        else:
+            assert fused[0] == u.sum(dtype=u.dtype), (dt, n)
+
+
+def test_muladd_sum_partials_are_shard_invariant(dev):
+    """pass 1 of the fused sum over shards + the ordinary ADD finish == the single call (multi-GPU combine)."""
+    from pnumpy_b200 import cabi
+    lib = cabi.load()
+    A = lib.pncu_reduce_block_elems()
+    n = 9 * A + 4321
+    for dt in ("float32", "float64", "int64"):
+        a, b, c = (reduction_input(dt, n=n, seed=s) for s in (31, 32, 33))
+        da, db, dc = dev.to_device(a), dev.to_device(b), dev.to_device(c)
+        whole = dev.muladd_sum(da, db, dc).to_host()
+        t = cabi.atop_of(dt)
+        pb = lib.pncu_reduce_partial_bytes(cabi.BINARY_OPS["ADD"], t)
+        nb = lib.pncu_reduce_partial_count(t, n)
+        parts = dev.empty(nb * pb, np.uint8)
+        units, isz = -(-n // A), a.dtype.itemsize
+        for shards in (1, 2, 4, 8):
+            cabi.check(lib.pncu_memset(parts.ptr, 0xFF, nb * pb, None), "memset")
+            per = -(-units // shards)
+            for s_ in range(shards):
+                e0, e1 = min(n, s_ * per * A), min(n, (s_ + 1) * per * A)
+                if e0 >= e1:
+                    continue
+                slot0 = lib.pncu_reduce_partial_count(t, e0)
+                cabi.check(lib.pncu_muladd_sum_partials(t, da.ptr + e0 * isz, db.ptr + e0 * isz, dc.ptr + e0 * isz,
+                                                        e1 - e0, parts.ptr + slot0 * pb, None), "muladd partials")
+            out = dev.empty(1, dt)
+            cabi.check(lib.pncu_reduce_finish(cabi.BINARY_OPS["ADD"], t, parts.ptr, nb, out.ptr, None, None), "finish")
+            assert out.to_host().tobytes() == whole.tobytes(), (dt, shards)
+
+
+def test_muladd_full_size_properties(dev):
+    """2^28 float32 elements: a*1 + 0 reproduces a bit for bit (no NaNs in the input), sum(a*1 + 0) is
+    sum(a) bit for bit, and sum(a*b + c) == sum over the materialised a*b + c."""
+    n = 1 << 28
+    rng = np.random.default_rng(99)
+    a = rng.random(n, dtype=np.float32) * 253 + 1
+    da = dev.to_device(a)
+    one = dev.to_device(np.ones(n, np.float32))
+    zero = dev.to_device(np.zeros(n, np.float32))
+    out = dev.muladd(da, one, zero)
+    eq = dev.compare("EQ", out, da)
+    assert bool(dev.reduce("MUL", eq).to_host()[0])  # logical AND over the bool result
+    assert dev.muladd_sum(da, one, zero).to_host().tobytes() == dev.reduce("ADD", da).to_host().tobytes()
+    del eq, zero
+    u = dev.muladd(da, da, one, out=out)
+    assert dev.muladd_sum(da, da, one).to_host().tobytes() == dev.reduce("ADD", u).to_host().tobytes()
