@@ -34,7 +34,9 @@ enum { C_EQ = 0, C_NE, C_LT, C_GT, C_LE, C_GE };
 enum { U_ABS = 1, U_SIGNBIT = 2, U_INVERT = 4, U_FLOOR = 5, U_CEIL = 6, U_TRUNC = 7, U_ROUND = 8,
        U_NEG = 9, U_SIGN = 11, U_SQRT = 15, U_LNOT = 18, U_ISINF = 19, U_ISNAN = 20, U_ISFINITE = 21,
        U_BITNOT = 28 };
-enum { G_SIN = 1, G_COS = 2, G_LOG = 13, G_EXP = 16 };
+enum { G_SIN = 1, G_COS = 2, G_TAN = 3, G_ASIN = 4, G_ACOS = 5, G_ATAN = 6, G_SINH = 7, G_COSH = 8, G_TANH = 9,
+       G_ASINH = 10, G_ACOSH = 11, G_ATANH = 12, G_LOG = 13, G_LOG2 = 14, G_LOG10 = 15, G_EXP = 16, G_EXP2 = 17,
+       G_EXPM1 = 18, G_LOG1P = 19, G_CBRT = 20 };
 
 int oracle_itemsize(int t) {
     switch (t) {
@@ -411,6 +413,24 @@ int oracle_trig(int op, int t, const void* in, void* out, int64_t n, int64_t s1,
             case G_COS: UN_LOOP(float, float, oracle_cosf(a))
             case G_LOG: UN_LOOP(float, float, oracle_logf(a))
             case G_EXP: UN_LOOP(float, float, oracle_expf(a))
+            /* no reference body (GetTrigOpFast returns NULL, src/atop/ops_trig.cpp:599-777): the reference
+             * threads NumPy's loop, i.e. the platform libm; glibc stands in, compared in ULP not bits */
+            case G_TAN: UN_LOOP(float, float, tanf(a))
+            case G_ASIN: UN_LOOP(float, float, asinf(a))
+            case G_ACOS: UN_LOOP(float, float, acosf(a))
+            case G_ATAN: UN_LOOP(float, float, atanf(a))
+            case G_SINH: UN_LOOP(float, float, sinhf(a))
+            case G_COSH: UN_LOOP(float, float, coshf(a))
+            case G_TANH: UN_LOOP(float, float, tanhf(a))
+            case G_ASINH: UN_LOOP(float, float, asinhf(a))
+            case G_ACOSH: UN_LOOP(float, float, acoshf(a))
+            case G_ATANH: UN_LOOP(float, float, atanhf(a))
+            case G_LOG2: UN_LOOP(float, float, log2f(a))
+            case G_LOG10: UN_LOOP(float, float, log10f(a))
+            case G_EXP2: UN_LOOP(float, float, exp2f(a))
+            case G_EXPM1: UN_LOOP(float, float, expm1f(a))
+            case G_LOG1P: UN_LOOP(float, float, log1pf(a))
+            case G_CBRT: UN_LOOP(float, float, cbrtf(a))
         }
     } else if (t == T_F64) {
         switch (op) {
@@ -418,6 +438,22 @@ int oracle_trig(int op, int t, const void* in, void* out, int64_t n, int64_t s1,
             case G_COS: UN_LOOP(double, double, cos(a))
             case G_LOG: UN_LOOP(double, double, log(a))
             case G_EXP: UN_LOOP(double, double, exp(a))
+            case G_TAN: UN_LOOP(double, double, tan(a))
+            case G_ASIN: UN_LOOP(double, double, asin(a))
+            case G_ACOS: UN_LOOP(double, double, acos(a))
+            case G_ATAN: UN_LOOP(double, double, atan(a))
+            case G_SINH: UN_LOOP(double, double, sinh(a))
+            case G_COSH: UN_LOOP(double, double, cosh(a))
+            case G_TANH: UN_LOOP(double, double, tanh(a))
+            case G_ASINH: UN_LOOP(double, double, asinh(a))
+            case G_ACOSH: UN_LOOP(double, double, acosh(a))
+            case G_ATANH: UN_LOOP(double, double, atanh(a))
+            case G_LOG2: UN_LOOP(double, double, log2(a))
+            case G_LOG10: UN_LOOP(double, double, log10(a))
+            case G_EXP2: UN_LOOP(double, double, exp2(a))
+            case G_EXPM1: UN_LOOP(double, double, expm1(a))
+            case G_LOG1P: UN_LOOP(double, double, log1p(a))
+            case G_CBRT: UN_LOOP(double, double, cbrt(a))
         }
     }
     return -1;

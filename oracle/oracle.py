@@ -23,7 +23,8 @@ BINARY = dict(ADD=1, SUB=2, MUL=3, MIN=5, MAX=6, FLOORDIV=9, DIV=13, LOGICAL_AND
 COMPARE = dict(EQ=0, NE=1, LT=2, GT=3, LTE=4, GTE=5)
 UNARY = dict(ABS=1, SIGNBIT=2, INVERT=4, FLOOR=5, CEIL=6, TRUNC=7, ROUND=8, NEGATIVE=9, SIGN=11,
              SQRT=15, LOGICAL_NOT=18, ISINF=19, ISNAN=20, ISFINITE=21, BITWISE_NOT=28)
-TRIG = dict(SIN=1, COS=2, LOG=13, EXP=16)
+TRIG = dict(SIN=1, COS=2, TAN=3, ASIN=4, ACOS=5, ATAN=6, SINH=7, COSH=8, TANH=9, ASINH=10, ACOSH=11, ATANH=12,
+            LOG=13, LOG2=14, LOG10=15, EXP=16, EXP2=17, EXPM1=18, LOG1P=19, CBRT=20)
 
 _i64 = ctypes.c_int64
 _vp = ctypes.c_void_p

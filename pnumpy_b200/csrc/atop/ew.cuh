@@ -188,7 +188,10 @@ ew2_strided_kernel(const char* a, const char* b, char* o, int64_t n,
 // then issues kUnroll 256-bit loads before its first use.  With one load per thread the time a warp
 // spends computing is time it has nothing in flight, and 64 warps/SM x 32 B no longer cover the
 // HBM latency-bandwidth product (measured: sin at 5.8 TB/s with 1 vector per thread).
-template <class F, class = void> struct unroll_of { static constexpr int value = 1; };
+#ifndef PNCU_EW1_UNROLL
+#define PNCU_EW1_UNROLL 1
+#endif
+template <class F, class = void> struct unroll_of { static constexpr int value = PNCU_EW1_UNROLL; };
 template <class F> struct unroll_of<F, decltype((void)F::kUnroll)> { static constexpr int value = F::kUnroll; };
 
 template <class F, int EPV>

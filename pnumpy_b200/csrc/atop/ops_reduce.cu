@@ -277,8 +277,11 @@ template <> struct WordOps<MaxR<int16_t>> : MinMaxWord<int16_t, true> {};
 template <> struct WordOps<MaxR<uint16_t>> : MinMaxWord<uint16_t, true> {};
 
 // ---- pass 1 --------------------------------------------------------------------------------------
+#ifndef PNCU_RED_MINB
+#define PNCU_RED_MINB 4
+#endif
 template <class R, bool VEC>
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(RED_THREADS, PNCU_RED_MINB)
 reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_base,
                      typename R::Acc* partials) {
     typedef typename R::In In;
@@ -287,6 +290,8 @@ reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_ba
     constexpr int EPV = 32 / (int)sizeof(In);
     __shared__ Acc smem[RED_THREADS / 32];
 
+    // let a finish kernel queued behind this grid (launch_finish_dependent) become resident early
+    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
@@ -359,6 +364,8 @@ muladd_sum_blocks_kernel(const typename R::In* a, const typename R::In* b, const
     static_assert(RED_NV % RED_CHAINS == 0, "vector j must map to accumulator j % RED_CHAINS");
     __shared__ Acc smem[RED_THREADS / 32];
 
+    // let a finish kernel queued behind this grid (launch_finish_dependent) become resident early
+    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
@@ -430,6 +437,8 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
     __shared__ W smem_v[RED_THREADS / 32];
     __shared__ int smem_i[RED_THREADS / 32];
 
+    // let a finish kernel queued behind this grid (launch_finish_dependent) become resident early
+    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
@@ -513,14 +522,26 @@ __global__ void __launch_bounds__(FIN_THREADS)
 reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, const void* startVal) {
     typedef typename R::Acc Acc;
     __shared__ Acc smem[FIN_THREADS / 32];
+    // launched with programmatic stream serialization right behind pass 1 (launch_reduce): this CTA may
+    // already be resident while pass 1 drains; wait here until that grid is complete and visible.  A no-op
+    // for an ordinary launch (pncu_reduce_finish after the multi-GPU gather).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // slots t, t+1024, ... in order; threads beyond `count` hold a copy of slot 0 (harmless for
-    // idempotent ops) or the identity
+    // idempotent ops) or the identity.  FIN_MLP loads are in flight per thread; the fold order is unchanged.
+    constexpr int FIN_MLP = 8;
     Acc a;
     if (R::kHasIdentity) a = R::identity(); else a = partials[0];
-    for (int64_t k = threadIdx.x; k < count; k += FIN_THREADS) {
-        if (!R::kHasIdentity && k == threadIdx.x) a = partials[k];
-        else a = R::combine(a, partials[k]);
+    int64_t k = threadIdx.x;
+    if (!R::kHasIdentity && k < count) { a = partials[k]; k += FIN_THREADS; }  // the first slot replaces the seed
+    // full batches: unconditional loads first (predicated ones get interleaved with the adds and serialise)
+    for (; k + (int64_t)(FIN_MLP - 1) * FIN_THREADS < count; k += (int64_t)FIN_THREADS * FIN_MLP) {
+        Acc x[FIN_MLP];
+#pragma unroll
+        for (int m = 0; m < FIN_MLP; ++m) x[m] = partials[k + (int64_t)m * FIN_THREADS];
+#pragma unroll
+        for (int m = 0; m < FIN_MLP; ++m) a = R::combine(a, x[m]);
     }
+    for (; k < count; k += FIN_THREADS) a = R::combine(a, partials[k]);
     a = block_fold<R, FIN_THREADS>(a, smem);
     if (threadIdx.x == 0) {
         if constexpr (VALUE) {
@@ -530,6 +551,25 @@ reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, 
             if constexpr (sizeof(Acc) == 16) *reinterpret_cast<int64_t*>(out) = a.idx;
         }
     }
+}
+
+// pass 2 queued right behind pass 1 on the same stream: with programmatic stream serialization the
+// finish CTA is scheduled as soon as every pass-1 CTA has started (griddepcontrol.launch_dependents) and
+// blocks in griddepcontrol.wait until that grid is complete, so its launch latency overlaps pass 1's tail.
+template <class R, bool VALUE>
+int launch_finish_dependent(const void* partials, int64_t count, void* out, const void* startVal, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(FIN_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_finish_kernel<R, VALUE>, (const typename R::Acc*)partials, count, out, startVal);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaLaunchKernelEx(reduce_finish_kernel)", __FILE__, __LINE__); }
+    return after_launch("reduce_finish_kernel");
 }
 
 // ---- host launchers ---------------------------------------------------------------------------------
@@ -593,8 +633,7 @@ int launch_reduce(const void* in, void* out, const void* startVal, int64_t len, 
     void* ws = NULL;
     if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
     if ((rc = launch_partials<R>(in, len, stride, 0, ws, st))) return rc;
-    reduce_finish_kernel<R, true><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)ws, nb, out, startVal);
-    return after_launch("reduce_finish_kernel");
+    return launch_finish_dependent<R, true>(ws, nb, out, startVal, st);
 }
 
 // sum(a*b + c): pass 1 (fused) and the ordinary pass 2 of the ADD reduction
@@ -630,8 +669,7 @@ int launch_muladd_sum(const void* a, const void* b, const void* c, void* out, in
     void* ws = NULL;
     if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
     if ((rc = launch_muladd_partials<R>(a, b, c, len, ws, st))) return rc;
-    reduce_finish_kernel<R, true><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)ws, nb, out, NULL);
-    return after_launch("reduce_finish_kernel");
+    return launch_finish_dependent<R, true>(ws, nb, out, NULL, st);
 }
 
 struct MulAddSumOps {
@@ -668,8 +706,7 @@ int launch_argminmax(const void* in, int64_t len, int64_t* out_index, pncu_strea
     void* ws = NULL;
     if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
     if ((rc = launch_arg_partials<typename R::In, R::kIsMax>(in, len, sizeof(typename R::In), 0, ws, st))) return rc;
-    reduce_finish_kernel<R, false><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)ws, nb, out_index, NULL);
-    return after_launch("reduce_finish_kernel");
+    return launch_finish_dependent<R, false>(ws, nb, out_index, NULL, st);
 }
 
 // type-erased entry for the two-pass building blocks

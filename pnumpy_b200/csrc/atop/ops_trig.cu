@@ -254,6 +254,8 @@ struct ExpF64 { typedef double In; typedef double Out; static constexpr int kUnr
 
 }  // namespace
 
+namespace pncu { pncu_unary_fn trig_more(int func, int t); }
+
 extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType) {
     if (!wantedOutType || func <= PNCU_TRIG_INVALID || func >= PNCU_TRIG_LAST) return NULL;
     // ops_trig.cpp:584-777: every op sets the out-type to the in-type, body or not -- the hook
@@ -276,6 +278,9 @@ extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType)
             if (t == PNCU_FLOAT) return launch_unary<ExpF32>;
             if (t == PNCU_DOUBLE) return launch_unary<ExpF64>;
             break;
+        default:
+            // the sixteen ufuncs the reference hooks without a body (ops_trig_more.cu)
+            return trig_more(func, t);
     }
     return NULL;
 }

@@ -1,0 +1,75 @@
+// The sixteen transcendental ufuncs the reference hooks WITHOUT a body of its own -- tan, arcsin,
+// arccos, arctan, sinh, cosh, tanh, arcsinh, arccosh, arctanh, cbrt, exp2, expm1, log2, log10, log1p
+// (GetTrigOpFast returns NULL for them, src/atop/ops_trig.cpp:599-777, and the dispatcher threads
+// NumPy's own loop over 16K chunks, src/pnumpy/_pnumpy.cpp:973-993).  SURVEY.md 8(f) row f-4.
+//
+// Here they get a GPU body: CUDA's math library inside the same streaming kernel as sin/log/exp
+// (ew1_vec_kernel, several 256-bit loads in flight per thread).  There is no reference arithmetic
+// to be bit-identical to -- NumPy's loops call the platform libm / SVML, whose results differ from
+// one libm to the next in the last place -- so the parity bar is stated in ULP against the
+// correctly rounded value: <= 4 ULP (tests/test_gpu_parity.py; CUDA documents 1-4 ULP for these),
+// with the IEEE special cases (NaN, +-inf, +-0, domain errors -> NaN, poles -> +-inf) exact.
+#include "ew.cuh"
+#include "functors.cuh"
+
+using namespace pncu;
+
+namespace {
+
+#define PNCU_LIBM_FUNCTOR(NAME, FN32, FN64)                                                                     \
+    struct NAME##F32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4;                 \
+                       static __device__ __forceinline__ float apply(float a) { return FN32(a); } };           \
+    struct NAME##F64 { typedef double In; typedef double Out; static constexpr int kUnroll = 1;               \
+                       static __device__ __forceinline__ double apply(double a) { return FN64(a); } };
+
+PNCU_LIBM_FUNCTOR(Tan, tanf, tan)
+PNCU_LIBM_FUNCTOR(Asin, asinf, asin)
+PNCU_LIBM_FUNCTOR(Acos, acosf, acos)
+PNCU_LIBM_FUNCTOR(Atan, atanf, atan)
+PNCU_LIBM_FUNCTOR(Sinh, sinhf, sinh)
+PNCU_LIBM_FUNCTOR(Cosh, coshf, cosh)
+PNCU_LIBM_FUNCTOR(Tanh, tanhf, tanh)
+PNCU_LIBM_FUNCTOR(Asinh, asinhf, asinh)
+PNCU_LIBM_FUNCTOR(Acosh, acoshf, acosh)
+PNCU_LIBM_FUNCTOR(Atanh, atanhf, atanh)
+PNCU_LIBM_FUNCTOR(Log2, log2f, log2)
+PNCU_LIBM_FUNCTOR(Log10, log10f, log10)
+PNCU_LIBM_FUNCTOR(Exp2, exp2f, exp2)
+PNCU_LIBM_FUNCTOR(Expm1, expm1f, expm1)
+PNCU_LIBM_FUNCTOR(Log1p, log1pf, log1p)
+PNCU_LIBM_FUNCTOR(Cbrt, cbrtf, cbrt)
+#undef PNCU_LIBM_FUNCTOR
+
+}  // namespace
+
+namespace pncu {
+
+pncu_unary_fn trig_more(int func, int t) {
+#define PNCU_PICK(OP, NAME)                                        \
+    case OP:                                                       \
+        if (t == PNCU_FLOAT) return launch_unary<NAME##F32>;       \
+        if (t == PNCU_DOUBLE) return launch_unary<NAME##F64>;      \
+        return NULL;
+    switch (func) {
+        PNCU_PICK(PNCU_TAN, Tan)
+        PNCU_PICK(PNCU_ASIN, Asin)
+        PNCU_PICK(PNCU_ACOS, Acos)
+        PNCU_PICK(PNCU_ATAN, Atan)
+        PNCU_PICK(PNCU_SINH, Sinh)
+        PNCU_PICK(PNCU_COSH, Cosh)
+        PNCU_PICK(PNCU_TANH, Tanh)
+        PNCU_PICK(PNCU_ASINH, Asinh)
+        PNCU_PICK(PNCU_ACOSH, Acosh)
+        PNCU_PICK(PNCU_ATANH, Atanh)
+        PNCU_PICK(PNCU_LOG2, Log2)
+        PNCU_PICK(PNCU_LOG10, Log10)
+        PNCU_PICK(PNCU_EXP2, Exp2)
+        PNCU_PICK(PNCU_EXPM1, Expm1)
+        PNCU_PICK(PNCU_LOG1P, Log1p)
+        PNCU_PICK(PNCU_CBRT, Cbrt)
+    }
+#undef PNCU_PICK
+    return NULL;
+}
+
+}  // namespace pncu

@@ -433,3 +433,20 @@ def test_fused_chain_on_resident_arrays_and_fallbacks(pn, rng):
         assert_bits_equal(pn.muladd(ha, hb, hc), want, "atop disabled -> NumPy chain")
     finally:
         pn.enable()
+
+
+@pytest.mark.parametrize("dt", FP_DTYPES)
+def test_more_transcendental_ufuncs_run_on_the_gpu(pn, rng, dt):
+    """tan ... cbrt (hooked by the reference without a body; it threads NumPy's loop): here the hooked call
+    reaches a GPU body, within 4 ULP of NumPy's own loop on the same input."""
+    n = 1 << 20
+    u = rng.uniform(-0.99, 0.99, n).astype(dt)
+    cases = {"tan": u * 10, "arcsin": u, "arccos": u, "arctan": u * 50, "sinh": u * 10, "cosh": u * 10, "tanh": u * 5,
+             "arcsinh": u * 1e3, "arccosh": np.abs(u) * 100 + 1, "arctanh": u, "log2": np.abs(u) * 1e3 + 1e-3,
+             "log10": np.abs(u) * 1e3 + 1e-3, "exp2": u * 60, "expm1": u * 10, "log1p": u * 100 + 99, "cbrt": u * 1e5}
+    for name, v in cases.items():
+        v = v.astype(dt)
+        got, want, calls = _both(pn, lambda: getattr(np, name)(v))
+        assert calls >= 1, name
+        assert got.dtype == want.dtype
+        assert ulp_error(got, want.astype(np.float64)).max() <= 4.0, (name, dt)

@@ -513,3 +513,59 @@ def test_muladd_full_size_properties(dev):
     del eq, zero
     u = dev.muladd(da, da, one, out=out)
     assert dev.muladd_sum(da, da, one).to_host().tobytes() == dev.reduce("ADD", u).to_host().tobytes()
+
+
+# ---- the sixteen transcendental ufuncs the reference hooks without a body ------------
+# (numpy function, input range) per op; the bar is <= 4 ULP of the correctly rounded value (CUDA documents
+# 1-4 ULP for these; NumPy's own loops differ between libm builds in the last place, so there are no
+# reference bits to match) and exact IEEE special cases.
+MORE_TRIG = {
+    "TAN": (np.tan, -20.0, 20.0), "ASIN": (np.arcsin, -1.0, 1.0), "ACOS": (np.arccos, -1.0, 1.0),
+    "ATAN": (np.arctan, -50.0, 50.0), "SINH": (np.sinh, -20.0, 20.0), "COSH": (np.cosh, -20.0, 20.0),
+    "TANH": (np.tanh, -10.0, 10.0), "ASINH": (np.arcsinh, -1e4, 1e4), "ACOSH": (np.arccosh, 1.0, 1e4),
+    "ATANH": (np.arctanh, -1.0, 1.0), "LOG2": (np.log2, 1e-30, 1e30), "LOG10": (np.log10, 1e-30, 1e30),
+    "EXP2": (np.exp2, -100.0, 100.0), "EXPM1": (np.expm1, -20.0, 20.0), "LOG1P": (np.log1p, -0.999, 1e4),
+    "CBRT": (np.cbrt, -1e6, 1e6),
+}
+
+
+@pytest.mark.parametrize("dt", FP_DTYPES)
+@pytest.mark.parametrize("op", sorted(MORE_TRIG))
+def test_more_transcendentals_within_4ulp(dev, O, rng, op, dt):
+    fn, lo, hi = MORE_TRIG[op]
+    n = 1 << 16
+    if op in ("LOG2", "LOG10"):
+        x = np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+    else:
+        x = rng.uniform(lo, hi, n)
+    small = rng.uniform(-1e-3, 1e-3, 1 << 12)                      # cancellation region of expm1/log1p/atanh/...
+    if op == "ACOSH":
+        small = 1.0 + np.abs(small)
+    elif op in ("LOG2", "LOG10"):
+        small = 1.0 + small
+    edge = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 2.0, -2.0, 0.5, 1e-40, -1e-40, 1e38, -1e38])
+    x = np.concatenate([x, small, edge]).astype(dt)
+    launches0 = _launches()
+    got = dev.unary(op, dev.to_device(x)).to_host()
+    assert _launches() > launches0 and got.dtype == x.dtype
+    with np.errstate(all="ignore"):
+        truth = fn(x.astype(np.longdouble))                        # x87 extended: 11 spare bits for float64
+        want = O.unary(op, x)                                      # glibc, what NumPy's loop calls
+    tf = truth.astype(np.float64)
+    g = got.astype(np.longdouble)
+    fin = np.isfinite(truth) & np.isfinite(got)
+    with np.errstate(all="ignore"):
+        tiny = float(np.finfo(x.dtype).smallest_subnormal)
+        sp = np.maximum(np.spacing(np.abs(truth[fin]).astype(x.dtype)).astype(np.float64), tiny)
+        err = np.abs(g[fin] - truth[fin]).astype(np.float64) / sp
+    assert err.max() <= 4.0, (op, dt, err.max(), x[fin][np.argmax(err)])
+    # non-finite results: same class as the libm oracle (NaN <-> NaN, +-inf exact), also where only one
+    # side overflowed the dtype
+    rest = ~fin
+    assert np.array_equal(np.isnan(got[rest]), np.isnan(want[rest])), (op, dt, x[rest], got[rest], want[rest])
+    nn = rest & ~np.isnan(got)
+    assert np.array_equal(got[nn], want[nn]), (op, dt, x[nn], got[nn], want[nn])
+    # and never far from the libm oracle either
+    both = np.isfinite(want) & np.isfinite(got)
+    assert np.all(ulp_error(got[both], want[both].astype(np.float64)) <= 8.0)
+    del tf
