@@ -522,13 +522,48 @@ def run_e2e(args):
                           "bit_identical_to_unfused": bool(np.asarray(rf).tobytes() == np.asarray(r).tobytes())}
     except Exception as e:  # pragma: no cover
         chain = {"error": str(e)}
+    # configs[4] at its stated size: 2^30 float32 per operand (4 GiB each; 5 pinned arrays = 20 GiB)
+    if args.chain_lg > args.e2e_lg and isinstance(chain, dict) and "error" not in chain:
+        try:
+            arrs.clear()
+            del a, b, o, c, t
+            m = 1 << args.chain_lg
+            big = [pn.pinned_empty(m, np.float32) for _ in range(5)]
+            piece = rng.random(1 << 22, dtype=np.float32) * 253 + 1
+            for x in big[:3]:
+                x.reshape(-1, piece.size)[:] = piece
+            a, b, c, t, o = big
+
+            def run_chain_big():
+                np.multiply(a, b, out=t)
+                np.add(t, c, out=o)
+                return o.sum()
+            r = run_chain_big()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r = run_chain_big()
+            ch_s = (time.perf_counter() - t0) / reps
+            rf = pn.muladd_sum(a, b, c)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                rf = pn.muladd_sum(a, b, c)
+            fu_s = (time.perf_counter() - t0) / reps
+            chain["at_2p%d" % args.chain_lg] = {
+                "elements": m, "unfused_ms": round(ch_s * 1e3, 2), "unfused_gbs": round(28.0 * m / ch_s / 1e9, 2),
+                "fused_ms": round(fu_s * 1e3, 2), "fused_pcie_gbs": round(12.0 * m / fu_s / 1e9, 2),
+                "fused_equivalent_gbs_at_28B_per_elem": round(28.0 * m / fu_s / 1e9, 2),
+                "bit_identical": bool(np.asarray(rf).tobytes() == np.asarray(r).tobytes()), "result": float(r)}
+            del big, a, b, c, t, o
+        except Exception as e:  # pragma: no cover
+            chain["at_2p%d" % args.chain_lg] = {"error": str(e)}
     # the same hooks on DEVICE-RESIDENT ndarrays (CUDA managed memory): no PCIe in steady state
     resident = None
     try:
         m = 1 << 28
         ma, mb, mo = pn.managed_empty(m, np.float32), pn.managed_empty(m, np.float32), pn.managed_empty(m, np.float32)
-        ma[:] = arrs["float32"][0][:m]
-        mb[:] = arrs["float32"][1][:m]
+        piece = rng.random(1 << 22, dtype=np.float32) * 253 + 1
+        ma.reshape(-1, piece.size)[:] = piece
+        mb.reshape(-1, piece.size)[:] = piece[::-1]
         np.add(ma, mb, out=mo)  # first call migrates the pages to the GPU
         np.add(ma, mb, out=mo)
         pn.cuda_reset_stats()
@@ -657,6 +692,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-detail", action="store_true")
     ap.add_argument("--e2e-lg", type=int, default=28, help="log2 elements per operand of the end-to-end sweep")
+    ap.add_argument("--chain-lg", type=int, default=30, help="log2 elements of the end-to-end a*b+c -> sum chain (configs[4]: 2^30)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-lg", type=int, default=27, help="log2 elements per operand of the CPU sample")
     args = ap.parse_args()
