@@ -194,6 +194,40 @@ ew2_strided_kernel(const char* a, const char* b, char* o, int64_t n,
 template <class F, class = void> struct unroll_of { static constexpr int value = PNCU_EW1_UNROLL; };
 template <class F> struct unroll_of<F, decltype((void)F::kUnroll)> { static constexpr int value = F::kUnroll; };
 
+// Functors with a branch-free FAST body valid on part of the domain declare
+//     static constexpr bool kHasFast = true;  static bool ok(In);  static Out fast(In [, const void* table]);
+// and make apply() the (out-of-line) general function.  The kernel then tests a thread's whole set of
+// inputs once: if every element is in the fast domain (the overwhelmingly common case) the packs run
+// the fast body with no per-element branch, so the independent chains interleave; otherwise the
+// thread falls back to apply() element by element.
+template <class F, class = void> struct has_fast { static constexpr bool value = false; };
+template <class F> struct has_fast<F, decltype((void)F::kHasFast)> { static constexpr bool value = F::kHasFast; };
+// Functors whose fast body reads a lookup table from shared memory declare
+//     static constexpr int kSmemBytes;  static void smem_init(void* smem) (all threads of the CTA);
+//     static const void* smem_lane(const void* smem) (this lane's view);  static Out fast(In, const void*)
+template <class F, class = void> struct smem_of { static constexpr int value = 0; };
+template <class F> struct smem_of<F, decltype((void)F::kSmemBytes)> { static constexpr int value = F::kSmemBytes; };
+
+template <class F, int EPV>
+__device__ __forceinline__ bool pack_ok(const Pack<typename F::In, EPV>& ra) {
+    bool ok = true;
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) ok = ok && F::ok(ra.get(e));
+    return ok;
+}
+template <class F, int EPV>
+__device__ __forceinline__ Pack<typename F::Out, EPV> fast_pack(const Pack<typename F::In, EPV>& ra, const void* table) {
+    typedef typename F::Out Out;
+    Pack<Out, EPV> r;
+    r.zero();
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) {
+        if constexpr (smem_of<F>::value != 0) r.set(e, F::fast(ra.get(e), table));
+        else r.set(e, F::fast(ra.get(e)));
+    }
+    return r;
+}
+
 template <class F, int EPV>
 __device__ __forceinline__ Pack<typename F::Out, EPV> apply_pack(const Pack<typename F::In, EPV>& ra) {
     typedef typename F::Out Out;
@@ -216,9 +250,22 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
         Pack<In, EPV> ra[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) ra[u] = ld_pack<In, EPV>(a + head + (v0 + (int64_t)u * EW_BLOCK) * EPV);
+        bool all_fast = has_fast<F>::value;
+        if constexpr (has_fast<F>::value) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-            st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
+            for (int u = 0; u < U; ++u) all_fast = all_fast && pack_ok<F, EPV>(ra[u]);
+        }
+        if (all_fast) {
+            if constexpr (has_fast<F>::value) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, fast_pack<F, EPV>(ra[u], nullptr));
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
+        }
     } else {
 #pragma unroll 1
         for (int u = 0; u < U; ++u) {
@@ -226,6 +273,63 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
             if (v < nvec) {
                 const Pack<In, EPV> ra = ld_pack<In, EPV>(a + head + v * EPV);
                 st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra));
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tail0 = head + nvec * EPV;
+        const int64_t nscalar = head + (n - tail0);
+        for (int64_t i = threadIdx.x; i < nscalar; i += EW_BLOCK) {
+            const int64_t idx = i < head ? i : tail0 + (i - head);
+            o[idx] = F::apply(a[idx]);
+        }
+    }
+}
+
+// Variant for functors with a shared-memory lookup table (float64 log): a CTA builds the table once
+// and then streams EW_TABLE_TILES tiles, so the set-up (16 KiB of shared-memory stores) is paid once
+// per 256 KiB of traffic.  The grid is still thousands of CTAs: the hardware scheduler balances it.
+constexpr int EW_TABLE_TILES = 8;
+
+template <class F>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew1_table_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    constexpr int EPV = Epv<In, Out>::value;
+    constexpr int U = unroll_of<F>::value;
+    __shared__ __align__(16) unsigned char smem[smem_of<F>::value];
+    F::smem_init(smem);
+    __syncthreads();
+    const void* table = F::smem_lane(smem);
+#pragma unroll 1
+    for (int t = 0; t < EW_TABLE_TILES; ++t) {
+        const int64_t v0 = ((int64_t)blockIdx.x * EW_TABLE_TILES + t) * (EW_BLOCK * U) + threadIdx.x;
+        if (v0 >= nvec) break;
+        if (v0 + (int64_t)(U - 1) * EW_BLOCK < nvec) {
+            Pack<In, EPV> ra[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) ra[u] = ld_pack<In, EPV>(a + head + (v0 + (int64_t)u * EW_BLOCK) * EPV);
+            bool all_fast = true;
+#pragma unroll
+            for (int u = 0; u < U; ++u) all_fast = all_fast && pack_ok<F, EPV>(ra[u]);
+            if (all_fast) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, fast_pack<F, EPV>(ra[u], table));
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
+            }
+        } else {
+#pragma unroll 1
+            for (int u = 0; u < U; ++u) {
+                const int64_t v = v0 + (int64_t)u * EW_BLOCK;
+                if (v < nvec) {
+                    const Pack<In, EPV> ra = ld_pack<In, EPV>(a + head + v * EPV);
+                    st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra));
+                }
             }
         }
     }
@@ -359,8 +463,14 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
         if (head > len) head = len;
         if (((uintptr_t)in + head * sizeof(In)) % IN_VB == 0) {
             const int64_t nvec = (len - head) / EPV;
-            ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
-            return after_launch("ew1_vec_kernel");
+            if constexpr (smem_of<F>::value != 0) {
+                ew1_table_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value * EW_TABLE_TILES), EW_BLOCK, 0, st>>>(
+                    (const In*)in, (Out*)out, head, nvec, len);
+                return after_launch("ew1_table_kernel");
+            } else {
+                ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
+                return after_launch("ew1_vec_kernel");
+            }
         }
     }
     ew1_strided_kernel<F><<<full_grid(len, EW_BLOCK), EW_BLOCK, 0, st>>>((const char*)in, (char*)out, len, s1, so);

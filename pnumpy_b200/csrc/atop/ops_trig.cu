@@ -15,13 +15,14 @@
 // non-finite sin/cos through CUDA's full-range sinf/cosf.
 //
 // float64: the reference's pd bodies are wrong (exponent-bias typo avx_mathfun.h:107, float
-// clamp :326-327, float coefficients :472-481), so there is nothing to match; the kernels use
-// CUDA's double-precision sin/cos/log/exp (<= 2 ULP, documented by NVIDIA) and are checked
-// against correctly rounded values.
+// clamp :326-327, float coefficients :472-481), so there is nothing to match; the kernels use the
+// hand-written bodies of f64_math.cuh (<= 1.5 ULP measured; CUDA's functions outside their fast
+// domain) and are checked against correctly rounded values.
 #include <float.h>
 #include <math.h>
 #include "ew.cuh"
 #include "functors.cuh"
+#include "f64_math.cuh"
 
 using namespace pncu;
 
@@ -84,10 +85,39 @@ __device__ __noinline__ float cephes_log_general(float x) {
     // denormal: rescale exactly by 2^23 (the reference clamps to FLT_MIN instead)
     return cephes_log_core(FM(x, 8388608.0f), 23.0f);
 }
+// fast body: x positive, normal, finite.  Same values as cephes_log_core(x, 0) with the exponent /
+// mantissa split done in integers: adding 0x3f800000 - bits(SQRTHF) carries into the exponent field
+// exactly when the mantissa is >= sqrt(1/2), so E' = E + !lt and the mantissa lands in
+// [sqrt(1/2), sqrt(2)) -- and m' - 1 is exactly the reference's (x - 1) + (lt ? x : 0), both being exact.
+__device__ __forceinline__ float cephes_log_fast(float x) {
+    const unsigned ix = __float_as_uint(x) + 0x004afb0du;                 // 0x3f800000 - 0x3f3504f3
+    const float e = FS(__uint_as_float(0x4B000000u + (ix >> 23)), 8388735.0f);  // (2^23 + E') - (2^23 + 127)
+    x = FS(__uint_as_float((ix & 0x007fffffu) + 0x3f3504f3u), 1.0f);
+    const float z = FM(x, x);
+    float y = 7.0376836292E-2f;
+    y = FM(y, x); y = FA(y, -1.1514610310E-1f);
+    y = FM(y, x); y = FA(y, 1.1676998740E-1f);
+    y = FM(y, x); y = FA(y, -1.2420140846E-1f);
+    y = FM(y, x); y = FA(y, +1.4249322787E-1f);
+    y = FM(y, x); y = FA(y, -1.6668057665E-1f);
+    y = FM(y, x); y = FA(y, +2.0000714765E-1f);
+    y = FM(y, x); y = FA(y, -2.4999993993E-1f);
+    y = FM(y, x); y = FA(y, +3.3333331174E-1f);
+    y = FM(y, x);
+    y = FM(y, z);
+    float tmp = FM(e, -2.12194440e-4f);  // cephes_log_q1
+    y = FA(y, tmp);
+    tmp = FM(z, 0.5f);
+    y = FS(y, tmp);
+    tmp = FM(e, 0.693359375f);  // cephes_log_q2
+    x = FA(x, y);
+    x = FA(x, tmp);
+    return x;
+}
 __device__ __forceinline__ float cephes_logf(float x) {
     // positive normal finite <=> bits in [0x00800000, 0x7f800000)
     if (__float_as_uint(x) - 0x00800000u >= 0x7f000000u) return cephes_log_general(x);
-    return cephes_log_core(x, 0.0f);
+    return cephes_log_fast(x);
 }
 
 // ---- exp ---------------------------------------------------------------------------------
@@ -128,8 +158,7 @@ __device__ __noinline__ float cephes_exp_general(float x) {
     }
     return FM(y, __uint_as_float((unsigned)(n + 0x7f) << 23));
 }
-__device__ __forceinline__ float cephes_expf(float x) {
-    if (!(fabsf(x) <= 87.0f)) return cephes_exp_general(x);  // n stays within [-126, 126]
+__device__ __forceinline__ float cephes_exp_fast(float x) {  // |x| <= 87: n stays within [-126, 126]
     float v = FM(x, 1.44269504088896341f);
     v = FA(v, 0.5f);
     // floor(v) by a round-down add of 1.5 * 2^23: t = 1.5*2^23 + floor(v) exactly, |v| < 2^22
@@ -139,6 +168,10 @@ __device__ __forceinline__ float cephes_expf(float x) {
     // bits(t) = 0x4B400000 + floor(v)  ->  2^n = (n + 127) << 23
     const unsigned pow2n = (__float_as_uint(t) - 0x4B400000u + 0x7fu) << 23;
     return FM(y, __uint_as_float(pow2n));
+}
+__device__ __forceinline__ float cephes_expf(float x) {
+    if (!(fabsf(x) <= 87.0f)) return cephes_exp_general(x);
+    return cephes_exp_fast(x);
 }
 
 // ---- sin / cos -----------------------------------------------------------------------------
@@ -170,9 +203,8 @@ __device__ __forceinline__ float cephes_sincos_core(float x, float y, bool sin_p
 __device__ __noinline__ float sin_general(float x) { return sinf(x); }
 __device__ __noinline__ float cos_general(float x) { return cosf(x); }
 
-__device__ __forceinline__ float cephes_sinf(float xin) {
+__device__ __forceinline__ float cephes_sinf_fast(float xin) {  // |x| <= 8192
     const float x = fabsf(xin);
-    if (!(x <= 8192.0f)) return sin_general(xin);  // outside the documented Cephes range, inf, NaN
     // j = ((int)y + 1) & ~1 ;  y = (float)j      (y < 2^14 here)
     const float yt = __fadd_rz(FM(x, 1.27323954473516f), 8388608.0f);   // 2^23 + trunc(x * 4/pi)
     const unsigned jb = (__float_as_uint(yt) + 1u) & ~1u;
@@ -180,16 +212,23 @@ __device__ __forceinline__ float cephes_sinf(float xin) {
     const unsigned sign = (__float_as_uint(xin) & 0x80000000u) ^ ((jb & 4u) << 29);
     return cephes_sincos_core(x, y, (jb & 2u) == 0u, sign);
 }
+__device__ __forceinline__ float cephes_sinf(float xin) {
+    if (!(fabsf(xin) <= 8192.0f)) return sin_general(xin);  // outside the documented Cephes range, inf, NaN
+    return cephes_sinf_fast(xin);
+}
 
-__device__ __forceinline__ float cephes_cosf(float xin) {
+__device__ __forceinline__ float cephes_cosf_fast(float xin) {
     const float x = fabsf(xin);
-    if (!(x <= 8192.0f)) return cos_general(xin);
     const float yt = __fadd_rz(FM(x, 1.27323954473516f), 8388608.0f);
     unsigned jb = (__float_as_uint(yt) + 1u) & ~1u;
     const float y = FS(__uint_as_float(jb), 8388608.0f);
     jb -= 2u;  // low three bits behave exactly as two's-complement j - 2
     const unsigned sign = (~jb & 4u) << 29;
     return cephes_sincos_core(x, y, (jb & 2u) == 0u, sign);
+}
+__device__ __forceinline__ float cephes_cosf(float xin) {
+    if (!(fabsf(xin) <= 8192.0f)) return cos_general(xin);
+    return cephes_cosf_fast(xin);
 }
 
 #undef FM
@@ -205,52 +244,99 @@ __device__ __forceinline__ float cephes_cosf(float xin) {
 // fma(a,1.0,b) with the constants hidden in __constant__ memory so that ptxas cannot re-fold and
 // then CONTRACT the pairs -- it does, even under -fmad=false) was bit-exact but no faster: FFMA2
 // retires two lanes at the cost of two scalar instructions on this part.  It was removed.
-struct SinF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_sinf(a); } };
-struct CosF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_cosf(a); } };
-struct LogF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_logf(a); } };
-struct ExpF32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4; static __device__ __forceinline__ float apply(float a) { return cephes_expf(a); } };
-struct SinF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return sin(a); } };
-struct CosF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return cos(a); } };
-// float64 log.  CUDA's log() costs ~50 FP64-pipe operations per element, which makes the kernel
-// FP64-bound on B200 (64 lanes/clk/SM): 5.7 TB/s.  This is the classic s = f/(2+f) formulation
-// (Sun fdlibm e_log.c: argument reduced to [sqrt(2)/2, sqrt(2)), 7-term minimax polynomial in s^2,
-// ln2 split hi/lo) with the division replaced by MUFU.RCP64H + two Newton steps -- `s` only scales
-// the O(f^2) correction term, so a reciprocal good to ~1e-16 costs nothing in accuracy.  About 28
-// FP64 operations; measured error < 1 ULP (tests: <= 2 ULP vs long double / decimal).
-// Zero, negatives, inf, NaN and denormals take CUDA's log() on a __noinline__ path.
-__device__ __noinline__ double log_f64_general(double x) { return log(x); }
+//
+// Every functor below has a branch-free fast body (`fast`, valid where `ok`) and an out-of-line
+// general function (`apply` = ok ? fast : IEEE edge cases), see ew.cuh: the kernel tests a thread's
+// whole set of inputs once, so a value's result never depends on its neighbours, only the speed does.
+__device__ __noinline__ float sinf_elem(float a) { return cephes_sinf(a); }
+__device__ __noinline__ float cosf_elem(float a) { return cephes_cosf(a); }
+__device__ __noinline__ float logf_elem(float a) { return cephes_logf(a); }
+__device__ __noinline__ float expf_elem(float a) { return cephes_expf(a); }
 
-__device__ __forceinline__ double log_f64(double x) {
-    const unsigned long long ix = (unsigned long long)__double_as_longlong(x);
-    if (ix - 0x0010000000000000ULL >= 0x7fe0000000000000ULL) return log_f64_general(x);  // not positive normal finite
-    int hx = (int)(ix >> 32);
-    int k = (hx >> 20) - 1023;
-    hx &= 0x000fffff;
-    const int i = (hx + 0x95f64) & 0x100000;                // 1 if the mantissa is above sqrt(2)
-    const double m = __hiloint2double(hx | (i ^ 0x3ff00000), (int)(unsigned)ix);  // m in [sqrt(2)/2, sqrt(2))
-    k += i >> 20;
-    const double f = m - 1.0;
-    const double d = 2.0 + f;
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));   // ~2^-23 relative
-    double e = fma(-d, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-d, r, 1.0);
-    r = fma(r, e, r);                                       // ~2^-92 before rounding
-    const double s = f * r;
-    const double dk = (double)k;
-    const double z = s * s;
-    const double w = z * z;
-    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01),
-                              6.666666666666735130e-01);
-    const double R = t2 + t1;
-    const double hfsq = 0.5 * f * f;
-    // k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f)
-    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+struct SinF32 {
+    typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(float a) { return fabsf(a) <= 8192.0f; }
+    static __device__ __forceinline__ float fast(float a) { return cephes_sinf_fast(a); }
+    static __device__ __forceinline__ float apply(float a) { return sinf_elem(a); }
+};
+struct CosF32 {
+    typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(float a) { return fabsf(a) <= 8192.0f; }
+    static __device__ __forceinline__ float fast(float a) { return cephes_cosf_fast(a); }
+    static __device__ __forceinline__ float apply(float a) { return cosf_elem(a); }
+};
+struct LogF32 {
+    typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(float a) { return __float_as_uint(a) - 0x00800000u < 0x7f000000u; }
+    static __device__ __forceinline__ float fast(float a) { return cephes_log_fast(a); }
+    static __device__ __forceinline__ float apply(float a) { return logf_elem(a); }
+};
+struct ExpF32 {
+    typedef float In; typedef float Out;
+    static constexpr int kUnroll = 4; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(float a) { return fabsf(a) <= 87.0f; }
+    static __device__ __forceinline__ float fast(float a) { return cephes_exp_fast(a); }
+    static __device__ __forceinline__ float apply(float a) { return expf_elem(a); }
+};
+
+// ---- float64 -------------------------------------------------------------------------------------
+// The reference's pd bodies are defective, so there is nothing to be bit-identical
+// to; the target is <= 2 ULP of the correctly rounded value.  Bodies: f64_math.cuh (why they are
+// hand-written, their cost and their measured accuracy are at its top).
+__device__ __noinline__ double sin64_elem(double a) { return f64_sincos_ok(a) ? f64_sincos_fast<0>(a) : sin(a); }
+__device__ __noinline__ double cos64_elem(double a) { return f64_sincos_ok(a) ? f64_sincos_fast<1>(a) : cos(a); }
+__device__ __noinline__ double exp64_elem(double a) { return f64_exp_ok(a) ? f64_exp_fast(a) : exp(a); }
+__device__ __noinline__ double log64_elem(double a) {
+    if (!f64_log_ok(a)) return log(a);
+    const int i = f64_log_index(a);
+    return f64_log_fast(a, kLogTab[2 * i], kLogTab[2 * i + 1]);  // flat table in constant memory: the rare path
 }
-struct LogF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return log_f64(a); } };
-struct ExpF64 { typedef double In; typedef double Out; static constexpr int kUnroll = 2; static __device__ __forceinline__ double apply(double a) { return exp(a); } };
+
+struct SinF64 {
+    typedef double In; typedef double Out;
+    static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(double a) { return f64_sincos_ok(a); }
+    static __device__ __forceinline__ double fast(double a) { return f64_sincos_fast<0>(a); }
+    static __device__ __forceinline__ double apply(double a) { return sin64_elem(a); }
+};
+struct CosF64 {
+    typedef double In; typedef double Out;
+    static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(double a) { return f64_sincos_ok(a); }
+    static __device__ __forceinline__ double fast(double a) { return f64_sincos_fast<1>(a); }
+    static __device__ __forceinline__ double apply(double a) { return cos64_elem(a); }
+};
+struct ExpF64 {
+    typedef double In; typedef double Out;
+    static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(double a) { return f64_exp_ok(a); }
+    static __device__ __forceinline__ double fast(double a) { return f64_exp_fast(a); }
+    static __device__ __forceinline__ double apply(double a) { return exp64_elem(a); }
+};
+// log: the 128-entry table lives in shared memory, 8 copies interleaved at 16-byte granularity:
+// copy j of entry i is at byte (i*8 + j)*16, and lane l reads copy l % 8, so the 8 lanes of a quarter
+// warp (one wavefront of an LDS.128) hit 8 different groups of 4 banks whatever their indices are.
+struct LogF64 {
+    typedef double In; typedef double Out;
+    static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
+    static constexpr int kSmemBytes = 128 * 8 * 16;
+    static __device__ __forceinline__ void smem_init(void* smem) {
+        ulonglong2* t = reinterpret_cast<ulonglong2*>(smem);
+        for (int s = threadIdx.x; s < 128 * 8; s += EW_BLOCK) t[s] = make_ulonglong2(kLogTab[2 * (s >> 3)], kLogTab[2 * (s >> 3) + 1]);
+    }
+    static __device__ __forceinline__ const void* smem_lane(const void* smem) {
+        return reinterpret_cast<const unsigned char*>(smem) + (threadIdx.x & 7) * 16;
+    }
+    static __device__ __forceinline__ bool ok(double a) { return f64_log_ok(a); }
+    static __device__ __forceinline__ double fast(double a, const void* table) {
+        const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(table) + f64_log_index(a) * 128);
+        return f64_log_fast(a, e.x, e.y);
+    }
+    static __device__ __forceinline__ double apply(double a) { return log64_elem(a); }
+};
 
 }  // namespace
 

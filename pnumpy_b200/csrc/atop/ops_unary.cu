@@ -98,6 +98,39 @@ PNCU_UNARY_FUNCTOR(SignBitF, bool8, (bool8)u_signbit(a))
 
 struct BoolNotF { typedef bool8 In; typedef bool8 Out; static __device__ __forceinline__ bool8 apply(bool8 a) { return (bool8)(a == 0); } };
 
+// Classifiers of an integer input are constants (no NaN/inf among integers): the reference memsets
+// (src/atop/ops_unary.cpp:1001-1013, 1651-1659).  A contiguous output is one cudaMemsetAsync -- a
+// write-only stream needs no read of the input; anything else takes the generic strided kernel.
+template <class T, int V> struct ConstF { typedef T In; typedef bool8 Out; static __device__ __forceinline__ bool8 apply(T) { return (bool8)V; } };
+template <class T, int V>
+int launch_const(const void* in, void* out, int64_t len, int64_t s1, int64_t so, pncu_stream_t stream) {
+    if (len > 0 && in && out && so == 1 && s1 % (int64_t)sizeof(T) == 0) {
+        int rc = ensure_init();
+        if (rc) return rc;
+        if ((rc = check_alias(in, s1, sizeof(T), out, so, 1, len))) return rc;
+        PNCU_CUDA(cudaMemsetAsync(out, V, (size_t)len, as_stream(stream)));  // a driver memset, not one of our kernels: not counted
+        return 0;
+    }
+    return launch_unary<ConstF<T, V>>(in, out, len, s1, so, stream);
+}
+template <int V>
+pncu_unary_fn pick_const_int(int t) {
+    switch (t) {
+        case PNCU_BOOL: case PNCU_UINT8: case PNCU_INT8: return launch_const<uint8_t, V>;
+        case PNCU_INT16: case PNCU_UINT16: return launch_const<uint16_t, V>;
+        case PNCU_INT32: case PNCU_UINT32: return launch_const<uint32_t, V>;
+        case PNCU_INT64: case PNCU_UINT64: return launch_const<uint64_t, V>;
+    }
+    return NULL;
+}
+// classifier getter: floats run the predicate kernel, integers the constant
+template <template <class> class F, int INT_VALUE>
+pncu_unary_fn pick_classifier(int t) {
+    if (t == PNCU_FLOAT) return launch_unary<F<float>>;
+    if (t == PNCU_DOUBLE) return launch_unary<F<double>>;
+    return pick_const_int<INT_VALUE>(t);
+}
+
 template <template <class> class F>
 pncu_unary_fn pick_all(int t) {
     switch (t) {
@@ -207,12 +240,12 @@ extern "C" pncu_unary_fn pncu_GetUnaryOpFast(int func, int t, int* wantedOutType
             *wantedOutType = PNCU_BOOL;
             return pick_all<LogicalNotF>(t);
         // classifiers: ops_unary.cpp:1646-1694 (fast) and 1347-1562 (slow); always -> bool
-        case PNCU_ISNAN: *wantedOutType = PNCU_BOOL; return pick_all<IsNanF>(t);
-        case PNCU_ISNOTNAN: *wantedOutType = PNCU_BOOL; return pick_all<IsNotNanF>(t);
-        case PNCU_ISINF: *wantedOutType = PNCU_BOOL; return pick_all<IsInfF>(t);
-        case PNCU_ISNOTINF: *wantedOutType = PNCU_BOOL; return pick_all<IsNotInfF>(t);
-        case PNCU_ISFINITE: *wantedOutType = PNCU_BOOL; return pick_all<IsFiniteF>(t);
-        case PNCU_ISNOTFINITE: *wantedOutType = PNCU_BOOL; return pick_all<IsNotFiniteF>(t);
+        case PNCU_ISNAN: *wantedOutType = PNCU_BOOL; return pick_classifier<IsNanF, 0>(t);
+        case PNCU_ISNOTNAN: *wantedOutType = PNCU_BOOL; return pick_classifier<IsNotNanF, 1>(t);
+        case PNCU_ISINF: *wantedOutType = PNCU_BOOL; return pick_classifier<IsInfF, 0>(t);
+        case PNCU_ISNOTINF: *wantedOutType = PNCU_BOOL; return pick_classifier<IsNotInfF, 1>(t);
+        case PNCU_ISFINITE: *wantedOutType = PNCU_BOOL; return pick_classifier<IsFiniteF, 1>(t);
+        case PNCU_ISNOTFINITE: *wantedOutType = PNCU_BOOL; return pick_classifier<IsNotFiniteF, 0>(t);
         case PNCU_ISNORMAL: *wantedOutType = PNCU_BOOL; return pick_all<IsNormalF>(t);
         case PNCU_ISNOTNORMAL: *wantedOutType = PNCU_BOOL; return pick_all<IsNotNormalF>(t);
         case PNCU_ISNANORZERO: *wantedOutType = PNCU_BOOL; return pick_all<IsNanOrZeroF>(t);

@@ -1,0 +1,94 @@
+// CPU check of pnumpy_b200/csrc/atop/f64_math.cuh (the float64 sin/cos/exp/log fast paths of the CUDA
+// kernels; the header compiles as plain C++).  Test infrastructure: built and run by
+// tests/test_f64_math_host.py with  g++ -O2 -mfma -ffp-contract=off.
+// Prints one line per function: name, samples, max ULP error against long double libm, worst input.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../pnumpy_b200/csrc/atop/f64_math.cuh"
+
+static uint64_t s_rng = 0x9E3779B97F4A7C15ull;
+static uint64_t rnd() { s_rng ^= s_rng << 13; s_rng ^= s_rng >> 7; s_rng ^= s_rng << 17; return s_rng; }
+static double uni(double lo, double hi) { return lo + (hi - lo) * ((rnd() >> 11) * (1.0 / 9007199254740992.0)); }
+static double from_bits(uint64_t b) { double x; memcpy(&x, &b, 8); return x; }
+
+static double ulp_err(double got, long double want) {
+    if (isnan(got) || isinf(got)) return 1e9;
+    double w = (double)want;
+    int e;
+    frexp(w, &e);
+    long double ulp = ldexpl(1.0L, e - 53);
+    if (fabs(w) < 2.2250738585072014e-308) ulp = 4.9406564584124654e-324L;
+    return (double)(fabsl((long double)got - want) / ulp);
+}
+
+static double hlog(double x) { const int i = f64_log_index(x); return f64_log_fast(x, kLogTab[2 * i], kLogTab[2 * i + 1]); }
+
+struct Stat { double worst = 0, at = 0; long n = 0; };
+static void upd(Stat& s, double x, double got, long double want) {
+    double e = ulp_err(got, want);
+    s.n++;
+    if (e > s.worst) { s.worst = e; s.at = x; }
+}
+
+int main(int argc, char** argv) {
+    long N = argc > 1 ? atol(argv[1]) : 1000000;
+    Stat ssin, scos, sexp, slog;
+    // sin / cos: uniform in several ranges + points next to multiples of pi/2
+    const double ranges[][2] = {{-1, 1}, {-20, 20}, {-8192, 8192}, {-105000, 105000}, {-1e-3, 1e-3}};
+    for (auto& rg : ranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_sincos_ok(x)) continue;
+            upd(ssin, x, f64_sincos_fast<0>(x), sinl((long double)x));
+            upd(scos, x, f64_sincos_fast<1>(x), cosl((long double)x));
+        }
+    for (long k = -60000; k <= 60000; ++k)
+        for (int d = -3; d <= 3; ++d) {
+            double x = (double)(k * 1.57079632679489661923L);
+            uint64_t b; memcpy(&b, &x, 8); b += (int64_t)d; x = from_bits(b);
+            if (!f64_sincos_ok(x)) continue;
+            upd(ssin, x, f64_sincos_fast<0>(x), sinl((long double)x));
+            upd(scos, x, f64_sincos_fast<1>(x), cosl((long double)x));
+        }
+    // exact values that must hold
+    int bad = 0;
+    if (f64_sincos_fast<1>(0.0) != 1.0) { printf("cos(0) != 1\n"); bad = 1; }
+    if (f64_sincos_fast<1>(1e-9) != 1.0) { printf("cos(1e-9) != 1\n"); bad = 1; }
+    { double s = f64_sincos_fast<0>(-0.0); if (s != 0.0 || !signbit(s)) { printf("sin(-0) != -0\n"); bad = 1; } }
+    if (f64_sincos_fast<0>(1e-300) != 1e-300) { printf("sin(1e-300) != 1e-300\n"); bad = 1; }
+    if (f64_sincos_fast<0>(5e-324) != 5e-324) { printf("sin(denormal min) wrong\n"); bad = 1; }
+    // exp
+    const double eranges[][2] = {{-1, 1}, {-80, 80}, {-707, 707}, {-1e-5, 1e-5}};
+    for (auto& rg : eranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_exp_ok(x)) continue;
+            upd(sexp, x, f64_exp_fast(x), expl((long double)x));
+        }
+    if (f64_exp_fast(0.0) != 1.0 || f64_exp_fast(-0.0) != 1.0) { printf("exp(0) != 1\n"); bad = 1; }
+    // log: uniform, near 1, random bit patterns of positive normals
+    const double lranges[][2] = {{0.5, 2}, {1e-3, 1e6}, {0.99, 1.01}, {1 - 1e-9, 1 + 1e-9}, {0.6, 0.8}, {1.3, 1.5}};
+    for (auto& rg : lranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            upd(slog, x, hlog(x), logl((long double)x));
+        }
+    for (long i = 0; i < N; ++i) {
+        double x = from_bits((rnd() & 0x7fffffffffffffffull));
+        if (!f64_log_ok(x)) continue;
+        upd(slog, x, hlog(x), logl((long double)x));
+    }
+    if (hlog(1.0) != 0.0) { printf("log(1) != 0\n"); bad = 1; }
+    if (f64_log_ok(0.0) || f64_log_ok(-1.0) || f64_log_ok(INFINITY) || f64_log_ok(NAN) || f64_log_ok(1e-310) || !f64_log_ok(2.3e-308) ||
+        !f64_log_ok(1.7e308)) { printf("f64_log_ok domain wrong\n"); bad = 1; }
+    if (f64_sincos_ok(INFINITY) || f64_sincos_ok(NAN) || f64_sincos_ok(2e5) || !f64_sincos_ok(-105000.0)) { printf("f64_sincos_ok domain wrong\n"); bad = 1; }
+    if (f64_exp_ok(INFINITY) || f64_exp_ok(NAN) || f64_exp_ok(708.0) || f64_exp_ok(-710.0) || !f64_exp_ok(-706.9)) { printf("f64_exp_ok domain wrong\n"); bad = 1; }
+    printf("sin %ld %.4f %.17g\n", ssin.n, ssin.worst, ssin.at);
+    printf("cos %ld %.4f %.17g\n", scos.n, scos.worst, scos.at);
+    printf("exp %ld %.4f %.17g\n", sexp.n, sexp.worst, sexp.at);
+    printf("log %ld %.4f %.17g\n", slog.n, slog.worst, slog.at);
+    return bad;
+}
