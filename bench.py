@@ -414,6 +414,69 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
                               "collective": "none (1 GPU)" if world == 1 else "one NCCL all_gather of float64 block partials",
                               "result": float(res.to_host()[0])}
 
+    # configs[3], the other reductions, with NaN inputs: every rank's float32 shard gets ONE NaN at a
+    # pseudo-random index (SURVEY.md 8d case iv).  min/max must come back NaN and argmin/argmax the GLOBAL
+    # index of the first NaN (rank 0's).  Pass 1 per shard, one all_gather of the block partials (4 B for
+    # min/max, 16 B {value, index} for the arg-reductions), one finish kernel -- timed like the sum.
+    import ctypes
+    xn = byname["float32"][2]  # the float32 output buffer, free at this point
+    cabi.check(lib.pncu_memcpy_d2d(xn.ptr, a.ptr, n * 4, stream), "copy")
+    nan_at = (1234567 * (rank + 1)) % n
+    nanv = np.array([np.nan], dtype=np.float32)
+    cabi.check(lib.pncu_memcpy_h2d(xn.ptr + 4 * nan_at, nanv.ctypes.data, 4, stream), "plant NaN")
+    cabi.check(lib.pncu_stream_sync(stream), "sync")
+    ri = dev.empty(1, np.int64)
+    nan_rows = {}
+    for name, kind in (("min", None), ("max", None), ("argmin", 1), ("argmax", 0)):
+        fop = cabi.BINARY_OPS["MIN" if name == "min" else "MAX"]
+        pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
+        if world == 1:
+            buf = dev.empty(cnt * pbytes, np.uint8)
+            mine_ptr, all_ptr = buf.ptr, buf.ptr
+        else:
+            import torch
+            mine_t = torch.empty(cnt * pbytes, dtype=torch.uint8, device="cuda")
+            all_t = torch.empty(world * cnt * pbytes, dtype=torch.uint8, device="cuda")
+            mine_ptr, all_ptr = mine_t.data_ptr(), all_t.data_ptr()
+
+        def sharded(kind=kind, fop=fop, mine_ptr=mine_ptr, all_ptr=all_ptr):
+            if kind is None:
+                cabi.check(lib.pncu_reduce_partials(fop, t, xn.ptr, n, mine_ptr, stream), "partials")
+            else:
+                cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(rank * n), mine_ptr, stream), "arg partials")
+            if world > 1:
+                cabi.check(lib.pncu_stream_sync(stream), "sync")
+                dist.all_gather_into_tensor(all_t, mine_t)
+                torch.cuda.current_stream().synchronize()
+            if kind is None:
+                cabi.check(lib.pncu_reduce_finish(fop, t, all_ptr, world * cnt, res.ptr, None, stream), "finish")
+            else:
+                cabi.check(lib.pncu_argminmax_finish(kind, t, all_ptr, world * cnt, ri.ptr, stream), "arg finish")
+        for _ in range(3):
+            sharded()
+        cabi.check(lib.pncu_device_sync(), "sync")
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sharded()
+        cabi.check(lib.pncu_device_sync(), "sync")
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        if dist:
+            import torch
+            tt_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            ms = float(tt_.item())
+        if kind is None:
+            ok = bool(np.isnan(res.to_host()[0]))
+        else:
+            ok = int(ri.to_host()[0]) == 1234567 % n  # rank 0's NaN is the first of the whole job
+        nan_rows[name] = {"ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1), "nan_semantics_ok": ok}
+    out["sharded_nan_reductions_f32"] = {
+        "elements_total": n * world, "nan_per_shard": 1,
+        "collective": "none (1 GPU)" if world == 1 else "one NCCL all_gather of block partials per reduction",
+        "timing": "host wall clock around 10 calls incl. the collective, max over ranks", **nan_rows}
+
     # configs[4], device-resident leg: t = a*b; u = t+c; r = u.sum() as three kernels (28 B/element)
     a, b, o = byname["float32"][0], byname["float32"][1], byname["float32"][2]
 
