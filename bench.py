@@ -650,8 +650,38 @@ def run_e2e(args):
         del ma, mb, mo
     except Exception as e:  # pragma: no cover
         resident = {"error": str(e)}
+    # configs[0]: np.add float32 on 1 000 000 contiguous elements (pn.benchmark's size), hooks off vs on.
+    # 12 MB of PCIe traffic per call: latency-bound, the GPU path has to beat ~0.5 ms of NumPy loop.
+    config0 = None
+    try:
+        m = 1_000_000
+        def med_us(fn, k=200):
+            fn()
+            ts = []
+            for _ in range(k):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return round(float(np.median(ts)) * 1e6, 1)
+        pa = (np.arange(m, dtype=np.float32) % 253) + 1  # the reference's benchmark data (benchmark.py:56-66)
+        pb, po = pa.copy(), np.empty(m, np.float32)
+        qa, qb, qo = pn.pinned_array(pa), pn.pinned_array(pa), pn.pinned_empty(m, np.float32)
+        old_thr = pn.cuda_setthreshold(1 << 16)
+        pn.disable()
+        t_numpy = med_us(lambda: np.add(pa, pb, out=po))
+        pn.enable()
+        t_pageable = med_us(lambda: np.add(pa, pb, out=po))
+        t_pinned = med_us(lambda: np.add(qa, qb, out=qo))
+        same = bool(np.array_equal(qo, pa + pb))
+        pn.cuda_setthreshold(old_thr)
+        config0 = {"what": "np.add float32, 1 000 000 contiguous elements, median of 200 calls (us)", "numpy_loop_us": t_numpy,
+                   "gpu_pageable_operands_us": t_pageable, "gpu_pinned_operands_us": t_pinned,
+                   "speedup_pinned_vs_numpy": round(t_numpy / t_pinned, 2), "result_equal": same}
+        del qa, qb, qo
+    except Exception as e:  # pragma: no cover
+        config0 = {"error": str(e)}
     pn.disable()
-    return {"value": round(SWEEP_BYTES_PER_ELEM * n / dt_s / 1e9, 2), "unit": UNIT, "elements": n, "steps": reps, "chain": chain, "resident": resident,
+    return {"value": round(SWEEP_BYTES_PER_ELEM * n / dt_s / 1e9, 2), "unit": UNIT, "elements": n, "steps": reps, "chain": chain, "resident": resident, "config0": config0,
             "ms_per_step": round(dt_s * 1e3, 2), "h2d_bytes_per_step": int(info["h2d_bytes"] // reps),
             "d2h_bytes_per_step": int(info["d2h_bytes"] // reps), "gpu_calls_per_step": int(info["calls"] // reps),
             "staged_bytes_per_step": int(info["staged_bytes"] // reps), "lanes": int(info["lanes_last"]),
@@ -703,7 +733,17 @@ chain()
 cs = []
 for _ in range(reps):
     t0 = time.perf_counter(); chain(); cs.append(time.perf_counter() - t0)
-print(json.dumps({"seconds": ts, "chain_seconds": cs, "cores": cores, "workers": pn.thread_getworkers(), "n": n, "cpustring": pn.cpustring()}))
+m = 1000000
+pa = (np.arange(m, dtype=np.float32) % 253) + 1; pb = pa.copy(); po = np.empty(m, np.float32)
+def med_us(k=200):
+    np.add(pa, pb, out=po); v = []
+    for _ in range(k):
+        t0 = time.perf_counter(); np.add(pa, pb, out=po); v.append(time.perf_counter() - t0)
+    return float(np.median(v)) * 1e6
+on_us = med_us()
+pn.atop_disable(); pn.thread_disable()
+off_us = med_us()
+print(json.dumps({"config0_on_us": on_us, "config0_off_us": off_us, "seconds": ts, "chain_seconds": cs, "cores": cores, "workers": pn.thread_getworkers(), "n": n, "cpustring": pn.cpustring()}))
 '''
 
 
@@ -728,7 +768,10 @@ def run_cpu_baseline(sample_lg=25, reps=3, maxthreads=1):
                       f"extension (oracle/_ref) enabled with thread_setworkers({d['workers']}) and atop_setworkers(.., 15): "
                       f"up to {threads} threads",
             "ms_per_pass": round(best * 1e3, 1), "cpu": d.get("cpustring"),
-            "chain_gbs": round(28.0 * d["n"] / min(d["chain_seconds"]) / 1e9, 2) if d.get("chain_seconds") else None}
+            "chain_gbs": round(28.0 * d["n"] / min(d["chain_seconds"]) / 1e9, 2) if d.get("chain_seconds") else None,
+            "config0": {"what": "np.add float32, 1 000 000 elements, median of 200 calls (us), reference enabled vs disabled",
+                        "reference_on_us": round(d["config0_on_us"], 1), "reference_off_us": round(d["config0_off_us"], 1)}
+            if "config0_on_us" in d else None}
 
 
 def run_reference(args):

@@ -288,7 +288,10 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
 
 // Variant for functors with a shared-memory lookup table (float64 log): a CTA builds the table once
 // and then streams EW_TABLE_TILES tiles, so the set-up (16 KiB of shared-memory stores) is paid once
-// per 256 KiB of traffic.  The grid is still thousands of CTAs: the hardware scheduler balances it.
+// per 256 KiB of traffic.  The first tile's loads are issued BEFORE the table is built and every
+// later tile's loads before the previous tile is computed, so neither the set-up nor the arithmetic
+// leaves the thread with nothing in flight.  The grid is still thousands of CTAs: the hardware
+// scheduler balances it.
 constexpr int EW_TABLE_TILES = 8;
 
 template <class F>
@@ -298,29 +301,42 @@ ew1_table_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int6
     typedef typename F::Out Out;
     constexpr int EPV = Epv<In, Out>::value;
     constexpr int U = unroll_of<F>::value;
+    static_assert(has_fast<F>::value, "a table functor needs ok()/fast()");
     __shared__ __align__(16) unsigned char smem[smem_of<F>::value];
+    // a tile is "full" when all U vectors of this thread exist; ragged tiles take the slow loop below
+    const int64_t vbase = (int64_t)blockIdx.x * EW_TABLE_TILES * (EW_BLOCK * U) + threadIdx.x;
+    Pack<In, EPV> cur[U];
+    bool cur_full = vbase + (int64_t)(U - 1) * EW_BLOCK < nvec;
+    if (cur_full) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = ld_pack<In, EPV>(a + head + (vbase + (int64_t)u * EW_BLOCK) * EPV);
+    }
     F::smem_init(smem);
     __syncthreads();
     const void* table = F::smem_lane(smem);
 #pragma unroll 1
     for (int t = 0; t < EW_TABLE_TILES; ++t) {
-        const int64_t v0 = ((int64_t)blockIdx.x * EW_TABLE_TILES + t) * (EW_BLOCK * U) + threadIdx.x;
+        const int64_t v0 = vbase + (int64_t)t * (EW_BLOCK * U);
         if (v0 >= nvec) break;
-        if (v0 + (int64_t)(U - 1) * EW_BLOCK < nvec) {
-            Pack<In, EPV> ra[U];
+        const int64_t v1 = v0 + (EW_BLOCK * U);
+        Pack<In, EPV> nxt[U];
+        const bool nxt_full = t + 1 < EW_TABLE_TILES && v1 + (int64_t)(U - 1) * EW_BLOCK < nvec;
+        if (nxt_full) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) ra[u] = ld_pack<In, EPV>(a + head + (v0 + (int64_t)u * EW_BLOCK) * EPV);
+            for (int u = 0; u < U; ++u) nxt[u] = ld_pack<In, EPV>(a + head + (v1 + (int64_t)u * EW_BLOCK) * EPV);
+        }
+        if (cur_full) {
             bool all_fast = true;
 #pragma unroll
-            for (int u = 0; u < U; ++u) all_fast = all_fast && pack_ok<F, EPV>(ra[u]);
+            for (int u = 0; u < U; ++u) all_fast = all_fast && pack_ok<F, EPV>(cur[u]);
             if (all_fast) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, fast_pack<F, EPV>(ra[u], table));
+                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, fast_pack<F, EPV>(cur[u], table));
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
+                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(cur[u]));
             }
         } else {
 #pragma unroll 1
@@ -332,6 +348,9 @@ ew1_table_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int6
                 }
             }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+        cur_full = nxt_full;
     }
     if (blockIdx.x == 0) {
         const int64_t tail0 = head + nvec * EPV;

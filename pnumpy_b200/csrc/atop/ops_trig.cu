@@ -316,6 +316,11 @@ struct ExpF64 {
     static __device__ __forceinline__ double fast(double a) { return f64_exp_fast(a); }
     static __device__ __forceinline__ double apply(double a) { return exp64_elem(a); }
 };
+// The log table once more in plain global memory: building the shared copy reads it with ordinary
+// (L2-resident, warp-coalesced) loads; a __constant__ array would serialise the 4 different entries a
+// warp reads per step.
+static __device__ const unsigned long long gLogTab[256] = F64_LOGTAB_INIT;
+
 // log: the 128-entry table lives in shared memory, 8 copies interleaved at 16-byte granularity:
 // copy j of entry i is at byte (i*8 + j)*16, and lane l reads copy l % 8, so the 8 lanes of a quarter
 // warp (one wavefront of an LDS.128) hit 8 different groups of 4 banks whatever their indices are.
@@ -325,7 +330,10 @@ struct LogF64 {
     static constexpr int kSmemBytes = 128 * 8 * 16;
     static __device__ __forceinline__ void smem_init(void* smem) {
         ulonglong2* t = reinterpret_cast<ulonglong2*>(smem);
-        for (int s = threadIdx.x; s < 128 * 8; s += EW_BLOCK) t[s] = make_ulonglong2(kLogTab[2 * (s >> 3)], kLogTab[2 * (s >> 3) + 1]);
+        const ulonglong2* g = reinterpret_cast<const ulonglong2*>(gLogTab);
+        // slot s = 8*entry + copy: the 8 lanes of a quarter warp write 8 different bank groups
+#pragma unroll
+        for (int s = threadIdx.x; s < 128 * 8; s += EW_BLOCK) t[s] = __ldg(g + (s >> 3));
     }
     static __device__ __forceinline__ const void* smem_lane(const void* smem) {
         return reinterpret_cast<const unsigned char*>(smem) + (threadIdx.x & 7) * 16;

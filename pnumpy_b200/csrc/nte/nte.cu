@@ -98,7 +98,8 @@ struct Job {
     const char* in3 = nullptr;
     char* out = nullptr;
     int64_t len = 0;
-    int64_t s1 = 0, s2 = 0;     // 0 (scalar) or the item size
+    int64_t s1 = 0, s2 = 0;     // input byte strides: 0 (scalar), the item size (contiguous) or anything else (gathered)
+    int64_t so = 0;             // output byte stride (0 = not set: contiguous)
     int pk_in1 = 0, pk_in2 = 0, pk_in3 = 0, pk_out = 0;
     int nlanes = 1;
     int64_t shard[kMaxLanes + 1];  // element boundaries
@@ -130,6 +131,47 @@ int classify(const void* p) {
         case cudaMemoryTypeManaged: return PK_MANAGED;
         default: return PK_PAGEABLE;
     }
+}
+
+// ---- strided host operands ------------------------------------------------------------------------------
+// NumPy hands an inner loop whatever strides the view has (a[::2], a[:, 3], a[::-1]); the reference runs its
+// generic strided scalar loop per chunk on its worker threads (src/atop/ops_binary.cpp:563-569).  Here the
+// lane thread gathers the elements of a slab into its pinned staging slab (and scatters results back), so
+// the GPU always sees contiguous slabs and every lane does its own share of the host-side strided traffic.
+template <class T>
+void gather_t(char* dst, const char* src, int64_t cnt, int64_t stride) {
+    T* d = reinterpret_cast<T*>(dst);
+    for (int64_t i = 0; i < cnt; ++i) d[i] = *reinterpret_cast<const T*>(src + i * stride);
+}
+template <class T>
+void scatter_t(char* dst, const char* src, int64_t cnt, int64_t stride) {
+    const T* s = reinterpret_cast<const T*>(src);
+    for (int64_t i = 0; i < cnt; ++i) *reinterpret_cast<T*>(dst + i * stride) = s[i];
+}
+void gather(char* dst, const char* src, int64_t cnt, int64_t stride, int isz) {
+    switch (isz) {
+        case 1: gather_t<uint8_t>(dst, src, cnt, stride); break;
+        case 2: gather_t<uint16_t>(dst, src, cnt, stride); break;
+        case 4: gather_t<uint32_t>(dst, src, cnt, stride); break;
+        default: gather_t<uint64_t>(dst, src, cnt, stride); break;
+    }
+}
+void scatter(char* dst, const char* src, int64_t cnt, int64_t stride, int isz) {
+    switch (isz) {
+        case 1: scatter_t<uint8_t>(dst, src, cnt, stride); break;
+        case 2: scatter_t<uint16_t>(dst, src, cnt, stride); break;
+        case 4: scatter_t<uint32_t>(dst, src, cnt, stride); break;
+        default: scatter_t<uint64_t>(dst, src, cnt, stride); break;
+    }
+}
+// byte extent [lo, lo + bytes) of `len` items of `isz` bytes at byte stride `stride` from `p`
+void extent_of(const char* p, int64_t len, int64_t stride, int isz, const char** lo, int64_t* bytes) {
+    const int64_t span = (len - 1) * stride;
+    if (span >= 0) { *lo = p; *bytes = span + isz; }
+    else { *lo = p + span; *bytes = -span + isz; }
+}
+bool stride_ok(const void* p, int64_t stride, int isz) {
+    return (isz == 1 || isz == 2 || isz == 4 || isz == 8) && stride % isz == 0 && (uintptr_t)p % isz == 0;
 }
 
 // ---- lane resources -----------------------------------------------------------------------------------
@@ -200,6 +242,8 @@ void lane_elementwise(Lane& L, Job& j, int li) {
     const int64_t slab_elems = ((int64_t)(L.slab_bytes / wide) / kAlign) * kAlign;
     const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
     const bool vec1 = j.s1 != 0, vec2 = binary && j.s2 != 0;
+    const bool out_strided = j.so != j.isz_out;
+    const bool stage_out = j.pk_out == PK_PAGEABLE || out_strided;
 
     // broadcast scalars: one tiny copy per call
     const char* d_s1 = nullptr;
@@ -223,10 +267,11 @@ void lane_elementwise(Lane& L, Job& j, int li) {
         const int r = (int)(i % kRing);
         cudaError_t e = cudaEventSynchronize(L.ev_d2h[r]);
         if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(d2h)", __FILE__, __LINE__);
-        if (j.pk_out == PK_PAGEABLE) {
+        if (stage_out) {
             int64_t off, cnt;
             slab_range(i, &off, &cnt);
-            memcpy(j.out + off * j.isz_out, L.h_buf[r][2], (size_t)(cnt * j.isz_out));
+            if (out_strided) scatter(j.out + off * j.so, L.h_buf[r][2], cnt, j.so, j.isz_out);
+            else memcpy(j.out + off * j.isz_out, L.h_buf[r][2], (size_t)(cnt * j.isz_out));
             g_stats.staged += cnt * j.isz_out;
         }
         return 0;
@@ -242,11 +287,13 @@ void lane_elementwise(Lane& L, Job& j, int li) {
         // ---- inputs -> device slab
         for (int k = 0; k < 2; ++k) {
             if (k == 0 ? !vec1 : !vec2) continue;
-            const char* src = (k == 0 ? j.in1 : j.in2) + off * j.isz_in;
+            const int64_t stride = k == 0 ? j.s1 : j.s2;
+            const char* src = (k == 0 ? j.in1 : j.in2) + off * stride;
             const int pk = k == 0 ? j.pk_in1 : j.pk_in2;
-            if (pk == PK_PAGEABLE) {
+            if (pk == PK_PAGEABLE || stride != j.isz_in) {
                 if ((rc = ensure_pinned_slab(L, r, k))) { fail(j, li, rc); return; }
-                memcpy(L.h_buf[r][k], src, in_bytes);
+                if (stride != j.isz_in) gather(L.h_buf[r][k], src, cnt, stride, j.isz_in);
+                else memcpy(L.h_buf[r][k], src, in_bytes);
                 g_stats.staged += in_bytes;
                 src = L.h_buf[r][k];
             }
@@ -269,7 +316,7 @@ void lane_elementwise(Lane& L, Job& j, int li) {
         LCUDA(cudaStreamWaitEvent(L.s_h2d, L.ev_k[r], 0));
         // ---- result -> host
         char* dst = j.out + off * j.isz_out;
-        if (j.pk_out == PK_PAGEABLE) {
+        if (stage_out) {
             if ((rc = ensure_pinned_slab(L, r, 2))) { fail(j, li, rc); return; }
             dst = L.h_buf[r][2];
         }
@@ -300,14 +347,15 @@ void lane_reduce(Lane& L, Job& j, int li) {
         const int64_t off = e0 + i * slab_elems;
         const int64_t cnt = (e1 - off) < slab_elems ? (e1 - off) : slab_elems;
         const size_t in_bytes = (size_t)(cnt * j.isz_in);
-        const char* src = j.in1 + off * j.isz_in;
+        const char* src = j.in1 + off * j.s1;
         if (i >= kRing) {  // slot reuse: the kernel that read it must be done before we overwrite staging
             cudaError_t e = cudaEventSynchronize(L.ev_k[r]);
             if (e != cudaSuccess) { cuda_fail(e, "cudaEventSynchronize(k)", __FILE__, __LINE__); fail(j, li, (int)e); return; }
         }
-        if (j.pk_in1 == PK_PAGEABLE) {
+        if (j.pk_in1 == PK_PAGEABLE || j.s1 != j.isz_in) {
             if ((rc = ensure_pinned_slab(L, r, 0))) { fail(j, li, rc); return; }
-            memcpy(L.h_buf[r][0], src, in_bytes);
+            if (j.s1 != j.isz_in) gather(L.h_buf[r][0], src, cnt, j.s1, j.isz_in);
+            else memcpy(L.h_buf[r][0], src, in_bytes);
             g_stats.staged += in_bytes;
             src = L.h_buf[r][0];
         }
@@ -546,13 +594,22 @@ int run_resident(Job& j) {
         PNCU_CUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
         in2 = L.d_scalar + 16;
     }
-    if ((rc = prefetch_managed(j.in1, j.s1 ? j.pk_in1 : PK_PAGEABLE, (size_t)j.len * j.isz_in, L))) return rc;
-    if (binary && (rc = prefetch_managed(j.in2, j.s2 ? j.pk_in2 : PK_PAGEABLE, (size_t)j.len * j.isz_in, L))) return rc;
-    if ((rc = prefetch_managed(j.out, j.pk_out, (size_t)j.len * j.isz_out, L))) return rc;
+    const char* lo;
+    int64_t bytes;
+    if (j.s1) {
+        extent_of(j.in1, j.len, j.s1, j.isz_in, &lo, &bytes);
+        if ((rc = prefetch_managed(lo, j.pk_in1, (size_t)bytes, L))) return rc;
+    }
+    if (binary && j.s2) {
+        extent_of(j.in2, j.len, j.s2, j.isz_in, &lo, &bytes);
+        if ((rc = prefetch_managed(lo, j.pk_in2, (size_t)bytes, L))) return rc;
+    }
+    extent_of(j.out, j.len, j.so, j.isz_out, &lo, &bytes);
+    if ((rc = prefetch_managed(lo, j.pk_out, (size_t)bytes, L))) return rc;
     if (binary)
-        rc = j.fn2(in1, in2, j.out, j.len, j.s1, j.s2, j.isz_out, (pncu_stream_t)L.s_k);
+        rc = j.fn2(in1, in2, j.out, j.len, j.s1, j.s2, j.so, (pncu_stream_t)L.s_k);
     else
-        rc = j.fn1(in1, j.out, j.len, j.s1, j.isz_out, (pncu_stream_t)L.s_k);
+        rc = j.fn1(in1, j.out, j.len, j.s1, j.so, (pncu_stream_t)L.s_k);
     if (rc) return rc;
     g_stats.launches += 1;
     PNCU_CUDA(cudaStreamSynchronize(L.s_k));
@@ -719,20 +776,26 @@ static int dispatch_elementwise(Job& j, int max_workers) {
         if (!rc) g_stats.calls += 1;
         return rc;
     }
-    // host operands must be contiguous (or scalar) to be staged
-    if (j.s1 != 0 && j.s1 != j.isz_in) return decline();
-    if (binary && j.s2 != 0 && j.s2 != j.isz_in) return decline();
+    // host operands: contiguous ones are DMA'd (pinned) or memcpy'd (pageable) into the slabs, any
+    // other stride (a multiple of the item size, negative allowed) is gathered / scattered by the lane
     if (j.s1 == 0 && (!binary || j.s2 == 0)) return decline();
-    // exact aliasing of out with an input is fine (staged); partial overlap is not
+    if (!stride_ok(j.in1, j.s1, j.isz_in) || (binary && !stride_ok(j.in2, j.s2, j.isz_in)) || !stride_ok(j.out, j.so, j.isz_out))
+        return decline();
+    // exact aliasing of out with an input is fine (every element is staged before its result is written
+    // back); any other overlap needs the sequential semantics of the caller's loop
     {
-        const char* olo = j.out; const int64_t ob = j.len * j.isz_out;
+        const char* olo;
+        int64_t ob;
+        extent_of(j.out, j.len, j.so, j.isz_out, &olo, &ob);
         const char* ins[2] = {j.in1, binary ? j.in2 : nullptr};
         const int64_t strides[2] = {j.s1, j.s2};
         for (int k = 0; k < 2; ++k) {
             if (!ins[k]) continue;
-            const int64_t ib = strides[k] ? j.len * j.isz_in : j.isz_in;
-            const bool overlap = ins[k] < olo + ob && olo < ins[k] + ib;
-            if (overlap && !(ins[k] == olo && strides[k] == j.isz_out && j.isz_in == j.isz_out)) return decline();
+            const char* ilo;
+            int64_t ib;
+            extent_of(ins[k], strides[k] ? j.len : 1, strides[k], j.isz_in, &ilo, &ib);
+            const bool overlap = ilo < olo + ob && olo < ilo + ib;
+            if (overlap && !(ins[k] == j.out && strides[k] == j.so && j.isz_in == j.isz_out)) return decline();
         }
     }
     int rc = plan(j, max_workers);
@@ -746,20 +809,20 @@ static int dispatch_elementwise(Job& j, int max_workers) {
 int nte_binary(pncu_any_two_fn launcher, int in_itemsize, int out_itemsize, const void* in1,
                const void* in2, void* out, int64_t len, int64_t s1, int64_t s2, int64_t so, int max_workers) {
     if (!launcher) return decline();
-    if (so != out_itemsize) return decline();
+    if (so == 0) return decline();
     Job j;
     j.kind = JOB_BINARY; j.fn2 = launcher; j.isz_in = in_itemsize; j.isz_out = out_itemsize;
-    j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.out = (char*)out; j.len = len; j.s1 = s1; j.s2 = s2;
+    j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.out = (char*)out; j.len = len; j.s1 = s1; j.s2 = s2; j.so = so;
     return dispatch_elementwise(j, max_workers);
 }
 
 int nte_unary(pncu_unary_fn launcher, int in_itemsize, int out_itemsize, const void* in, void* out,
               int64_t len, int64_t s1, int64_t so, int max_workers) {
     if (!launcher) return decline();
-    if (so != out_itemsize || s1 != in_itemsize) return decline();
+    if (so == 0 || s1 == 0) return decline();
     Job j;
     j.kind = JOB_UNARY; j.fn1 = launcher; j.isz_in = in_itemsize; j.isz_out = out_itemsize;
-    j.in1 = (const char*)in; j.out = (char*)out; j.len = len; j.s1 = s1;
+    j.in1 = (const char*)in; j.out = (char*)out; j.len = len; j.s1 = s1; j.so = so;
     return dispatch_elementwise(j, max_workers);
 }
 
@@ -821,7 +884,8 @@ static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* ho
     j.pk_in1 = classify(j.in1);
     int rc;
     if (!host_kind(j.pk_in1)) {
-        // resident input: both passes on its GPU
+        // resident input: both passes on its GPU (contiguous only: pass 1 streams whole blocks)
+        if (j.s1 != j.isz_in) return decline();
         const int dev = device_of(j.in1);
         if ((rc = ensure_lane(dev))) return rc;
         Lane& L = g.lanes[dev];
@@ -858,10 +922,10 @@ int nte_reduce(int func, int atype, const void* in, void* out, int use_out_as_st
                int64_t strideIn, int max_workers) {
     const int isz = pncu_itemsize(atype);
     const int pb = pncu_reduce_partial_bytes(func, atype);
-    if (!isz || !pb || strideIn != isz) return decline();
+    if (!isz || !pb || strideIn == 0 || !stride_ok(in, strideIn, isz)) return decline();
     Job j;
     j.kind = JOB_REDUCE; j.func = func; j.atype = atype; j.isz_in = isz; j.isz_out = isz; j.partial_bytes = pb;
-    j.in1 = (const char*)in; j.len = len; j.s1 = isz;
+    j.in1 = (const char*)in; j.len = len; j.s1 = strideIn;
     return dispatch_reduce(j, out, isz, use_out_as_start ? out : nullptr, max_workers);
 }
 

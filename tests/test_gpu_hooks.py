@@ -192,11 +192,19 @@ def test_layouts_inplace_and_declines(pn, rng):
     out = np.empty_like(a)
     np.add(a, b, out=out)
     assert_bits_equal(out, want, "out=")
-    # non-contiguous operands are declined by nte and computed by NumPy's loop, correctly
-    d0 = pn.cuda_info()["declined"]
+    # non-contiguous host operands are gathered / scattered by the lanes and run on the GPU
+    # (the reference threads its generic strided loop there, src/atop/ops_binary.cpp:563-569)
+    c0 = pn.cuda_info()["calls"]
     s = a[::2] + b[::2]
-    assert pn.cuda_info()["declined"] > d0
+    assert pn.cuda_info()["calls"] == c0 + 1
     assert_bits_equal(s, want[::2].copy(), "strided")
+    # partial overlap: NumPy copies the overlapping input itself before calling the loop (and nte
+    # would decline a loop-level overlap); either way the answer is NumPy's
+    ov = a.copy()
+    np.add(ov[:-1], ov[1:], out=ov[1:])
+    ref = a.copy()
+    pn.disable(); np.add(ref[:-1], ref[1:], out=ref[1:]); pn.enable()
+    assert_bits_equal(ov, ref, "overlap")
     # 2-D reduction along axis 1: many short reduce calls, all correct
     m = rng.normal(size=(512, 2048)).astype(np.float64)
     got, wantm, _ = _both(pn, lambda: m.max(axis=1))
@@ -207,6 +215,53 @@ def test_layouts_inplace_and_declines(pn, rng):
     assert_bits_equal(a + b, want, "below threshold")
     assert pn.cuda_info()["calls"] == c1
     pn.cuda_setthreshold(old)
+
+
+@pytest.mark.parametrize("dt", ["int16", "int32", "float32", "float64"])
+def test_strided_host_operands(pn, rng, dt):
+    """Every stride NumPy can hand an inner loop (steps a multiple of the item size, negative included):
+    inputs, outputs, in place, reductions -- same bits as NumPy's own loops."""
+    n = (1 << 19) + 77
+    base_a = (rng.normal(0, 100, 3 * n)).astype(dt)
+    base_b = (rng.normal(0, 100, 2 * n) + 1).astype(dt)
+    a, b = base_a[::3], base_b[::-2]
+    cases = {
+        "add": lambda: np.add(a, b),
+        "sub_out_strided": lambda: _strided_out(np.subtract, a, b, n, dt),
+        "greater": lambda: np.greater(a, b),
+        "abs": lambda: np.abs(a),
+        "mul_scalar": lambda: a * np.dtype(dt).type(3),
+        "neg_reversed": lambda: np.negative(a[::-1]),
+        "max": lambda: a.max(),
+        "min_rev": lambda: b.min(),
+    }
+    if dt.startswith("float"):
+        cases["sqrt"] = lambda: np.sqrt(np.abs(a))
+        cases["sin"] = lambda: np.sin(b)
+    for name, fn in cases.items():
+        c0 = pn.cuda_info()["calls"]
+        got, want, _ = _both(pn, fn)
+        assert pn.cuda_info()["calls"] > c0, name
+        if name == "sin":  # not NumPy's bits (Cephes / own float64 body): the contiguous GPU result is the reference
+            assert_bits_equal(got, np.sin(np.ascontiguousarray(b)), f"sin {dt}")
+        else:
+            assert_bits_equal(np.asarray(got), np.asarray(want), f"{name} {dt}")
+    # in place on a strided view
+    v = base_a.copy()
+    w = base_a.copy()
+    v[::3] += b
+    pn.disable(); w[::3] += b; pn.enable()
+    assert_bits_equal(v, w, "in-place strided")
+    # a column of a C-ordered matrix (stride = row length)
+    m = rng.normal(size=(1 << 17, 8)).astype(dt)
+    got, want, _ = _both(pn, lambda: m[:, 3] + m[:, 5])
+    assert_bits_equal(got, want, "columns")
+
+
+def _strided_out(ufunc, a, b, n, dt):
+    out = np.zeros(2 * n, dtype=dt)
+    ufunc(a, b, out=out[1::2])
+    return out
 
 
 def test_lanes_do_not_change_results(pn, rng):
