@@ -25,7 +25,10 @@
  *
  * Operands are HOST pointers as NumPy hands them to a ufunc inner loop (pageable, or pinned when
  * they came from nte_alloc_pinned / the recycler), or device / managed pointers, which are used in
- * place with no PCIe traffic.  Strides are in bytes; 0 broadcasts a scalar.
+ * place with no PCIe traffic.  Strides are in bytes, as in the reference's loop types: 0 broadcasts a
+ * scalar, the item size is a contiguous array, any other multiple of the item size (negative included)
+ * is a strided view whose elements the lanes gather into / scatter from their pinned slabs (the
+ * reference's generic strided loop, src/atop/ops_binary.cpp:563-569).
  */
 #ifndef PNUMPY_NTE_H
 #define PNUMPY_NTE_H
@@ -38,7 +41,8 @@ extern "C" {
 
 /* returned by the nte_* ops when the caller should run its previous (NumPy) loop instead:
  * fewer elements than the threshold, dispatcher disabled or busy on another thread, or a layout
- * that cannot be staged (non-contiguous host operand, partial overlap).  Never a failure. */
+ * that cannot be staged (a stride that is not a multiple of the item size, an output that overlaps an
+ * input without aliasing it exactly).  Never a failure. */
 #define NTE_DECLINED 1
 
 /* Bring up the dispatcher: pncu_init + per-GPU lane state on first use.  Returns 0, or
