@@ -346,6 +346,51 @@ struct LogF64 {
     static __device__ __forceinline__ double apply(double a) { return log64_elem(a); }
 };
 
+// log2 / log10 / log1p / expm1 (float64): the same machinery with a different recombination
+// (f64_math.cuh); float32 and the other twelve ufuncs of SURVEY.md 8(f) f-4 are in ops_trig_more.cu.
+__device__ __noinline__ double log2_64_elem(double a) {
+    if (!f64_log_ok(a)) return log2(a);
+    const int i = f64_log_index(a);
+    return f64_log2_fast(a, kLogTab[2 * i], kLogTab[2 * i + 1]);
+}
+__device__ __noinline__ double log10_64_elem(double a) {
+    if (!f64_log_ok(a)) return log10(a);
+    const int i = f64_log_index(a);
+    return f64_log10_fast(a, kLogTab[2 * i], kLogTab[2 * i + 1]);
+}
+__device__ __noinline__ double log1p_64_elem(double a) {
+    if (!f64_log1p_ok(a)) return log1p(a);
+    const int i = f64_log1p_index(a);
+    return f64_log1p_fast(a, kLogTab[2 * i], kLogTab[2 * i + 1]);
+}
+__device__ __noinline__ double expm1_64_elem(double a) { return f64_exp_ok(a) ? f64_expm1_fast(a) : expm1(a); }
+
+#define PNCU_LOG_TABLE_FUNCTOR(NAME, OK, INDEX, FAST, ELEM)                                                        \
+    struct NAME {                                                                                                  \
+        typedef double In; typedef double Out;                                                                     \
+        static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;                                   \
+        static constexpr int kSmemBytes = LogF64::kSmemBytes;                                                      \
+        static __device__ __forceinline__ void smem_init(void* smem) { LogF64::smem_init(smem); }                  \
+        static __device__ __forceinline__ const void* smem_lane(const void* smem) { return LogF64::smem_lane(smem); } \
+        static __device__ __forceinline__ bool ok(double a) { return OK(a); }                                      \
+        static __device__ __forceinline__ double fast(double a, const void* table) {                               \
+            const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(table) + INDEX(a) * 128); \
+            return FAST(a, e.x, e.y);                                                                              \
+        }                                                                                                          \
+        static __device__ __forceinline__ double apply(double a) { return ELEM(a); }                               \
+    };
+PNCU_LOG_TABLE_FUNCTOR(Log2F64, f64_log_ok, f64_log_index, f64_log2_fast, log2_64_elem)
+PNCU_LOG_TABLE_FUNCTOR(Log10F64, f64_log_ok, f64_log_index, f64_log10_fast, log10_64_elem)
+PNCU_LOG_TABLE_FUNCTOR(Log1pF64, f64_log1p_ok, f64_log1p_index, f64_log1p_fast, log1p_64_elem)
+#undef PNCU_LOG_TABLE_FUNCTOR
+struct Expm1F64 {
+    typedef double In; typedef double Out;
+    static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(double a) { return f64_exp_ok(a); }
+    static __device__ __forceinline__ double fast(double a) { return f64_expm1_fast(a); }
+    static __device__ __forceinline__ double apply(double a) { return expm1_64_elem(a); }
+};
+
 }  // namespace
 
 namespace pncu { pncu_unary_fn trig_more(int func, int t); }
@@ -372,8 +417,20 @@ extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType)
             if (t == PNCU_FLOAT) return launch_unary<ExpF32>;
             if (t == PNCU_DOUBLE) return launch_unary<ExpF64>;
             break;
+        case PNCU_LOG2:
+            if (t == PNCU_DOUBLE) return launch_unary<Log2F64>;
+            return trig_more(func, t);
+        case PNCU_LOG10:
+            if (t == PNCU_DOUBLE) return launch_unary<Log10F64>;
+            return trig_more(func, t);
+        case PNCU_LOG1P:
+            if (t == PNCU_DOUBLE) return launch_unary<Log1pF64>;
+            return trig_more(func, t);
+        case PNCU_EXPM1:
+            if (t == PNCU_DOUBLE) return launch_unary<Expm1F64>;
+            return trig_more(func, t);
         default:
-            // the sixteen ufuncs the reference hooks without a body (ops_trig_more.cu)
+            // the other ufuncs the reference hooks without a body (ops_trig_more.cu)
             return trig_more(func, t);
     }
     return NULL;

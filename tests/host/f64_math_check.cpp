@@ -26,6 +26,10 @@ static double ulp_err(double got, long double want) {
 
 static double hlog(double x) { const int i = f64_log_index(x); return f64_log_fast(x, kLogTab[2 * i], kLogTab[2 * i + 1]); }
 
+static double hlog2(double x) { const int i = f64_log_index(x); return f64_log2_fast(x, kLogTab[2 * i], kLogTab[2 * i + 1]); }
+static double hlog10(double x) { const int i = f64_log_index(x); return f64_log10_fast(x, kLogTab[2 * i], kLogTab[2 * i + 1]); }
+static double hlog1p(double x) { const int i = f64_log1p_index(x); return f64_log1p_fast(x, kLogTab[2 * i], kLogTab[2 * i + 1]); }
+
 struct Stat { double worst = 0, at = 0; long n = 0; };
 static void upd(Stat& s, double x, double got, long double want) {
     double e = ulp_err(got, want);
@@ -86,6 +90,46 @@ int main(int argc, char** argv) {
         !f64_log_ok(1.7e308)) { printf("f64_log_ok domain wrong\n"); bad = 1; }
     if (f64_sincos_ok(INFINITY) || f64_sincos_ok(NAN) || f64_sincos_ok(2e5) || !f64_sincos_ok(-105000.0)) { printf("f64_sincos_ok domain wrong\n"); bad = 1; }
     if (f64_exp_ok(INFINITY) || f64_exp_ok(NAN) || f64_exp_ok(708.0) || f64_exp_ok(-710.0) || !f64_exp_ok(-706.9)) { printf("f64_exp_ok domain wrong\n"); bad = 1; }
+    // log2 / log10: same inputs as log; exact at powers of 2 / 10
+    Stat slog2, slog10, slog1p, sexpm1;
+    for (auto& rg : lranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            upd(slog2, x, hlog2(x), log2l((long double)x));
+            upd(slog10, x, hlog10(x), log10l((long double)x));
+        }
+    for (long i = 0; i < N; ++i) {
+        double x = from_bits((rnd() & 0x7fffffffffffffffull));
+        if (!f64_log_ok(x)) continue;
+        upd(slog2, x, hlog2(x), log2l((long double)x));
+        upd(slog10, x, hlog10(x), log10l((long double)x));
+    }
+    for (int k = -1022; k <= 1023; ++k) if (hlog2(ldexp(1.0, k)) != (double)k) { printf("log2(2^%d) inexact\n", k); bad = 1; break; }
+    { double p10 = 1.0; for (int k = 0; k <= 22; ++k) { if (hlog10(p10) != (double)k) { printf("log10(1e%d) = %.17g\n", k, hlog10(p10)); bad = 1; } p10 *= 10.0; } }
+    // log1p
+    const double pranges[][2] = {{-0.999, 1}, {-1e-3, 1e-3}, {-1e-12, 1e-12}, {0, 1e6}, {-0.5, 0.5}, {1e6, 1e17}, {-1e-300, 1e-300}};
+    for (auto& rg : pranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_log1p_ok(x)) continue;
+            upd(slog1p, x, hlog1p(x), log1pl((long double)x));
+        }
+    { double z = hlog1p(-0.0); if (z != 0.0 || !signbit(z) || hlog1p(0.0) != 0.0 || signbit(hlog1p(0.0))) { printf("log1p(+-0) wrong\n"); bad = 1; } }
+    if (f64_log1p_ok(-1.0) || f64_log1p_ok(-2.0) || f64_log1p_ok(INFINITY) || f64_log1p_ok(NAN) || f64_log1p_ok(1e19) || !f64_log1p_ok(-0.99) ||
+        !f64_log1p_ok(1e17) || !f64_log1p_ok(5e-324) || !f64_log1p_ok(-5e-324)) { printf("f64_log1p_ok domain wrong\n"); bad = 1; }
+    // expm1
+    const double mranges[][2] = {{-1, 1}, {-40, 40}, {-707, 707}, {-1e-5, 1e-5}, {-0.4, 0.4}, {-1e-300, 1e-300}};
+    for (auto& rg : mranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_exp_ok(x)) continue;
+            upd(sexpm1, x, f64_expm1_fast(x), expm1l((long double)x));
+        }
+    { double z = f64_expm1_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("expm1(-0) wrong\n"); bad = 1; } }
+    printf("log2 %ld %.4f %.17g\n", slog2.n, slog2.worst, slog2.at);
+    printf("log10 %ld %.4f %.17g\n", slog10.n, slog10.worst, slog10.at);
+    printf("log1p %ld %.4f %.17g\n", slog1p.n, slog1p.worst, slog1p.at);
+    printf("expm1 %ld %.4f %.17g\n", sexpm1.n, sexpm1.worst, sexpm1.at);
     printf("sin %ld %.4f %.17g\n", ssin.n, ssin.worst, ssin.at);
     printf("cos %ld %.4f %.17g\n", scos.n, scos.worst, scos.at);
     printf("exp %ld %.4f %.17g\n", sexp.n, sexp.worst, sexp.at);
