@@ -505,3 +505,56 @@ def test_more_transcendental_ufuncs_run_on_the_gpu(pn, rng, dt):
         assert calls >= 1, name
         assert got.dtype == want.dtype
         assert ulp_error(got, want.astype(np.float64)).max() <= 4.0, (name, dt)
+
+
+def test_concurrent_python_threads(pn, rng):
+    """NumPy releases the GIL around these loops, so two Python threads can be inside the hooked loop at
+    once.  The reference degrades the second caller to its unthreaded path (src/atop/threads.h:1064-1073);
+    here nte's try_lock hands it NumPy's own loop.  Either way every result is right and nothing hangs."""
+    import threading
+    n = (1 << 22) + 3
+    data = [(rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)) for _ in range(4)]
+    want = [(a + b, np.sin(a), a.sum(dtype=np.float32), int(np.argmax(b))) for a, b in data]
+    got = [None] * 4
+    errs = []
+
+    def work(i):
+        try:
+            a, b = data[i]
+            for _ in range(5):
+                got[i] = (a + b, np.sin(a), a.sum(), int(b.argmax()))
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+    c0, d0 = pn.cuda_info()["calls"], pn.cuda_info()["declined"]
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in ths), "a hooked call hung"
+    assert not errs, errs
+    info = pn.cuda_info()
+    assert info["calls"] > c0  # some calls ran on the GPU ...
+    for i in range(4):
+        assert_bits_equal(got[i][0], want[i][0], "add under contention")
+        # sin: the GPU body (Cephes) and NumPy's differ in the last place; whichever ran is within 2 ULP here
+        assert np.all(ulp_error(got[i][1], np.sin(data[i][0].astype(np.float64)).astype(np.float32)) <= 2)
+        assert abs(float(got[i][2]) - float(want[i][2])) <= 2.0 ** -20 * np.abs(data[i][0]).sum()
+        assert got[i][3] == want[i][3]
+    assert info["declined"] >= d0
+
+
+def test_degenerate_sizes(pn):
+    """empty, one-element and just-below/above-a-vector arrays through the hooks (threshold 0: all on the GPU)"""
+    for n in (0, 1, 2, 7, 8, 9, 31, 32, 33, 255, 256, 257):
+        for dt in ("int8", "int32", "float32", "float64"):
+            a = (np.arange(n) % 5 + 1).astype(dt)
+            b = (np.arange(n) % 3 + 1).astype(dt)
+            got, want, _ = _both(pn, lambda: (a + b, a * b, a > b, np.abs(a), a.sum() if n else 0, a.max() if n else 0,
+                                               int(a.argmax()) if n else 0))
+            for g, w in zip(got, want):
+                assert np.asarray(g).tobytes() == np.asarray(w).tobytes(), (n, dt)
+    with pytest.raises(ValueError):
+        np.empty(0, np.float32).argmax()
+    with pytest.raises(ValueError):
+        np.empty(0, np.float32).max()
