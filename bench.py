@@ -377,6 +377,30 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
     pb = lib.pncu_reduce_partial_bytes(f, t)
     cnt = lib.pncu_reduce_partial_count(t, n)
     res = dev.empty(1, np.float32)
+    xch = None
+    counts = [cnt] * world
+
+    def timed_ms(fn):
+        """host wall clock around `reps` calls (the collective included), max over ranks"""
+        for _ in range(3):
+            fn()
+        cabi.check(lib.pncu_device_sync(), "sync")
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        cabi.check(lib.pncu_device_sync(), "sync")
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        if dist:
+            import torch
+            tt_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            ms = float(tt_.item())
+        return ms
+
+    reps = 10
+    nccl_ms = None
     if world == 1:
         parts = dev.empty(cnt * pb, np.uint8)
 
@@ -385,40 +409,40 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
             cabi.check(lib.pncu_reduce_finish(f, t, parts.ptr, cnt, res.ptr, None, stream), "finish")
     else:
         import torch
+        from pnumpy_b200 import exchange
         mine = torch.empty(cnt, dtype=torch.float64, device="cuda")
         allp = torch.empty(world * cnt, dtype=torch.float64, device="cuda")
 
-        def sharded_sum():
+        def sharded_sum_nccl():  # the plain way, timed beside the fused exchange
             cabi.check(lib.pncu_reduce_partials(f, t, a.ptr, n, mine.data_ptr(), stream), "partials")
             cabi.check(lib.pncu_stream_sync(stream), "sync")
             dist.all_gather_into_tensor(allp, mine)
             torch.cuda.current_stream().synchronize()
             cabi.check(lib.pncu_reduce_finish(f, t, allp.data_ptr(), world * cnt, res.ptr, None, stream), "finish")
-    for _ in range(3):
-        sharded_sum()
-    cabi.check(lib.pncu_device_sync(), "sync")
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    reps = 10
-    for _ in range(reps):
-        sharded_sum()
-    cabi.check(lib.pncu_device_sync(), "sync")
-    ms = (time.perf_counter() - t0) * 1e3 / reps
-    if dist:
-        import torch
-        tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+        nccl_ms = timed_ms(sharded_sum_nccl)
+        nccl_bits = res.to_host().tobytes()
+        # the product path: pass 2 is one kernel that stores this rank's block partials into every rank's slot
+        # table over NVLink (CUDA IPC mappings), waits on the device for the others' and folds -- no collective
+        # call, no host synchronisation in between
+        xch = exchange.Exchange.from_torch_distributed(max_slots=world * cnt)
+
+        def sharded_sum():
+            xch.reduce("ADD", a, counts, res, stream=stream)
+    ms = timed_ms(sharded_sum)
     out["sharded_sum_f32"] = {"elements_total": n * world, "ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1),
-                              "collective": "none (1 GPU)" if world == 1 else "one NCCL all_gather of float64 block partials",
+                              "collective": "none (1 GPU)" if world == 1 else
+                              "fused into pass 2: one kernel per rank stores its block partials into every rank's slot table over "
+                              "NVLink (CUDA IPC mappings), waits on the device for the others' and folds; no NCCL call, no host sync",
                               "result": float(res.to_host()[0])}
+    if nccl_ms is not None:
+        out["sharded_sum_f32"].update({"nccl_all_gather_variant_ms": round(nccl_ms, 4),
+                                       "nccl_all_gather_variant_gbs": round(4.0 * n * world / (nccl_ms * 1e-3) / 1e9, 1),
+                                       "same_bits_as_nccl_variant": res.to_host().tobytes() == nccl_bits})
 
     # configs[3], the other reductions, with NaN inputs: every rank's float32 shard gets ONE NaN at a
     # pseudo-random index (SURVEY.md 8d case iv).  min/max must come back NaN and argmin/argmax the GLOBAL
-    # index of the first NaN (rank 0's).  Pass 1 per shard, one all_gather of the block partials (4 B for
-    # min/max, 16 B {value, index} for the arg-reductions), one finish kernel -- timed like the sum.
-    import ctypes
+    # index of the first NaN (rank 0's).  Same two passes with the exchange fused in (4 B partials for min/max,
+    # 16 B {value, index} for the arg-reductions) -- timed like the sum.
     xn = byname["float32"][2]  # the float32 output buffer, free at this point
     cabi.check(lib.pncu_memcpy_d2d(xn.ptr, a.ptr, n * 4, stream), "copy")
     nan_at = (1234567 * (rank + 1)) % n
@@ -429,52 +453,34 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
     nan_rows = {}
     for name, kind in (("min", None), ("max", None), ("argmin", 1), ("argmax", 0)):
         fop = cabi.BINARY_OPS["MIN" if name == "min" else "MAX"]
-        pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
         if world == 1:
+            pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
             buf = dev.empty(cnt * pbytes, np.uint8)
-            mine_ptr, all_ptr = buf.ptr, buf.ptr
-        else:
-            import torch
-            mine_t = torch.empty(cnt * pbytes, dtype=torch.uint8, device="cuda")
-            all_t = torch.empty(world * cnt * pbytes, dtype=torch.uint8, device="cuda")
-            mine_ptr, all_ptr = mine_t.data_ptr(), all_t.data_ptr()
 
-        def sharded(kind=kind, fop=fop, mine_ptr=mine_ptr, all_ptr=all_ptr):
-            if kind is None:
-                cabi.check(lib.pncu_reduce_partials(fop, t, xn.ptr, n, mine_ptr, stream), "partials")
-            else:
-                cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(rank * n), mine_ptr, stream), "arg partials")
-            if world > 1:
-                cabi.check(lib.pncu_stream_sync(stream), "sync")
-                dist.all_gather_into_tensor(all_t, mine_t)
-                torch.cuda.current_stream().synchronize()
-            if kind is None:
-                cabi.check(lib.pncu_reduce_finish(fop, t, all_ptr, world * cnt, res.ptr, None, stream), "finish")
-            else:
-                cabi.check(lib.pncu_argminmax_finish(kind, t, all_ptr, world * cnt, ri.ptr, stream), "arg finish")
-        for _ in range(3):
-            sharded()
-        cabi.check(lib.pncu_device_sync(), "sync")
-        if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            sharded()
-        cabi.check(lib.pncu_device_sync(), "sync")
-        ms = (time.perf_counter() - t0) * 1e3 / reps
-        if dist:
-            import torch
-            tt_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
-            ms = float(tt_.item())
+            def sharded(kind=kind, fop=fop, buf=buf):
+                if kind is None:
+                    cabi.check(lib.pncu_reduce_partials(fop, t, xn.ptr, n, buf.ptr, stream), "partials")
+                    cabi.check(lib.pncu_reduce_finish(fop, t, buf.ptr, cnt, res.ptr, None, stream), "finish")
+                else:
+                    cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(0), buf.ptr, stream), "arg partials")
+                    cabi.check(lib.pncu_argminmax_finish(kind, t, buf.ptr, cnt, ri.ptr, stream), "arg finish")
+        else:
+            def sharded(kind=kind, name=name):
+                if kind is None:
+                    xch.reduce("MIN" if name == "min" else "MAX", xn, counts, res, stream=stream)
+                else:
+                    xch.argminmax(kind, xn, counts, rank * n, ri, stream=stream)
+        ms = timed_ms(sharded)
         if kind is None:
             ok = bool(np.isnan(res.to_host()[0]))
         else:
             ok = int(ri.to_host()[0]) == 1234567 % n  # rank 0's NaN is the first of the whole job
         nan_rows[name] = {"ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1), "nan_semantics_ok": ok}
+    if xch is not None:
+        nan_rows["exchange_timeouts"] = int(lib.pncu_exchange_timeouts())
     out["sharded_nan_reductions_f32"] = {
         "elements_total": n * world, "nan_per_shard": 1,
-        "collective": "none (1 GPU)" if world == 1 else "one NCCL all_gather of block partials per reduction",
+        "collective": "none (1 GPU)" if world == 1 else "fused exchange over NVLink peer memory (see sharded_sum_f32)",
         "timing": "host wall clock around 10 calls incl. the collective, max over ranks", **nan_rows}
 
     # configs[4], device-resident leg: t = a*b; u = t+c; r = u.sum() as three kernels (28 B/element)

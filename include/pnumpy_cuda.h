@@ -257,6 +257,51 @@ PNCU_API int pncu_argminmax_finish(int kind, int atype, const void* partials, in
                                    int64_t* out_index, pncu_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * The cross-GPU exchange fused into pass 2 (the path's ONE exchange step).
+ *
+ * The reference folds its per-chunk partials on the calling thread (src/pnumpy/_pnumpy.cpp:697-699); with
+ * the input sharded over G GPUs the block partials of all shards have to meet.  Instead of a collective
+ * between the passes, each participant's pass 2 is ONE kernel that (i) stores its own block partials into
+ * slot `slot_base ..` of EVERY participant's slot table -- ordinary stores into peer memory over NVLink,
+ * pncu_exchange_slices() CTAs per destination, each followed by a system-scope fence and one arrival count
+ * on the destination's counter -- (ii) waits ON THE DEVICE until the slices of all participants have
+ * arrived in its own table and (iii) folds the complete table in slot order.  Every GPU ends with the same
+ * bits (an all-reduce), identical to the single-GPU result, with no NCCL call, no extra launch and no host
+ * synchronisation between the passes.
+ *
+ * Tables: `slots[d]` points to participant d's slot array (element size pncu_reduce_partial_bytes(), or 16
+ * for arg-reductions), `arrived[d]` to its 64-bit counter; both device memory of GPU d that the calling
+ * GPU can write (same process: pncu_enable_peer_access; other processes: pncu_ipc_export / pncu_ipc_import).
+ * Counters only ever grow: every call adds n * pncu_exchange_slices() arrivals to each table, and the
+ * caller passes the running total as `expected`.  Alternate between two tables on successive calls (a fast
+ * rank may start call e+1 while a slow one still folds the table of call e).
+ * ------------------------------------------------------------------------- */
+#define PNCU_MAX_PEERS 8
+typedef struct pncu_peer_table {
+    int n;                                        /* participants, 1..PNCU_MAX_PEERS */
+    void* slots[PNCU_MAX_PEERS];
+    unsigned long long* arrived[PNCU_MAX_PEERS];
+} pncu_peer_table;
+PNCU_API int pncu_exchange_slices(void);
+/* `local_partials`: the output of pncu_reduce_partials() on this participant's shard (local_count slots);
+ * `self`: this participant's index in `peers`; `total_count`: slots of all participants together */
+PNCU_API int pncu_reduce_exchange_finish(int func, int atype, const void* local_partials, int64_t local_count,
+                                         int64_t slot_base, const pncu_peer_table* peers, int self,
+                                         int64_t total_count, void* out, const void* startVal,
+                                         unsigned long long expected, pncu_stream_t stream);
+PNCU_API int pncu_argminmax_exchange_finish(int kind, int atype, const void* local_partials, int64_t local_count,
+                                            int64_t slot_base, const pncu_peer_table* peers, int self,
+                                            int64_t total_count, int64_t* out_index,
+                                            unsigned long long expected, pncu_stream_t stream);
+/* pass-2 waits that gave up after ~4 s (a participant never arrived) on the current device; 0 in a healthy job */
+PNCU_API int64_t pncu_exchange_timeouts(void);
+/* peer memory plumbing: same-process peer access, and CUDA IPC handles (64 bytes) for one-process-per-GPU jobs */
+PNCU_API int pncu_enable_peer_access(int peer_device);     /* from the current device; idempotent */
+PNCU_API int pncu_ipc_export(void* dev_ptr, void* handle64);
+PNCU_API int pncu_ipc_import(const void* handle64, void** dev_ptr);
+PNCU_API int pncu_ipc_close(void* dev_ptr);
+
+/* ---------------------------------------------------------------------------
  * Device memory / stream / event helpers (thin cudart wrappers) so that callers
  * written in C, ctypes or cgo need no CUDA headers.
  * ------------------------------------------------------------------------- */

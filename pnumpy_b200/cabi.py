@@ -111,7 +111,24 @@ SIGNATURES = {
     "pncu_event_sync": (ctypes.c_int, [_vp]),
     "pncu_event_elapsed_ms": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_float)]),
     "pncu_pointer_kind": (ctypes.c_int, [_vp, _P_INT]),
+    "pncu_exchange_slices": (ctypes.c_int, []),
+    "pncu_reduce_exchange_finish": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _c_i64, _vp, ctypes.c_int, _c_i64, _vp, _vp,
+                                                   ctypes.c_uint64, _vp]),
+    "pncu_argminmax_exchange_finish": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _c_i64, _vp, ctypes.c_int, _c_i64, _vp,
+                                                      ctypes.c_uint64, _vp]),
+    "pncu_exchange_timeouts": (_c_i64, []),
+    "pncu_enable_peer_access": (ctypes.c_int, [ctypes.c_int]),
+    "pncu_ipc_export": (ctypes.c_int, [_vp, _vp]),
+    "pncu_ipc_import": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
+    "pncu_ipc_close": (ctypes.c_int, [_vp]),
 }
+
+PNCU_MAX_PEERS = 8
+
+
+class PeerTable(ctypes.Structure):
+    """pncu_peer_table (include/pnumpy_cuda.h)"""
+    _fields_ = [("n", ctypes.c_int), ("slots", _vp * PNCU_MAX_PEERS), ("arrived", _vp * PNCU_MAX_PEERS)]
 
 _lib = None
 

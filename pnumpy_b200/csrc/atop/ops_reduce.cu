@@ -553,6 +553,86 @@ reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, 
     }
 }
 
+// ---- pass 2 with the cross-GPU exchange fused in ---------------------------------------------------------
+// G participants (GPUs), each with `local_count` block partials from its own pass 1.  One kernel per
+// participant does the whole exchange and the fold:
+//   CTA (s, d), s < EXCH_SLICES, d < G: copies slice s of the local partials into participant d's slot table
+//       at slot_base (plain stores into peer memory over NVLink; d == self is the local table), then one
+//       system-scope fence and one arrival count on d's counter;
+//   CTA (0, self) then waits ON THE DEVICE until all G * EXCH_SLICES slices of this call have arrived in its
+//       own table and folds the complete table exactly like reduce_finish_kernel (same order, same bits).
+// No collective call, no host synchronisation, no extra launch compared with a single GPU; the payload is
+// 4-16 bytes per 64 KiB of input.  All G * EXCH_SLICES CTAs (<= 64) are co-resident, so the waiting CTA
+// cannot starve the pushing ones.  The wait is bounded (~4 s -> g_exchange_timeouts) so a lost participant
+// is an error on the host, not a hung GPU.
+constexpr int EXCH_SLICES = 8;
+struct PeerOut {
+    int n, self;
+    long long slot_base;
+    void* slots[PNCU_MAX_PEERS];
+    unsigned long long* arrived[PNCU_MAX_PEERS];
+};
+__device__ unsigned long long g_exchange_timeouts = 0;
+
+template <class R, bool VALUE>
+__global__ void __launch_bounds__(FIN_THREADS)
+exchange_finish_kernel(const typename R::Acc* local, int64_t local_count, const PeerOut po, int64_t total_count,
+                       void* out, const void* startVal, unsigned long long expected) {
+    typedef typename R::Acc Acc;
+    __shared__ Acc smem[FIN_THREADS / 32];
+    const int s = blockIdx.x, d = blockIdx.y;
+    // ---- push slice s to participant d
+    {
+        const int64_t per = (local_count + EXCH_SLICES - 1) / EXCH_SLICES;
+        const int64_t lo = (int64_t)s * per;
+        const int64_t hi = lo + per < local_count ? lo + per : local_count;
+        Acc* dst = reinterpret_cast<Acc*>(po.slots[d]) + po.slot_base;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += FIN_THREADS) dst[i] = local[i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            atomicAdd_system(po.arrived[d], 1ULL);
+        }
+    }
+    if (s != 0 || d != po.self) return;
+    // ---- wait for everybody's slices, then fold the whole table
+    if (threadIdx.x == 0) {
+        unsigned long long t0, t1, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(po.arrived[po.self]) : "memory");
+            if (v >= expected) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ULL) { atomicAdd(&g_exchange_timeouts, 1ULL); break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    const Acc* partials = reinterpret_cast<const Acc*>(po.slots[po.self]);
+    const int64_t count = total_count;
+    constexpr int FIN_MLP = 8;
+    Acc a;
+    if (R::kHasIdentity) a = R::identity(); else a = partials[0];
+    int64_t k = threadIdx.x;
+    if (!R::kHasIdentity && k < count) { a = partials[k]; k += FIN_THREADS; }
+    for (; k + (int64_t)(FIN_MLP - 1) * FIN_THREADS < count; k += (int64_t)FIN_THREADS * FIN_MLP) {
+        Acc x[FIN_MLP];
+#pragma unroll
+        for (int m = 0; m < FIN_MLP; ++m) x[m] = partials[k + (int64_t)m * FIN_THREADS];
+#pragma unroll
+        for (int m = 0; m < FIN_MLP; ++m) a = R::combine(a, x[m]);
+    }
+    for (; k < count; k += FIN_THREADS) a = R::combine(a, partials[k]);
+    a = block_fold<R, FIN_THREADS>(a, smem);
+    if (threadIdx.x == 0) {
+        if constexpr (VALUE) {
+            write_result<R>(a, reinterpret_cast<typename R::In*>(out), reinterpret_cast<const typename R::In*>(startVal));
+        } else {
+            if constexpr (sizeof(Acc) == 16) *reinterpret_cast<int64_t*>(out) = a.idx;
+        }
+    }
+}
+
 // pass 2 queued right behind pass 1 on the same stream: with programmatic stream serialization the
 // finish CTA is scheduled as soon as every pass-1 CTA has started (griddepcontrol.launch_dependents) and
 // blocks in griddepcontrol.wait until that grid is complete, so its launch latency overlaps pass 1's tail.
@@ -715,11 +795,19 @@ struct ReduceOps {
     pncu_reduce_fn full;
     int (*partials)(const void*, int64_t, int64_t, int64_t, void*, cudaStream_t);
     int (*finish)(const void*, int64_t, void*, const void*, cudaStream_t);
+    int (*exchange_finish)(const void*, int64_t, const PeerOut*, int64_t, void*, const void*, unsigned long long, cudaStream_t);
 };
 template <class R, bool VALUE>
 int finish_thunk(const void* partials, int64_t count, void* out, const void* startVal, cudaStream_t st) {
     reduce_finish_kernel<R, VALUE><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)partials, count, out, startVal);
     return after_launch("reduce_finish_kernel");
+}
+template <class R, bool VALUE>
+int exchange_finish_thunk(const void* local, int64_t local_count, const PeerOut* po, int64_t total_count, void* out,
+                          const void* startVal, unsigned long long expected, cudaStream_t st) {
+    exchange_finish_kernel<R, VALUE><<<dim3(EXCH_SLICES, po->n), FIN_THREADS, 0, st>>>(
+        (const typename R::Acc*)local, local_count, *po, total_count, out, startVal, expected);
+    return after_launch("exchange_finish_kernel");
 }
 template <class R>
 ReduceOps make_ops() {
@@ -728,6 +816,7 @@ ReduceOps make_ops() {
     o.full = launch_reduce<R>;
     o.partials = launch_partials<R>;
     o.finish = finish_thunk<R, true>;
+    o.exchange_finish = exchange_finish_thunk<R, true>;
     return o;
 }
 template <class R>
@@ -737,6 +826,7 @@ ReduceOps make_arg_ops() {
     o.full = NULL;
     o.partials = launch_arg_partials<typename R::In, R::kIsMax>;
     o.finish = finish_thunk<R, false>;
+    o.exchange_finish = exchange_finish_thunk<R, false>;
     return o;
 }
 
@@ -912,6 +1002,58 @@ extern "C" int pncu_argminmax_finish(int kind, int t, const void* partials, int6
     if (rc) return rc;
     if (!out_index || count <= 0) { set_error("bad arguments"); return PNCU_ERR_ARGUMENT; }
     return o.finish(partials, count, out_index, NULL, as_stream(stream));
+}
+
+// ---- cross-GPU exchange fused into pass 2 (include/pnumpy_cuda.h) ---------------------------------------------
+static int fill_peers(const pncu_peer_table* peers, int self, int64_t slot_base, PeerOut* po) {
+    if (!peers || peers->n < 1 || peers->n > PNCU_MAX_PEERS || self < 0 || self >= peers->n) {
+        set_error("peer table: n must be 1..%d and 0 <= self < n", PNCU_MAX_PEERS);
+        return PNCU_ERR_ARGUMENT;
+    }
+    po->n = peers->n;
+    po->self = self;
+    po->slot_base = slot_base;
+    for (int d = 0; d < peers->n; ++d) {
+        if (!peers->slots[d] || !peers->arrived[d]) { set_error("peer table: null pointer for participant %d", d); return PNCU_ERR_ARGUMENT; }
+        po->slots[d] = peers->slots[d];
+        po->arrived[d] = peers->arrived[d];
+    }
+    return 0;
+}
+
+extern "C" int pncu_exchange_slices(void) { return EXCH_SLICES; }
+
+extern "C" int pncu_reduce_exchange_finish(int func, int t, const void* local_partials, int64_t local_count,
+                                           int64_t slot_base, const pncu_peer_table* peers, int self, int64_t total_count,
+                                           void* out, const void* startVal, unsigned long long expected, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_reduce(func, t, &o)) { set_error("no reduction kernel for func %d type %d", func, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!out || !local_partials || local_count <= 0 || total_count < local_count) { set_error("bad arguments"); return PNCU_ERR_ARGUMENT; }
+    PeerOut po;
+    if ((rc = fill_peers(peers, self, slot_base, &po))) return rc;
+    return o.exchange_finish(local_partials, local_count, &po, total_count, out, startVal, expected, as_stream(stream));
+}
+
+extern "C" int pncu_argminmax_exchange_finish(int kind, int t, const void* local_partials, int64_t local_count,
+                                              int64_t slot_base, const pncu_peer_table* peers, int self, int64_t total_count,
+                                              int64_t* out_index, unsigned long long expected, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_arg(kind, t, &o)) { set_error("no arg-reduction kernel for kind %d type %d", kind, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (!out_index || !local_partials || local_count <= 0 || total_count < local_count) { set_error("bad arguments"); return PNCU_ERR_ARGUMENT; }
+    PeerOut po;
+    if ((rc = fill_peers(peers, self, slot_base, &po))) return rc;
+    return o.exchange_finish(local_partials, local_count, &po, total_count, out_index, NULL, expected, as_stream(stream));
+}
+
+extern "C" int64_t pncu_exchange_timeouts(void) {
+    unsigned long long v = 0;
+    if (ensure_init()) return -1;
+    if (cudaMemcpyFromSymbol(&v, g_exchange_timeouts, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int64_t)v;
 }
 
 extern "C" pncu_three_reduce_fn pncu_GetMulAddSumFast(int t) {

@@ -229,4 +229,41 @@ int pncu_pointer_kind(const void* ptr, int* device) {
     }
 }
 
+// ---- peer memory plumbing for the fused exchange (ops_reduce.cu) -----------------------------------------
+int pncu_enable_peer_access(int peer_device) {
+    int rc = ensure_init(); if (rc) return rc;
+    int cur = 0;
+    PNCU_CUDA(cudaGetDevice(&cur));
+    if (cur == peer_device) return 0;
+    int can = 0;
+    PNCU_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    if (!can) { set_error("device %d cannot access device %d directly", cur, peer_device); return PNCU_ERR_UNSUPPORTED; }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+    return 0;
+}
+int pncu_ipc_export(void* dev_ptr, void* handle64) {
+    int rc = ensure_init(); if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!dev_ptr || !handle64) { set_error("null argument"); return PNCU_ERR_ARGUMENT; }
+    cudaIpcMemHandle_t h;
+    PNCU_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int pncu_ipc_import(const void* handle64, void** dev_ptr) {
+    int rc = ensure_init(); if (rc) return rc;
+    if (!dev_ptr || !handle64) { set_error("null argument"); return PNCU_ERR_ARGUMENT; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PNCU_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int pncu_ipc_close(void* dev_ptr) {
+    int rc = ensure_init(); if (rc) return rc;
+    PNCU_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
 }  // extern "C"

@@ -612,3 +612,72 @@ def test_more_transcendentals_within_4ulp(dev, O, rng, op, dt):
     both = np.isfinite(want) & np.isfinite(got)
     assert np.all(ulp_error(got[both], want[both].astype(np.float64)) <= 8.0)
     del tf
+
+
+# ---- the cross-GPU exchange fused into the two passes -------------------------------------------------
+def _exchange_case(dev, devices, rng):
+    """sum / min / max / argmax of one array cut into len(devices) shards, every shard on its own GPU, through
+    Exchange: every participant must end with the bits a single GPU produces."""
+    from pnumpy_b200 import cabi, exchange
+    lib = cabi.load()
+    world = len(devices)
+    align = int(lib.pncu_reduce_block_elems())
+    n = 5 * align * world + 12345
+    for dt in ("float32", "float64", "int32"):
+        a = (rng.normal(0, 100, n)).astype(dt)
+        if dt != "int32":
+            a[n // 2 + 7] = np.nan
+        units = -(-n // align)
+        per = -(-units // world)
+        bounds = [min(n, r * per * align) for r in range(world + 1)]
+        cabi.check(lib.pncu_set_device(devices[0]), "set_device")
+        whole = dev.to_device(a)
+        want = {op: dev.reduce(op, whole).to_host().tobytes() for op in ("ADD", "MIN", "MAX")}
+        want_arg = [int(dev.argminmax(k, whole).to_host()[0]) for k in (0, 1)]
+        xs = exchange.Exchange.in_process(devices, max_slots=8192)
+        shards, outs, idxs = [], [], []
+        for r, d in enumerate(devices):
+            cabi.check(lib.pncu_set_device(d), "set_device")
+            shards.append(dev.to_device(a[bounds[r]:bounds[r + 1]]))
+            outs.append(dev.empty(1, dt))
+            idxs.append(dev.empty(1, np.int64))
+        counts = exchange.block_counts([s.size for s in shards], dt)
+        for rep in range(3):  # several calls: both tables, growing counters
+            for op in ("ADD", "MIN", "MAX"):
+                for r, d in enumerate(devices):
+                    cabi.check(lib.pncu_set_device(d), "set_device")
+                    xs[r].reduce(op, shards[r], counts, outs[r])
+                for r, d in enumerate(devices):
+                    cabi.check(lib.pncu_set_device(d), "set_device")
+                    dev.sync()
+                    got = outs[r].to_host()
+                    if op != "ADD" and dt != "int32":
+                        assert np.isnan(got[0])
+                    else:
+                        assert got.tobytes() == want[op], (dt, op, r, rep)
+            for kind in (0, 1):
+                for r, d in enumerate(devices):
+                    cabi.check(lib.pncu_set_device(d), "set_device")
+                    xs[r].argminmax(kind, shards[r], counts, bounds[r], idxs[r])
+                for r, d in enumerate(devices):
+                    cabi.check(lib.pncu_set_device(d), "set_device")
+                    dev.sync()
+                    assert int(idxs[r].to_host()[0]) == want_arg[kind], (dt, kind, r, rep)
+        for r, d in enumerate(devices):
+            cabi.check(lib.pncu_set_device(d), "set_device")
+            assert lib.pncu_exchange_timeouts() == 0
+            xs[r].close()
+    cabi.check(lib.pncu_set_device(devices[0]), "set_device")
+
+
+def test_fused_exchange_one_gpu(dev, rng):
+    """world = 1: the exchange path (stores + arrival counter + waiting finish) equals the plain two passes"""
+    _exchange_case(dev, [0], rng)
+
+
+def test_fused_exchange_two_gpus(dev, rng):
+    """two GPUs in one process: pass 1 on each stores into both slot tables over NVLink"""
+    from pnumpy_b200 import cabi
+    if cabi.load().pncu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _exchange_case(dev, [0, 1], rng)
