@@ -519,6 +519,8 @@ def run_e2e(args):
     """The same sweep through the reference-facing API: np.add / np.multiply / np.true_divide /
     np.greater on pinned HOST ndarrays with pnumpy_b200 enabled.  H2D and D2H copies are inside the
     timed region (nte stages 8 MiB slabs through 3-deep rings on separate copy/compute streams)."""
+    # the dispatcher spreads a call over the visible GPUs: use exactly the N of `--gpus N`, whatever the box has
+    os.environ["PNUMPY_CUDA_DEVICES"] = str(max(1, int(os.environ.get("WORLD_SIZE", args.gpus))))
     import pnumpy_b200 as pn
     try:
         pn.init()
