@@ -383,6 +383,21 @@ PNCU_LOG_TABLE_FUNCTOR(Log2F64, f64_log_ok, f64_log_index, f64_log2_fast, log2_6
 PNCU_LOG_TABLE_FUNCTOR(Log10F64, f64_log_ok, f64_log_index, f64_log10_fast, log10_64_elem)
 PNCU_LOG_TABLE_FUNCTOR(Log1pF64, f64_log1p_ok, f64_log1p_index, f64_log1p_fast, log1p_64_elem)
 #undef PNCU_LOG_TABLE_FUNCTOR
+__device__ __noinline__ double tanh64_elem(double a) { return f64_tanh_ok(a) ? f64_tanh_fast(a) : tanh(a); }
+__device__ __noinline__ double sinh64_elem(double a) { return f64_exp_ok(a) ? f64_sinh_fast(a) : sinh(a); }
+__device__ __noinline__ double tan64_elem(double a) { return f64_sincos_ok(a) ? f64_tan_fast(a) : tan(a); }
+#define PNCU_F64_FAST_FUNCTOR(NAME, OK, FAST, ELEM)                                                \
+    struct NAME {                                                                                  \
+        typedef double In; typedef double Out;                                                     \
+        static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;                   \
+        static __device__ __forceinline__ bool ok(double a) { return OK(a); }                      \
+        static __device__ __forceinline__ double fast(double a) { return FAST(a); }                \
+        static __device__ __forceinline__ double apply(double a) { return ELEM(a); }               \
+    };
+PNCU_F64_FAST_FUNCTOR(TanhF64, f64_tanh_ok, f64_tanh_fast, tanh64_elem)
+PNCU_F64_FAST_FUNCTOR(SinhF64, f64_exp_ok, f64_sinh_fast, sinh64_elem)
+PNCU_F64_FAST_FUNCTOR(TanF64, f64_sincos_ok, f64_tan_fast, tan64_elem)
+#undef PNCU_F64_FAST_FUNCTOR
 struct Expm1F64 {
     typedef double In; typedef double Out;
     static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
@@ -428,6 +443,15 @@ extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType)
             return trig_more(func, t);
         case PNCU_EXPM1:
             if (t == PNCU_DOUBLE) return launch_unary<Expm1F64>;
+            return trig_more(func, t);
+        case PNCU_TANH:
+            if (t == PNCU_DOUBLE) return launch_unary<TanhF64>;
+            return trig_more(func, t);
+        case PNCU_SINH:
+            if (t == PNCU_DOUBLE) return launch_unary<SinhF64>;
+            return trig_more(func, t);
+        case PNCU_TAN:
+            if (t == PNCU_DOUBLE) return launch_unary<TanF64>;
             return trig_more(func, t);
         default:
             // the other ufuncs the reference hooks without a body (ops_trig_more.cu)

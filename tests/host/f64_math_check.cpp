@@ -126,6 +126,36 @@ int main(int argc, char** argv) {
             upd(sexpm1, x, f64_expm1_fast(x), expm1l((long double)x));
         }
     { double z = f64_expm1_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("expm1(-0) wrong\n"); bad = 1; } }
+    // tanh / sinh / tan
+    Stat stanh, ssinh, stan;
+    const double hranges[][2] = {{-1, 1}, {-20, 20}, {-350, 350}, {-1e-5, 1e-5}, {-0.5, 0.5}, {-1e-300, 1e-300}};
+    for (auto& rg : hranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (f64_tanh_ok(x)) upd(stanh, x, f64_tanh_fast(x), tanhl((long double)x));
+            if (f64_exp_ok(x)) upd(ssinh, x, f64_sinh_fast(x), sinhl((long double)x));
+        }
+    for (auto& rg : ranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_sincos_ok(x)) continue;
+            upd(stan, x, f64_tan_fast(x), tanl((long double)x));
+        }
+    for (long k = -60000; k <= 60000; ++k)
+        for (int d = -3; d <= 3; ++d) {
+            double x = (double)(k * 1.57079632679489661923L);
+            uint64_t b; memcpy(&b, &x, 8); b += (int64_t)d; x = from_bits(b);
+            if (!f64_sincos_ok(x)) continue;
+            upd(stan, x, f64_tan_fast(x), tanl((long double)x));
+        }
+    if (f64_tanh_fast(40.0) != 1.0 || f64_tanh_fast(-40.0) != -1.0) { printf("tanh(+-40) != +-1\n"); bad = 1; }
+    { double z = f64_tanh_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("tanh(-0) wrong\n"); bad = 1; } }
+    { double z = f64_sinh_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("sinh(-0) wrong\n"); bad = 1; } }
+    { double z = f64_tan_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("tan(-0) wrong\n"); bad = 1; } }
+    if (f64_tanh_fast(1e-300) != 1e-300 || f64_sinh_fast(1e-300) != 1e-300 || f64_tan_fast(1e-300) != 1e-300) { printf("tiny argument wrong\n"); bad = 1; }
+    printf("tanh %ld %.4f %.17g\n", stanh.n, stanh.worst, stanh.at);
+    printf("sinh %ld %.4f %.17g\n", ssinh.n, ssinh.worst, ssinh.at);
+    printf("tan %ld %.4f %.17g\n", stan.n, stan.worst, stan.at);
     printf("log2 %ld %.4f %.17g\n", slog2.n, slog2.worst, slog2.at);
     printf("log10 %ld %.4f %.17g\n", slog10.n, slog10.worst, slog10.at);
     printf("log1p %ld %.4f %.17g\n", slog1p.n, slog1p.worst, slog1p.at);
