@@ -379,6 +379,32 @@ __device__ __noinline__ double expm1_64_elem(double a) { return f64_exp_ok(a) ? 
         }                                                                                                          \
         static __device__ __forceinline__ double apply(double a) { return ELEM(a); }                               \
     };
+// atanh / asinh / acosh: log1p of an argument computed in the body, so they take the table accessor
+struct SmemLogTable {  // this lane's copy of the bank-replicated shared-memory table (LogF64::smem_lane)
+    const void* base;
+    __device__ __forceinline__ F64LogEntry get(int i) const {
+        const ulonglong2 e = *reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned char*>(base) + i * 128);
+        F64LogEntry r; r.e0 = e.x; r.e1 = e.y; return r;
+    }
+};
+__device__ __noinline__ double atanh64_elem(double a) { return f64_atanh_ok(a) ? f64_atanh_fast(a, F64FlatLogTable()) : atanh(a); }
+__device__ __noinline__ double asinh64_elem(double a) { return f64_asinh_ok(a) ? f64_asinh_fast(a, F64FlatLogTable()) : asinh(a); }
+__device__ __noinline__ double acosh64_elem(double a) { return f64_acosh_ok(a) ? f64_acosh_fast(a, F64FlatLogTable()) : acosh(a); }
+#define PNCU_LOG_ACCESSOR_FUNCTOR(NAME, OK, FAST, ELEM)                                                            \
+    struct NAME {                                                                                                  \
+        typedef double In; typedef double Out;                                                                     \
+        static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;                                   \
+        static constexpr int kSmemBytes = LogF64::kSmemBytes;                                                      \
+        static __device__ __forceinline__ void smem_init(void* smem) { LogF64::smem_init(smem); }                  \
+        static __device__ __forceinline__ const void* smem_lane(const void* smem) { return LogF64::smem_lane(smem); } \
+        static __device__ __forceinline__ bool ok(double a) { return OK(a); }                                      \
+        static __device__ __forceinline__ double fast(double a, const void* table) { return FAST(a, SmemLogTable{table}); } \
+        static __device__ __forceinline__ double apply(double a) { return ELEM(a); }                               \
+    };
+PNCU_LOG_ACCESSOR_FUNCTOR(AtanhF64, f64_atanh_ok, f64_atanh_fast, atanh64_elem)
+PNCU_LOG_ACCESSOR_FUNCTOR(AsinhF64, f64_asinh_ok, f64_asinh_fast, asinh64_elem)
+PNCU_LOG_ACCESSOR_FUNCTOR(AcoshF64, f64_acosh_ok, f64_acosh_fast, acosh64_elem)
+#undef PNCU_LOG_ACCESSOR_FUNCTOR
 PNCU_LOG_TABLE_FUNCTOR(Log2F64, f64_log_ok, f64_log_index, f64_log2_fast, log2_64_elem)
 PNCU_LOG_TABLE_FUNCTOR(Log10F64, f64_log_ok, f64_log_index, f64_log10_fast, log10_64_elem)
 PNCU_LOG_TABLE_FUNCTOR(Log1pF64, f64_log1p_ok, f64_log1p_index, f64_log1p_fast, log1p_64_elem)
@@ -443,6 +469,15 @@ extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType)
             return trig_more(func, t);
         case PNCU_EXPM1:
             if (t == PNCU_DOUBLE) return launch_unary<Expm1F64>;
+            return trig_more(func, t);
+        case PNCU_ATANH:
+            if (t == PNCU_DOUBLE) return launch_unary<AtanhF64>;
+            return trig_more(func, t);
+        case PNCU_ASINH:
+            if (t == PNCU_DOUBLE) return launch_unary<AsinhF64>;
+            return trig_more(func, t);
+        case PNCU_ACOSH:
+            if (t == PNCU_DOUBLE) return launch_unary<AcoshF64>;
             return trig_more(func, t);
         case PNCU_TANH:
             if (t == PNCU_DOUBLE) return launch_unary<TanhF64>;

@@ -153,6 +153,35 @@ int main(int argc, char** argv) {
     { double z = f64_sinh_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("sinh(-0) wrong\n"); bad = 1; } }
     { double z = f64_tan_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("tan(-0) wrong\n"); bad = 1; } }
     if (f64_tanh_fast(1e-300) != 1e-300 || f64_sinh_fast(1e-300) != 1e-300 || f64_tan_fast(1e-300) != 1e-300) { printf("tiny argument wrong\n"); bad = 1; }
+    // atanh / asinh / acosh
+    Stat satanh, sasinh, sacosh;
+    F64FlatLogTable flat;
+    const double aranges[][2] = {{-0.999, 0.999}, {-0.5, 0.5}, {-1e-4, 1e-4}, {-1e-300, 1e-300}};
+    for (auto& rg : aranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (f64_atanh_ok(x)) upd(satanh, x, f64_atanh_fast(x, flat), atanhl((long double)x));
+        }
+    const double sranges[][2] = {{-1, 1}, {-100, 100}, {-1e8, 1e8}, {-1e-4, 1e-4}, {-1e-300, 1e-300}, {-3, 3}};
+    for (auto& rg : sranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (f64_asinh_ok(x)) upd(sasinh, x, f64_asinh_fast(x, flat), asinhl((long double)x));
+        }
+    const double cranges[][2] = {{1, 2}, {1, 100}, {1, 1e8}, {1, 1.0001}, {1, 1.0000000001}};
+    for (auto& rg : cranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (f64_acosh_ok(x)) upd(sacosh, x, f64_acosh_fast(x, flat), acoshl((long double)x));
+        }
+    if (f64_acosh_fast(1.0, flat) != 0.0) { printf("acosh(1) != 0\n"); bad = 1; }
+    if (f64_acosh_ok(0.999) || f64_acosh_ok(-2.0) || f64_acosh_ok(NAN) || f64_acosh_ok(1e9) || !f64_acosh_ok(1.0) || !f64_acosh_ok(1e8)) { printf("f64_acosh_ok domain wrong\n"); bad = 1; }
+    { double z = f64_atanh_fast(-0.0, flat); if (z != 0.0 || !signbit(z)) { printf("atanh(-0) wrong\n"); bad = 1; } }
+    { double z = f64_asinh_fast(-0.0, flat); if (z != 0.0 || !signbit(z)) { printf("asinh(-0) wrong\n"); bad = 1; } }
+    { Stat ssq; for (long i = 0; i < N; ++i) { double v = uni(1e-3, 1e6); upd(ssq, v, f64_sqrt(v), sqrtl((long double)v)); } printf("sqrt %ld %.4f %.17g\n", ssq.n, ssq.worst, ssq.at); }
+    printf("atanh %ld %.4f %.17g\n", satanh.n, satanh.worst, satanh.at);
+    printf("asinh %ld %.4f %.17g\n", sasinh.n, sasinh.worst, sasinh.at);
+    printf("acosh %ld %.4f %.17g\n", sacosh.n, sacosh.worst, sacosh.at);
     printf("tanh %ld %.4f %.17g\n", stanh.n, stanh.worst, stanh.at);
     printf("sinh %ld %.4f %.17g\n", ssinh.n, ssinh.worst, ssinh.at);
     printf("tan %ld %.4f %.17g\n", stan.n, stan.worst, stan.at);
