@@ -420,6 +420,12 @@ __device__ __noinline__ double tan64_elem(double a) { return f64_sincos_ok(a) ? 
         static __device__ __forceinline__ double fast(double a) { return FAST(a); }                \
         static __device__ __forceinline__ double apply(double a) { return ELEM(a); }               \
     };
+__device__ __noinline__ double atan64_elem(double a) { return f64_atan_ok(a) ? f64_atan_fast(a) : atan(a); }
+__device__ __noinline__ double asin64_elem(double a) { return f64_asin_ok(a) ? f64_asin_fast(a) : asin(a); }
+__device__ __noinline__ double acos64_elem(double a) { return f64_asin_ok(a) ? f64_acos_fast(a) : acos(a); }
+PNCU_F64_FAST_FUNCTOR(AtanF64, f64_atan_ok, f64_atan_fast, atan64_elem)
+PNCU_F64_FAST_FUNCTOR(AsinF64, f64_asin_ok, f64_asin_fast, asin64_elem)
+PNCU_F64_FAST_FUNCTOR(AcosF64, f64_asin_ok, f64_acos_fast, acos64_elem)
 PNCU_F64_FAST_FUNCTOR(TanhF64, f64_tanh_ok, f64_tanh_fast, tanh64_elem)
 PNCU_F64_FAST_FUNCTOR(SinhF64, f64_exp_ok, f64_sinh_fast, sinh64_elem)
 PNCU_F64_FAST_FUNCTOR(TanF64, f64_sincos_ok, f64_tan_fast, tan64_elem)
@@ -469,6 +475,15 @@ extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType)
             return trig_more(func, t);
         case PNCU_EXPM1:
             if (t == PNCU_DOUBLE) return launch_unary<Expm1F64>;
+            return trig_more(func, t);
+        case PNCU_ATAN:
+            if (t == PNCU_DOUBLE) return launch_unary<AtanF64>;
+            return trig_more(func, t);
+        case PNCU_ASIN:
+            if (t == PNCU_DOUBLE) return launch_unary<AsinF64>;
+            return trig_more(func, t);
+        case PNCU_ACOS:
+            if (t == PNCU_DOUBLE) return launch_unary<AcosF64>;
             return trig_more(func, t);
         case PNCU_ATANH:
             if (t == PNCU_DOUBLE) return launch_unary<AtanhF64>;

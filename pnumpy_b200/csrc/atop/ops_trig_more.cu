@@ -3,8 +3,10 @@
 // (GetTrigOpFast returns NULL for them, src/atop/ops_trig.cpp:599-777, and the dispatcher threads
 // NumPy's own loop over 16K chunks, src/pnumpy/_pnumpy.cpp:973-993).  SURVEY.md 8(f) row f-4.
 //
-// Here they get a GPU body: CUDA's math library inside the same streaming kernel as sin/log/exp
-// (ew1_vec_kernel, several 256-bit loads in flight per thread).  There is no reference arithmetic
+// Here they get a GPU body.  This file holds the ones that are CUDA's math library inside the same
+// streaming kernel as sin/log/exp (ew1_vec_kernel, several 256-bit loads in flight per thread): all
+// float32 ones and float64 exp2, cosh, cbrt.  The other thirteen float64 ones have lean bodies in
+// f64_math.cuh and are picked in ops_trig.cu before this getter is asked.  There is no reference arithmetic
 // to be bit-identical to -- NumPy's loops call the platform libm / SVML, whose results differ from
 // one libm to the next in the last place -- so the parity bar is stated in ULP against the
 // correctly rounded value: <= 4 ULP (tests/test_gpu_parity.py; CUDA documents 1-4 ULP for these),

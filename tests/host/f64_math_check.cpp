@@ -179,6 +179,31 @@ int main(int argc, char** argv) {
     { double z = f64_atanh_fast(-0.0, flat); if (z != 0.0 || !signbit(z)) { printf("atanh(-0) wrong\n"); bad = 1; } }
     { double z = f64_asinh_fast(-0.0, flat); if (z != 0.0 || !signbit(z)) { printf("asinh(-0) wrong\n"); bad = 1; } }
     { Stat ssq; for (long i = 0; i < N; ++i) { double v = uni(1e-3, 1e6); upd(ssq, v, f64_sqrt(v), sqrtl((long double)v)); } printf("sqrt %ld %.4f %.17g\n", ssq.n, ssq.worst, ssq.at); }
+    // atan / asin / acos
+    Stat satan, sasin, sacos;
+    const double tranges[][2] = {{-1, 1}, {-0.45, 0.45}, {-3, 3}, {-100, 100}, {-1e6, 1e6}, {-1e-5, 1e-5}, {-1e-300, 1e-300}};
+    for (auto& rg : tranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            upd(satan, x, f64_atan_fast(x), atanl((long double)x));
+        }
+    const double iranges[][2] = {{-0.999999, 0.999999}, {-0.5, 0.5}, {0.4, 0.6}, {0.99, 0.9999999}, {-1e-5, 1e-5}, {-1e-300, 1e-300}};
+    for (auto& rg : iranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_asin_ok(x)) continue;
+            upd(sasin, x, f64_asin_fast(x), asinl((long double)x));
+            upd(sacos, x, f64_acos_fast(x), acosl((long double)x));
+        }
+    { double z = f64_atan_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("atan(-0) wrong\n"); bad = 1; } }
+    { double z = f64_asin_fast(-0.0); if (z != 0.0 || !signbit(z)) { printf("asin(-0) wrong\n"); bad = 1; } }
+    if (f64_atan_fast(1e300) != 1.5707963267948966 || f64_atan_fast(-1e300) != -1.5707963267948966) { printf("atan(huge) wrong\n"); bad = 1; }
+    if (f64_atan_fast(1.0) != 0.7853981633974483) { printf("atan(1) = %.17g\n", f64_atan_fast(1.0)); bad = 1; }
+    if (f64_acos_fast(0.0) != 1.5707963267948966) { printf("acos(0) = %.17g\n", f64_acos_fast(0.0)); bad = 1; }
+    if (f64_asin_ok(1.0) || f64_asin_ok(-1.0) || f64_asin_ok(NAN) || f64_asin_ok(2.0) || !f64_asin_ok(0.9999999999)) { printf("f64_asin_ok domain wrong\n"); bad = 1; }
+    printf("atan %ld %.4f %.17g\n", satan.n, satan.worst, satan.at);
+    printf("asin %ld %.4f %.17g\n", sasin.n, sasin.worst, sasin.at);
+    printf("acos %ld %.4f %.17g\n", sacos.n, sacos.worst, sacos.at);
     printf("atanh %ld %.4f %.17g\n", satanh.n, satanh.worst, satanh.at);
     printf("asinh %ld %.4f %.17g\n", sasinh.n, sasinh.worst, sasinh.at);
     printf("acosh %ld %.4f %.17g\n", sacosh.n, sacosh.worst, sacosh.at);
