@@ -412,10 +412,11 @@ PNCU_LOG_TABLE_FUNCTOR(Log1pF64, f64_log1p_ok, f64_log1p_index, f64_log1p_fast, 
 __device__ __noinline__ double tanh64_elem(double a) { return f64_tanh_ok(a) ? f64_tanh_fast(a) : tanh(a); }
 __device__ __noinline__ double sinh64_elem(double a) { return f64_exp_ok(a) ? f64_sinh_fast(a) : sinh(a); }
 __device__ __noinline__ double tan64_elem(double a) { return f64_sincos_ok(a) ? f64_tan_fast(a) : tan(a); }
-#define PNCU_F64_FAST_FUNCTOR(NAME, OK, FAST, ELEM)                                                \
+#define PNCU_F64_FAST_FUNCTOR(NAME, OK, FAST, ELEM) PNCU_F64_FAST_FUNCTOR_U(NAME, OK, FAST, ELEM, 2)
+#define PNCU_F64_FAST_FUNCTOR_U(NAME, OK, FAST, ELEM, UNROLL)                                      \
     struct NAME {                                                                                  \
         typedef double In; typedef double Out;                                                     \
-        static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;                   \
+        static constexpr int kUnroll = UNROLL; static constexpr bool kHasFast = true;              \
         static __device__ __forceinline__ bool ok(double a) { return OK(a); }                      \
         static __device__ __forceinline__ double fast(double a) { return FAST(a); }                \
         static __device__ __forceinline__ double apply(double a) { return ELEM(a); }               \
@@ -430,6 +431,7 @@ PNCU_F64_FAST_FUNCTOR(TanhF64, f64_tanh_ok, f64_tanh_fast, tanh64_elem)
 PNCU_F64_FAST_FUNCTOR(SinhF64, f64_exp_ok, f64_sinh_fast, sinh64_elem)
 PNCU_F64_FAST_FUNCTOR(TanF64, f64_sincos_ok, f64_tan_fast, tan64_elem)
 #undef PNCU_F64_FAST_FUNCTOR
+#undef PNCU_F64_FAST_FUNCTOR_U
 struct Expm1F64 {
     typedef double In; typedef double Out;
     static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;

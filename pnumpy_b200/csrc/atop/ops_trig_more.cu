@@ -18,29 +18,34 @@ using namespace pncu;
 
 namespace {
 
-#define PNCU_LIBM_FUNCTOR(NAME, FN32, FN64)                                                                     \
+#define PNCU_LIBM_F32(NAME, FN32)                                                                              \
     struct NAME##F32 { typedef float In; typedef float Out; static constexpr int kUnroll = 4;                 \
-                       static __device__ __forceinline__ float apply(float a) { return FN32(a); } };           \
+                       static __device__ __forceinline__ float apply(float a) { return FN32(a); } };
+#define PNCU_LIBM_F64(NAME, FN64)                                                                              \
     struct NAME##F64 { typedef double In; typedef double Out; static constexpr int kUnroll = 1;               \
                        static __device__ __forceinline__ double apply(double a) { return FN64(a); } };
 
-PNCU_LIBM_FUNCTOR(Tan, tanf, tan)
-PNCU_LIBM_FUNCTOR(Asin, asinf, asin)
-PNCU_LIBM_FUNCTOR(Acos, acosf, acos)
-PNCU_LIBM_FUNCTOR(Atan, atanf, atan)
-PNCU_LIBM_FUNCTOR(Sinh, sinhf, sinh)
-PNCU_LIBM_FUNCTOR(Cosh, coshf, cosh)
-PNCU_LIBM_FUNCTOR(Tanh, tanhf, tanh)
-PNCU_LIBM_FUNCTOR(Asinh, asinhf, asinh)
-PNCU_LIBM_FUNCTOR(Acosh, acoshf, acosh)
-PNCU_LIBM_FUNCTOR(Atanh, atanhf, atanh)
-PNCU_LIBM_FUNCTOR(Log2, log2f, log2)
-PNCU_LIBM_FUNCTOR(Log10, log10f, log10)
-PNCU_LIBM_FUNCTOR(Exp2, exp2f, exp2)
-PNCU_LIBM_FUNCTOR(Expm1, expm1f, expm1)
-PNCU_LIBM_FUNCTOR(Log1p, log1pf, log1p)
-PNCU_LIBM_FUNCTOR(Cbrt, cbrtf, cbrt)
-#undef PNCU_LIBM_FUNCTOR
+PNCU_LIBM_F32(Tan, tanf)
+PNCU_LIBM_F32(Asin, asinf)
+PNCU_LIBM_F32(Acos, acosf)
+PNCU_LIBM_F32(Atan, atanf)
+PNCU_LIBM_F32(Sinh, sinhf)
+PNCU_LIBM_F32(Cosh, coshf)
+PNCU_LIBM_F32(Tanh, tanhf)
+PNCU_LIBM_F32(Asinh, asinhf)
+PNCU_LIBM_F32(Acosh, acoshf)
+PNCU_LIBM_F32(Atanh, atanhf)
+PNCU_LIBM_F32(Log2, log2f)
+PNCU_LIBM_F32(Log10, log10f)
+PNCU_LIBM_F32(Exp2, exp2f)
+PNCU_LIBM_F32(Expm1, expm1f)
+PNCU_LIBM_F32(Log1p, log1pf)
+PNCU_LIBM_F32(Cbrt, cbrtf)
+PNCU_LIBM_F64(Cosh, cosh)
+PNCU_LIBM_F64(Exp2, exp2)
+PNCU_LIBM_F64(Cbrt, cbrt)
+#undef PNCU_LIBM_F32
+#undef PNCU_LIBM_F64
 
 }  // namespace
 
@@ -48,6 +53,10 @@ namespace pncu {
 
 pncu_unary_fn trig_more(int func, int t) {
 #define PNCU_PICK(OP, NAME)                                        \
+    case OP:                                                       \
+        if (t == PNCU_FLOAT) return launch_unary<NAME##F32>;       \
+        return NULL;
+#define PNCU_PICK2(OP, NAME)                                       \
     case OP:                                                       \
         if (t == PNCU_FLOAT) return launch_unary<NAME##F32>;       \
         if (t == PNCU_DOUBLE) return launch_unary<NAME##F64>;      \
@@ -58,19 +67,20 @@ pncu_unary_fn trig_more(int func, int t) {
         PNCU_PICK(PNCU_ACOS, Acos)
         PNCU_PICK(PNCU_ATAN, Atan)
         PNCU_PICK(PNCU_SINH, Sinh)
-        PNCU_PICK(PNCU_COSH, Cosh)
+        PNCU_PICK2(PNCU_COSH, Cosh)
         PNCU_PICK(PNCU_TANH, Tanh)
         PNCU_PICK(PNCU_ASINH, Asinh)
         PNCU_PICK(PNCU_ACOSH, Acosh)
         PNCU_PICK(PNCU_ATANH, Atanh)
         PNCU_PICK(PNCU_LOG2, Log2)
         PNCU_PICK(PNCU_LOG10, Log10)
-        PNCU_PICK(PNCU_EXP2, Exp2)
+        PNCU_PICK2(PNCU_EXP2, Exp2)
         PNCU_PICK(PNCU_EXPM1, Expm1)
         PNCU_PICK(PNCU_LOG1P, Log1p)
-        PNCU_PICK(PNCU_CBRT, Cbrt)
+        PNCU_PICK2(PNCU_CBRT, Cbrt)
     }
 #undef PNCU_PICK
+#undef PNCU_PICK2
     return NULL;
 }
 
