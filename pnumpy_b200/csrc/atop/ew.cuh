@@ -18,6 +18,7 @@
 //     thread, loads precede stores (volatile asm keeps program order), nothing is __restrict__.
 #pragma once
 #include "common.cuh"
+#include "functors.cuh"
 
 namespace pncu {
 
@@ -150,10 +151,18 @@ ew2_vec_kernel(const typename F::In* a, const typename F::In* b, typename F::Out
         if (LAYOUT != LAY_SV) ra = ld_pack<In, EPV>(a + e0);
         if (LAYOUT != LAY_VS) rb = ld_pack<In, EPV>(b + e0);
         Pack<Out, EPV> r;
-        r.zero();
+        if constexpr (WordOp<F>::enabled && sizeof(In) == sizeof(Out)) {
+            // 1- and 2-byte types: whole words through the SIMD-in-a-word form (functors.cuh)
+            const unsigned wa = splat_word<In>(sa), wb = splat_word<In>(sb);
 #pragma unroll
-        for (int e = 0; e < EPV; ++e)
-            r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra.get(e), LAYOUT == LAY_VS ? sb : rb.get(e)));
+            for (int w = 0; w < Pack<Out, EPV>::WORDS; ++w)
+                r.w[w] = WordOp<F>::word(LAYOUT == LAY_SV ? wa : ra.w[w], LAYOUT == LAY_VS ? wb : rb.w[w]);
+        } else {
+            r.zero();
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra.get(e), LAYOUT == LAY_VS ? sb : rb.get(e)));
+        }
         st_pack<Out, EPV>(o + e0, r);
     }
     // head + tail scalars: elements before the first / after the last aligned wide vector
@@ -232,9 +241,14 @@ template <class F, int EPV>
 __device__ __forceinline__ Pack<typename F::Out, EPV> apply_pack(const Pack<typename F::In, EPV>& ra) {
     typedef typename F::Out Out;
     Pack<Out, EPV> r;
-    r.zero();
+    if constexpr (WordOp1<F>::enabled && sizeof(typename F::In) == sizeof(Out)) {
 #pragma unroll
-    for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
+        for (int w = 0; w < Pack<Out, EPV>::WORDS; ++w) r.w[w] = WordOp1<F>::word(ra.w[w]);
+    } else {
+        r.zero();
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) r.set(e, F::apply(ra.get(e)));
+    }
     return r;
 }
 

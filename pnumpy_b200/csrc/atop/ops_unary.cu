@@ -96,6 +96,23 @@ PNCU_UNARY_FUNCTOR(IsNotNormalF, bool8, (bool8)!u_isnormal(a))
 PNCU_UNARY_FUNCTOR(IsNanOrZeroF, bool8, (bool8)(u_isnan<T>(a) || a == 0))
 PNCU_UNARY_FUNCTOR(SignBitF, bool8, (bool8)u_signbit(a))
 
+}  // namespace
+namespace pncu {
+// word-at-a-time forms of the 1- and 2-byte unary ops (see functors.cuh)
+#define PNCU_WORD1(FUNCTOR, EXPR)                                                          \
+    template <> struct WordOp1<FUNCTOR> {                                                  \
+        static constexpr bool enabled = true;                                              \
+        static __device__ __forceinline__ unsigned word(unsigned a) { return EXPR; }       \
+    };
+PNCU_WORD1(AbsF<int8_t>, __vabs4(a)) PNCU_WORD1(AbsF<int16_t>, __vabs2(a))
+PNCU_WORD1(NegF<uint8_t>, __vneg4(a)) PNCU_WORD1(NegF<uint16_t>, __vneg2(a))
+PNCU_WORD1(InvertF<uint8_t>, ~a) PNCU_WORD1(InvertF<uint16_t>, ~a)
+PNCU_WORD1(IdentF<uint8_t>, a) PNCU_WORD1(IdentF<uint16_t>, a)
+PNCU_WORD1(LogicalNotF<uint8_t>, __vseteq4(a, 0u)) PNCU_WORD1(LogicalNotF<int8_t>, __vseteq4(a, 0u))
+#undef PNCU_WORD1
+}  // namespace pncu
+namespace {
+
 struct BoolNotF { typedef bool8 In; typedef bool8 Out; static __device__ __forceinline__ bool8 apply(bool8 a) { return (bool8)(a == 0); } };
 
 // Classifiers of an integer input are constants (no NaN/inf among integers): the reference memsets
