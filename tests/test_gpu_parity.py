@@ -625,11 +625,17 @@ def _exchange_case(dev, devices, rng):
     n = 5 * align * world + 12345
     for dt in ("float32", "float64", "int32"):
         a = (rng.normal(0, 100, n)).astype(dt)
-        if dt != "int32":
-            a[n // 2 + 7] = np.nan
         units = -(-n // align)
         per = -(-units // world)
         bounds = [min(n, r * per * align) for r in range(world + 1)]
+        if dt != "int32":
+            a[n // 2 + 7] = np.nan
+        else:
+            # SURVEY.md 8d case (v): the extreme value tied on both sides of a shard (or block) boundary --
+            # the first occurrence must win whichever participant saw it
+            edge = bounds[1] if world > 1 else 3 * align
+            a[edge - 1] = a[edge] = a[edge + 5] = 10 ** 6
+            a[edge - 2] = a[edge + 1] = -(10 ** 6)
         cabi.check(lib.pncu_set_device(devices[0]), "set_device")
         whole = dev.to_device(a)
         want = {op: dev.reduce(op, whole).to_host().tobytes() for op in ("ADD", "MIN", "MAX")}
