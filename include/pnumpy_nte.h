@@ -65,6 +65,13 @@ PNCU_API int nte_get_threading(void);
 
 /* Size policy.  The reference threads a call iff n >= 65536 (src/atop/threads.h:199,1058); the
  * analogue here is "worth a PCIe round trip".  Returns the previous value. */
+/* Size threshold.  `n` is the base: streaming element-wise ops on pinned operands decline below it; the
+ * effective value is x4 when an operand is pageable, /4 for NTE_CLASS_HEAVY ops (transcendentals), x2 for
+ * reductions -- the measured crossovers against NumPy's own loops (tools/threshold_probe.py).  Resident
+ * (device / managed) operands always run on the GPU.  Default 2^19; 0 sends everything to the GPU. */
+#define NTE_CLASS_STREAM 0
+#define NTE_CLASS_HEAVY 1
+#define NTE_CLASS_REDUCE 2
 PNCU_API int64_t nte_set_min_elems(int64_t n);
 PNCU_API int64_t nte_get_min_elems(void);
 /* bytes of one staging slab (rounded to a multiple of 65536 * 8); returns the previous value */
@@ -88,6 +95,10 @@ PNCU_API int nte_unary(pncu_unary_fn launcher, int in_itemsize, int out_itemsize
  * when use_out_as_start, else fold(in) alone.  `out` is a HOST pointer to one element. */
 PNCU_API int nte_reduce(int func, int atype, const void* in, void* out, int use_out_as_start,
                         int64_t len, int64_t strideIn, int max_workers);
+/* nte_unary with the op's cost class (AtopTrigMathFunction passes NTE_CLASS_HEAVY) */
+PNCU_API int nte_unary_class(pncu_unary_fn launcher, int in_itemsize, int out_itemsize,
+                             const void* in, void* out, int64_t len, int64_t strideIn, int64_t strideOut,
+                             int max_workers, int op_class);
 /* AtopArgMinMaxMathFunction (src/pnumpy/_pnumpy.cpp:1105-1118); `in` contiguous */
 PNCU_API int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out_index,
                            int max_workers);

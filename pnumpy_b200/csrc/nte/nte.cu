@@ -75,7 +75,12 @@ struct State {
     int workers = 3;              // extra lanes beside the caller's (reference default futex wake count is
                                   // min(11, cores-1), threads.h:67,891-894; per-op MaxThreads caps it at 3 or 7)
     bool threading = true;
-    int64_t min_elems = 1 << 20;  // below this a PCIe round trip cannot win; the caller's loop runs
+    // Below the threshold a PCIe round trip cannot beat the caller's own loop.  `min_elems` is the base: it applies
+    // to streaming element-wise ops on PINNED operands; the effective value is x4 when an operand is pageable (the
+    // staging memcpy), /4 for transcendental ops (NumPy's loop is ~10x slower per element there), x2 for reductions
+    // (no D2H to overlap).  Measured crossovers against NumPy's single-threaded loops on float32
+    // (tools/threshold_probe.py): add 2^19 pinned / 2^21 pageable, sin 2^17 / 2^19, sum 2^20 / 2^22.
+    int64_t min_elems = 1 << 19;
     size_t slab_bytes = 32u << 20;  // tools/e2e_probe.py on B200: 32 MiB slabs give 75 GB/s of PCIe traffic vs 73 at 8 MiB (pinned), 43 vs 31 (pageable, 4 lanes)
     Lane lanes[kMaxLanes];
     Worker* pool[kMaxLanes] = {nullptr};
@@ -100,6 +105,7 @@ struct Job {
     int64_t len = 0;
     int64_t s1 = 0, s2 = 0;     // input byte strides: 0 (scalar), the item size (contiguous) or anything else (gathered)
     int64_t so = 0;             // output byte stride (0 = not set: contiguous)
+    int op_class = 0;           // NTE_CLASS_STREAM / _HEAVY / _REDUCE: scales the size threshold
     int pk_in1 = 0, pk_in2 = 0, pk_in3 = 0, pk_out = 0;
     int nlanes = 1;
     int64_t shard[kMaxLanes + 1];  // element boundaries
@@ -232,6 +238,8 @@ int ensure_partials(Lane& L, size_t bytes) {
     return 0;
 }
 
+int64_t slab_elems_for(size_t slab_bytes, int64_t wide, int64_t shard_elems, bool staged);
+
 // ---- one lane of an element-wise job: slabs through the H2D -> kernel -> D2H pipeline --------------------
 void lane_elementwise(Lane& L, Job& j, int li) {
     if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
@@ -239,11 +247,12 @@ void lane_elementwise(Lane& L, Job& j, int li) {
     if (e0 >= e1) return;
     const bool binary = j.kind == JOB_BINARY;
     const int64_t wide = j.isz_in > j.isz_out ? j.isz_in : j.isz_out;
-    const int64_t slab_elems = ((int64_t)(L.slab_bytes / wide) / kAlign) * kAlign;
-    const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
     const bool vec1 = j.s1 != 0, vec2 = binary && j.s2 != 0;
     const bool out_strided = j.so != j.isz_out;
     const bool stage_out = j.pk_out == PK_PAGEABLE || out_strided;
+    const bool stage_in = (vec1 && (j.pk_in1 == PK_PAGEABLE || j.s1 != j.isz_in)) || (vec2 && (j.pk_in2 == PK_PAGEABLE || j.s2 != j.isz_in));
+    const int64_t slab_elems = slab_elems_for(L.slab_bytes, wide, e1 - e0, stage_in || stage_out);
+    const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
 
     // broadcast scalars: one tiny copy per call
     const char* d_s1 = nullptr;
@@ -340,7 +349,7 @@ void lane_reduce(Lane& L, Job& j, int li) {
     const int64_t nslots = j.slot0[li + 1] - j.slot0[li];
     int rc;
     if ((rc = ensure_partials(L, (size_t)nslots * j.partial_bytes))) { fail(j, li, rc); return; }
-    const int64_t slab_elems = ((int64_t)(L.slab_bytes / j.isz_in) / kAlign) * kAlign;
+    const int64_t slab_elems = slab_elems_for(L.slab_bytes, j.isz_in, e1 - e0, j.pk_in1 == PK_PAGEABLE || j.s1 != j.isz_in);
     const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
     for (int64_t i = 0; i < nslabs; ++i) {
         const int r = (int)(i % kRing);
@@ -388,7 +397,9 @@ void lane_fused(Lane& L, Job& j, int li) {
     int rc;
     if ((rc = ensure_third_input(L))) { fail(j, li, rc); return; }
     if (to_sum && (rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
-    const int64_t slab_elems = ((int64_t)(L.slab_bytes / isz) / kAlign) * kAlign;
+    const int64_t slab_elems = slab_elems_for(L.slab_bytes, isz, e1 - e0,
+                                              j.pk_in1 == PK_PAGEABLE || j.pk_in2 == PK_PAGEABLE || j.pk_in3 == PK_PAGEABLE ||
+                                                  (!to_sum && j.pk_out == PK_PAGEABLE));
     const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
     const char* ins[3] = {j.in1, j.in2, j.in3};
     const int pks[3] = {j.pk_in1, j.pk_in2, j.pk_in3};
@@ -497,6 +508,26 @@ void run_lanes(Job& j, LaneFn fn) {
         std::unique_lock<std::mutex> lk(w->mu);
         w->cv.wait(lk, [&] { return w->done; });
     }
+}
+
+// the size below which the caller's own loop is faster (see State::min_elems)
+int64_t threshold_for(int op_class, bool any_pageable) {
+    int64_t t = g.min_elems;
+    if (any_pageable) t *= 4;
+    if (op_class == NTE_CLASS_HEAVY) t /= 4;
+    if (op_class == NTE_CLASS_REDUCE) t *= 2;
+    return t;
+}
+// slab length for a shard of `shard_elems`: big shards use the full slab; when an operand has to be STAGED (pageable
+// or strided: a host-side copy per slab) smaller shards are cut in up to four slabs of at least 2 MiB so that the
+// staging copy of slab i+1 overlaps the DMA and kernel of slab i (pageable sum at 2^24 float32: 2.9 -> 1.9 ms)
+int64_t slab_elems_for(size_t slab_bytes, int64_t wide, int64_t shard_elems, bool staged) {
+    const int64_t full = ((int64_t)(slab_bytes / wide) / kAlign) * kAlign;
+    if (!staged) return full;  // pinned operands are DMA'd in place: fewer, larger transfers win (measured)
+    int64_t quarter = (((shard_elems + 3) / 4 + kAlign - 1) / kAlign) * kAlign;
+    int64_t floor_e = ((((int64_t)2 << 20) / wide + kAlign - 1) / kAlign) * kAlign;
+    int64_t e = quarter > floor_e ? quarter : floor_e;
+    return e < full ? e : full;
 }
 
 // lanes for a call: min(op_max_workers, workers) + 1, never more than one per 65536-element unit
@@ -757,7 +788,7 @@ void nte_reset_stats(void) {
 
 static int dispatch_elementwise(Job& j, int max_workers) {
     if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len < g.min_elems || j.len <= 0) return decline();
+    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false)) return decline();  // below every class's threshold
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();  // re-entrant / concurrent caller: run the old loop
     const bool binary = j.kind == JOB_BINARY;
@@ -775,6 +806,11 @@ static int dispatch_elementwise(Job& j, int max_workers) {
         int rc = run_resident(j);
         if (!rc) g_stats.calls += 1;
         return rc;
+    }
+    {
+        const bool pageable = j.pk_out == PK_PAGEABLE || (j.s1 != 0 && j.pk_in1 == PK_PAGEABLE) ||
+                              (binary && j.s2 != 0 && j.pk_in2 == PK_PAGEABLE);
+        if (j.len < threshold_for(j.op_class, pageable)) return decline();
     }
     // host operands: contiguous ones are DMA'd (pinned) or memcpy'd (pageable) into the slabs, any
     // other stride (a multiple of the item size, negative allowed) is gathered / scattered by the lane
@@ -818,11 +854,16 @@ int nte_binary(pncu_any_two_fn launcher, int in_itemsize, int out_itemsize, cons
 
 int nte_unary(pncu_unary_fn launcher, int in_itemsize, int out_itemsize, const void* in, void* out,
               int64_t len, int64_t s1, int64_t so, int max_workers) {
+    return nte_unary_class(launcher, in_itemsize, out_itemsize, in, out, len, s1, so, max_workers, NTE_CLASS_STREAM);
+}
+
+int nte_unary_class(pncu_unary_fn launcher, int in_itemsize, int out_itemsize, const void* in, void* out,
+                    int64_t len, int64_t s1, int64_t so, int max_workers, int op_class) {
     if (!launcher) return decline();
     if (so == 0 || s1 == 0) return decline();
     Job j;
     j.kind = JOB_UNARY; j.fn1 = launcher; j.isz_in = in_itemsize; j.isz_out = out_itemsize;
-    j.in1 = (const char*)in; j.out = (char*)out; j.len = len; j.s1 = s1; j.so = so;
+    j.in1 = (const char*)in; j.out = (char*)out; j.len = len; j.s1 = s1; j.so = so; j.op_class = op_class;
     return dispatch_elementwise(j, max_workers);
 }
 
@@ -878,10 +919,11 @@ static int finish_on_gpu0(Job& j, void* host_out, int out_bytes, const void* hos
 
 static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* host_start, int max_workers) {
     if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len < g.min_elems || j.len <= 0) return decline();
+    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false)) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
     j.pk_in1 = classify(j.in1);
+    if (host_kind(j.pk_in1) && j.len < threshold_for(NTE_CLASS_REDUCE, j.pk_in1 == PK_PAGEABLE)) return decline();
     int rc;
     if (!host_kind(j.pk_in1)) {
         // resident input: both passes on its GPU (contiguous only: pass 1 streams whole blocks)
@@ -941,16 +983,17 @@ int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out
 // fused chain: element-wise (out != NULL) or summed (host_out)
 static int dispatch_fused(Job& j, void* host_out, int max_workers) {
     if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len < g.min_elems || j.len <= 0) return decline();
+    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false)) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
     const bool to_sum = j.kind == JOB_MULADD_SUM;
     j.pk_in1 = classify(j.in1); j.pk_in2 = classify(j.in2); j.pk_in3 = classify(j.in3);
     j.pk_out = to_sum ? j.pk_in1 : classify(j.out);
     const int pks[4] = {j.pk_in1, j.pk_in2, j.pk_in3, j.pk_out};
-    int nhost = 0;
-    for (int k = 0; k < 4; ++k) nhost += host_kind(pks[k]);
+    int nhost = 0, npageable = 0;
+    for (int k = 0; k < 4; ++k) { nhost += host_kind(pks[k]); npageable += pks[k] == PK_PAGEABLE; }
     if (nhost != 0 && nhost != 4) return decline();  // host and resident arrays mixed: the caller's loops
+    if (nhost == 4 && j.len < threshold_for(NTE_CLASS_STREAM, npageable != 0)) return decline();
     const size_t bytes = (size_t)j.len * j.isz_in;
     int rc;
     if (nhost == 0) {

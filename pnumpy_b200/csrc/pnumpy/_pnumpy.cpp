@@ -183,8 +183,9 @@ static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimen
     const npy_intp n = dimensions[0];
     // the reference drops the fast pointer when the output stride is 0 (:882-884, 946-948)
     if (g_Settings.AtopEnabled && p->pUnaryFunc && steps[1] != 0) {
-        int rc = nte_unary(p->pUnaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], (int64_t)n,
-                           (int64_t)steps[0], (int64_t)steps[1], p->MaxThreads);
+        int rc = nte_unary_class(p->pUnaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], (int64_t)n,
+                                 (int64_t)steps[0], (int64_t)steps[1], p->MaxThreads,
+                                 cat == CAT_TRIG ? NTE_CLASS_HEAVY : NTE_CLASS_STREAM);
         if (rc == 0) { ledger(cat, true, n); return; }
         if (rc != NTE_DECLINED) { raise_cuda_error("unary ufunc loop", rc); return; }
     }
