@@ -424,15 +424,28 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
         # the product path: pass 2 is one kernel that stores this rank's block partials into every rank's slot
         # table over NVLink (CUDA IPC mappings), waits on the device for the others' and folds -- no collective
         # call, no host synchronisation in between
-        xch = exchange.Exchange.from_torch_distributed(max_slots=world * cnt)
-
-        def sharded_sum():
-            xch.reduce("ADD", a, counts, res, stream=stream)
+        xch_error = None
+        try:
+            xch = exchange.Exchange.from_torch_distributed(max_slots=world * cnt, sync=False)
+        except Exception as e:  # e.g. CUDA IPC not permitted in this container: every rank must agree to fall back
+            xch_error = str(e)
+        okflag = torch.tensor([0 if xch_error else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(okflag, op=dist.ReduceOp.MIN)
+        if int(okflag.item()) == 0:
+            if xch is not None:
+                xch.close()
+            xch = None
+            xch_error = xch_error or "another rank could not map the peer tables"
+            sharded_sum = sharded_sum_nccl
+        else:
+            def sharded_sum():
+                xch.reduce("ADD", a, counts, res, stream=stream)
     ms = timed_ms(sharded_sum)
     out["sharded_sum_f32"] = {"elements_total": n * world, "ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1),
                               "collective": "none (1 GPU)" if world == 1 else
-                              "fused into pass 2: one kernel per rank stores its block partials into every rank's slot table over "
-                              "NVLink (CUDA IPC mappings), waits on the device for the others' and folds; no NCCL call, no host sync",
+                              ("fused into pass 2: one kernel per rank stores its block partials into every rank's slot table over "
+                               "NVLink (CUDA IPC mappings), waits on the device for the others' and folds; no NCCL call, no host sync"
+                               if xch is not None else f"NCCL all_gather between the passes (fused exchange unavailable: {xch_error})"),
                               "result": float(res.to_host()[0])}
     if nccl_ms is not None:
         out["sharded_sum_f32"].update({"nccl_all_gather_variant_ms": round(nccl_ms, 4),
@@ -464,12 +477,30 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
                 else:
                     cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(0), buf.ptr, stream), "arg partials")
                     cabi.check(lib.pncu_argminmax_finish(kind, t, buf.ptr, cnt, ri.ptr, stream), "arg finish")
-        else:
+        elif xch is not None:
             def sharded(kind=kind, name=name):
                 if kind is None:
                     xch.reduce("MIN" if name == "min" else "MAX", xn, counts, res, stream=stream)
                 else:
                     xch.argminmax(kind, xn, counts, rank * n, ri, stream=stream)
+        else:  # fused exchange unavailable: NCCL all_gather of the block partials between the passes
+            import torch
+            pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
+            mine_t = torch.empty(cnt * pbytes, dtype=torch.uint8, device="cuda")
+            all_t = torch.empty(world * cnt * pbytes, dtype=torch.uint8, device="cuda")
+
+            def sharded(kind=kind, fop=fop, mine_t=mine_t, all_t=all_t):
+                if kind is None:
+                    cabi.check(lib.pncu_reduce_partials(fop, t, xn.ptr, n, mine_t.data_ptr(), stream), "partials")
+                else:
+                    cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(rank * n), mine_t.data_ptr(), stream), "arg partials")
+                cabi.check(lib.pncu_stream_sync(stream), "sync")
+                dist.all_gather_into_tensor(all_t, mine_t)
+                torch.cuda.current_stream().synchronize()
+                if kind is None:
+                    cabi.check(lib.pncu_reduce_finish(fop, t, all_t.data_ptr(), world * cnt, res.ptr, None, stream), "finish")
+                else:
+                    cabi.check(lib.pncu_argminmax_finish(kind, t, all_t.data_ptr(), world * cnt, ri.ptr, stream), "arg finish")
         ms = timed_ms(sharded)
         if kind is None:
             ok = bool(np.isnan(res.to_host()[0]))
@@ -480,7 +511,8 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
         nan_rows["exchange_timeouts"] = int(lib.pncu_exchange_timeouts())
     out["sharded_nan_reductions_f32"] = {
         "elements_total": n * world, "nan_per_shard": 1,
-        "collective": "none (1 GPU)" if world == 1 else "fused exchange over NVLink peer memory (see sharded_sum_f32)",
+        "collective": "none (1 GPU)" if world == 1 else ("fused exchange over NVLink peer memory (see sharded_sum_f32)"
+                                                        if xch is not None else "NCCL all_gather between the passes"),
         "timing": "host wall clock around 10 calls incl. the collective, max over ranks", **nan_rows}
 
     # configs[4], device-resident leg: t = a*b; u = t+c; r = u.sum() as three kernels (28 B/element)

@@ -71,8 +71,10 @@ class Exchange:
         return out
 
     @classmethod
-    def from_torch_distributed(cls, max_slots):
-        """This rank's Exchange in a one-process-per-GPU job (torch.distributed initialised, device set)."""
+    def from_torch_distributed(cls, max_slots, sync=True):
+        """This rank's Exchange in a one-process-per-GPU job (torch.distributed initialised, device set).
+        With sync=False the caller must synchronise the ranks itself before the first reduction (and can
+        turn a failure on one rank -- e.g. CUDA IPC not permitted -- into a collective decision)."""
         import torch.distributed as dist
         lib = cabi.load()
         rank, world = dist.get_rank(), dist.get_world_size()
@@ -96,7 +98,8 @@ class Exchange:
         lay = [cls._layout(b, max_slots) for b in raw]
         x = cls(rank, world, [l[0] for l in lay], [l[1] for l in lay], max_slots, dev.value, imported)
         x._own = own
-        dist.barrier()
+        if sync:
+            dist.barrier()
         return x
 
     def close(self):
