@@ -256,8 +256,16 @@ template <class T, bool IS_MAX> struct MinMaxWord {
         if constexpr (sizeof(T) == 2) {
             return mm16x2<IS_MAX, kSigned>(a, w);
         } else {  // bytes -> two 16x2 words (sign- or zero-extended) by PRMT
-            const unsigned lo = kSigned ? __byte_perm(w, 0u, 0x9180) : __byte_perm(w, 0u, 0x4140);
-            const unsigned hi = kSigned ? __byte_perm(w, 0u, 0xb3a2) : __byte_perm(w, 0u, 0x4342);
+            // NB: the __byte_perm intrinsic masks the selector to 3 bits per nibble and so cannot ask for
+            // sign replication (selector bit 3); the PTX instruction can.
+            unsigned lo, hi;
+            if (kSigned) {
+                asm("prmt.b32 %0, %1, %2, 0x9180;" : "=r"(lo) : "r"(w), "r"(0u));   // {b0, sign b0, b1, sign b1}
+                asm("prmt.b32 %0, %1, %2, 0xb3a2;" : "=r"(hi) : "r"(w), "r"(0u));   // {b2, sign b2, b3, sign b3}
+            } else {
+                lo = __byte_perm(w, 0u, 0x4140);
+                hi = __byte_perm(w, 0u, 0x4342);
+            }
             return mm16x2<IS_MAX, kSigned>(mm16x2<IS_MAX, kSigned>(a, lo), hi);
         }
     }

@@ -687,3 +687,83 @@ def test_fused_exchange_two_gpus(dev, rng):
     if cabi.load().pncu_device_count() < 2:
         pytest.skip("needs two GPUs")
     _exchange_case(dev, [0, 1], rng)
+
+
+@pytest.mark.parametrize("dt", ["int8", "uint8", "int16", "uint16", "int32", "float32"])
+def test_extreme_in_the_ragged_last_block(dev, dt):
+    """Regression: the 1-byte word-at-a-time min/max of FULL 64 KiB blocks produced packed partials that compared
+    wrongly with the plain partial of a ragged last block (signed bytes were not sign-extended).  Extremes of
+    either sign, in the tail and in the body, several block counts."""
+    be = 65536 // np.dtype(dt).itemsize
+    signed = np.dtype(dt).kind != "u"
+    for nblocks in (1, 2, 5):
+        for tail in (1, 7, 300):
+            n = nblocks * be + tail
+            for body, tailv in ((1, 100), (100, 1), (-3 if signed else 2, -100 if signed else 0), (-100 if signed else 0, -3 if signed else 2)):
+                a = np.full(n, 50, dtype=dt)
+                a[be // 2] = body
+                a[n - 1 - tail // 2] = tailv
+                d = dev.to_device(a)
+                assert dev.reduce("MAX", d).to_host()[0] == a.max(), (dt, n, body, tailv)
+                assert dev.reduce("MIN", d).to_host()[0] == a.min(), (dt, n, body, tailv)
+                assert int(dev.argminmax(0, d).to_host()[0]) == int(a.argmax())
+                assert int(dev.argminmax(1, d).to_host()[0]) == int(a.argmin())
+
+
+def test_reductions_at_2p30_with_nan_and_64bit_indices(dev):
+    """configs[3] at its stated size on one GPU: 2^30 float32 (4 GiB) with NaNs planted, and a 2^32+5-element
+    int8 array whose extreme sits beyond the 32-bit index range."""
+    from pnumpy_b200 import cabi
+    lib = cabi.load()
+
+    def tiled(n, dt):
+        period = 253 * 4096
+        host = (np.arange(period, dtype=np.int64) % 253 + 1).astype(dt)
+        d = dev.empty(n, dt)
+        piece = dev.to_device(host)
+        off, isz = 0, host.dtype.itemsize
+        while off < n:
+            m = min(period, n - off)
+            cabi.check(lib.pncu_memcpy_d2d(d.ptr + off * isz, piece.ptr, m * isz, None), "tile")
+            off += m
+        dev.sync()
+        piece.free()
+        return d
+
+    def poke(d, index, value):
+        v = np.array([value], dtype=d.dtype)
+        cabi.check(lib.pncu_memcpy_h2d(d.ptr + index * d.dtype.itemsize, v.ctypes.data, d.dtype.itemsize, None), "poke")
+        dev.sync()
+
+    n = 1 << 30
+    a = tiled(n, np.float32)
+    full, rem = divmod(n, 253)
+    exact = full * sum(range(1, 254)) + sum(range(1, rem + 1))
+    got = float(dev.reduce("ADD", a).to_host()[0])
+    assert abs(got - exact) <= 2.0 ** -23 * exact            # float64 accumulation, rounded once
+    assert dev.argminmax(0, a).to_host()[0] == 252 and dev.argminmax(1, a).to_host()[0] == 0
+    poke(a, n - 1, np.nan)                                     # (iii) NaN in the last element
+    assert np.isnan(dev.reduce("MIN", a).to_host()[0]) and np.isnan(dev.reduce("MAX", a).to_host()[0])
+    assert np.isnan(dev.reduce("ADD", a).to_host()[0])
+    assert dev.argminmax(0, a).to_host()[0] == n - 1 and dev.argminmax(1, a).to_host()[0] == n - 1
+    mid = 5 * (1 << 27) + 3
+    poke(a, mid, np.nan)                                       # an earlier NaN wins
+    assert dev.argminmax(0, a).to_host()[0] == mid and dev.argminmax(1, a).to_host()[0] == mid
+    poke(a, 0, np.nan)                                         # (ii) NaN at index 0
+    assert dev.argminmax(0, a).to_host()[0] == 0
+    a.free()
+
+    m = (1 << 32) + 5                                          # int8: 4 GiB, indices beyond 32 bits
+    b = dev.empty(m, np.int8)
+    cabi.check(lib.pncu_memset(b.ptr, 1, m, None), "memset")
+    dev.sync()
+    poke(b, (1 << 32) + 2, 5)
+    poke(b, (1 << 32) + 4, -3)
+    assert dev.reduce("MAX", b).to_host()[0] == 5 and dev.reduce("MIN", b).to_host()[0] == -3
+    assert int(dev.argminmax(0, b).to_host()[0]) == (1 << 32) + 2
+    assert int(dev.argminmax(1, b).to_host()[0]) == (1 << 32) + 4
+    c = dev.binary("ADD", b, b)                                # element-wise grid over > 2^32 elements
+    assert dev.reduce("MAX", c).to_host()[0] == 10 and int(dev.argminmax(0, c).to_host()[0]) == (1 << 32) + 2
+    assert int(dev.argminmax(1, c).to_host()[0]) == (1 << 32) + 4 and dev.reduce("MIN", c).to_host()[0] == -6
+    b.free()
+    c.free()
