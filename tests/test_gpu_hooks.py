@@ -558,3 +558,33 @@ def test_degenerate_sizes(pn):
         np.empty(0, np.float32).argmax()
     with pytest.raises(ValueError):
         np.empty(0, np.float32).max()
+
+
+@pytest.mark.parametrize("dt", ["int8", "int16", "int32", "float32", "float64"])
+def test_host_shapes_around_shard_and_slab_boundaries(pn, rng, dt):
+    """lengths around the 65 536-element shard unit (1..5 lanes' worth), host pointers at odd element offsets,
+    1, 2 and 4 lanes: element-wise results bit-exact, reductions exact or in tolerance, against NumPy's loops."""
+    unit = 65536
+    base_a = rng.normal(0, 100, 5 * unit + 600).astype(dt)
+    base_b = (rng.normal(0, 100, 5 * unit + 600) + 1).astype(dt)
+    oldw = pn.thread_getworkers()
+    try:
+        for workers, threading in ((1, False), (1, True), (3, True)):
+            pn.thread_enable() if threading else pn.thread_disable()
+            pn.thread_setworkers(workers)
+            for n in (unit - 1, unit, unit + 1, 2 * unit + 33, 4 * unit, 4 * unit + 511, 5 * unit + 257):
+                for off in (0, 1, 5):
+                    a, b = base_a[off:off + n], base_b[off + 2:off + 2 + n]
+                    got, want, calls = _both(pn, lambda: (a + b, a * b, a > b, np.abs(a), a.max(), a.min(), int(a.argmax()), int(a.argmin())))
+                    assert calls >= 8, (n, off, calls)
+                    for g, w in zip(got, want):
+                        assert np.asarray(g).tobytes() == np.asarray(w).tobytes(), (dt, n, off, workers)
+                    s_got, s_want, _ = _both(pn, lambda: a.sum())
+                    if np.dtype(dt).kind == "f":
+                        tol = (2.0 ** -22 if dt == "float32" else 2.0 ** -48) * float(np.abs(a.astype(np.float64)).sum())
+                        assert abs(float(s_got) - float(s_want)) <= tol, (dt, n, off)
+                    else:
+                        assert s_got == s_want
+    finally:
+        pn.thread_enable()
+        pn.thread_setworkers(oldw)

@@ -767,3 +767,63 @@ def test_reductions_at_2p30_with_nan_and_64bit_indices(dev):
     assert int(dev.argminmax(1, c).to_host()[0]) == (1 << 32) + 4 and dev.reduce("MIN", c).to_host()[0] == -6
     b.free()
     c.free()
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_random_shapes_and_alignments(dev, rng, dt):
+    """Differential sweep over what the reference's tests do not pin: lengths around the 32-byte vector and the
+    64 KiB reduction-block boundaries, device pointers at every element alignment (views into a larger buffer),
+    extremes anywhere.  Element-wise ops bit-exact against NumPy, reductions exact (integers, min/max, arg) or
+    within the stated tolerance (float sums)."""
+    isz = np.dtype(dt).itemsize
+    be = 65536 // isz
+    big = 3 * be + 300
+    if np.dtype(dt).kind == "f":
+        host_a = rng.normal(0, 1000, big + 64).astype(dt)
+        host_b = (rng.normal(0, 1000, big + 64) + 0.5).astype(dt)
+    elif dt == "bool":
+        host_a = rng.integers(0, 2, big + 64).astype(dt)
+        host_b = rng.integers(0, 2, big + 64).astype(dt)
+    else:
+        info = np.iinfo(dt)
+        host_a = rng.integers(info.min, info.max, big + 64, dtype=dt, endpoint=True)
+        host_b = rng.integers(info.min, info.max, big + 64, dtype=dt, endpoint=True)
+    da, db = dev.to_device(host_a), dev.to_device(host_b)
+    lengths = [1, 2, 31, 32, 33, 255, 257, 1000, be - 1, be, be + 1, be + 7, 2 * be, 2 * be + 300, 3 * be + 255]
+    for n in lengths:
+        for off in (0, 1, 3, int(rng.integers(4, 60))):
+            a, b = host_a[off:off + n], host_b[off + 1:off + 1 + n]
+            va, vb = da.view(off, n), db.view(off + 1, n)
+            with np.errstate(all="ignore"):
+                if dt != "bool":
+                    assert_bits_equal(dev.binary("ADD", va, vb).to_host(), a + b, f"add {dt} n={n} off={off}")
+                    assert_bits_equal(dev.binary("SUB", va, vb).to_host(), a - b, f"sub {dt} n={n} off={off}")
+                    assert_bits_equal(dev.binary("MAX", va, vb).to_host(), np.maximum(a, b), f"maximum {dt} n={n} off={off}")
+                    assert_bits_equal(dev.unary("ABS", va).to_host(), np.abs(a), f"abs {dt} n={n} off={off}")
+                    # scalar second / first operand (stride 0), and in place on a misaligned view
+                    sc = db.view(off + 7, 1)
+                    assert_bits_equal(dev.binary("SUB", va, sc, b_scalar=True).to_host(), a - host_b[off + 7], f"a-s {dt} n={n} off={off}")
+                    assert_bits_equal(dev.binary("SUB", sc, va, a_scalar=True).to_host(), host_b[off + 7] - a, f"s-a {dt} n={n} off={off}")
+                    scratch = dev.to_device(host_a[:off + n + 8])
+                    vs = scratch.view(off, n)
+                    dev.binary("ADD", vs, vb, out=vs)
+                    whole = scratch.to_host()
+                    assert_bits_equal(whole[off:off + n], a + b, f"in place {dt} n={n} off={off}")
+                    assert_bits_equal(whole[:off], host_a[:off], "bytes before the view untouched")
+                    assert_bits_equal(whole[off + n:], host_a[off + n:off + n + 8], "bytes after the view untouched")
+                    scratch.free()
+                assert_bits_equal(dev.compare("GT", va, vb).to_host(), a > b, f"greater {dt} n={n} off={off}")
+                assert_bits_equal(dev.compare("NE", va, vb).to_host(), a != b, f"not_equal {dt} n={n} off={off}")
+                assert_bits_equal(dev.compare("LTE", va, sc, b_scalar=True).to_host(), a <= host_b[off + 7], f"a<=s {dt} n={n} off={off}") if dt != "bool" else None
+                assert dev.reduce("MAX", va).to_host()[0] == a.max(), (dt, n, off)
+                assert dev.reduce("MIN", va).to_host()[0] == a.min(), (dt, n, off)
+                assert int(dev.argminmax(0, va).to_host()[0]) == int(a.argmax()), (dt, n, off)
+                assert int(dev.argminmax(1, va).to_host()[0]) == int(a.argmin()), (dt, n, off)
+                got = dev.reduce("ADD", va).to_host()[0]
+                if np.dtype(dt).kind == "f":
+                    ref = math.fsum(a.astype(np.float64))
+                    assert abs(float(got) - ref) <= _sum_tol(a)(ref), (dt, n, off, got, ref)
+                elif dt == "bool":
+                    assert bool(got) == bool(a.any())
+                else:
+                    assert got == np.add.reduce(a, dtype=a.dtype), (dt, n, off)
