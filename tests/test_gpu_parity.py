@@ -614,6 +614,35 @@ def test_more_transcendentals_within_4ulp(dev, O, rng, op, dt):
     del tf
 
 
+@pytest.mark.parametrize("op", sorted(MORE_TRIG))
+def test_more_transcendentals_do_not_depend_on_neighbours(dev, rng, op):
+    """float64: the lean bodies run when a thread's whole set of inputs is in the fast domain, the general
+    function otherwise -- a value must get the same bits either way, and from the strided kernel."""
+    from pnumpy_b200 import cabi
+    fn, lo, hi = MORE_TRIG[op]
+    n = (1 << 15) + 3
+    x = rng.uniform(lo, hi, n)
+    clean = dev.unary(op, dev.to_device(x)).to_host()
+    y = x.copy()
+    pos = rng.choice(n, 300, replace=False)
+    edges = np.array([np.nan, np.inf, -np.inf, 1e300, -1e300, 0.0, -0.0, 1.0, -1.0, 5e-324, 2.0 ** 80, -3.0])
+    y[pos] = edges[np.arange(pos.size) % edges.size]
+    mixed = dev.unary(op, dev.to_device(y)).to_host()
+    keep = np.ones(n, bool)
+    keep[pos] = False
+    assert np.array_equal(mixed[keep].view(np.uint8), clean[keep].view(np.uint8)), op
+    wide = np.zeros(2 * n)
+    wide[::2] = y
+    dw, do = dev.to_device(wide), dev.empty(n, np.float64)
+    fnp = cabi.get_trig(cabi.TRIG_OPS[op], do.atype)[0]
+    cabi.check(fnp(dw.ptr, do.ptr, n, 16, 8, None), "strided")
+    dev.sync()
+    strided = do.to_host()
+    assert np.array_equal(np.isnan(strided), np.isnan(mixed))
+    ok = ~np.isnan(mixed)
+    assert np.array_equal(strided[ok].view(np.uint8), mixed[ok].view(np.uint8)), op
+
+
 # ---- the cross-GPU exchange fused into the two passes -------------------------------------------------
 def _exchange_case(dev, devices, rng):
     """sum / min / max / argmax of one array cut into len(devices) shards, every shard on its own GPU, through
