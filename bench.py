@@ -185,6 +185,9 @@ def run_cuda(args):
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side group for the final wait: ranks > 0 must not sit in an NCCL barrier (a kernel spinning on
+        # their GPU) while rank 0 measures the end-to-end path across all GPUs
+        cpu_group = dist.new_group(backend="gloo")
     cabi.init()
     lib = cabi.load()
     cabi.check(lib.pncu_set_device(local), "pncu_set_device")
@@ -310,7 +313,9 @@ def run_cuda(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
     if dist:
-        dist.barrier()
+        if rank != 0:
+            torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)   # blocks on the CPU: the other ranks' GPUs stay idle during rank 0's e2e phase
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)

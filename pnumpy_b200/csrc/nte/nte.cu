@@ -585,20 +585,33 @@ int device_of(const void* p) {
 // trusted afterwards; if host code touched some pages in between, the kernel demand-faults those back
 // (correct, slower, and then they are resident again).  Guarded by g.api_mu (held by every dispatch).
 std::map<const void*, size_t> g_prefetched[kMaxLanes];
+std::mutex g_prefetch_mu;  // the lanes of a sharded resident call prefetch concurrently
 std::map<const void*, size_t> g_managed_allocs;  // blocks handed out by nte_alloc_managed
 
 int prefetch_managed(const void* p, int pk, size_t bytes, Lane& L) {
     if (pk != PK_MANAGED || !bytes) return 0;
+    std::lock_guard<std::mutex> lk(g_prefetch_mu);
     std::map<const void*, size_t>& seen = g_prefetched[L.device];
     auto it = seen.find(p);
     if (it != seen.end() && it->second >= bytes) return 0;
     PNCU_CUDA(cudaMemPrefetchAsync(p, bytes, L.device, L.s_k));
     if (seen.size() > 4096) seen.clear();
     seen[p] = bytes;
+    // the pages leave whichever GPU had them: drop the other devices' records that overlap the range
+    for (int d = 0; d < kMaxLanes; ++d) {
+        if (d == L.device) continue;
+        std::map<const void*, size_t>& other = g_prefetched[d];
+        for (auto o = other.begin(); o != other.end();) {
+            const char* lo = (const char*)o->first;
+            if (lo < (const char*)p + bytes && (const char*)p < lo + o->second) o = other.erase(o);
+            else ++o;
+        }
+    }
     return 0;
 }
 
 void forget_prefetched(const void* lo, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_prefetch_mu);
     for (int d = 0; d < kMaxLanes; ++d) {
         std::map<const void*, size_t>& seen = g_prefetched[d];
         for (auto it = seen.lower_bound(lo); it != seen.end() && (const char*)it->first < (const char*)lo + bytes;) it = seen.erase(it);
@@ -645,6 +658,95 @@ int run_resident(Job& j) {
     g_stats.launches += 1;
     PNCU_CUDA(cudaStreamSynchronize(L.s_k));
     return 0;
+}
+
+// ---- managed operands spread over all GPUs ----------------------------------------------------------------
+// A managed (cudaMallocManaged) ndarray is addressable from every GPU, so a large one does not have to live
+// on one: shard l of every operand -- the same contiguous split at multiples of 65 536 elements the host path
+// uses -- is prefetched to GPU l the first time it is seen there, and every call then runs one kernel per GPU on
+// its own shard, in place, with no PCIe and no exchange (reductions: block partials gathered on GPU 0 as in the
+// host path).  np.add(a, b, out=c) on managed arrays thus runs at G times one GPU's HBM rate.
+constexpr size_t kShardResidentMinBytes = (size_t)64 << 20;  // smaller arrays stay on one GPU
+
+bool shard_resident(const Job& j, bool binary) {
+    if (g.ndev < 2 || !g.threading) return false;
+    if (j.pk_out != PK_MANAGED || j.so != j.isz_out) return false;
+    if (j.s1 != 0 && (j.pk_in1 != PK_MANAGED || j.s1 != j.isz_in)) return false;
+    if (binary && j.s2 != 0 && (j.pk_in2 != PK_MANAGED || j.s2 != j.isz_in)) return false;
+    return (size_t)j.len * (size_t)(j.isz_in > j.isz_out ? j.isz_in : j.isz_out) >= kShardResidentMinBytes;
+}
+
+int plan_one_lane_per_gpu(Job& j) {
+    const int64_t units = (j.len + kAlign - 1) / kAlign;
+    int lanes = g.ndev < units ? g.ndev : (int)units;
+    if (lanes < 1) lanes = 1;
+    j.nlanes = lanes;
+    const int64_t per = (units + lanes - 1) / lanes;
+    for (int l = 0; l <= lanes; ++l) {
+        const int64_t e = (int64_t)l * per * kAlign;
+        j.shard[l] = e < j.len ? e : j.len;
+    }
+    for (int l = 0; l < lanes; ++l) {
+        j.rc[l] = 0; j.err[l][0] = 0;
+        int rc = ensure_lane(l);
+        if (rc) return rc;
+    }
+    g_stats.lanes_last = lanes;
+    g_stats.gpus_last = lanes;
+    return 0;
+}
+
+void lane_resident(Lane& L, Job& j, int li) {
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
+    if (e0 >= e1) return;
+    const int64_t n = e1 - e0;
+    const bool binary = j.kind == JOB_BINARY;
+    const char* in1 = j.s1 ? j.in1 + e0 * j.isz_in : j.in1;
+    const char* in2 = binary ? (j.s2 ? j.in2 + e0 * j.isz_in : j.in2) : nullptr;
+    char* out = j.out + e0 * j.isz_out;
+    int rc;
+    if (j.s1 == 0 && host_kind(j.pk_in1)) {
+        memcpy(L.h_small, j.in1, j.isz_in);
+        LCUDA(cudaMemcpyAsync(L.d_scalar, L.h_small, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
+        in1 = L.d_scalar;
+    }
+    if (binary && j.s2 == 0 && host_kind(j.pk_in2)) {
+        memcpy(L.h_small + 16, j.in2, j.isz_in);
+        LCUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
+        in2 = L.d_scalar + 16;
+    }
+    if (j.s1 && (rc = prefetch_managed(in1, j.pk_in1, (size_t)n * j.isz_in, L))) { fail(j, li, rc); return; }
+    if (binary && j.s2 && (rc = prefetch_managed(in2, j.pk_in2, (size_t)n * j.isz_in, L))) { fail(j, li, rc); return; }
+    if ((rc = prefetch_managed(out, j.pk_out, (size_t)n * j.isz_out, L))) { fail(j, li, rc); return; }
+    if (binary) rc = j.fn2(in1, in2, out, n, j.s1, j.s2, j.so, (pncu_stream_t)L.s_k);
+    else rc = j.fn1(in1, out, n, j.s1, j.so, (pncu_stream_t)L.s_k);
+    if (rc) { fail(j, li, rc); return; }
+    g_stats.launches += 1;
+    LCUDA(cudaStreamSynchronize(L.s_k));
+}
+
+void lane_reduce_resident(Lane& L, Job& j, int li) {
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
+    if (e0 >= e1) return;
+    const int64_t n = e1 - e0;
+    const char* in = j.in1 + e0 * j.isz_in;
+    int rc;
+    if ((rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
+    if ((rc = prefetch_managed(in, j.pk_in1, (size_t)n * j.isz_in, L))) { fail(j, li, rc); return; }
+    if (j.kind == JOB_REDUCE) rc = pncu_reduce_partials(j.func, j.atype, in, n, L.d_partials, (pncu_stream_t)L.s_k);
+    else rc = pncu_argminmax_partials(j.argkind, j.atype, in, n, e0, L.d_partials, (pncu_stream_t)L.s_k);
+    if (rc) { fail(j, li, rc); return; }
+    g_stats.launches += 1;
+    LCUDA(cudaStreamSynchronize(L.s_k));
+}
+
+int run_resident_sharded(Job& j) {
+    int rc = plan_one_lane_per_gpu(j);
+    if (rc) return rc;
+    run_lanes(j, lane_resident);
+    return first_error(j);
 }
 
 }  // namespace
@@ -803,7 +905,7 @@ static int dispatch_elementwise(Job& j, int max_workers) {
         const bool all_ok = !host_kind(j.pk_out) && (j.s1 == 0 || !host_kind(j.pk_in1)) &&
                             (!binary || j.s2 == 0 || !host_kind(j.pk_in2));
         if (!all_ok) return decline();
-        int rc = run_resident(j);
+        int rc = shard_resident(j, binary) ? run_resident_sharded(j) : run_resident(j);
         if (!rc) g_stats.calls += 1;
         return rc;
     }
@@ -928,6 +1030,16 @@ static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* ho
     if (!host_kind(j.pk_in1)) {
         // resident input: both passes on its GPU (contiguous only: pass 1 streams whole blocks)
         if (j.s1 != j.isz_in) return decline();
+        if (g.ndev > 1 && g.threading && j.pk_in1 == PK_MANAGED && (size_t)j.len * j.isz_in >= kShardResidentMinBytes) {
+            // a large managed array: one shard per GPU (see run_resident_sharded), partials gathered on GPU 0
+            if ((rc = plan_one_lane_per_gpu(j))) return rc;
+            for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
+            run_lanes(j, lane_reduce_resident);
+            if ((rc = first_error(j))) return rc;
+            rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
+            if (!rc) g_stats.calls += 1;
+            return rc;
+        }
         const int dev = device_of(j.in1);
         if ((rc = ensure_lane(dev))) return rc;
         Lane& L = g.lanes[dev];

@@ -334,6 +334,44 @@ def test_managed_arrays_run_in_place(pn, rng):
     assert abs(float(s) - ref) <= 2.0 ** -23 * abs(ref) + 2.0 ** -45 * float(np.abs(want_u).sum())
 
 
+def test_large_managed_arrays_shard_over_all_gpus(pn, rng):
+    """On a multi-GPU box a large managed ndarray is spread over the GPUs (shard l prefetched to GPU l) and every
+    call runs one kernel per GPU in place: same bits as one GPU, no PCIe, `gpus_last` == the device count.
+    On one GPU the same calls take the single-GPU resident path (checked for the same results)."""
+    n = (1 << 25) + 12345   # 128 MiB float32: above the 64 MiB sharding threshold
+    ha, hb = rng.normal(0, 10, n).astype(np.float32), rng.normal(0, 10, n).astype(np.float32)
+    ha[n // 3] = np.float32(1e6)
+    a, b = pn.managed_array(ha), pn.managed_array(hb)
+    t, u = pn.managed_empty(n, np.float32), pn.managed_empty(n, np.float32)
+    ndev = pn.cuda_info()["devices"]
+    pn.cuda_reset_stats()
+    for _ in range(2):   # second round: the shards are already where they belong
+        np.multiply(a, b, out=t)
+        np.add(t, np.float32(1.5), out=u)
+        np.sin(u, out=t)
+        u += a
+        s, m, i, k = u.sum(), u.max(), int(u.argmax()), int(u.argmin())
+    info = pn.cuda_info()
+    assert info["h2d_bytes"] == 0 and info["staged_bytes"] == 0, info
+    assert info["gpus_last"] == ndev and info["lanes_last"] == ndev, info
+    want_u = ha * hb + np.float32(1.5)
+    pn.disable()
+    want_t = None
+    try:
+        from pnumpy_b200 import device as dev
+        want_t = dev.unary("SIN", dev.to_device(want_u)).to_host()   # the GPU body's bits (Cephes), on one GPU
+    finally:
+        pn.enable()
+    want_u2 = want_u + ha
+    assert_bits_equal(np.asarray(t), want_t, "sin on sharded managed arrays")
+    assert_bits_equal(np.asarray(u), want_u2, "in place on sharded managed arrays")
+    assert m == want_u2.max() and i == int(want_u2.argmax()) and k == int(want_u2.argmin())
+    ref = float(np.sum(want_u2.astype(np.float64)))
+    assert abs(float(s) - ref) <= 2.0 ** -23 * abs(ref) + 2.0 ** -45 * float(np.abs(want_u2).sum())
+    # the sum does not depend on how many GPUs hold the array: compare with one GPU's two passes
+    assert np.float32(s).tobytes() == dev.reduce("ADD", dev.to_device(want_u2)).to_host().tobytes()
+
+
 def test_recycler_gives_pinned_arrays(pn, rng):
     assert pn.recycler_isenabled() is False
     pn.recycler_enable()
