@@ -742,6 +742,33 @@ void lane_reduce_resident(Lane& L, Job& j, int li) {
     LCUDA(cudaStreamSynchronize(L.s_k));
 }
 
+// fused chain on sharded managed operands: a*b+c in place per GPU, or pass 1 of its sum into the lane's partials
+void lane_fused_resident(Lane& L, Job& j, int li) {
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
+    if (e0 >= e1) return;
+    const int64_t n = e1 - e0;
+    const size_t bytes = (size_t)n * j.isz_in;
+    const bool to_sum = j.kind == JOB_MULADD_SUM;
+    const char* a = j.in1 + e0 * j.isz_in;
+    const char* b = j.in2 + e0 * j.isz_in;
+    const char* c = j.in3 + e0 * j.isz_in;
+    int rc;
+    if ((rc = prefetch_managed(a, j.pk_in1, bytes, L)) || (rc = prefetch_managed(b, j.pk_in2, bytes, L)) ||
+        (rc = prefetch_managed(c, j.pk_in3, bytes, L))) { fail(j, li, rc); return; }
+    if (!to_sum) {
+        char* o = j.out + e0 * j.isz_in;
+        if ((rc = prefetch_managed(o, j.pk_out, bytes, L))) { fail(j, li, rc); return; }
+        rc = j.fn3(a, b, c, o, n, (pncu_stream_t)L.s_k);
+    } else {
+        if ((rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
+        rc = pncu_muladd_sum_partials(j.atype, a, b, c, n, L.d_partials, (pncu_stream_t)L.s_k);
+    }
+    if (rc) { fail(j, li, rc); return; }
+    g_stats.launches += 1;
+    LCUDA(cudaStreamSynchronize(L.s_k));
+}
+
 int run_resident_sharded(Job& j) {
     int rc = plan_one_lane_per_gpu(j);
     if (rc) return rc;
@@ -1110,6 +1137,23 @@ static int dispatch_fused(Job& j, void* host_out, int max_workers) {
     int rc;
     if (nhost == 0) {
         // resident operands: in place on their GPU, no PCIe
+        const bool all_managed = j.pk_in1 == PK_MANAGED && j.pk_in2 == PK_MANAGED && j.pk_in3 == PK_MANAGED &&
+                                 (to_sum || j.pk_out == PK_MANAGED);
+        if (g.ndev > 1 && g.threading && all_managed && bytes >= kShardResidentMinBytes) {
+            // large managed operands live sharded over the GPUs (run_resident_sharded): so does the fused chain
+            if ((rc = plan_one_lane_per_gpu(j))) return rc;
+            if (to_sum)
+                for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
+            run_lanes(j, lane_fused_resident);
+            if ((rc = first_error(j))) return rc;
+            if (to_sum) {
+                j.kind = JOB_REDUCE;
+                j.func = PNCU_ADD;
+                if ((rc = finish_on_gpu0(j, host_out, j.isz_in, nullptr))) return rc;
+            }
+            g_stats.calls += 1;
+            return 0;
+        }
         const int dev = device_of(j.in1);
         if ((rc = ensure_lane(dev))) return rc;
         Lane& L = g.lanes[dev];

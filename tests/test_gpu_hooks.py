@@ -370,6 +370,14 @@ def test_large_managed_arrays_shard_over_all_gpus(pn, rng):
     assert abs(float(s) - ref) <= 2.0 ** -23 * abs(ref) + 2.0 ** -45 * float(np.abs(want_u2).sum())
     # the sum does not depend on how many GPUs hold the array: compare with one GPU's two passes
     assert np.float32(s).tobytes() == dev.reduce("ADD", dev.to_device(want_u2)).to_host().tobytes()
+    # the fused chain follows the shards too
+    pn.cuda_reset_stats()
+    f = pn.muladd(a, b, u)
+    fs = pn.muladd_sum(a, b, u)
+    info = pn.cuda_info()
+    assert info["calls"] == 2 and info["h2d_bytes"] == 0 and info["gpus_last"] == ndev, info
+    assert_bits_equal(np.asarray(f), ha * hb + want_u2, "muladd on sharded managed arrays")
+    assert np.float32(fs).tobytes() == dev.reduce("ADD", dev.to_device(ha * hb + want_u2)).to_host().tobytes()
 
 
 def test_recycler_gives_pinned_arrays(pn, rng):
