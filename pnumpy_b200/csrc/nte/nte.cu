@@ -723,7 +723,6 @@ void lane_resident(Lane& L, Job& j, int li) {
     else rc = j.fn1(in1, out, n, j.s1, j.so, (pncu_stream_t)L.s_k);
     if (rc) { fail(j, li, rc); return; }
     g_stats.launches += 1;
-    LCUDA(cudaStreamSynchronize(L.s_k));
 }
 
 void lane_reduce_resident(Lane& L, Job& j, int li) {
@@ -739,7 +738,6 @@ void lane_reduce_resident(Lane& L, Job& j, int li) {
     else rc = pncu_argminmax_partials(j.argkind, j.atype, in, n, e0, L.d_partials, (pncu_stream_t)L.s_k);
     if (rc) { fail(j, li, rc); return; }
     g_stats.launches += 1;
-    LCUDA(cudaStreamSynchronize(L.s_k));
 }
 
 // fused chain on sharded managed operands: a*b+c in place per GPU, or pass 1 of its sum into the lane's partials
@@ -766,13 +764,26 @@ void lane_fused_resident(Lane& L, Job& j, int li) {
     }
     if (rc) { fail(j, li, rc); return; }
     g_stats.launches += 1;
-    LCUDA(cudaStreamSynchronize(L.s_k));
+}
+
+// Resident shards need no host-side copying, so no worker threads either: the calling thread queues the work of
+// every GPU (asynchronous launches, ~5 us each) and then waits for all of them -- a condition-variable wake-up per
+// lane would cost more than a 128 MiB shard takes to stream.
+void run_resident_lanes(Job& j, LaneFn fn) {
+    for (int li = 0; li < j.nlanes; ++li) fn(g.lanes[li], j, li);
+    for (int li = 0; li < j.nlanes; ++li) {
+        if (j.rc[li]) continue;
+        Lane& L = g.lanes[li];
+        cudaError_t e = cudaSetDevice(L.device);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(L.s_k);
+        if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize(resident shard)", __FILE__, __LINE__); fail(j, li, (int)e); }
+    }
 }
 
 int run_resident_sharded(Job& j) {
     int rc = plan_one_lane_per_gpu(j);
     if (rc) return rc;
-    run_lanes(j, lane_resident);
+    run_resident_lanes(j, lane_resident);
     return first_error(j);
 }
 
@@ -1061,7 +1072,7 @@ static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* ho
             // a large managed array: one shard per GPU (see run_resident_sharded), partials gathered on GPU 0
             if ((rc = plan_one_lane_per_gpu(j))) return rc;
             for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
-            run_lanes(j, lane_reduce_resident);
+            run_resident_lanes(j, lane_reduce_resident);
             if ((rc = first_error(j))) return rc;
             rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
             if (!rc) g_stats.calls += 1;
@@ -1144,7 +1155,7 @@ static int dispatch_fused(Job& j, void* host_out, int max_workers) {
             if ((rc = plan_one_lane_per_gpu(j))) return rc;
             if (to_sum)
                 for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
-            run_lanes(j, lane_fused_resident);
+            run_resident_lanes(j, lane_fused_resident);
             if ((rc = first_error(j))) return rc;
             if (to_sum) {
                 j.kind = JOB_REDUCE;
