@@ -856,3 +856,65 @@ def test_random_shapes_and_alignments(dev, rng, dt):
                     assert bool(got) == bool(a.any())
                 else:
                     assert got == np.add.reduce(a, dtype=a.dtype), (dt, n, off)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_every_op_on_misaligned_views(dev, rng, dt):
+    """every element-wise op the getters offer for this dtype, on views that start at odd element offsets and
+    end off the vector grid, against NumPy's own loops (bit-exact; float results compared as bits, NaN <-> NaN)"""
+    from pnumpy_b200 import cabi
+    kind = np.dtype(dt).kind
+    n_all = 70000
+    if kind == "f":
+        ha = rng.normal(0, 50, n_all).astype(dt)
+        hb = rng.normal(0, 50, n_all).astype(dt)
+        ha[::97] = np.nan; hb[::89] = np.inf; ha[::101] = -0.0; hb[::103] = 0.0
+    elif dt == "bool":
+        ha = rng.integers(0, 2, n_all).astype(dt); hb = rng.integers(0, 2, n_all).astype(dt)
+    else:
+        info = np.iinfo(dt)
+        ha = rng.integers(info.min, info.max, n_all, dtype=dt, endpoint=True)
+        hb = rng.integers(info.min, info.max, n_all, dtype=dt, endpoint=True)
+        hb[::7] = rng.integers(0, 8 * np.dtype(dt).itemsize + 3, hb[::7].size).astype(dt)  # shift counts incl. >= bits
+    da, db = dev.to_device(ha), dev.to_device(hb)
+    binary = {"ADD": np.add, "SUB": np.subtract, "MUL": np.multiply, "MIN": np.minimum, "MAX": np.maximum,
+              "BITWISE_AND": np.bitwise_and, "BITWISE_OR": np.bitwise_or, "BITWISE_XOR": np.bitwise_xor,
+              "BITWISE_LSHIFT": np.left_shift, "BITWISE_RSHIFT": np.right_shift, "DIV": np.true_divide,
+              "FLOORDIV": np.floor_divide, "LOGICAL_AND": np.logical_and, "LOGICAL_OR": np.logical_or}
+    unary = {"ABS": np.abs, "NEGATIVE": np.negative, "SIGN": np.sign, "INVERT": np.invert, "LOGICAL_NOT": np.logical_not,
+             "ISNAN": np.isnan, "ISINF": np.isinf, "ISFINITE": np.isfinite, "FLOOR": np.floor, "CEIL": np.ceil,
+             "TRUNC": np.trunc, "ROUND": np.rint, "SQRT": np.sqrt, "SIGNBIT": np.signbit}
+    compares = {"EQ": np.equal, "NE": np.not_equal, "LT": np.less, "GT": np.greater, "LTE": np.less_equal, "GTE": np.greater_equal}
+    tested = 0
+    for off, n in ((1, 4099), (3, 65537), (5, 31), (0, 69990)):
+        a, b = ha[off:off + n], hb[off + 2:off + 2 + n]
+        va, vb = da.view(off, n), db.view(off + 2, n)
+        with np.errstate(all="ignore"):
+            for name, f in binary.items():
+                fn, out_t = cabi.get_binary(cabi.BINARY_OPS[name], va.atype)
+                if fn is None:
+                    continue
+                if dt == "bool" and name in ("SUB",):
+                    continue
+                want = f(a, b)
+                got = dev.binary(name, va, vb).to_host()
+                if dt == "bool":
+                    want = want.astype(np.bool_)
+                assert got.dtype == want.dtype, (name, dt, got.dtype, want.dtype)
+                assert_bits_equal(got, want, f"{name} {dt} off={off} n={n}")
+                tested += 1
+            for name, f in unary.items():
+                fn, out_t = cabi.get_unary(cabi.UNARY_OPS[name], va.atype)
+                if fn is None:
+                    continue
+                if dt == "bool" and name in ("NEGATIVE", "SIGN", "ABS"):
+                    continue
+                want = f(a)
+                got = dev.unary(name, va).to_host()
+                assert got.dtype == want.dtype, (name, dt, got.dtype, want.dtype)
+                assert_bits_equal(got, want, f"{name} {dt} off={off} n={n}")
+                tested += 1
+            for name, f in compares.items():
+                assert_bits_equal(dev.compare(name, va, vb).to_host(), f(a, b), f"{name} {dt} off={off} n={n}")
+                tested += 1
+    assert tested >= 4 * 8
