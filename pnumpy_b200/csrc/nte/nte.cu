@@ -622,6 +622,8 @@ int run_resident(Job& j) {
     const int dev = device_of(j.out);
     int rc = ensure_lane(dev);
     if (rc) return rc;
+    g_stats.lanes_last = 1;
+    g_stats.gpus_last = 1;
     Lane& L = g.lanes[dev];
     PNCU_CUDA(cudaSetDevice(L.device));
     const bool binary = j.kind == JOB_BINARY;
@@ -1080,6 +1082,8 @@ static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* ho
         }
         const int dev = device_of(j.in1);
         if ((rc = ensure_lane(dev))) return rc;
+        g_stats.lanes_last = 1;
+        g_stats.gpus_last = 1;
         Lane& L = g.lanes[dev];
         PNCU_CUDA(cudaSetDevice(L.device));
         if ((rc = prefetch_managed(j.in1, j.pk_in1, (size_t)j.len * j.isz_in, L))) return rc;
@@ -1167,6 +1171,8 @@ static int dispatch_fused(Job& j, void* host_out, int max_workers) {
         }
         const int dev = device_of(j.in1);
         if ((rc = ensure_lane(dev))) return rc;
+        g_stats.lanes_last = 1;
+        g_stats.gpus_last = 1;
         Lane& L = g.lanes[dev];
         PNCU_CUDA(cudaSetDevice(L.device));
         if ((rc = prefetch_managed(j.in1, j.pk_in1, bytes, L))) return rc;
