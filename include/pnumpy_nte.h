@@ -66,12 +66,14 @@ PNCU_API int nte_get_threading(void);
 /* Size policy.  The reference threads a call iff n >= 65536 (src/atop/threads.h:199,1058); the
  * analogue here is "worth a PCIe round trip".  Returns the previous value. */
 /* Size threshold.  `n` is the base: streaming element-wise ops on pinned operands decline below it; the
- * effective value is x4 when an operand is pageable, /4 for NTE_CLASS_HEAVY ops (transcendentals), x2 for
- * reductions -- the measured crossovers against NumPy's own loops (tools/threshold_probe.py).  Resident
+ * effective value is x4 when an operand is pageable, /2 for NTE_CLASS_HEAVY ops (transcendentals), x2 for
+ * reductions, and it is applied to BYTES (n x 4 bytes of the widest operand; x3 for 1-byte types) -- the measured
+ * crossovers against NumPy's own loops (tools/threshold_probe.py, tools/pn_benchmark.py).  Resident
  * (device / managed) operands always run on the GPU.  Default 2^19; 0 sends everything to the GPU. */
 #define NTE_CLASS_STREAM 0
 #define NTE_CLASS_HEAVY 1
 #define NTE_CLASS_REDUCE 2
+#define NTE_CLASS_CONST 3   /* output independent of the input (integer isnan ...): host operands are always declined */
 PNCU_API int64_t nte_set_min_elems(int64_t n);
 PNCU_API int64_t nte_get_min_elems(void);
 /* bytes of one staging slab (rounded to a multiple of 65536 * 8); returns the previous value */

@@ -26,9 +26,9 @@ def benchmark_timeit(func=np.equal, ctypes=_DEFAULT_CTYPES, scalar=False, unary=
             if ctype is np.bool_:
                 a = np.arange(s, dtype=np.int8).astype(ctype) + 1
             else:
-                a = np.arange(s, dtype=ctype)
-                a = a % 253
-                a += 1
+                # the reference's data, `arange(s) % 253 + 1` (benchmark.py:58-61), built in int64 and cast: NumPy 2
+                # refuses `int8_array % 253` (NEP 50), where NumPy < 1.20 silently widened the array
+                a = (np.arange(s, dtype=np.int64) % 253 + 1).astype(ctype)
             if pinned:
                 a = pinned_array(a)
             b = a[5] if scalar else (pinned_array(a) if pinned else a.copy())

@@ -77,9 +77,10 @@ struct State {
     bool threading = true;
     // Below the threshold a PCIe round trip cannot beat the caller's own loop.  `min_elems` is the base: it applies
     // to streaming element-wise ops on PINNED operands; the effective value is x4 when an operand is pageable (the
-    // staging memcpy), /4 for transcendental ops (NumPy's loop is ~10x slower per element there), x2 for reductions
+    // staging memcpy), /2 for transcendental ops (NumPy's loop is several times slower per element there), x2 for reductions
     // (no D2H to overlap).  Measured crossovers against NumPy's single-threaded loops on float32
-    // (tools/threshold_probe.py): add 2^19 pinned / 2^21 pageable, sin 2^17 / 2^19, sum 2^20 / 2^22.
+    // (tools/threshold_probe.py, tools/pn_benchmark.py): add 2^19 pinned / 2^21 pageable, sin 2^17-2^18 / 2^19-2^20
+    // (depends on how hard the arguments are for NumPy's sin), sum 2^20 / 2^22.
     int64_t min_elems = 1 << 19;
     size_t slab_bytes = 32u << 20;  // tools/e2e_probe.py on B200: 32 MiB slabs give 75 GB/s of PCIe traffic vs 73 at 8 MiB (pinned), 43 vs 31 (pageable, 4 lanes)
     Lane lanes[kMaxLanes];
@@ -510,13 +511,19 @@ void run_lanes(Job& j, LaneFn fn) {
     }
 }
 
-// the size below which the caller's own loop is faster (see State::min_elems)
-int64_t threshold_for(int op_class, bool any_pageable) {
-    int64_t t = g.min_elems;
-    if (any_pageable) t *= 4;
-    if (op_class == NTE_CLASS_HEAVY) t /= 4;
-    if (op_class == NTE_CLASS_REDUCE) t *= 2;
-    return t;
+// the size below which the caller's own loop is faster (see State::min_elems).  The base is stated in 4-byte
+// elements and applied to BYTES of the widest operand: NumPy's loops run at a byte rate, not an element rate (an int8
+// add of 2^20 elements is 1 MiB per operand and over in 30 us).  1-byte types get another x3: their NumPy loops stay
+// in cache and vectorise 32 lanes wide (pn.benchmark() on the B200 box: int8 a+b breaks even near 6 MiB per operand,
+// int16 / float32 near 2 MiB).
+int64_t threshold_for(int op_class, bool any_pageable, int wide_itemsize = 4) {
+    int64_t bytes = g.min_elems * 4;
+    if (any_pageable) bytes *= 4;
+    if (op_class == NTE_CLASS_HEAVY) bytes /= 2;
+    if (op_class == NTE_CLASS_REDUCE) bytes *= 2;
+    if (wide_itemsize == 1) bytes *= 3;
+    if (wide_itemsize < 1) wide_itemsize = 1;
+    return bytes / wide_itemsize;   // in elements of the widest operand
 }
 // slab length for a shard of `shard_elems`: big shards use the full slab; when an operand has to be STAGED (pageable
 // or strided: a host-side copy per slab) smaller shards are cut in up to four slabs of at least 2 MiB so that the
@@ -930,7 +937,7 @@ void nte_reset_stats(void) {
 
 static int dispatch_elementwise(Job& j, int max_workers) {
     if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false)) return decline();  // below every class's threshold
+    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false, 8)) return decline();  // below every class's threshold
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();  // re-entrant / concurrent caller: run the old loop
     const bool binary = j.kind == JOB_BINARY;
@@ -949,10 +956,13 @@ static int dispatch_elementwise(Job& j, int max_workers) {
         if (!rc) g_stats.calls += 1;
         return rc;
     }
+    // an op whose output does not depend on its input (isnan / isinf / isfinite of integers): shipping the input
+    // over PCIe to memset the output would be absurd -- NumPy's own loop is a memset already
+    if (j.op_class == NTE_CLASS_CONST) return decline();
     {
         const bool pageable = j.pk_out == PK_PAGEABLE || (j.s1 != 0 && j.pk_in1 == PK_PAGEABLE) ||
                               (binary && j.s2 != 0 && j.pk_in2 == PK_PAGEABLE);
-        if (j.len < threshold_for(j.op_class, pageable)) return decline();
+        if (j.len < threshold_for(j.op_class, pageable, j.isz_in > j.isz_out ? j.isz_in : j.isz_out)) return decline();
     }
     // host operands: contiguous ones are DMA'd (pinned) or memcpy'd (pageable) into the slabs, any
     // other stride (a multiple of the item size, negative allowed) is gathered / scattered by the lane
@@ -1061,11 +1071,11 @@ static int finish_on_gpu0(Job& j, void* host_out, int out_bytes, const void* hos
 
 static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* host_start, int max_workers) {
     if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false)) return decline();
+    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false, 8)) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
     j.pk_in1 = classify(j.in1);
-    if (host_kind(j.pk_in1) && j.len < threshold_for(NTE_CLASS_REDUCE, j.pk_in1 == PK_PAGEABLE)) return decline();
+    if (host_kind(j.pk_in1) && j.len < threshold_for(NTE_CLASS_REDUCE, j.pk_in1 == PK_PAGEABLE, j.isz_in)) return decline();
     int rc;
     if (!host_kind(j.pk_in1)) {
         // resident input: both passes on its GPU (contiguous only: pass 1 streams whole blocks)
@@ -1137,7 +1147,7 @@ int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out
 // fused chain: element-wise (out != NULL) or summed (host_out)
 static int dispatch_fused(Job& j, void* host_out, int max_workers) {
     if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false)) return decline();
+    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false, 8)) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
     const bool to_sum = j.kind == JOB_MULADD_SUM;
@@ -1147,7 +1157,7 @@ static int dispatch_fused(Job& j, void* host_out, int max_workers) {
     int nhost = 0, npageable = 0;
     for (int k = 0; k < 4; ++k) { nhost += host_kind(pks[k]); npageable += pks[k] == PK_PAGEABLE; }
     if (nhost != 0 && nhost != 4) return decline();  // host and resident arrays mixed: the caller's loops
-    if (nhost == 4 && j.len < threshold_for(NTE_CLASS_STREAM, npageable != 0)) return decline();
+    if (nhost == 4 && j.len < threshold_for(NTE_CLASS_STREAM, npageable != 0, j.isz_in)) return decline();
     const size_t bytes = (size_t)j.len * j.isz_in;
     int rc;
     if (nhost == 0) {

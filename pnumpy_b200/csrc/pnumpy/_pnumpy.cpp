@@ -179,13 +179,17 @@ static void AtopCompareMathFunction(char** args, const npy_intp* dimensions, con
     p->pOldFunc(args, dimensions, steps, innerloop);
 }
 
-static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int atype) {
+static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int atype,
+                         bool const_output = false) {
     const npy_intp n = dimensions[0];
     // the reference drops the fast pointer when the output stride is 0 (:882-884, 946-948)
     if (g_Settings.AtopEnabled && p->pUnaryFunc && steps[1] != 0) {
+        // integer classifiers (isnan(int) == False everywhere): constant output, see NTE_CLASS_CONST
+        const bool is_int = atype <= PNCU_UINT64;
+        const int op_class = cat == CAT_TRIG ? NTE_CLASS_HEAVY : ((is_int && const_output) ? NTE_CLASS_CONST : NTE_CLASS_STREAM);
         int rc = nte_unary_class(p->pUnaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], (int64_t)n,
                                  (int64_t)steps[0], (int64_t)steps[1], p->MaxThreads,
-                                 cat == CAT_TRIG ? NTE_CLASS_HEAVY : NTE_CLASS_STREAM);
+                                 op_class);
         if (rc == 0) { ledger(cat, true, n); return; }
         if (rc != NTE_DECLINED) { raise_cuda_error("unary ufunc loop", rc); return; }
     }
@@ -194,7 +198,9 @@ static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimen
 }
 // reference: AtopUnaryMathFunction, src/pnumpy/_pnumpy.cpp:874-932
 static void AtopUnaryMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
-    unary_common(&g_UnaryFuncLUT[funcop][atype], CAT_UNARY, args, dimensions, steps, innerloop, atype);
+    const bool classifier = funcop == PNCU_ISNAN || funcop == PNCU_ISINF || funcop == PNCU_ISFINITE || funcop == PNCU_ISNOTNAN ||
+                            funcop == PNCU_ISNOTINF || funcop == PNCU_ISNOTFINITE;
+    unary_common(&g_UnaryFuncLUT[funcop][atype], CAT_UNARY, args, dimensions, steps, innerloop, atype, classifier);
 }
 // reference: AtopTrigMathFunction, src/pnumpy/_pnumpy.cpp:938-996
 static void AtopTrigMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {

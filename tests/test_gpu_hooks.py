@@ -460,6 +460,9 @@ def test_benchmark_plumbing(pn, capsys):
         pn.benchmark(ctypes=[np.float32], sizes=[1 << 17], loop_size=3)
         out = capsys.readouterr().out
         assert out.startswith("131072 rows,float32,") and "a+b," in out and "sum," in out and "min," in out
+        pn.benchmark(sizes=[1 << 16], loop_size=2)          # the default dtype list (bool, int8 ... float64) must run
+        out = capsys.readouterr().out
+        assert out.startswith("65536 rows,bool,int8,int16,int32,int64,float32,float64,") and out.count("\n") >= 12
     finally:
         pn.cuda_setthreshold(old)
 
