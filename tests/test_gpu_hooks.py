@@ -637,3 +637,48 @@ def test_host_shapes_around_shard_and_slab_boundaries(pn, rng, dt):
     finally:
         pn.thread_enable()
         pn.thread_setworkers(oldw)
+
+
+def test_other_ways_numpy_calls_a_hooked_loop(pn, rng):
+    """accumulate (the output of element i is the input of element i+1: an overlapping call the dispatcher must
+    hand back), where= masks, ufunc.at, outer, reduceat, broadcasting and keepdims/axis reductions: whatever
+    argument shapes NumPy builds, the results are NumPy's."""
+    n = (1 << 20) + 11
+    a = rng.normal(0, 3, n).astype(np.float64)
+    b = rng.normal(0, 3, n).astype(np.float64)
+    ai = rng.integers(-50, 50, n).astype(np.int32)
+    m = rng.random(n) > 0.3
+    idx = rng.integers(0, 1000, 50000)
+    cases = {
+        "cumsum": lambda: np.cumsum(a),
+        "cumsum int": lambda: np.add.accumulate(ai),
+        "maximum.accumulate": lambda: np.maximum.accumulate(a),
+        "where": lambda: np.add(a, b, out=np.zeros(n), where=m),
+        "where sqrt": lambda: np.sqrt(np.abs(a), out=np.full(n, -1.0), where=m),
+        "at": lambda: _at(np.zeros(1000), idx),
+        "outer": lambda: np.multiply.outer(a[:1500], b[:1200]),
+        "reduceat": lambda: np.add.reduceat(ai, np.arange(0, n, 70001)),
+        "broadcast row": lambda: a.reshape(-1, 1)[:4096] * b[:2048],
+        "broadcast scalar arr": lambda: a.reshape(1, -1) + b[:1].reshape(1, 1),
+        "axis0": lambda: a[: 1 << 20].reshape(16, -1).sum(axis=0),
+        "axis1 keepdims": lambda: a[: 1 << 20].reshape(16, -1).max(axis=1, keepdims=True),
+        "sum initial": lambda: np.add.reduce(ai, initial=7),
+        "min initial": lambda: np.minimum.reduce(a, initial=-1e9),
+        "sum where": lambda: np.add.reduce(a, where=m),
+        "sum dtype": lambda: a.astype(np.float32).sum(dtype=np.float64),
+        "divmod path": lambda: np.floor_divide(a, b),
+        "comparison chain": lambda: (a > b) & (a < 2 * b) | (ai == 3),
+    }
+    for name, fn in cases.items():
+        got, want, _ = _both(pn, fn)
+        g, w = np.asarray(got), np.asarray(want)
+        assert g.dtype == w.dtype and g.shape == w.shape, name
+        if g.dtype.kind == "f" and ("sum" in name or name in ("axis0",)):
+            assert np.allclose(g, w, rtol=1e-12, atol=1e-9), name        # float sums: order of summation differs
+        else:
+            assert_bits_equal(g, w, name)
+
+
+def _at(z, idx):
+    np.add.at(z, idx, 1.0)
+    return z
