@@ -54,7 +54,7 @@ int ensure_init() {
         g_props[d].cc_major = p.major;
         g_props[d].cc_minor = p.minor;
         g_props[d].total_mem = p.totalGlobalMem;
-        snprintf(g_props[d].name, sizeof(g_props[d].name), "%s", p.name);
+        snprintf(g_props[d].name, sizeof(g_props[d].name), "%.127s", p.name);
         g_props[d].valid = true;
     }
     // the fat binary holds sm_100a SASS only: refuse anything else up front with a clear message
