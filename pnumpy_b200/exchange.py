@@ -27,6 +27,7 @@ class Exchange:
         self._bases, self._counters, self._imported = bases, counters, list(imported)  # [participant][parity] addresses
         self.epoch = 0
         self.expected = [0, 0]
+        self._scratch, self._scratch_bytes, self._retired = None, 0, []
         self._tables = []
         for parity in (0, 1):
             t = cabi.PeerTable()
@@ -107,8 +108,12 @@ class Exchange:
         for p in self._imported:
             lib.pncu_ipc_close(p)
         self._imported = []
+        lib.pncu_set_device(self.device)
+        lib.pncu_device_sync()
+        for p in self._retired + ([self._scratch] if self._scratch else []):
+            lib.pncu_free(p)
+        self._retired, self._scratch, self._scratch_bytes = [], None, 0
         if getattr(self, "_own", None):
-            lib.pncu_set_device(self.device)
             lib.pncu_free(self._own)
             self._own = None
 
@@ -128,7 +133,9 @@ class Exchange:
             p = ctypes.c_void_p()
             cabi.check(lib.pncu_set_device(self.device), "set_device")
             cabi.check(lib.pncu_malloc(ctypes.byref(p), max(need, 1 << 20)), "pncu_malloc")
-            self._scratch, self._scratch_bytes = p.value, max(need, 1 << 20)   # (an older, smaller one is left to the driver)
+            if getattr(self, "_scratch", None):
+                self._retired.append(self._scratch)   # may still be read by queued work: freed in close()
+            self._scratch, self._scratch_bytes = p.value, max(need, 1 << 20)
         return self._tables[parity], int(sum(counts[: self.rank])), total, self.expected[parity], self._scratch
 
     def reduce(self, op, shard, counts, out, start=None, stream=None):
