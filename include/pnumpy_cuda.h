@@ -119,7 +119,8 @@ enum pncu_status {
     PNCU_ERR_UNSUPPORTED = -2,  /* op/type/layout has no kernel */
     PNCU_ERR_OVERLAP     = -3,  /* out partially overlaps an input (not exact aliasing) */
     PNCU_ERR_ARGUMENT    = -4,
-    PNCU_ERR_NOMEM       = -5
+    PNCU_ERR_NOMEM       = -5,
+    PNCU_ERR_TIMEOUT     = -6   /* a participant of a cross-GPU exchange never arrived; no result was produced */
 };
 
 /* opaque: a cudaStream_t (NULL = the legacy default stream of the current device) */
@@ -284,17 +285,69 @@ typedef struct pncu_peer_table {
 } pncu_peer_table;
 PNCU_API int pncu_exchange_slices(void);
 /* `local_partials`: the output of pncu_reduce_partials() on this participant's shard (local_count slots);
- * `self`: this participant's index in `peers`; `total_count`: slots of all participants together */
+ * `self`: this participant's index in `peers`; `total_count`: slots of all participants together.
+ * `status` (optional, device-visible memory, zero-initialised): when a participant has not arrived within the
+ * bounded wait (~2 s) the kernel does NOT fold the incomplete table and does NOT write `out`; it ORs
+ * PNCU_FUSED_TIMEOUT_BIT into *status and counts the event (pncu_exchange_timeouts).  The caller must check
+ * one of the two before using `out`. */
 PNCU_API int pncu_reduce_exchange_finish(int func, int atype, const void* local_partials, int64_t local_count,
                                          int64_t slot_base, const pncu_peer_table* peers, int self,
                                          int64_t total_count, void* out, const void* startVal,
-                                         unsigned long long expected, pncu_stream_t stream);
+                                         unsigned long long expected, unsigned long long* status,
+                                         pncu_stream_t stream);
 PNCU_API int pncu_argminmax_exchange_finish(int kind, int atype, const void* local_partials, int64_t local_count,
                                             int64_t slot_base, const pncu_peer_table* peers, int self,
                                             int64_t total_count, int64_t* out_index,
-                                            unsigned long long expected, pncu_stream_t stream);
-/* pass-2 waits that gave up after ~4 s (a participant never arrived) on the current device; 0 in a healthy job */
+                                            unsigned long long expected, unsigned long long* status,
+                                            pncu_stream_t stream);
+/* bounded waits that gave up (a participant never arrived) on the current device; 0 in a healthy job */
 PNCU_API int64_t pncu_exchange_timeouts(void);
+
+/* ---------------------------------------------------------------------------
+ * ONE-LAUNCH reductions: pass 1, the exchange and pass 2 in a single kernel per GPU.
+ *
+ * Every pass-1 CTA takes a ticket after storing its block partial; the CTA that draws the last ticket does
+ * pass 2 itself, in the fold order of pncu_reduce_finish, so the result has the same bits as the two-launch
+ * building blocks above (this is also what the pncu_GetReduceMathOpFast / pncu_GetArgMinMaxOpFast /
+ * pncu_GetMulAddSumFast launchers run).  With `x->n > 1` participants (one shard per GPU, shard boundaries at
+ * multiples of pncu_reduce_block_elems()), the last CTA of every participant first stores the shard's partials
+ * into slot `slot_base ..` of each CONSUMER's table over NVLink (one system-scope fence, one arrival count per
+ * consumer) and a consumer's last CTA waits on the device for the other n-1 shards before it folds the complete
+ * table of `total_count` slots.  Consumers: every participant when `all` (an all-reduce: what one process per
+ * GPU wants), else only `root` (what a single process driving n GPUs wants).  A consumer's own pass 1 writes
+ * straight into its table, so `slots[self]` must be memory of the launching GPU.  `arrived[d]` only ever grows:
+ * each call adds n-1 to every consumer's counter and passes the running total as `expected`.  When calls can
+ * overlap in time (all-reduce across processes) alternate between two tables, as for pncu_reduce_exchange_finish.
+ * `out` / `startVal` may be device memory or MAPPED pinned host memory; `done_flag` (optional, device or mapped
+ * host memory) receives `done_value` with a system-scope release store after `out` is written, so a host thread
+ * can poll it instead of synchronising the stream.  If a shard never arrives (~2 s) the consumer does not fold
+ * and does not write `out`; it publishes `done_value | PNCU_FUSED_TIMEOUT_BIT` and counts the event
+ * (pncu_exchange_timeouts).  After such a failure call pncu_fused_reset(stream) before reusing the stream.
+ * x == NULL: a single GPU with no completion flag.
+ * replaces: the per-chunk partials + second pass on the caller, src/pnumpy/_pnumpy.cpp:666-700.
+ * ------------------------------------------------------------------------- */
+#define PNCU_FUSED_TIMEOUT_BIT (1ULL << 63)
+typedef struct pncu_fused_exchange {
+    int n;                                        /* participants, 1..PNCU_MAX_PEERS (1 = no exchange) */
+    int self;                                     /* this participant */
+    int all;                                      /* 1: every participant folds; 0: only `root` */
+    int root;
+    int64_t slot_base;                            /* first slot of this participant's shard */
+    int64_t total_count;                          /* slots of all shards together */
+    void* slots[PNCU_MAX_PEERS];                  /* consumers' tables (others may be NULL) */
+    unsigned long long* arrived[PNCU_MAX_PEERS];  /* consumers' arrival counters */
+    unsigned long long expected;                  /* running total a consumer's counter reaches with this call */
+    unsigned long long* done_flag;                /* optional */
+    unsigned long long done_value;
+} pncu_fused_exchange;
+PNCU_API int pncu_reduce_fused(int func, int atype, const void* in, int64_t len, const pncu_fused_exchange* x,
+                               void* out, const void* startVal, pncu_stream_t stream);
+PNCU_API int pncu_argminmax_fused(int kind, int atype, const void* in, int64_t len, int64_t index_base,
+                                  const pncu_fused_exchange* x, int64_t* out_index, pncu_stream_t stream);
+PNCU_API int pncu_muladd_sum_fused(int atype, const void* in1, const void* in2, const void* in3, int64_t len,
+                                   const pncu_fused_exchange* x, void* out, pncu_stream_t stream);
+/* re-arm the stream's ticket counter after a failed or timed-out one-launch reduction */
+PNCU_API int pncu_fused_reset(pncu_stream_t stream);
 /* peer memory plumbing: same-process peer access, and CUDA IPC handles (64 bytes) for one-process-per-GPU jobs */
 PNCU_API int pncu_enable_peer_access(int peer_device);     /* from the current device; idempotent */
 PNCU_API int pncu_ipc_export(void* dev_ptr, void* handle64);

@@ -19,16 +19,21 @@
  * [0, n) is split into `lanes` contiguous shards (boundaries at multiples of the 65536-element
  * reduction block); lane l drives GPU l % G with its own three streams (H2D, compute, D2H) and a
  * ring of pinned staging slabs, so the copy engines and the SMs of every GPU overlap.  Element-wise
- * work needs no exchange between lanes; reductions gather every lane's block partials on GPU 0
- * (peer copies over NVLink) and fold them there in fixed order -- the "second pass" of
- * src/pnumpy/_pnumpy.cpp:697-699 -- so the result is independent of the number of lanes and GPUs.
+ * work needs no exchange between lanes.  Reductions need one: for RESIDENT operands every GPU runs ONE
+ * kernel (pncu_*_fused) whose last CTA stores the shard's block partials into GPU 0's table over NVLink,
+ * and GPU 0's last CTA folds the table in fixed order and writes the result into mapped host memory;
+ * for host operands the lanes' partials are gathered on GPU 0 (peer copies) and folded by one finish
+ * kernel -- the "second pass" of src/pnumpy/_pnumpy.cpp:697-699 either way, so the result is
+ * independent of the number of lanes and GPUs.
  *
  * Operands are HOST pointers as NumPy hands them to a ufunc inner loop (pageable, or pinned when
  * they came from nte_alloc_pinned / the recycler), or device / managed pointers, which are used in
- * place with no PCIe traffic.  Strides are in bytes, as in the reference's loop types: 0 broadcasts a
- * scalar, the item size is a contiguous array, any other multiple of the item size (negative included)
- * is a strided view whose elements the lanes gather into / scatter from their pinned slabs (the
- * reference's generic strided loop, src/atop/ops_binary.cpp:563-569).
+ * place with no PCIe traffic AT EVERY SIZE (no threshold applies to them); a call may mix the two
+ * (resident arrays are used in place, host arrays are staged).  Strides are in bytes, as in the
+ * reference's loop types: 0 broadcasts a scalar, the item size is a contiguous array, any other
+ * multiple of the item size (negative included) is a strided view whose elements the lanes gather
+ * into / scatter from their pinned slabs (the reference's generic strided loop,
+ * src/atop/ops_binary.cpp:563-569); resident strided views go to the strided kernels as they are.
  */
 #ifndef PNUMPY_NTE_H
 #define PNUMPY_NTE_H
@@ -78,6 +83,14 @@ PNCU_API int64_t nte_set_min_elems(int64_t n);
 PNCU_API int64_t nte_get_min_elems(void);
 /* bytes of one staging slab (rounded to a multiple of 65536 * 8); returns the previous value */
 PNCU_API int64_t nte_set_slab_bytes(int64_t bytes);
+/* Fault injection for the error-path tests (also env PNUMPY_CUDA_FAULT_INJECT=n at nte_init): the n-th
+ * dispatch from now that would have gone to the GPU returns cudaErrorLaunchFailure (719) without touching
+ * the device, exactly as a failed launch would.  0 disarms.  Returns the previous countdown. */
+PNCU_API int64_t nte_inject_fault(int64_t nth);
+/* 1 in a fork()ed child of a process that had initialised the dispatcher.  CUDA cannot be used there: every
+ * nte_* op returns NTE_DECLINED (the caller's NumPy loop runs), the allocators return NULL, the free
+ * functions only forget the block.  Start worker processes with the "spawn" method to use the GPU in them. */
+PNCU_API int nte_is_forked_child(void);
 
 /* ---- the four dispatch entry points (one per hook-layer dispatcher) --------------------------------
  * `launcher` is what pncu_Get*OpFast returned; item sizes are of one input / output element.
@@ -126,6 +139,10 @@ PNCU_API void nte_free_pinned(void* ptr);
  * host reads a result. */
 PNCU_API void* nte_alloc_managed(size_t bytes);
 PNCU_API void nte_free_managed(void* ptr);
+/* zero a managed block on the GPU (its pages end up resident on GPU 0); 0 or a status */
+PNCU_API int nte_zero_managed(void* ptr, size_t bytes);
+/* forget where the pages of a managed block were last placed (the next call prefetches them again) */
+PNCU_API void nte_forget_residency(void* ptr);
 
 /* ---- accounting (feeds atop_info()/ledger and the tests) ------------------------------------------- */
 typedef struct nte_stats {
@@ -137,6 +154,7 @@ typedef struct nte_stats {
     int64_t staged_bytes;   /* bytes memcpy'd through pinned staging slabs (pageable operands) */
     int64_t lanes_last;     /* lanes used by the last call */
     int64_t gpus_last;      /* distinct GPUs used by the last call */
+    int64_t prefetches;     /* cudaMemPrefetchAsync calls issued for managed operands */
 } nte_stats;
 PNCU_API void nte_get_stats(nte_stats* out);
 PNCU_API void nte_reset_stats(void);

@@ -19,11 +19,16 @@ through ``PyUFunc_ReplaceLoopBySignature``.  You can then enable/disable the sub
         extra threads); ``thread_disable()`` pins every call to one lane on GPU 0.
 
   - ledger
-        Per-category call counters (GPU loop vs NumPy loop) while enabled.
+        While enabled: per-category call counters (GPU loop vs NumPy loop) and a ring of per-call
+        records (op, dtype, elements, bytes, start/end ticks, where it ran): ``ledger_records()``.
 
   - recycler
-        A NEP-49 allocator: large ndarrays are born in recycled *pinned* host memory, so the
-        dispatcher can DMA them in place instead of staging them.
+        A NEP-49 allocator.  ``recycler_enable()``: large ndarrays are born in recycled *pinned*
+        host memory, so the dispatcher can DMA them in place instead of staging them.
+        ``recycler_enable(kind="managed")``: they are born in CUDA *managed* memory instead -- the
+        arrays NumPy itself creates (``np.empty``, ufunc outputs, the temporaries of ``a*b+c``) are
+        device-capable, hooked calls on them run in place on the GPU at every size, and nothing
+        crosses PCIe until host code touches a result.
 
 There is no CPU fallback inside the GPU library: importing this package on a machine without a
 B200 raises ImportError (the reference raises on a CPU without AVX2).  Set
@@ -36,12 +41,12 @@ __version__ = "0.1.0"
 __all__ = [
     'initialize', 'atop_enable', 'atop_disable', 'atop_isenabled', 'atop_info', 'atop_setworkers', 'cpustring',
     'thread_enable', 'thread_disable', 'thread_isenabled', 'thread_getworkers', 'thread_setworkers', 'thread_zigzag',
-    'ledger_enable', 'ledger_disable', 'ledger_isenabled', 'ledger_info',
-    'recycler_enable', 'recycler_disable', 'recycler_isenabled', 'recycler_info',
+    'ledger_enable', 'ledger_disable', 'ledger_isenabled', 'ledger_info', 'ledger_records', 'ledger_clear',
+    'recycler_enable', 'recycler_disable', 'recycler_isenabled', 'recycler_info', 'recycler_trim',
     'timer_gettsc', 'timer_getutc', 'benchmark', 'benchmark_func', 'init', 'enable', 'disable', 'cpu_count_linux',
     'argmin', 'argmax',
     # additions of this build (nothing above changes meaning)
-    'cuda_info', 'cuda_reset_stats', 'cuda_setthreshold', 'cuda_getthreshold', 'cuda_setslab',
+    'cuda_info', 'cuda_reset_stats', 'cuda_setthreshold', 'cuda_getthreshold', 'cuda_setslab', 'cuda_inject_fault',
     'pinned_empty', 'pinned_array', 'managed_empty', 'managed_array', 'muladd', 'muladd_sum',
 ]
 
@@ -57,9 +62,9 @@ except ImportError as _e:  # the extension is the product: no Python fallback
 from ._pnumpy import atop_enable, atop_disable, atop_isenabled, atop_info, atop_setworkers, cpustring  # noqa: E402
 from ._pnumpy import thread_enable, thread_disable, thread_isenabled, thread_getworkers, thread_setworkers, thread_zigzag  # noqa: E402
 from ._pnumpy import timer_gettsc, timer_getutc  # noqa: E402
-from ._pnumpy import ledger_enable, ledger_disable, ledger_isenabled, ledger_info  # noqa: E402
-from ._pnumpy import recycler_enable, recycler_disable, recycler_isenabled, recycler_info  # noqa: E402
-from ._pnumpy import cuda_info, cuda_reset_stats, cuda_setthreshold, cuda_getthreshold, cuda_setslab  # noqa: E402
+from ._pnumpy import ledger_enable, ledger_disable, ledger_isenabled, ledger_info, ledger_records, ledger_clear  # noqa: E402
+from ._pnumpy import recycler_enable, recycler_disable, recycler_isenabled, recycler_info, recycler_trim  # noqa: E402
+from ._pnumpy import cuda_info, cuda_reset_stats, cuda_setthreshold, cuda_getthreshold, cuda_setslab, cuda_inject_fault  # noqa: E402
 
 from .cpu import cpu_count_linux, init, enable, disable  # noqa: E402
 from .benchmark import benchmark, benchmark_func  # noqa: E402

@@ -113,10 +113,14 @@ SIGNATURES = {
     "pncu_pointer_kind": (ctypes.c_int, [_vp, _P_INT]),
     "pncu_exchange_slices": (ctypes.c_int, []),
     "pncu_reduce_exchange_finish": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _c_i64, _vp, ctypes.c_int, _c_i64, _vp, _vp,
-                                                   ctypes.c_uint64, _vp]),
+                                                   ctypes.c_uint64, _vp, _vp]),
     "pncu_argminmax_exchange_finish": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _c_i64, _vp, ctypes.c_int, _c_i64, _vp,
-                                                      ctypes.c_uint64, _vp]),
+                                                      ctypes.c_uint64, _vp, _vp]),
     "pncu_exchange_timeouts": (_c_i64, []),
+    "pncu_reduce_fused": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _vp, _vp, _vp, _vp]),
+    "pncu_argminmax_fused": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _c_i64, _vp, _vp, _vp]),
+    "pncu_muladd_sum_fused": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _c_i64, _vp, _vp, _vp]),
+    "pncu_fused_reset": (ctypes.c_int, [_vp]),
     "pncu_enable_peer_access": (ctypes.c_int, [ctypes.c_int]),
     "pncu_ipc_export": (ctypes.c_int, [_vp, _vp]),
     "pncu_ipc_import": (ctypes.c_int, [_vp, ctypes.POINTER(_vp)]),
@@ -129,6 +133,19 @@ PNCU_MAX_PEERS = 8
 class PeerTable(ctypes.Structure):
     """pncu_peer_table (include/pnumpy_cuda.h)"""
     _fields_ = [("n", ctypes.c_int), ("slots", _vp * PNCU_MAX_PEERS), ("arrived", _vp * PNCU_MAX_PEERS)]
+
+
+
+class FusedExchange(ctypes.Structure):
+    """pncu_fused_exchange (include/pnumpy_cuda.h)"""
+    _fields_ = [("n", ctypes.c_int), ("self", ctypes.c_int), ("all", ctypes.c_int), ("root", ctypes.c_int),
+                ("slot_base", _c_i64), ("total_count", _c_i64),
+                ("slots", _vp * PNCU_MAX_PEERS), ("arrived", _vp * PNCU_MAX_PEERS),
+                ("expected", ctypes.c_uint64), ("done_flag", _vp), ("done_value", ctypes.c_uint64)]
+
+
+FUSED_TIMEOUT_BIT = 1 << 63
+ERR_TIMEOUT = -6
 
 _lib = None
 

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <vector>
 #include "../../../include/pnumpy_cuda.h"
 
 namespace pncu {
@@ -51,7 +52,32 @@ const DevProps* dev_props();          // of the current device, NULL on failure
 int ensure_init();                    // 0 or PNCU_ERR_NO_DEVICE
 
 // Per-(device, stream) scratch for reduction partials; grows on demand, never shrinks.
-int get_workspace(cudaStream_t stream, size_t bytes, void** out);
+// `ticket` (optional): the (device, stream)'s zeroed 32-bit counter for one-launch reductions.
+int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** ticket = nullptr);
+int reset_ticket(cudaStream_t stream);
+
+// ---- allocation registry ---------------------------------------------------------------------------
+// Every block this library hands out (pncu_malloc, pncu_malloc_host, pncu_host_register, nte_alloc_pinned,
+// nte_alloc_managed) is recorded by base address, so that the dispatcher can tell what kind of memory an
+// operand lives in with one ordered-map lookup under a shared lock (~30 ns) instead of a driver call per
+// operand per call.  Pointers that are not in the registry are classified by cudaPointerGetAttributes.
+enum MemKind { MK_UNKNOWN = -1, MK_PAGEABLE = 0, MK_PINNED = 1, MK_DEVICE = 2, MK_MANAGED = 3 };
+struct ResidencyNote {      // "the managed range [lo, lo + bytes) was prefetched to ..."
+    const char* lo;
+    size_t bytes;
+    int where;              // GPU index, or 100 + G: sharded over G GPUs in pieces of `piece` bytes
+    size_t piece;
+};
+struct AllocInfo {
+    const char* base;
+    size_t bytes;
+    int kind;               // MemKind
+    int device;             // owning device (MK_DEVICE), -1 otherwise
+    std::vector<ResidencyNote>* notes;  // managed blocks only; owned by the registry, guarded by the dispatcher's lock
+};
+void registry_add(const void* base, size_t bytes, int kind, int device);
+bool registry_remove(const void* base, size_t* bytes = nullptr);
+bool registry_find(const void* p, AllocInfo* out);   // the block containing p
 
 inline cudaStream_t as_stream(pncu_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

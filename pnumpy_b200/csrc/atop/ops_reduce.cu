@@ -16,8 +16,16 @@
 //           Arg-reductions keep the block in registers: phase A finds the block extreme
 //           (NaN-propagating), phase B scans the registers for its first occurrence; HBM is read
 //           once and there is no per-element index arithmetic.
-//   pass 2: ONE CTA folds the partials: thread t takes slots t, t+1024, ... in order, then the
-//           same warp/shared tree, then applies the start value and writes the result.
+//   pass 2: ONE CTA folds the partials: (virtual) thread t of 1024 takes slots t, t+1024, ... in order,
+//           then the same warp/shared tree, then applies the start value and writes the result.
+//   ONE LAUNCH: the complete reductions (pncu_GetReduceMathOpFast launchers, pncu_*_fused) do not launch
+//           pass 2 at all.  Every pass-1 CTA takes a ticket after storing its partial (one atomicAdd, used
+//           for NOTHING but the ticket); the CTA that draws the last ticket runs pass 2 itself, its 256
+//           threads standing in for the 1024 of the finish kernel (thread t plays t, t+256, t+512, t+768),
+//           so the fold order -- and every bit of the result -- is that of the two-launch building blocks.
+//           With several GPUs the last CTA of each first stores its shard's partials into the consumers'
+//           slot tables over NVLink (one system fence, one arrival count per destination) and the
+//           consumer's last CTA waits on the device for the other shards before it folds the whole table.
 // Every choice above is a function of (n, type) only -- not of the grid, the SM count or the
 // arrival order of CTAs -- so results are bit-reproducible run to run, and a multi-GPU split
 // at multiples of 65536 elements that gathers all partials before pass 2 is bit-identical to
@@ -197,6 +205,175 @@ __device__ __forceinline__ void write_result(typename R::Acc total, typename R::
     *out = R::result(t);
 }
 
+// ---- pass 2 as a device function -------------------------------------------------------------------------
+// loads that bypass L1: the table was written by other SMs (or other GPUs) during this kernel
+template <class A> __device__ __forceinline__ A ld_cg(const A* p) {
+    A r;
+    if constexpr (sizeof(A) == 4) {
+        unsigned v;
+        asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        memcpy(&r, &v, 4);
+    } else if constexpr (sizeof(A) == 8) {
+        unsigned long long v;
+        asm volatile("ld.global.cg.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        memcpy(&r, &v, 8);
+    } else {
+        static_assert(sizeof(A) == 16, "partials are 4, 8 or 16 bytes");
+        unsigned long long v[2];
+        asm volatile("ld.global.cg.v2.b64 {%0,%1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "l"(p) : "memory");
+        memcpy(&r, v, 16);
+    }
+    return r;
+}
+
+// Fold `count` partials in the order of a 1024-thread finish CTA, with THREADS real threads: real thread t
+// plays the virtual threads t + q*THREADS.  Virtual thread v takes slots v, v+1024, ... in ascending order;
+// threads beyond `count` hold a copy of slot 0 (harmless for idempotent ops) or the identity; then a
+// shuffle-down tree per (virtual) warp, the 32 warp values through shared memory, folded by thread 0 in warp
+// order.  Result valid in thread 0.  `smem`: 32 entries.
+template <class R, int THREADS>
+__device__ __forceinline__ typename R::Acc fold_table(const typename R::Acc* partials, int64_t count, typename R::Acc* smem) {
+    typedef typename R::Acc Acc;
+    constexpr int VT = FIN_THREADS / THREADS;
+    constexpr int MLP = VT == 1 ? 8 : (sizeof(Acc) >= 16 ? 2 : 4);   // loads in flight per virtual thread
+    Acc a[VT];
+#pragma unroll
+    for (int q = 0; q < VT; ++q) {
+        const int64_t v = (int64_t)threadIdx.x + q * THREADS;
+        if (R::kHasIdentity) a[q] = R::identity();
+        else a[q] = ld_cg(partials + (v < count ? v : 0));   // the first slot replaces the seed
+    }
+    int64_t k = (int64_t)threadIdx.x + (R::kHasIdentity ? 0 : FIN_THREADS);
+    // full batches: unconditional loads first (predicated ones get interleaved with the adds and serialise)
+    for (; k + (int64_t)(VT - 1) * THREADS + (int64_t)(MLP - 1) * FIN_THREADS < count; k += (int64_t)FIN_THREADS * MLP) {
+        Acc x[VT][MLP];
+#pragma unroll
+        for (int q = 0; q < VT; ++q)
+#pragma unroll
+            for (int m = 0; m < MLP; ++m) x[q][m] = ld_cg(partials + k + q * THREADS + (int64_t)m * FIN_THREADS);
+#pragma unroll
+        for (int q = 0; q < VT; ++q)
+#pragma unroll
+            for (int m = 0; m < MLP; ++m) a[q] = R::combine(a[q], x[q][m]);
+    }
+#pragma unroll
+    for (int q = 0; q < VT; ++q)
+        for (int64_t kk = k + q * THREADS; kk < count; kk += FIN_THREADS) a[q] = R::combine(a[q], ld_cg(partials + kk));
+#pragma unroll
+    for (int q = 0; q < VT; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[q] = R::combine(a[q], Shfl<Acc>::down(a[q], o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < VT; ++q) smem[warp + q * (THREADS / 32)] = a[q];
+    }
+    __syncthreads();
+    Acc r = a[0];
+    if (threadIdx.x == 0) {
+        r = smem[0];
+        for (int w = 1; w < FIN_THREADS / 32; ++w) r = R::combine(r, smem[w]);
+    }
+    return r;
+}
+
+template <class R, bool VALUE>
+__device__ __forceinline__ void store_result(typename R::Acc a, void* out, const void* startVal) {
+    if constexpr (VALUE) {
+        write_result<R>(a, reinterpret_cast<typename R::In*>(out), reinterpret_cast<const typename R::In*>(startVal));
+    } else {
+        if constexpr (sizeof(typename R::Acc) == 16) *reinterpret_cast<int64_t*>(out) = a.idx;
+    }
+}
+
+// ---- the tail of a ONE-LAUNCH reduction ------------------------------------------------------------------
+// What the last CTA of a pass-1 grid needs to finish the reduction (and, with n > 1 participants, to exchange
+// the shard's partials first).  Passed by value.
+struct FusedArgs {
+    unsigned* ticket;                 // this GPU's ticket counter: 0 between launches (the last CTA re-arms it)
+    int n, self, all, root;           // participants; `all`: every participant folds (all-reduce), else only `root`
+    long long slot_base, total_count; // this shard's first slot in a consumer's table; slots of all shards
+    void* slots[PNCU_MAX_PEERS];      // consumers' slot tables (peer memory); slots[self] + slot_base is where a
+                                      // consuming participant's own pass 1 writes directly
+    unsigned long long* arrived[PNCU_MAX_PEERS];
+    unsigned long long expected;      // arrivals a consumer's counter shows once every other shard is in
+    void* out;
+    const void* startVal;
+    unsigned long long* done_flag;    // optional (may be mapped host memory): receives done_value after `out`,
+    unsigned long long done_value;    //   or done_value | PNCU_FUSED_TIMEOUT_BIT when a shard never arrived
+};
+__device__ unsigned long long g_exchange_timeouts = 0;
+constexpr unsigned long long EXCH_WAIT_NS = 2000000000ULL;
+
+// thread 0: wait until *counter >= expected; false after EXCH_WAIT_NS (a lost participant is reported, not hung on)
+__device__ __forceinline__ bool wait_arrivals(const unsigned long long* counter, unsigned long long expected) {
+    unsigned long long t0, t1, v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
+        if (v >= expected) return true;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > EXCH_WAIT_NS) { atomicAdd(&g_exchange_timeouts, 1ULL); return false; }
+        __nanosleep(64);
+    }
+}
+__device__ __forceinline__ void publish(unsigned long long* flag, unsigned long long value) {
+    if (flag) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(value) : "memory");
+}
+
+template <class R, bool VALUE>
+__device__ __noinline__ void fused_finish(const typename R::Acc* local, int64_t local_count, const FusedArgs& fa) {
+    typedef typename R::Acc Acc;
+    __shared__ Acc fin_smem[FIN_THREADS / 32];
+    __shared__ int s_ok;
+    __threadfence();                         // the other CTAs' partials (acquire side of their tickets)
+    if (threadIdx.x == 0) *fa.ticket = 0u;   // re-arm for the next launch on this stream
+    const Acc* table = local;
+    int64_t count = local_count;
+    if (fa.n > 1) {
+        const bool consumer = fa.all || fa.self == fa.root;
+        for (int d = 0; d < fa.n; ++d) {
+            if (d == fa.self || !(fa.all || d == fa.root)) continue;
+            Acc* dst = reinterpret_cast<Acc*>(fa.slots[d]) + fa.slot_base;
+            for (int64_t i = threadIdx.x; i < local_count; i += RED_THREADS) dst[i] = ld_cg(local + i);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            for (int d = 0; d < fa.n; ++d)
+                if (d != fa.self && (fa.all || d == fa.root)) atomicAdd_system(fa.arrived[d], 1ULL);
+            s_ok = 1;
+            if (consumer) s_ok = wait_arrivals(fa.arrived[fa.self], fa.expected) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!consumer) return;
+        if (!s_ok) {   // never fold an incomplete table: report, leave `out` alone
+            if (threadIdx.x == 0) publish(fa.done_flag, fa.done_value | PNCU_FUSED_TIMEOUT_BIT);
+            return;
+        }
+        table = reinterpret_cast<const Acc*>(fa.slots[fa.self]);
+        count = fa.total_count;
+    }
+    Acc a = fold_table<R, RED_THREADS>(table, count, fin_smem);
+    if (threadIdx.x == 0) {
+        store_result<R, VALUE>(a, fa.out, fa.startVal);
+        publish(fa.done_flag, fa.done_value);
+    }
+}
+
+// called by every CTA of a FUSED pass-1 grid after thread 0 stored partials[blockIdx.x]
+template <class R, bool VALUE>
+__device__ __forceinline__ void fused_tail(const typename R::Acc* partials, const FusedArgs& fa) {
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(fa.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) fused_finish<R, VALUE>(partials, (int64_t)gridDim.x, fa);
+}
+
 // ---- word-at-a-time folds for the 1- and 2-byte types ----------------------------------------------
 // Extracting bytes one by one costs ~3 ALU instructions per element.  These fold a whole 32-bit word
 // per step with the integer dot-product unit (IDP.4A / IDP.2A: sum of the 4 or 2 packed lanes in one
@@ -288,18 +465,16 @@ template <> struct WordOps<MaxR<uint16_t>> : MinMaxWord<uint16_t, true> {};
 #ifndef PNCU_RED_MINB
 #define PNCU_RED_MINB 4
 #endif
-template <class R, bool VEC>
+template <class R, bool VEC, bool FUSED>
 __global__ void __launch_bounds__(RED_THREADS, PNCU_RED_MINB)
 reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_base,
-                     typename R::Acc* partials) {
+                     typename R::Acc* partials, const __grid_constant__ FusedArgs fa) {
     typedef typename R::In In;
     typedef typename R::Acc Acc;
     constexpr int64_t BE = block_elems<In>();
     constexpr int EPV = 32 / (int)sizeof(In);
     __shared__ Acc smem[RED_THREADS / 32];
 
-    // let a finish kernel queued behind this grid (launch_finish_dependent) become resident early
-    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
@@ -352,6 +527,7 @@ reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_ba
     for (int c = 1; c < RED_CHAINS; ++c) a = R::combine(a, acc[c]);
     a = block_fold<R, RED_THREADS>(a, smem);
     if (threadIdx.x == 0) partials[k] = a;
+    if constexpr (FUSED) fused_tail<R, true>(partials, fa);
 }
 
 // ---- pass 1 of sum(a*b + c) ------------------------------------------------------
@@ -361,10 +537,10 @@ reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_ba
 // ascending), so partial[k], and therefore the final sum, is bit-identical to the three-call chain
 // while HBM is read once (12 B per float32 element instead of 28).  The three operands are
 // loaded four vectors at a time (384 B in flight per thread).
-template <class R, bool VEC>
+template <class R, bool VEC, bool FUSED>
 __global__ void __launch_bounds__(RED_THREADS)
 muladd_sum_blocks_kernel(const typename R::In* a, const typename R::In* b, const typename R::In* c,
-                         int64_t n, typename R::Acc* partials) {
+                         int64_t n, typename R::Acc* partials, const __grid_constant__ FusedArgs fa) {
     typedef typename R::In In;
     typedef typename R::Acc Acc;
     constexpr int64_t BE = block_elems<In>();
@@ -372,8 +548,6 @@ muladd_sum_blocks_kernel(const typename R::In* a, const typename R::In* b, const
     static_assert(RED_NV % RED_CHAINS == 0, "vector j must map to accumulator j % RED_CHAINS");
     __shared__ Acc smem[RED_THREADS / 32];
 
-    // let a finish kernel queued behind this grid (launch_finish_dependent) become resident early
-    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
@@ -410,6 +584,7 @@ muladd_sum_blocks_kernel(const typename R::In* a, const typename R::In* b, const
     for (int ch = 1; ch < RED_CHAINS; ++ch) t = R::combine(t, acc[ch]);
     t = block_fold<R, RED_THREADS>(t, smem);
     if (threadIdx.x == 0) partials[k] = t;
+    if constexpr (FUSED) fused_tail<R, true>(partials, fa);
 }
 
 // NaN-propagating extreme for phase A of the arg kernels
@@ -435,9 +610,9 @@ struct IdxMinR {  // block fold of phase B
 };
 
 // arg-reduction pass 1: partial[k] = {extreme of block k, global index of its first occurrence}
-template <class T, bool IS_MAX, bool VEC>
-__global__ void __launch_bounds__(RED_THREADS)
-arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partials) {
+template <class T, bool IS_MAX, bool VEC, bool FUSED>
+__global__ void __launch_bounds__(RED_THREADS, 3)
+arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partials, const __grid_constant__ FusedArgs fa) {
     typedef typename Widen<T>::type W;
     constexpr int64_t BE = block_elems<T>();
     constexpr int EPV = 32 / (int)sizeof(T);
@@ -445,8 +620,6 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
     __shared__ W smem_v[RED_THREADS / 32];
     __shared__ int smem_i[RED_THREADS / 32];
 
-    // let a finish kernel queued behind this grid (launch_finish_dependent) become resident early
-    asm volatile("griddepcontrol.launch_dependents;");
     const int64_t k = blockIdx.x;
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
@@ -521,44 +694,20 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
         out.idx = start + index_base + local;
         partials[k] = out;
     }
+    if constexpr (FUSED) fused_tail<ArgR<T, IS_MAX>, false>(partials, fa);
 }
 
 // ---- pass 2 --------------------------------------------------------------------------------------
-// VALUE: write R::result into `out` (reductions); else write the index (arg-reductions)
+// The two-launch building block (pncu_reduce_finish / pncu_argminmax_finish: the multi-GPU dispatcher's
+// "gather, then fold" and the shard-invariance tests).  VALUE: write R::result into `out` (reductions);
+// else write the index (arg-reductions).
 template <class R, bool VALUE>
 __global__ void __launch_bounds__(FIN_THREADS)
 reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, const void* startVal) {
     typedef typename R::Acc Acc;
     __shared__ Acc smem[FIN_THREADS / 32];
-    // launched with programmatic stream serialization right behind pass 1 (launch_reduce): this CTA may
-    // already be resident while pass 1 drains; wait here until that grid is complete and visible.  A no-op
-    // for an ordinary launch (pncu_reduce_finish after the multi-GPU gather).
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    // slots t, t+1024, ... in order; threads beyond `count` hold a copy of slot 0 (harmless for
-    // idempotent ops) or the identity.  FIN_MLP loads are in flight per thread; the fold order is unchanged.
-    constexpr int FIN_MLP = 8;
-    Acc a;
-    if (R::kHasIdentity) a = R::identity(); else a = partials[0];
-    int64_t k = threadIdx.x;
-    if (!R::kHasIdentity && k < count) { a = partials[k]; k += FIN_THREADS; }  // the first slot replaces the seed
-    // full batches: unconditional loads first (predicated ones get interleaved with the adds and serialise)
-    for (; k + (int64_t)(FIN_MLP - 1) * FIN_THREADS < count; k += (int64_t)FIN_THREADS * FIN_MLP) {
-        Acc x[FIN_MLP];
-#pragma unroll
-        for (int m = 0; m < FIN_MLP; ++m) x[m] = partials[k + (int64_t)m * FIN_THREADS];
-#pragma unroll
-        for (int m = 0; m < FIN_MLP; ++m) a = R::combine(a, x[m]);
-    }
-    for (; k < count; k += FIN_THREADS) a = R::combine(a, partials[k]);
-    a = block_fold<R, FIN_THREADS>(a, smem);
-    if (threadIdx.x == 0) {
-        if constexpr (VALUE) {
-            write_result<R>(a, reinterpret_cast<typename R::In*>(out),
-                            reinterpret_cast<const typename R::In*>(startVal));
-        } else {
-            if constexpr (sizeof(Acc) == 16) *reinterpret_cast<int64_t*>(out) = a.idx;
-        }
-    }
+    Acc a = fold_table<R, FIN_THREADS>(partials, count, smem);
+    if (threadIdx.x == 0) store_result<R, VALUE>(a, out, startVal);
 }
 
 // ---- pass 2 with the cross-GPU exchange fused in ---------------------------------------------------------
@@ -571,8 +720,11 @@ reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, 
 //       own table and folds the complete table exactly like reduce_finish_kernel (same order, same bits).
 // No collective call, no host synchronisation, no extra launch compared with a single GPU; the payload is
 // 4-16 bytes per 64 KiB of input.  All G * EXCH_SLICES CTAs (<= 64) are co-resident, so the waiting CTA
-// cannot starve the pushing ones.  The wait is bounded (~4 s -> g_exchange_timeouts) so a lost participant
-// is an error on the host, not a hung GPU.
+// cannot starve the pushing ones.  The wait is bounded (EXCH_WAIT_NS): when a participant never arrives the
+// table is NOT folded and `out` is NOT written; the kernel counts the timeout (pncu_exchange_timeouts) and
+// writes PNCU_FUSED_TIMEOUT_BIT into `status` so that the host raises instead of using a partial result.
+// (The one-launch form of the same exchange is fused_finish above; this kernel remains for callers that
+// produce their partials separately.)
 constexpr int EXCH_SLICES = 8;
 struct PeerOut {
     int n, self;
@@ -580,14 +732,14 @@ struct PeerOut {
     void* slots[PNCU_MAX_PEERS];
     unsigned long long* arrived[PNCU_MAX_PEERS];
 };
-__device__ unsigned long long g_exchange_timeouts = 0;
 
 template <class R, bool VALUE>
 __global__ void __launch_bounds__(FIN_THREADS)
 exchange_finish_kernel(const typename R::Acc* local, int64_t local_count, const PeerOut po, int64_t total_count,
-                       void* out, const void* startVal, unsigned long long expected) {
+                       void* out, const void* startVal, unsigned long long expected, unsigned long long* status) {
     typedef typename R::Acc Acc;
     __shared__ Acc smem[FIN_THREADS / 32];
+    __shared__ int s_ok;
     const int s = blockIdx.x, d = blockIdx.y;
     // ---- push slice s to participant d
     {
@@ -604,90 +756,95 @@ exchange_finish_kernel(const typename R::Acc* local, int64_t local_count, const 
     }
     if (s != 0 || d != po.self) return;
     // ---- wait for everybody's slices, then fold the whole table
-    if (threadIdx.x == 0) {
-        unsigned long long t0, t1, v;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(po.arrived[po.self]) : "memory");
-            if (v >= expected) break;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ULL) { atomicAdd(&g_exchange_timeouts, 1ULL); break; }
-            __nanosleep(100);
-        }
-    }
+    if (threadIdx.x == 0) s_ok = wait_arrivals(po.arrived[po.self], expected) ? 1 : 0;
     __syncthreads();
-    const Acc* partials = reinterpret_cast<const Acc*>(po.slots[po.self]);
-    const int64_t count = total_count;
-    constexpr int FIN_MLP = 8;
-    Acc a;
-    if (R::kHasIdentity) a = R::identity(); else a = partials[0];
-    int64_t k = threadIdx.x;
-    if (!R::kHasIdentity && k < count) { a = partials[k]; k += FIN_THREADS; }
-    for (; k + (int64_t)(FIN_MLP - 1) * FIN_THREADS < count; k += (int64_t)FIN_THREADS * FIN_MLP) {
-        Acc x[FIN_MLP];
-#pragma unroll
-        for (int m = 0; m < FIN_MLP; ++m) x[m] = partials[k + (int64_t)m * FIN_THREADS];
-#pragma unroll
-        for (int m = 0; m < FIN_MLP; ++m) a = R::combine(a, x[m]);
+    if (!s_ok) {
+        if (threadIdx.x == 0 && status) atomicOr(status, PNCU_FUSED_TIMEOUT_BIT);
+        return;
     }
-    for (; k < count; k += FIN_THREADS) a = R::combine(a, partials[k]);
-    a = block_fold<R, FIN_THREADS>(a, smem);
-    if (threadIdx.x == 0) {
-        if constexpr (VALUE) {
-            write_result<R>(a, reinterpret_cast<typename R::In*>(out), reinterpret_cast<const typename R::In*>(startVal));
-        } else {
-            if constexpr (sizeof(Acc) == 16) *reinterpret_cast<int64_t*>(out) = a.idx;
-        }
-    }
-}
-
-// pass 2 queued right behind pass 1 on the same stream: with programmatic stream serialization the
-// finish CTA is scheduled as soon as every pass-1 CTA has started (griddepcontrol.launch_dependents) and
-// blocks in griddepcontrol.wait until that grid is complete, so its launch latency overlaps pass 1's tail.
-template <class R, bool VALUE>
-int launch_finish_dependent(const void* partials, int64_t count, void* out, const void* startVal, cudaStream_t st) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(1);
-    cfg.blockDim = dim3(FIN_THREADS);
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_finish_kernel<R, VALUE>, (const typename R::Acc*)partials, count, out, startVal);
-    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaLaunchKernelEx(reduce_finish_kernel)", __FILE__, __LINE__); }
-    return after_launch("reduce_finish_kernel");
+    Acc a = fold_table<R, FIN_THREADS>(reinterpret_cast<const Acc*>(po.slots[po.self]), total_count, smem);
+    if (threadIdx.x == 0) store_result<R, VALUE>(a, out, startVal);
 }
 
 // ---- host launchers ---------------------------------------------------------------------------------
 template <class In> inline int64_t nblocks_for(int64_t len) { return (len + block_elems<In>() - 1) / block_elems<In>(); }
 
+static const FusedArgs kNoFuse = {};
+
+// FusedArgs and the place pass 1 writes its partials for a ONE-LAUNCH reduction of `nb` blocks.
+// x == NULL (or x->n == 1): single GPU, partials in the stream's scratch.  x->n > 1: see pncu_fused_exchange.
+int prepare_fused(const pncu_fused_exchange* x, size_t acc_bytes, int64_t nb, void* out, const void* startVal,
+                  cudaStream_t st, FusedArgs* fa, void** partials) {
+    void* ws = NULL;
+    unsigned* ticket = NULL;
+    int rc = get_workspace(st, (size_t)nb * acc_bytes, &ws, &ticket);
+    if (rc) return rc;
+    *fa = FusedArgs();
+    fa->ticket = ticket;
+    fa->n = 1;
+    fa->out = out;
+    fa->startVal = startVal;
+    *partials = ws;
+    if (!x) return 0;
+    fa->done_flag = x->done_flag;
+    fa->done_value = x->done_value;
+    if (x->n == 1) return 0;
+    if (x->n < 1 || x->n > PNCU_MAX_PEERS || x->self < 0 || x->self >= x->n || x->root < 0 || x->root >= x->n) {
+        set_error("fused exchange: n must be 1..%d, 0 <= self, root < n", PNCU_MAX_PEERS);
+        return PNCU_ERR_ARGUMENT;
+    }
+    if (x->slot_base < 0 || x->slot_base + nb > x->total_count) {
+        set_error("fused exchange: slots [%lld, %lld) do not fit a table of %lld", (long long)x->slot_base,
+                  (long long)(x->slot_base + nb), (long long)x->total_count);
+        return PNCU_ERR_ARGUMENT;
+    }
+    fa->n = x->n; fa->self = x->self; fa->all = x->all ? 1 : 0; fa->root = x->root;
+    fa->slot_base = x->slot_base; fa->total_count = x->total_count; fa->expected = x->expected;
+    for (int d = 0; d < x->n; ++d) {
+        const bool used = x->all || d == x->root;
+        if (used && (!x->slots[d] || !x->arrived[d])) { set_error("fused exchange: null table for participant %d", d); return PNCU_ERR_ARGUMENT; }
+        fa->slots[d] = x->slots[d];
+        fa->arrived[d] = x->arrived[d];
+    }
+    if (x->all || x->self == x->root) *partials = (char*)x->slots[x->self] + (size_t)x->slot_base * acc_bytes;
+    return 0;
+}
+
 template <class R>
 int launch_partials(const void* in, int64_t len, int64_t stride, int64_t index_base, void* partials,
-                    cudaStream_t st) {
+                    cudaStream_t st, const FusedArgs* fa = nullptr) {
     typedef typename R::In In;
+    typedef typename R::Acc Acc;
     const int64_t nb = nblocks_for<In>(len);
     if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
     const bool vec = stride == (int64_t)sizeof(In) && ((uintptr_t)in % 32) == 0;
-    if (vec)
-        reduce_blocks_kernel<R, true><<<(unsigned)nb, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
-                                                                          (typename R::Acc*)partials);
-    else
-        reduce_blocks_kernel<R, false><<<(unsigned)nb, RED_THREADS, 0, st>>>((const char*)in, len, stride, index_base,
-                                                                           (typename R::Acc*)partials);
+    const char* p = (const char*)in;
+    const unsigned g = (unsigned)nb;
+    if (fa) {
+        if (vec) reduce_blocks_kernel<R, true, true><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, *fa);
+        else reduce_blocks_kernel<R, false, true><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, *fa);
+    } else {
+        if (vec) reduce_blocks_kernel<R, true, false><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, kNoFuse);
+        else reduce_blocks_kernel<R, false, false><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, kNoFuse);
+    }
     return after_launch("reduce_blocks_kernel");
 }
 
 template <class T, bool IS_MAX>
 int launch_arg_partials(const void* in, int64_t len, int64_t /*stride*/, int64_t index_base, void* partials,
-                        cudaStream_t st) {
+                        cudaStream_t st, const FusedArgs* fa = nullptr) {
     const int64_t nb = nblocks_for<T>(len);
     if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
-    if (((uintptr_t)in % 32) == 0)
-        arg_blocks_kernel<T, IS_MAX, true><<<(unsigned)nb, RED_THREADS, 0, st>>>((const T*)in, len, index_base, (ArgPair<T>*)partials);
-    else
-        arg_blocks_kernel<T, IS_MAX, false><<<(unsigned)nb, RED_THREADS, 0, st>>>((const T*)in, len, index_base, (ArgPair<T>*)partials);
+    const bool vec = ((uintptr_t)in % 32) == 0;
+    const unsigned g = (unsigned)nb;
+    ArgPair<T>* pp = (ArgPair<T>*)partials;
+    if (fa) {
+        if (vec) arg_blocks_kernel<T, IS_MAX, true, true><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, *fa);
+        else arg_blocks_kernel<T, IS_MAX, false, true><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, *fa);
+    } else {
+        if (vec) arg_blocks_kernel<T, IS_MAX, true, false><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, kNoFuse);
+        else arg_blocks_kernel<T, IS_MAX, false, false><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, kNoFuse);
+    }
     return after_launch("arg_blocks_kernel");
 }
 
@@ -703,6 +860,21 @@ int check_reduce_args(const void* in, int64_t stride) {
     return 0;
 }
 
+// the complete reduction in ONE launch (optionally with the cross-GPU exchange)
+template <class R>
+int launch_reduce_fused(const void* in, int64_t len, int64_t stride, int64_t /*index_base*/, const pncu_fused_exchange* x,
+                        void* out, const void* startVal, cudaStream_t st) {
+    typedef typename R::In In;
+    int rc;
+    if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (len <= 0) { set_error("one-launch reduction of an empty shard"); return PNCU_ERR_ARGUMENT; }
+    if ((rc = check_reduce_args<R>(in, stride))) return rc;
+    FusedArgs fa;
+    void* partials = NULL;
+    if ((rc = prepare_fused(x, sizeof(typename R::Acc), nblocks_for<In>(len), out, startVal, st, &fa, &partials))) return rc;
+    return launch_partials<R>(in, len, stride, 0, partials, st, &fa);
+}
+
 // REDUCE_FUNC
 template <class R>
 int launch_reduce(const void* in, void* out, const void* startVal, int64_t len, int64_t stride,
@@ -716,18 +888,15 @@ int launch_reduce(const void* in, void* out, const void* startVal, int64_t len, 
         if (startVal && startVal != out) PNCU_CUDA(cudaMemcpyAsync(out, startVal, sizeof(In), cudaMemcpyDeviceToDevice, st));
         return 0;
     }
-    if ((rc = check_reduce_args<R>(in, stride))) return rc;
-    const int64_t nb = nblocks_for<In>(len);
-    void* ws = NULL;
-    if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
-    if ((rc = launch_partials<R>(in, len, stride, 0, ws, st))) return rc;
-    return launch_finish_dependent<R, true>(ws, nb, out, startVal, st);
+    return launch_reduce_fused<R>(in, len, stride, 0, NULL, out, startVal, st);
 }
 
-// sum(a*b + c): pass 1 (fused) and the ordinary pass 2 of the ADD reduction
+// sum(a*b + c): pass 1 (fused multiply-add) with the block structure of the ADD reduction
 template <class R>
-int launch_muladd_partials(const void* a, const void* b, const void* c, int64_t len, void* partials, cudaStream_t st) {
+int launch_muladd_partials(const void* a, const void* b, const void* c, int64_t len, void* partials, cudaStream_t st,
+                           const FusedArgs* fa = nullptr) {
     typedef typename R::In In;
+    typedef typename R::Acc Acc;
     if (!a || !b || !c || !partials) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
     if (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % sizeof(In)) {
         set_error("operand pointer is not a multiple of the item size");
@@ -736,13 +905,29 @@ int launch_muladd_partials(const void* a, const void* b, const void* c, int64_t 
     const int64_t nb = nblocks_for<In>(len);
     if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
     const bool vec = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) % 32) == 0;
-    if (vec)
-        muladd_sum_blocks_kernel<R, true><<<(unsigned)nb, RED_THREADS, 0, st>>>((const In*)a, (const In*)b, (const In*)c, len,
-                                                                              (typename R::Acc*)partials);
-    else
-        muladd_sum_blocks_kernel<R, false><<<(unsigned)nb, RED_THREADS, 0, st>>>((const In*)a, (const In*)b, (const In*)c, len,
-                                                                               (typename R::Acc*)partials);
+    const unsigned g = (unsigned)nb;
+    const In *pa = (const In*)a, *pb = (const In*)b, *pc = (const In*)c;
+    if (fa) {
+        if (vec) muladd_sum_blocks_kernel<R, true, true><<<g, RED_THREADS, 0, st>>>(pa, pb, pc, len, (Acc*)partials, *fa);
+        else muladd_sum_blocks_kernel<R, false, true><<<g, RED_THREADS, 0, st>>>(pa, pb, pc, len, (Acc*)partials, *fa);
+    } else {
+        if (vec) muladd_sum_blocks_kernel<R, true, false><<<g, RED_THREADS, 0, st>>>(pa, pb, pc, len, (Acc*)partials, kNoFuse);
+        else muladd_sum_blocks_kernel<R, false, false><<<g, RED_THREADS, 0, st>>>(pa, pb, pc, len, (Acc*)partials, kNoFuse);
+    }
     return after_launch("muladd_sum_blocks_kernel");
+}
+
+template <class R>
+int launch_muladd_sum_fused(const void* a, const void* b, const void* c, int64_t len, const pncu_fused_exchange* x, void* out,
+                            cudaStream_t st) {
+    typedef typename R::In In;
+    int rc;
+    if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (len <= 0) { set_error("one-launch reduction of an empty shard"); return PNCU_ERR_ARGUMENT; }
+    FusedArgs fa;
+    void* partials = NULL;
+    if ((rc = prepare_fused(x, sizeof(typename R::Acc), nblocks_for<In>(len), out, NULL, st, &fa, &partials))) return rc;
+    return launch_muladd_partials<R>(a, b, c, len, partials, st, &fa);
 }
 
 template <class R>
@@ -753,21 +938,19 @@ int launch_muladd_sum(const void* a, const void* b, const void* c, void* out, in
     cudaStream_t st = as_stream(stream);
     if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
     if (len <= 0) { PNCU_CUDA(cudaMemsetAsync(out, 0, sizeof(In), st)); return 0; }
-    const int64_t nb = nblocks_for<In>(len);
-    void* ws = NULL;
-    if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
-    if ((rc = launch_muladd_partials<R>(a, b, c, len, ws, st))) return rc;
-    return launch_finish_dependent<R, true>(ws, nb, out, NULL, st);
+    return launch_muladd_sum_fused<R>(a, b, c, len, NULL, out, st);
 }
 
 struct MulAddSumOps {
     pncu_three_reduce_fn full;
-    int (*partials)(const void*, const void*, const void*, int64_t, void*, cudaStream_t);
+    int (*partials)(const void*, const void*, const void*, int64_t, void*, cudaStream_t, const FusedArgs*);
+    int (*fused)(const void*, const void*, const void*, int64_t, const pncu_fused_exchange*, void*, cudaStream_t);
 };
 template <class R> MulAddSumOps make_muladd_ops() {
     MulAddSumOps o;
     o.full = launch_muladd_sum<R>;
     o.partials = launch_muladd_partials<R>;
+    o.fused = launch_muladd_sum_fused<R>;
     return o;
 }
 bool lookup_muladd_sum(int t, MulAddSumOps* o) {
@@ -783,27 +966,34 @@ bool lookup_muladd_sum(int t, MulAddSumOps* o) {
 }
 
 template <class R>
-int launch_argminmax(const void* in, int64_t len, int64_t* out_index, pncu_stream_t stream) {
-    int rc = ensure_init();
-    if (rc) return rc;
-    cudaStream_t st = as_stream(stream);
+int launch_arg_fused(const void* in, int64_t len, int64_t /*stride*/, int64_t index_base, const pncu_fused_exchange* x,
+                     void* out_index, const void* /*startVal*/, cudaStream_t st) {
+    int rc;
     if (!out_index) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
     if (len <= 0) { set_error("arg-reduction of an empty sequence"); return PNCU_ERR_ARGUMENT; }
     if ((rc = check_reduce_args<R>(in, sizeof(typename R::In)))) return rc;
-    const int64_t nb = nblocks_for<typename R::In>(len);
-    void* ws = NULL;
-    if ((rc = get_workspace(st, (size_t)nb * sizeof(typename R::Acc), &ws))) return rc;
-    if ((rc = launch_arg_partials<typename R::In, R::kIsMax>(in, len, sizeof(typename R::In), 0, ws, st))) return rc;
-    return launch_finish_dependent<R, false>(ws, nb, out_index, NULL, st);
+    FusedArgs fa;
+    void* partials = NULL;
+    if ((rc = prepare_fused(x, sizeof(typename R::Acc), nblocks_for<typename R::In>(len), out_index, NULL, st, &fa, &partials))) return rc;
+    return launch_arg_partials<typename R::In, R::kIsMax>(in, len, sizeof(typename R::In), index_base, partials, st, &fa);
 }
 
-// type-erased entry for the two-pass building blocks
+template <class R>
+int launch_argminmax(const void* in, int64_t len, int64_t* out_index, pncu_stream_t stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    return launch_arg_fused<R>(in, len, sizeof(typename R::In), 0, NULL, out_index, NULL, as_stream(stream));
+}
+
+// type-erased entry for the building blocks
 struct ReduceOps {
     int partial_bytes;
     pncu_reduce_fn full;
-    int (*partials)(const void*, int64_t, int64_t, int64_t, void*, cudaStream_t);
+    int (*partials)(const void*, int64_t, int64_t, int64_t, void*, cudaStream_t, const FusedArgs*);
     int (*finish)(const void*, int64_t, void*, const void*, cudaStream_t);
-    int (*exchange_finish)(const void*, int64_t, const PeerOut*, int64_t, void*, const void*, unsigned long long, cudaStream_t);
+    int (*exchange_finish)(const void*, int64_t, const PeerOut*, int64_t, void*, const void*, unsigned long long,
+                           unsigned long long*, cudaStream_t);
+    int (*fused)(const void*, int64_t, int64_t, int64_t, const pncu_fused_exchange*, void*, const void*, cudaStream_t);
 };
 template <class R, bool VALUE>
 int finish_thunk(const void* partials, int64_t count, void* out, const void* startVal, cudaStream_t st) {
@@ -812,9 +1002,9 @@ int finish_thunk(const void* partials, int64_t count, void* out, const void* sta
 }
 template <class R, bool VALUE>
 int exchange_finish_thunk(const void* local, int64_t local_count, const PeerOut* po, int64_t total_count, void* out,
-                          const void* startVal, unsigned long long expected, cudaStream_t st) {
+                          const void* startVal, unsigned long long expected, unsigned long long* status, cudaStream_t st) {
     exchange_finish_kernel<R, VALUE><<<dim3(EXCH_SLICES, po->n), FIN_THREADS, 0, st>>>(
-        (const typename R::Acc*)local, local_count, *po, total_count, out, startVal, expected);
+        (const typename R::Acc*)local, local_count, *po, total_count, out, startVal, expected, status);
     return after_launch("exchange_finish_kernel");
 }
 template <class R>
@@ -825,6 +1015,7 @@ ReduceOps make_ops() {
     o.partials = launch_partials<R>;
     o.finish = finish_thunk<R, true>;
     o.exchange_finish = exchange_finish_thunk<R, true>;
+    o.fused = launch_reduce_fused<R>;
     return o;
 }
 template <class R>
@@ -835,6 +1026,7 @@ ReduceOps make_arg_ops() {
     o.partials = launch_arg_partials<typename R::In, R::kIsMax>;
     o.finish = finish_thunk<R, false>;
     o.exchange_finish = exchange_finish_thunk<R, false>;
+    o.fused = launch_arg_fused<R>;
     return o;
 }
 
@@ -973,7 +1165,7 @@ extern "C" int pncu_reduce_partials(int func, int t, const void* in, int64_t len
     if (rc) return rc;
     if (len <= 0) return 0;
     if (!in || !partials) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
-    return o.partials(in, len, pncu_itemsize(t), 0, partials, as_stream(stream));
+    return o.partials(in, len, pncu_itemsize(t), 0, partials, as_stream(stream), nullptr);
 }
 
 extern "C" int pncu_reduce_finish(int func, int t, const void* partials, int64_t count, void* out,
@@ -999,7 +1191,7 @@ extern "C" int pncu_argminmax_partials(int kind, int t, const void* in, int64_t 
     if (rc) return rc;
     if (len <= 0) return 0;
     if (!in || !partials) { set_error("null operand"); return PNCU_ERR_ARGUMENT; }
-    return o.partials(in, len, pncu_itemsize(t), index_base, partials, as_stream(stream));
+    return o.partials(in, len, pncu_itemsize(t), index_base, partials, as_stream(stream), nullptr);
 }
 
 extern "C" int pncu_argminmax_finish(int kind, int t, const void* partials, int64_t count,
@@ -1033,7 +1225,8 @@ extern "C" int pncu_exchange_slices(void) { return EXCH_SLICES; }
 
 extern "C" int pncu_reduce_exchange_finish(int func, int t, const void* local_partials, int64_t local_count,
                                            int64_t slot_base, const pncu_peer_table* peers, int self, int64_t total_count,
-                                           void* out, const void* startVal, unsigned long long expected, pncu_stream_t stream) {
+                                           void* out, const void* startVal, unsigned long long expected,
+                                           unsigned long long* status, pncu_stream_t stream) {
     ReduceOps o;
     if (!lookup_reduce(func, t, &o)) { set_error("no reduction kernel for func %d type %d", func, t); return PNCU_ERR_UNSUPPORTED; }
     int rc = ensure_init();
@@ -1041,12 +1234,13 @@ extern "C" int pncu_reduce_exchange_finish(int func, int t, const void* local_pa
     if (!out || !local_partials || local_count <= 0 || total_count < local_count) { set_error("bad arguments"); return PNCU_ERR_ARGUMENT; }
     PeerOut po;
     if ((rc = fill_peers(peers, self, slot_base, &po))) return rc;
-    return o.exchange_finish(local_partials, local_count, &po, total_count, out, startVal, expected, as_stream(stream));
+    return o.exchange_finish(local_partials, local_count, &po, total_count, out, startVal, expected, status, as_stream(stream));
 }
 
 extern "C" int pncu_argminmax_exchange_finish(int kind, int t, const void* local_partials, int64_t local_count,
                                               int64_t slot_base, const pncu_peer_table* peers, int self, int64_t total_count,
-                                              int64_t* out_index, unsigned long long expected, pncu_stream_t stream) {
+                                              int64_t* out_index, unsigned long long expected, unsigned long long* status,
+                                              pncu_stream_t stream) {
     ReduceOps o;
     if (!lookup_arg(kind, t, &o)) { set_error("no arg-reduction kernel for kind %d type %d", kind, t); return PNCU_ERR_UNSUPPORTED; }
     int rc = ensure_init();
@@ -1054,7 +1248,7 @@ extern "C" int pncu_argminmax_exchange_finish(int kind, int t, const void* local
     if (!out_index || !local_partials || local_count <= 0 || total_count < local_count) { set_error("bad arguments"); return PNCU_ERR_ARGUMENT; }
     PeerOut po;
     if ((rc = fill_peers(peers, self, slot_base, &po))) return rc;
-    return o.exchange_finish(local_partials, local_count, &po, total_count, out_index, NULL, expected, as_stream(stream));
+    return o.exchange_finish(local_partials, local_count, &po, total_count, out_index, NULL, expected, status, as_stream(stream));
 }
 
 extern "C" int64_t pncu_exchange_timeouts(void) {
@@ -1062,6 +1256,40 @@ extern "C" int64_t pncu_exchange_timeouts(void) {
     if (ensure_init()) return -1;
     if (cudaMemcpyFromSymbol(&v, g_exchange_timeouts, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
     return (int64_t)v;
+}
+
+// ---- one-launch reductions (include/pnumpy_cuda.h) ---------------------------------------------------------
+extern "C" int pncu_reduce_fused(int func, int t, const void* in, int64_t len, const pncu_fused_exchange* x, void* out,
+                                 const void* startVal, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_reduce(func, t, &o)) { set_error("no reduction kernel for func %d type %d", func, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    return o.fused(in, len, pncu_itemsize(t), 0, x, out, startVal, as_stream(stream));
+}
+
+extern "C" int pncu_argminmax_fused(int kind, int t, const void* in, int64_t len, int64_t index_base,
+                                    const pncu_fused_exchange* x, int64_t* out_index, pncu_stream_t stream) {
+    ReduceOps o;
+    if (!lookup_arg(kind, t, &o)) { set_error("no arg-reduction kernel for kind %d type %d", kind, t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    return o.fused(in, len, pncu_itemsize(t), index_base, x, out_index, NULL, as_stream(stream));
+}
+
+extern "C" int pncu_muladd_sum_fused(int t, const void* in1, const void* in2, const void* in3, int64_t len,
+                                     const pncu_fused_exchange* x, void* out, pncu_stream_t stream) {
+    MulAddSumOps o;
+    if (!lookup_muladd_sum(t, &o)) { set_error("no fused multiply-add-sum kernel for type %d", t); return PNCU_ERR_UNSUPPORTED; }
+    int rc = ensure_init();
+    if (rc) return rc;
+    return o.fused(in1, in2, in3, len, x, out, as_stream(stream));
+}
+
+extern "C" int pncu_fused_reset(pncu_stream_t stream) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    return reset_ticket(as_stream(stream));
 }
 
 extern "C" pncu_three_reduce_fn pncu_GetMulAddSumFast(int t) {
@@ -1076,5 +1304,5 @@ extern "C" int pncu_muladd_sum_partials(int t, const void* in1, const void* in2,
     int rc = ensure_init();
     if (rc) return rc;
     if (len <= 0) return 0;
-    return o.partials(in1, in2, in3, len, partials, as_stream(stream));
+    return o.partials(in1, in2, in3, len, partials, as_stream(stream), nullptr);
 }

@@ -5,6 +5,7 @@
 #include <string.h>
 #include <map>
 #include <mutex>
+#include <shared_mutex>
 #include <utility>
 #include "common.cuh"
 
@@ -75,14 +76,23 @@ const DevProps* dev_props() {
 }
 
 // ---- reduction scratch, keyed by (device, stream) --------------------------------------------
-struct Scratch { void* ptr; size_t bytes; };
+// `ticket`: one 32-bit counter per (device, stream), zero between launches (the last CTA of a one-launch
+// reduction re-arms it); lives in its own allocation so that growing the scratch never disturbs it.
+struct Scratch { void* ptr; size_t bytes; unsigned* ticket; };
 static std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
 
-int get_workspace(cudaStream_t stream, size_t bytes, void** out) {
+int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** ticket) {
     int d = 0;
     PNCU_CUDA(cudaGetDevice(&d));
     std::lock_guard<std::mutex> lk(g_mu);
     Scratch& s = g_scratch[std::make_pair(d, stream)];
+    if (ticket && !s.ticket) {
+        void* t = NULL;
+        cudaError_t e = cudaMalloc(&t, 256);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(256) for a reduction ticket failed: %s", cudaGetErrorString(e)); return PNCU_ERR_NOMEM; }
+        PNCU_CUDA(cudaMemset(t, 0, 256));   // synchronous: visible to whatever stream uses it next
+        s.ticket = (unsigned*)t;
+    }
     if (s.bytes < bytes) {
         size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
         void* p = NULL;
@@ -96,8 +106,58 @@ int get_workspace(cudaStream_t stream, size_t bytes, void** out) {
         s.ptr = p;
         s.bytes = want;
     }
-    *out = s.ptr;
+    if (out) *out = s.ptr;
+    if (ticket) *ticket = s.ticket;
     return 0;
+}
+
+// after a failed / timed-out launch the counter may be left non-zero
+int reset_ticket(cudaStream_t stream) {
+    int d = 0;
+    PNCU_CUDA(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_scratch.find(std::make_pair(d, stream));
+    if (it != g_scratch.end() && it->second.ticket) PNCU_CUDA(cudaMemsetAsync(it->second.ticket, 0, 256, stream));
+    return 0;
+}
+
+// ---- allocation registry (common.cuh) -------------------------------------------------------------------
+static std::shared_mutex g_reg_mu;
+static std::map<uintptr_t, AllocInfo> g_registry;
+
+void registry_add(const void* base, size_t bytes, int kind, int device) {
+    if (!base) return;
+    AllocInfo a;
+    a.base = (const char*)base;
+    a.bytes = bytes ? bytes : 1;
+    a.kind = kind;
+    a.device = device;
+    a.notes = kind == MK_MANAGED ? new std::vector<ResidencyNote>() : nullptr;
+    std::unique_lock<std::shared_mutex> lk(g_reg_mu);
+    auto it = g_registry.find((uintptr_t)base);
+    if (it != g_registry.end()) { delete it->second.notes; g_registry.erase(it); }
+    g_registry[(uintptr_t)base] = a;
+}
+
+bool registry_remove(const void* base, size_t* bytes) {
+    std::unique_lock<std::shared_mutex> lk(g_reg_mu);
+    auto it = g_registry.find((uintptr_t)base);
+    if (it == g_registry.end()) return false;
+    if (bytes) *bytes = it->second.bytes;
+    delete it->second.notes;
+    g_registry.erase(it);
+    return true;
+}
+
+bool registry_find(const void* p, AllocInfo* out) {
+    std::shared_lock<std::shared_mutex> lk(g_reg_mu);
+    if (g_registry.empty()) return false;
+    auto it = g_registry.upper_bound((uintptr_t)p);
+    if (it == g_registry.begin()) return false;
+    --it;
+    if ((uintptr_t)p >= it->first + it->second.bytes) return false;
+    if (out) *out = it->second;
+    return true;
 }
 
 }  // namespace pncu
@@ -115,9 +175,10 @@ int pncu_init(int* device_count) {
 int pncu_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     for (auto& kv : g_scratch) {
-        if (kv.second.ptr) {
+        if (kv.second.ptr || kv.second.ticket) {
             cudaSetDevice(kv.first.first);
-            cudaFree(kv.second.ptr);
+            if (kv.second.ptr) cudaFree(kv.second.ptr);
+            if (kv.second.ticket) cudaFree(kv.second.ticket);
         }
     }
     g_scratch.clear();
@@ -166,20 +227,29 @@ int pncu_itemsize(int atype) {
 
 int pncu_set_device(int device) { int rc = ensure_init(); if (rc) return rc; PNCU_CUDA(cudaSetDevice(device)); return 0; }
 int pncu_get_device(int* device) { int rc = ensure_init(); if (rc) return rc; PNCU_CUDA(cudaGetDevice(device)); return 0; }
-int pncu_malloc(void** ptr, size_t bytes) { int rc = ensure_init(); if (rc) return rc; PNCU_CUDA(cudaMalloc(ptr, bytes)); return 0; }
-int pncu_free(void* ptr) { PNCU_CUDA(cudaFree(ptr)); return 0; }
+int pncu_malloc(void** ptr, size_t bytes) {
+    int rc = ensure_init(); if (rc) return rc;
+    PNCU_CUDA(cudaMalloc(ptr, bytes));
+    int d = 0;
+    cudaGetDevice(&d);
+    registry_add(*ptr, bytes, MK_DEVICE, d);
+    return 0;
+}
+int pncu_free(void* ptr) { registry_remove(ptr); PNCU_CUDA(cudaFree(ptr)); return 0; }
 int pncu_malloc_host(void** ptr, size_t bytes) {
     int rc = ensure_init(); if (rc) return rc;
     PNCU_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    registry_add(*ptr, bytes, MK_PINNED, -1);
     return 0;
 }
-int pncu_free_host(void* ptr) { PNCU_CUDA(cudaFreeHost(ptr)); return 0; }
+int pncu_free_host(void* ptr) { registry_remove(ptr); PNCU_CUDA(cudaFreeHost(ptr)); return 0; }
 int pncu_host_register(void* ptr, size_t bytes) {
     int rc = ensure_init(); if (rc) return rc;
     PNCU_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    registry_add(ptr, bytes, MK_PINNED, -1);
     return 0;
 }
-int pncu_host_unregister(void* ptr) { PNCU_CUDA(cudaHostUnregister(ptr)); return 0; }
+int pncu_host_unregister(void* ptr) { registry_remove(ptr); PNCU_CUDA(cudaHostUnregister(ptr)); return 0; }
 int pncu_memcpy_h2d(void* dst, const void* src, size_t bytes, pncu_stream_t s) {
     PNCU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(s))); return 0;
 }
@@ -217,6 +287,11 @@ int pncu_event_elapsed_ms(pncu_event_t a, pncu_event_t b, float* ms) {
 }
 int pncu_pointer_kind(const void* ptr, int* device) {
     int rc = ensure_init(); if (rc) return -1;
+    AllocInfo ai;
+    if (registry_find(ptr, &ai)) {
+        if (device) *device = ai.device;
+        return ai.kind;
+    }
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, ptr);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -8,25 +8,30 @@
 // --------------------------------------------+---------------------------------------------------
 // 16384-element chunks dealt round-robin to   | [0, n) cut into `lanes` contiguous shards at
 // per-core channels (threads.h:319-389)       | multiples of 65536 elements; lane l -> GPU l % G
-// futex-woken worker threads (threads.cpp:164)| persistent host threads, one per extra lane, woken
-//                                             | by a condition variable; the caller runs lane 0
-//                                             | (threads.h:1143: "main thread works as core 0")
-// loop body on the chunk, in cache            | per lane: pinned staging ring -> H2D stream ->
+// futex-woken worker threads (threads.cpp:164)| persistent host threads, one per extra lane, that spin
+//                                             | for a while after a job and then sleep in a futex
+//                                             | (pool.h); the caller runs lane 0 (threads.h:1143:
+//                                             | "main thread works as core 0")
+// loop body on the chunk, in cache            | host operands: pinned staging ring -> H2D stream ->
 //                                             | compute stream (libpnumpy_cuda launcher) -> D2H
-//                                             | stream, slabs pipelined through 3 ring slots
-// partials[chunk] then the same reduce on the | block partials gathered on GPU 0 (peer copies over
-// caller thread (_pnumpy.cpp:666-700)         | NVLink), ONE finish kernel in fixed order
-// spin until BlocksCompleted (threads.h:1148) | join lanes; stream-synchronize; return
+//                                             | stream, slabs pipelined through 3 ring slots;
+//                                             | resident operands (managed / device memory): ONE
+//                                             | launch per GPU, in place, no PCIe
+// partials[chunk] then the same reduce on the | resident: ONE kernel per GPU does pass 1, pushes the
+// caller thread (_pnumpy.cpp:666-700)         | shard's block partials into GPU 0's table over NVLink
+//                                             | and GPU 0's last CTA folds the table and writes the
+//                                             | result into mapped host memory (pncu_*_fused);
+//                                             | host operands: partials gathered on GPU 0 + finish
+// spin until BlocksCompleted (threads.h:1148) | wait for the workers / the result flag; return
 // re-entrant call -> unthreaded (:1064-1073)  | try_lock fails -> NTE_DECLINED (caller's old loop)
+#include <pthread.h>
 #include <string.h>
 #include <atomic>
-#include <condition_variable>
-#include <map>
 #include <mutex>
-#include <thread>
 #include <vector>
 #include "../../../include/pnumpy_nte.h"
 #include "../atop/common.cuh"
+#include "pool.h"
 
 using namespace pncu;
 
@@ -37,9 +42,14 @@ constexpr int kMaxLanes = 16;     // the reference's hard maximum: 15 workers + 
 constexpr int64_t kAlign = 65536; // == pncu_reduce_block_elems()
 
 struct Stats {
-    std::atomic<int64_t> calls{0}, declined{0}, launches{0}, h2d{0}, d2h{0}, staged{0}, lanes_last{0}, gpus_last{0};
+    std::atomic<int64_t> calls{0}, declined{0}, launches{0}, h2d{0}, d2h{0}, staged{0}, lanes_last{0}, gpus_last{0},
+        prefetches{0};
 };
 Stats g_stats;
+
+// layout of a lane's 256-byte mapped host scratch (`h_small`) and device scratch (`d_scalar`)
+constexpr int kOffScalar1 = 0, kOffScalar2 = 16, kOffResult = 32, kOffStart = 48, kOffFlag = 64;
+constexpr int kOffArrived = 128;  // d_scalar of lane 0 only: arrival counter of the reduction exchange
 
 struct Lane {
     int device = -1;
@@ -48,30 +58,24 @@ struct Lane {
     cudaEvent_t ev_h2d[kRing], ev_k[kRing], ev_d2h[kRing];
     char* d_buf[kRing][4];   // device slabs: in1, in2, out, in3 (in3: fused chain only, allocated lazily)
     char* h_buf[kRing][4];   // pinned staging slabs (allocated lazily, pageable operands only)
+    bool slabs = false;      // device slabs allocated (host operands only need them)
     size_t slab_bytes = 0;
-    char* d_scalar = nullptr;   // 2 x 16 B for broadcast scalars
-    char* d_partials = nullptr; // reduction block partials of this lane's shard
+    char* d_scalar = nullptr;   // 256 B of device scratch (see kOff*)
+    char* d_partials = nullptr; // reduction block partials of this lane's shard (host-operand path)
     size_t partials_bytes = 0;
-    char* h_small = nullptr;    // pinned scratch for scalars / results (64 B)
+    char* h_small = nullptr;    // 256 B of MAPPED pinned scratch: scalars in, results and the completion flag out
+    uint64_t seq = 0;           // completion values handed to one-launch reductions
 };
 
 struct Job;
 typedef void (*LaneFn)(Lane&, Job&, int lane_index);
 
-struct Worker {
-    std::thread th;
-    std::mutex mu;
-    std::condition_variable cv;
-    LaneFn fn = nullptr;
-    Job* job = nullptr;
-    int lane_index = 0;
-    bool has_work = false, done = false, quit = false;
-};
-
 struct State {
     std::mutex api_mu;            // one dispatch at a time (re-entrant callers are declined)
     bool inited = false;
+    std::atomic<bool> forked{false};
     int ndev = 0;
+    bool peer_all = false;        // every GPU can store into GPU 0's memory (the reduction exchange needs it)
     int workers = 3;              // extra lanes beside the caller's (reference default futex wake count is
                                   // min(11, cores-1), threads.h:67,891-894; per-op MaxThreads caps it at 3 or 7)
     bool threading = true;
@@ -81,16 +85,30 @@ struct State {
     // (no D2H to overlap).  Measured crossovers against NumPy's single-threaded loops on float32
     // (tools/threshold_probe.py, tools/pn_benchmark.py): add 2^19 pinned / 2^21 pageable, sin 2^17-2^18 / 2^19-2^20
     // (depends on how hard the arguments are for NumPy's sin), sum 2^20 / 2^22.
+    // RESIDENT operands (managed / device memory) never see a threshold: they always run on the GPU.
     int64_t min_elems = 1 << 19;
     size_t slab_bytes = 32u << 20;  // tools/e2e_probe.py on B200: 32 MiB slabs give 75 GB/s of PCIe traffic vs 73 at 8 MiB (pinned), 43 vs 31 (pageable, 4 lanes)
+    uint64_t spin_ns = 200000;      // how long a worker spins for the next job before it sleeps
+    int64_t fault_countdown = 0;    // fault injection (tests): the n-th GPU dispatch from now fails
     Lane lanes[kMaxLanes];
-    Worker* pool[kMaxLanes] = {nullptr};
+    nte::Worker* pool[kMaxLanes] = {nullptr};
+    // reduction exchange of the resident multi-GPU path: GPU 0 is the root
+    char* x_table = nullptr;        // slot table on GPU 0
+    size_t x_table_bytes = 0;
+    unsigned long long x_expected = 0;
 };
 State g;
 
 // ---- per-call job ---------------------------------------------------------------------------------
 enum JobKind { JOB_BINARY, JOB_UNARY, JOB_REDUCE, JOB_ARG, JOB_MULADD, JOB_MULADD_SUM };
-enum PtrKind { PK_PAGEABLE = 0, PK_PINNED = 1, PK_DEVICE = 2, PK_MANAGED = 3 };
+
+struct Operand {
+    int kind = MK_UNKNOWN;
+    int device = -1;
+    std::vector<ResidencyNote>* notes = nullptr;
+    bool resident() const { return kind == MK_DEVICE || kind == MK_MANAGED; }
+    bool host() const { return kind == MK_PAGEABLE || kind == MK_PINNED; }
+};
 
 struct Job {
     JobKind kind;
@@ -104,17 +122,22 @@ struct Job {
     const char* in3 = nullptr;
     char* out = nullptr;
     int64_t len = 0;
-    int64_t s1 = 0, s2 = 0;     // input byte strides: 0 (scalar), the item size (contiguous) or anything else (gathered)
-    int64_t so = 0;             // output byte stride (0 = not set: contiguous)
+    int64_t s1 = 0, s2 = 0;     // input byte strides: 0 (scalar), the item size (contiguous) or anything else
+    int64_t so = 0;             // output byte stride
     int op_class = 0;           // NTE_CLASS_STREAM / _HEAVY / _REDUCE: scales the size threshold
-    int pk_in1 = 0, pk_in2 = 0, pk_in3 = 0, pk_out = 0;
+    Operand k1, k2, k3, ko;
     int nlanes = 1;
+    int lane_id[kMaxLanes];        // physical lane (-> GPU lane_id % G) of logical lane l
     int64_t shard[kMaxLanes + 1];  // element boundaries
     int rc[kMaxLanes];
     char err[kMaxLanes][256];
     // reductions
     int partial_bytes = 0;
     int64_t slot0[kMaxLanes + 1];  // first partial slot of each lane
+    // one-launch reductions
+    void* host_out = nullptr;
+    const void* host_start = nullptr;
+    int out_bytes = 0;
 };
 
 int fail(Job& j, int lane, int rc) {
@@ -128,15 +151,31 @@ int fail(Job& j, int lane, int rc) {
         if (_e != cudaSuccess) { cuda_fail(_e, #call, __FILE__, __LINE__); fail(j, li, (int)_e); return; } \
     } while (0)
 
-int classify(const void* p) {
+// the calling thread's current device is left as it was found (torch / cupy code in the same thread)
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+    ~DeviceGuard() { if (prev >= 0 && cudaSetDevice(prev) != cudaSuccess) cudaGetLastError(); }
+};
+
+// ---- what memory does an operand live in? ------------------------------------------------------------------
+bool lookup_registry(const void* p, Operand* o) {
+    AllocInfo ai;
+    if (!registry_find(p, &ai)) return false;
+    o->kind = ai.kind;
+    o->device = ai.device;
+    o->notes = ai.notes;
+    return true;
+}
+void classify_driver(const void* p, Operand* o) {
     cudaPointerAttributes at;
     cudaError_t e = cudaPointerGetAttributes(&at, p);
-    if (e != cudaSuccess) { cudaGetLastError(); return PK_PAGEABLE; }
+    if (e != cudaSuccess) { cudaGetLastError(); o->kind = MK_PAGEABLE; return; }
     switch (at.type) {
-        case cudaMemoryTypeHost: return PK_PINNED;
-        case cudaMemoryTypeDevice: return PK_DEVICE;
-        case cudaMemoryTypeManaged: return PK_MANAGED;
-        default: return PK_PAGEABLE;
+        case cudaMemoryTypeHost: o->kind = MK_PINNED; break;
+        case cudaMemoryTypeDevice: o->kind = MK_DEVICE; o->device = at.device; break;
+        case cudaMemoryTypeManaged: o->kind = MK_MANAGED; break;
+        default: o->kind = MK_PAGEABLE; break;
     }
 }
 
@@ -182,37 +221,49 @@ bool stride_ok(const void* p, int64_t stride, int isz) {
 }
 
 // ---- lane resources -----------------------------------------------------------------------------------
+// streams, events and the small scratch blocks: everything a RESIDENT call needs
 int ensure_lane(int li) {
     Lane& L = g.lanes[li];
+    if (L.ready) return 0;
     const int dev = li % g.ndev;
-    if (L.ready && L.slab_bytes == g.slab_bytes) return 0;
     PNCU_CUDA(cudaSetDevice(dev));
-    if (!L.ready) {
-        L.device = dev;
-        PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_h2d, cudaStreamNonBlocking));
-        PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_k, cudaStreamNonBlocking));
-        PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_d2h, cudaStreamNonBlocking));
-        for (int r = 0; r < kRing; ++r) {
-            PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_h2d[r], cudaEventDisableTiming));
-            PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_k[r], cudaEventDisableTiming));
-            PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_d2h[r], cudaEventDisableTiming));
-            for (int k = 0; k < 4; ++k) { L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr; }
-        }
-        PNCU_CUDA(cudaMalloc((void**)&L.d_scalar, 64));
-        PNCU_CUDA(cudaHostAlloc((void**)&L.h_small, 64, cudaHostAllocPortable));
-    } else {
-        for (int r = 0; r < kRing; ++r)
-            for (int k = 0; k < 4; ++k) {
-                if (L.d_buf[r][k]) cudaFree(L.d_buf[r][k]);
-                if (L.h_buf[r][k]) cudaFreeHost(L.h_buf[r][k]);
-                L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr;
-            }
+    L.device = dev;
+    PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_h2d, cudaStreamNonBlocking));
+    PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_k, cudaStreamNonBlocking));
+    PNCU_CUDA(cudaStreamCreateWithFlags(&L.s_d2h, cudaStreamNonBlocking));
+    for (int r = 0; r < kRing; ++r) {
+        PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_h2d[r], cudaEventDisableTiming));
+        PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_k[r], cudaEventDisableTiming));
+        PNCU_CUDA(cudaEventCreateWithFlags(&L.ev_d2h[r], cudaEventDisableTiming));
+        for (int k = 0; k < 4; ++k) { L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr; }
     }
+    PNCU_CUDA(cudaMalloc((void**)&L.d_scalar, 256));
+    PNCU_CUDA(cudaMemset(L.d_scalar, 0, 256));
+    PNCU_CUDA(cudaHostAlloc((void**)&L.h_small, 256, cudaHostAllocPortable | cudaHostAllocMapped));
+    memset(L.h_small, 0, 256);
+    L.ready = true;
+    return 0;
+}
+
+// + the device slabs of the staging ring: host operands only
+int ensure_slabs(int li) {
+    int rc = ensure_lane(li);
+    if (rc) return rc;
+    Lane& L = g.lanes[li];
+    if (L.slabs && L.slab_bytes == g.slab_bytes) return 0;
+    PNCU_CUDA(cudaSetDevice(L.device));
+    for (int r = 0; r < kRing; ++r)
+        for (int k = 0; k < 4; ++k) {
+            if (L.d_buf[r][k]) cudaFree(L.d_buf[r][k]);
+            if (L.h_buf[r][k]) cudaFreeHost(L.h_buf[r][k]);
+            L.d_buf[r][k] = nullptr; L.h_buf[r][k] = nullptr;
+        }
+    L.slabs = false;
     // device slabs now; pinned slabs lazily (only pageable operands need them)
     for (int r = 0; r < kRing; ++r)
         for (int k = 0; k < 3; ++k) PNCU_CUDA(cudaMalloc((void**)&L.d_buf[r][k], g.slab_bytes));
     L.slab_bytes = g.slab_bytes;
-    L.ready = true;
+    L.slabs = true;
     return 0;
 }
 
@@ -239,9 +290,161 @@ int ensure_partials(Lane& L, size_t bytes) {
     return 0;
 }
 
-int64_t slab_elems_for(size_t slab_bytes, int64_t wide, int64_t shard_elems, bool staged);
+// a host scalar operand (NumPy's `a + 5.0`): one tiny copy on the compute stream; returns the device address
+int stage_scalar(Lane& L, const char* host, int isz, int which, const char** dptr) {
+    const int off = which == 0 ? kOffScalar1 : kOffScalar2;
+    memcpy(L.h_small + off, host, isz);
+    PNCU_CUDA(cudaMemcpyAsync(L.d_scalar + off, L.h_small + off, isz, cudaMemcpyHostToDevice, L.s_k));
+    *dptr = L.d_scalar + off;
+    return 0;
+}
 
-// ---- one lane of an element-wise job: slabs through the H2D -> kernel -> D2H pipeline --------------------
+// ---- managed operands: where do the pages live? ------------------------------------------------------------
+// A kernel that touches managed pages which are not resident on its GPU demand-faults them over PCIe at a
+// fraction of the copy rate, so a managed range is prefetched to the GPU that is about to use it.  Prefetching
+// a range that is already there still costs ~1 ms of driver time per GiB (page-table walk), 5x the kernel it
+// precedes.  So a range is prefetched the FIRST time it is seen in a given placement and trusted afterwards
+// (the note lives with the allocation in the registry); if host code touched some pages in between, the kernel
+// faults those back (correct, slower, and then they are resident again).
+std::mutex g_note_mu;
+
+// `where`: GPU index for a whole range; 100 + G with `piece` for "sharded over G GPUs in pieces of `piece` bytes"
+bool note_hit(const Operand& o, const char* lo, size_t bytes, int where, size_t piece) {
+    if (!o.notes) return false;
+    for (const ResidencyNote& n : *o.notes)
+        if (n.where == where && n.piece == piece && n.lo <= lo && lo + bytes <= n.lo + n.bytes &&
+            (where < 100 || (n.lo == lo && n.bytes == bytes)))
+            return true;
+    return false;
+}
+void note_set(const Operand& o, const char* lo, size_t bytes, int where, size_t piece) {
+    if (!o.notes) return;
+    std::vector<ResidencyNote>& v = *o.notes;
+    for (size_t i = 0; i < v.size();) {   // whatever was recorded for overlapping bytes is stale now
+        if (v[i].lo < lo + bytes && lo < v[i].lo + v[i].bytes) { v[i] = v.back(); v.pop_back(); }
+        else ++i;
+    }
+    if (v.size() >= 32) v.clear();
+    ResidencyNote n = {lo, bytes, where, piece};
+    v.push_back(n);
+}
+// the GPU a managed range was last placed on as a whole (0 when unknown)
+int home_of(const Operand& o, const char* lo, size_t bytes) {
+    if (o.kind == MK_DEVICE && o.device >= 0 && o.device < g.ndev) return o.device;
+    if (o.notes) {
+        std::lock_guard<std::mutex> lk(g_note_mu);
+        for (const ResidencyNote& n : *o.notes)
+            if (n.where < 100 && n.where < g.ndev && n.lo <= lo && lo + bytes <= n.lo + n.bytes) return n.where;
+    }
+    return 0;
+}
+// make [lo, lo + bytes) of a managed operand resident on lane L's GPU (no-op for device memory / known placement)
+int place_whole(const Operand& o, const char* lo, size_t bytes, Lane& L) {
+    if (o.kind != MK_MANAGED || !bytes) return 0;
+    std::lock_guard<std::mutex> lk(g_note_mu);
+    if (note_hit(o, lo, bytes, L.device, 0)) return 0;
+    PNCU_CUDA(cudaSetDevice(L.device));
+    PNCU_CUDA(cudaMemPrefetchAsync(lo, bytes, L.device, L.s_k));
+    g_stats.prefetches += 1;
+    note_set(o, lo, bytes, L.device, 0);
+    return 0;
+}
+
+// ---- shard plans ----------------------------------------------------------------------------------------
+// `lanes` contiguous shards at multiples of 65536 elements, as even as the unit allows (no empty shard)
+void cut_shards(Job& j, int lanes) {
+    const int64_t units = (j.len + kAlign - 1) / kAlign;
+    if (lanes > units) lanes = (int)units;
+    if (lanes < 1) lanes = 1;
+    j.nlanes = lanes;
+    const int64_t base = units / lanes, extra = units % lanes;
+    int64_t u = 0;
+    for (int l = 0; l <= lanes; ++l) {
+        const int64_t e = u * kAlign;
+        j.shard[l] = e < j.len ? e : j.len;
+        u += base + (l < extra ? 1 : 0);
+    }
+    j.shard[lanes] = j.len;
+    for (int l = 0; l < lanes; ++l) { j.rc[l] = 0; j.err[l][0] = 0; j.lane_id[l] = l; }
+}
+
+// lanes for a call on HOST operands: min(op_max_workers, workers) + 1, never more than one per 65536-element unit
+int plan(Job& j, int max_workers) {
+    int lanes = 1;
+    if (g.threading) {
+        int extra = max_workers < g.workers ? max_workers : g.workers;
+        if (extra < 0) extra = 0;
+        lanes = extra + 1;
+    }
+    if (lanes > kMaxLanes) lanes = kMaxLanes;
+    cut_shards(j, lanes);
+    g_stats.lanes_last = j.nlanes;
+    g_stats.gpus_last = j.nlanes < g.ndev ? j.nlanes : g.ndev;
+    for (int l = 0; l < j.nlanes; ++l) {
+        int rc = ensure_slabs(l);
+        if (rc) return rc;
+    }
+    return 0;
+}
+// one lane, on the GPU that owns a device-memory operand
+int plan_on_device(Job& j, int dev, bool slabs) {
+    cut_shards(j, 1);
+    j.lane_id[0] = dev;
+    g_stats.lanes_last = 1;
+    g_stats.gpus_last = 1;
+    return slabs ? ensure_slabs(dev) : ensure_lane(dev);
+}
+// resident operands: one lane per GPU
+int plan_one_lane_per_gpu(Job& j) {
+    cut_shards(j, g.ndev);
+    for (int l = 0; l < j.nlanes; ++l) {
+        int rc = ensure_lane(l);
+        if (rc) return rc;
+    }
+    g_stats.lanes_last = j.nlanes;
+    g_stats.gpus_last = j.nlanes;
+    return 0;
+}
+
+int first_error(Job& j) {
+    for (int l = 0; l < j.nlanes; ++l)
+        if (j.rc[l]) { set_error("lane %d (GPU %d): %s", l, g.lanes[j.lane_id[l]].device, j.err[l]); return j.rc[l]; }
+    return 0;
+}
+
+int decline() { g_stats.declined += 1; return NTE_DECLINED; }
+
+// the size below which the caller's own loop is faster (see State::min_elems).  The base is stated in 4-byte
+// elements and applied to BYTES of the widest operand: NumPy's loops run at a byte rate, not an element rate (an int8
+// add of 2^20 elements is 1 MiB per operand and over in 30 us).  1-byte types get another x3: their NumPy loops stay
+// in cache and vectorise 32 lanes wide (pn.benchmark() on the B200 box: int8 a+b breaks even near 6 MiB per operand,
+// int16 / float32 near 2 MiB).
+int64_t threshold_for(int op_class, bool any_pageable, int wide_itemsize = 4) {
+    int64_t bytes = g.min_elems * 4;
+    if (any_pageable) bytes *= 4;
+    if (op_class == NTE_CLASS_HEAVY) bytes /= 2;
+    if (op_class == NTE_CLASS_REDUCE) bytes *= 2;
+    if (wide_itemsize == 1) bytes *= 3;
+    if (wide_itemsize < 1) wide_itemsize = 1;
+    return bytes / wide_itemsize;   // in elements of the widest operand
+}
+int64_t lowest_threshold() { return threshold_for(NTE_CLASS_HEAVY, false, 8); }
+
+// slab length for a shard of `shard_elems`: big shards use the full slab; when an operand has to be STAGED (pageable
+// or strided: a host-side copy per slab) smaller shards are cut in up to four slabs of at least 2 MiB so that the
+// staging copy of slab i+1 overlaps the DMA and kernel of slab i (pageable sum at 2^24 float32: 2.9 -> 1.9 ms)
+int64_t slab_elems_for(size_t slab_bytes, int64_t wide, int64_t shard_elems, bool staged) {
+    const int64_t full = ((int64_t)(slab_bytes / wide) / kAlign) * kAlign;
+    if (!staged) return full;  // pinned operands are DMA'd in place: fewer, larger transfers win (measured)
+    int64_t quarter = (((shard_elems + 3) / 4 + kAlign - 1) / kAlign) * kAlign;
+    int64_t floor_e = ((((int64_t)2 << 20) / wide + kAlign - 1) / kAlign) * kAlign;
+    int64_t e = quarter > floor_e ? quarter : floor_e;
+    return e < full ? e : full;
+}
+
+// ---- one lane of an element-wise job with at least one HOST operand -----------------------------------------
+// Host operands go slab by slab through the H2D -> kernel -> D2H pipeline; operands that are RESIDENT (managed or
+// device memory next to host arrays) are used in place by the same kernels and cross no bus.
 void lane_elementwise(Lane& L, Job& j, int li) {
     if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
     const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
@@ -249,34 +452,48 @@ void lane_elementwise(Lane& L, Job& j, int li) {
     const bool binary = j.kind == JOB_BINARY;
     const int64_t wide = j.isz_in > j.isz_out ? j.isz_in : j.isz_out;
     const bool vec1 = j.s1 != 0, vec2 = binary && j.s2 != 0;
+    const bool res1 = j.k1.resident(), res2 = binary && j.k2.resident(), reso = j.ko.resident();
+    // the same array twice (np.multiply(a, a); reference: in1 == in2 loads once, src/atop/ops_binary.cpp:631-658)
+    const bool same12 = vec1 && vec2 && !res1 && j.in1 == j.in2 && j.s1 == j.s2;
     const bool out_strided = j.so != j.isz_out;
-    const bool stage_out = j.pk_out == PK_PAGEABLE || out_strided;
-    const bool stage_in = (vec1 && (j.pk_in1 == PK_PAGEABLE || j.s1 != j.isz_in)) || (vec2 && (j.pk_in2 == PK_PAGEABLE || j.s2 != j.isz_in));
+    const bool stage_out = !reso && (j.ko.kind == MK_PAGEABLE || out_strided);
+    const bool stage_in = (vec1 && !res1 && (j.k1.kind == MK_PAGEABLE || j.s1 != j.isz_in)) ||
+                          (vec2 && !res2 && !same12 && (j.k2.kind == MK_PAGEABLE || j.s2 != j.isz_in));
     const int64_t slab_elems = slab_elems_for(L.slab_bytes, wide, e1 - e0, stage_in || stage_out);
     const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
+    int rc;
 
-    // broadcast scalars: one tiny copy per call
-    const char* d_s1 = nullptr;
-    const char* d_s2 = nullptr;
-    if (!vec1) {
-        memcpy(L.h_small, j.in1, j.isz_in);
-        LCUDA(cudaMemcpyAsync(L.d_scalar, L.h_small, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
-        d_s1 = L.d_scalar;
-    }
-    if (binary && !vec2) {
-        memcpy(L.h_small + 16, j.in2, j.isz_in);
-        LCUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
-        d_s2 = L.d_scalar + 16;
+    // broadcast scalars: one tiny copy per call (a resident scalar is read in place)
+    const char* d_s1 = j.in1;
+    const char* d_s2 = j.in2;
+    if (!vec1 && !res1 && (rc = stage_scalar(L, j.in1, j.isz_in, 0, &d_s1))) { fail(j, li, rc); return; }
+    if (binary && !vec2 && !res2 && (rc = stage_scalar(L, j.in2, j.isz_in, 1, &d_s2))) { fail(j, li, rc); return; }
+    // resident array operands: this lane's shard onto this lane's GPU
+    {
+        const char* lo;
+        int64_t bytes;
+        if (vec1 && res1) {
+            extent_of(j.in1 + e0 * j.s1, e1 - e0, j.s1, j.isz_in, &lo, &bytes);
+            if ((rc = place_whole(j.k1, lo, (size_t)bytes, L))) { fail(j, li, rc); return; }
+        }
+        if (vec2 && res2) {
+            extent_of(j.in2 + e0 * j.s2, e1 - e0, j.s2, j.isz_in, &lo, &bytes);
+            if ((rc = place_whole(j.k2, lo, (size_t)bytes, L))) { fail(j, li, rc); return; }
+        }
+        if (reso) {
+            extent_of(j.out + e0 * j.so, e1 - e0, j.so, j.isz_out, &lo, &bytes);
+            if ((rc = place_whole(j.ko, lo, (size_t)bytes, L))) { fail(j, li, rc); return; }
+        }
     }
 
     auto slab_range = [&](int64_t i, int64_t* off, int64_t* cnt) {
         *off = e0 + i * slab_elems;
         *cnt = (e1 - *off) < slab_elems ? (e1 - *off) : slab_elems;
     };
-    auto retire = [&](int64_t i) -> int {  // slab i's result is on the host once ev_d2h fires
+    auto retire = [&](int64_t i) -> int {  // slab i's result is where it belongs once its last event fires
         const int r = (int)(i % kRing);
-        cudaError_t e = cudaEventSynchronize(L.ev_d2h[r]);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(d2h)", __FILE__, __LINE__);
+        cudaError_t e = cudaEventSynchronize(reso ? L.ev_k[r] : L.ev_d2h[r]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(slab)", __FILE__, __LINE__);
         if (stage_out) {
             int64_t off, cnt;
             slab_range(i, &off, &cnt);
@@ -289,18 +506,17 @@ void lane_elementwise(Lane& L, Job& j, int li) {
 
     for (int64_t i = 0; i < nslabs; ++i) {
         const int r = (int)(i % kRing);
-        int rc;
         if (i >= kRing && (rc = retire(i - kRing))) { fail(j, li, rc); return; }
         int64_t off, cnt;
         slab_range(i, &off, &cnt);
         const size_t in_bytes = (size_t)(cnt * j.isz_in), out_bytes = (size_t)(cnt * j.isz_out);
-        // ---- inputs -> device slab
+        // ---- host inputs -> device slab
         for (int k = 0; k < 2; ++k) {
-            if (k == 0 ? !vec1 : !vec2) continue;
+            if (k == 0 ? (!vec1 || res1) : (!vec2 || res2 || same12)) continue;
             const int64_t stride = k == 0 ? j.s1 : j.s2;
             const char* src = (k == 0 ? j.in1 : j.in2) + off * stride;
-            const int pk = k == 0 ? j.pk_in1 : j.pk_in2;
-            if (pk == PK_PAGEABLE || stride != j.isz_in) {
+            const int pk = k == 0 ? j.k1.kind : j.k2.kind;
+            if (pk == MK_PAGEABLE || stride != j.isz_in) {
                 if ((rc = ensure_pinned_slab(L, r, k))) { fail(j, li, rc); return; }
                 if (stride != j.isz_in) gather(L.h_buf[r][k], src, cnt, stride, j.isz_in);
                 else memcpy(L.h_buf[r][k], src, in_bytes);
@@ -313,18 +529,25 @@ void lane_elementwise(Lane& L, Job& j, int li) {
         LCUDA(cudaEventRecord(L.ev_h2d[r], L.s_h2d));
         LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_h2d[r], 0));
         // ---- kernel
-        if (binary)
-            rc = j.fn2(vec1 ? L.d_buf[r][0] : d_s1, vec2 ? L.d_buf[r][1] : d_s2, L.d_buf[r][2], cnt,
-                       vec1 ? j.isz_in : 0, vec2 ? j.isz_in : 0, j.isz_out, (pncu_stream_t)L.s_k);
-        else
-            rc = j.fn1(L.d_buf[r][0], L.d_buf[r][2], cnt, j.isz_in, j.isz_out, (pncu_stream_t)L.s_k);
+        const char* p1 = !vec1 ? d_s1 : (res1 ? j.in1 + off * j.s1 : L.d_buf[r][0]);
+        const int64_t st1 = !vec1 ? 0 : (res1 ? j.s1 : j.isz_in);
+        char* po = reso ? j.out + off * j.so : L.d_buf[r][2];
+        const int64_t sto = reso ? j.so : j.isz_out;
+        if (binary) {
+            const char* p2 = !vec2 ? d_s2 : (res2 ? j.in2 + off * j.s2 : (same12 ? L.d_buf[r][0] : L.d_buf[r][1]));
+            const int64_t st2 = !vec2 ? 0 : (res2 ? j.s2 : j.isz_in);
+            rc = j.fn2(p1, p2, po, cnt, st1, st2, sto, (pncu_stream_t)L.s_k);
+        } else {
+            rc = j.fn1(p1, po, cnt, st1, sto, (pncu_stream_t)L.s_k);
+        }
         if (rc) { fail(j, li, rc); return; }
         g_stats.launches += 1;
         LCUDA(cudaEventRecord(L.ev_k[r], L.s_k));
-        LCUDA(cudaStreamWaitEvent(L.s_d2h, L.ev_k[r], 0));
         // the next H2D into this slot must not overtake this kernel's reads
         LCUDA(cudaStreamWaitEvent(L.s_h2d, L.ev_k[r], 0));
+        if (reso) continue;
         // ---- result -> host
+        LCUDA(cudaStreamWaitEvent(L.s_d2h, L.ev_k[r], 0));
         char* dst = j.out + off * j.isz_out;
         if (stage_out) {
             if ((rc = ensure_pinned_slab(L, r, 2))) { fail(j, li, rc); return; }
@@ -337,12 +560,11 @@ void lane_elementwise(Lane& L, Job& j, int li) {
         LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_d2h[r], 0));
     }
     for (int64_t i = nslabs > kRing ? nslabs - kRing : 0; i < nslabs; ++i) {
-        int rc = retire(i);
-        if (rc) { fail(j, li, rc); return; }
+        if ((rc = retire(i))) { fail(j, li, rc); return; }
     }
 }
 
-// ---- one lane of a reduction / arg-reduction: slabs H2D -> pass-1 partials on this lane's GPU ------------
+// ---- one lane of a reduction / arg-reduction over a HOST array: slabs H2D -> pass-1 partials on this lane's GPU
 void lane_reduce(Lane& L, Job& j, int li) {
     if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
     const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
@@ -350,7 +572,8 @@ void lane_reduce(Lane& L, Job& j, int li) {
     const int64_t nslots = j.slot0[li + 1] - j.slot0[li];
     int rc;
     if ((rc = ensure_partials(L, (size_t)nslots * j.partial_bytes))) { fail(j, li, rc); return; }
-    const int64_t slab_elems = slab_elems_for(L.slab_bytes, j.isz_in, e1 - e0, j.pk_in1 == PK_PAGEABLE || j.s1 != j.isz_in);
+    const bool staged = j.k1.kind == MK_PAGEABLE || j.s1 != j.isz_in;
+    const int64_t slab_elems = slab_elems_for(L.slab_bytes, j.isz_in, e1 - e0, staged);
     const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
     for (int64_t i = 0; i < nslabs; ++i) {
         const int r = (int)(i % kRing);
@@ -362,7 +585,7 @@ void lane_reduce(Lane& L, Job& j, int li) {
             cudaError_t e = cudaEventSynchronize(L.ev_k[r]);
             if (e != cudaSuccess) { cuda_fail(e, "cudaEventSynchronize(k)", __FILE__, __LINE__); fail(j, li, (int)e); return; }
         }
-        if (j.pk_in1 == PK_PAGEABLE || j.s1 != j.isz_in) {
+        if (staged) {
             if ((rc = ensure_pinned_slab(L, r, 0))) { fail(j, li, rc); return; }
             if (j.s1 != j.isz_in) gather(L.h_buf[r][0], src, cnt, j.s1, j.isz_in);
             else memcpy(L.h_buf[r][0], src, in_bytes);
@@ -388,7 +611,7 @@ void lane_reduce(Lane& L, Job& j, int li) {
     if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__); fail(j, li, (int)e); }
 }
 
-// ---- one lane of the fused chain: three input slabs -> a*b+c (-> D2H) or -> block partials of its sum ------
+// ---- one lane of the fused chain over HOST arrays: three input slabs -> a*b+c (-> D2H) or -> block partials of its sum
 void lane_fused(Lane& L, Job& j, int li) {
     if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
     const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
@@ -398,12 +621,12 @@ void lane_fused(Lane& L, Job& j, int li) {
     int rc;
     if ((rc = ensure_third_input(L))) { fail(j, li, rc); return; }
     if (to_sum && (rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
+    const bool out_pageable = !to_sum && j.ko.kind == MK_PAGEABLE;
     const int64_t slab_elems = slab_elems_for(L.slab_bytes, isz, e1 - e0,
-                                              j.pk_in1 == PK_PAGEABLE || j.pk_in2 == PK_PAGEABLE || j.pk_in3 == PK_PAGEABLE ||
-                                                  (!to_sum && j.pk_out == PK_PAGEABLE));
+                                              j.k1.kind == MK_PAGEABLE || j.k2.kind == MK_PAGEABLE || j.k3.kind == MK_PAGEABLE || out_pageable);
     const int64_t nslabs = (e1 - e0 + slab_elems - 1) / slab_elems;
     const char* ins[3] = {j.in1, j.in2, j.in3};
-    const int pks[3] = {j.pk_in1, j.pk_in2, j.pk_in3};
+    const int pks[3] = {j.k1.kind, j.k2.kind, j.k3.kind};
     const int slot_of[3] = {0, 1, 3};  // d_buf / h_buf index of each input (2 is `out`)
 
     auto slab_range = [&](int64_t i, int64_t* off, int64_t* cnt) {
@@ -416,7 +639,7 @@ void lane_fused(Lane& L, Job& j, int li) {
         const int r = (int)(i % kRing);
         cudaError_t e = cudaEventSynchronize(to_sum ? L.ev_k[r] : L.ev_d2h[r]);
         if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(fused)", __FILE__, __LINE__);
-        if (!to_sum && j.pk_out == PK_PAGEABLE) {
+        if (out_pageable) {
             int64_t off, cnt;
             slab_range(i, &off, &cnt);
             memcpy(j.out + off * isz, L.h_buf[r][2], (size_t)(cnt * isz));
@@ -431,9 +654,16 @@ void lane_fused(Lane& L, Job& j, int li) {
         int64_t off, cnt;
         slab_range(i, &off, &cnt);
         const size_t bytes = (size_t)(cnt * isz);
+        int dslot[3];
         for (int k = 0; k < 3; ++k) {
+            // an operand passed twice (a*a + c) is uploaded once
+            dslot[k] = slot_of[k];
+            bool dup = false;
+            for (int q = 0; q < k; ++q)
+                if (ins[q] == ins[k]) { dslot[k] = dslot[q]; dup = true; break; }
+            if (dup) continue;
             const char* src = ins[k] + off * isz;
-            if (pks[k] == PK_PAGEABLE) {
+            if (pks[k] == MK_PAGEABLE) {
                 if ((rc = ensure_pinned_slab(L, r, slot_of[k]))) { fail(j, li, rc); return; }
                 memcpy(L.h_buf[r][slot_of[k]], src, bytes);
                 g_stats.staged += bytes;
@@ -446,10 +676,10 @@ void lane_fused(Lane& L, Job& j, int li) {
         LCUDA(cudaStreamWaitEvent(L.s_k, L.ev_h2d[r], 0));
         if (to_sum) {
             const int64_t slot = pncu_reduce_partial_count(j.atype, off - e0);
-            rc = pncu_muladd_sum_partials(j.atype, L.d_buf[r][0], L.d_buf[r][1], L.d_buf[r][3], cnt,
+            rc = pncu_muladd_sum_partials(j.atype, L.d_buf[r][dslot[0]], L.d_buf[r][dslot[1]], L.d_buf[r][dslot[2]], cnt,
                                           L.d_partials + slot * j.partial_bytes, (pncu_stream_t)L.s_k);
         } else {
-            rc = j.fn3(L.d_buf[r][0], L.d_buf[r][1], L.d_buf[r][3], L.d_buf[r][2], cnt, (pncu_stream_t)L.s_k);
+            rc = j.fn3(L.d_buf[r][dslot[0]], L.d_buf[r][dslot[1]], L.d_buf[r][dslot[2]], L.d_buf[r][2], cnt, (pncu_stream_t)L.s_k);
         }
         if (rc) { fail(j, li, rc); return; }
         g_stats.launches += 1;
@@ -458,7 +688,7 @@ void lane_fused(Lane& L, Job& j, int li) {
         if (!to_sum) {
             LCUDA(cudaStreamWaitEvent(L.s_d2h, L.ev_k[r], 0));
             char* dst = j.out + off * isz;
-            if (j.pk_out == PK_PAGEABLE) {
+            if (out_pageable) {
                 if ((rc = ensure_pinned_slab(L, r, 2))) { fail(j, li, rc); return; }
                 dst = L.h_buf[r][2];
             }
@@ -478,323 +708,308 @@ void lane_fused(Lane& L, Job& j, int li) {
 }
 
 // ---- worker pool -----------------------------------------------------------------------------------------
-void worker_main(Worker* w) {
-    std::unique_lock<std::mutex> lk(w->mu);
-    for (;;) {
-        w->cv.wait(lk, [&] { return w->has_work || w->quit; });
-        if (w->quit) return;
-        w->has_work = false;
-        lk.unlock();
-        w->fn(g.lanes[w->lane_index], *w->job, w->lane_index);
-        lk.lock();
-        w->done = true;
-        w->cv.notify_all();
-    }
+struct Post { Job* job; LaneFn fn; int logical; };
+Post g_post[kMaxLanes];
+
+void worker_thunk(void* ctx, int physical_lane) {
+    Post* p = (Post*)ctx;
+    p->fn(g.lanes[physical_lane], *p->job, p->logical);
 }
 
+// one wake, one wait (WorkMain, src/atop/threads.h:1079-1168): post every other lane to its worker, run lane 0
+// on the calling thread, then wait for the workers
 void run_lanes(Job& j, LaneFn fn) {
-    for (int li = 1; li < j.nlanes; ++li) {
-        Worker*& w = g.pool[li];
+    for (int l = 1; l < j.nlanes; ++l) {
+        const int p = j.lane_id[l];
+        nte::Worker*& w = g.pool[p];
         if (!w) {
-            w = new Worker();
-            w->th = std::thread(worker_main, w);
+            w = new nte::Worker();
+            w->start(p, g.spin_ns);
         }
-        std::lock_guard<std::mutex> lk(w->mu);
-        w->fn = fn; w->job = &j; w->lane_index = li; w->done = false; w->has_work = true;
-        w->cv.notify_all();
+        g_post[p].job = &j; g_post[p].fn = fn; g_post[p].logical = l;
+        w->post(worker_thunk, &g_post[p]);
     }
-    fn(g.lanes[0], j, 0);  // the caller is lane 0
-    for (int li = 1; li < j.nlanes; ++li) {
-        Worker* w = g.pool[li];
-        std::unique_lock<std::mutex> lk(w->mu);
-        w->cv.wait(lk, [&] { return w->done; });
-    }
+    fn(g.lanes[j.lane_id[0]], j, 0);  // the caller is lane 0
+    for (int l = 1; l < j.nlanes; ++l) g.pool[j.lane_id[l]]->wait();
 }
 
-// the size below which the caller's own loop is faster (see State::min_elems).  The base is stated in 4-byte
-// elements and applied to BYTES of the widest operand: NumPy's loops run at a byte rate, not an element rate (an int8
-// add of 2^20 elements is 1 MiB per operand and over in 30 us).  1-byte types get another x3: their NumPy loops stay
-// in cache and vectorise 32 lanes wide (pn.benchmark() on the B200 box: int8 a+b breaks even near 6 MiB per operand,
-// int16 / float32 near 2 MiB).
-int64_t threshold_for(int op_class, bool any_pageable, int wide_itemsize = 4) {
-    int64_t bytes = g.min_elems * 4;
-    if (any_pageable) bytes *= 4;
-    if (op_class == NTE_CLASS_HEAVY) bytes /= 2;
-    if (op_class == NTE_CLASS_REDUCE) bytes *= 2;
-    if (wide_itemsize == 1) bytes *= 3;
-    if (wide_itemsize < 1) wide_itemsize = 1;
-    return bytes / wide_itemsize;   // in elements of the widest operand
-}
-// slab length for a shard of `shard_elems`: big shards use the full slab; when an operand has to be STAGED (pageable
-// or strided: a host-side copy per slab) smaller shards are cut in up to four slabs of at least 2 MiB so that the
-// staging copy of slab i+1 overlaps the DMA and kernel of slab i (pageable sum at 2^24 float32: 2.9 -> 1.9 ms)
-int64_t slab_elems_for(size_t slab_bytes, int64_t wide, int64_t shard_elems, bool staged) {
-    const int64_t full = ((int64_t)(slab_bytes / wide) / kAlign) * kAlign;
-    if (!staged) return full;  // pinned operands are DMA'd in place: fewer, larger transfers win (measured)
-    int64_t quarter = (((shard_elems + 3) / 4 + kAlign - 1) / kAlign) * kAlign;
-    int64_t floor_e = ((((int64_t)2 << 20) / wide + kAlign - 1) / kAlign) * kAlign;
-    int64_t e = quarter > floor_e ? quarter : floor_e;
-    return e < full ? e : full;
-}
-
-// lanes for a call: min(op_max_workers, workers) + 1, never more than one per 65536-element unit
-int plan(Job& j, int max_workers) {
-    int lanes = 1;
-    if (g.threading) {
-        int extra = max_workers < g.workers ? max_workers : g.workers;
-        if (extra < 0) extra = 0;
-        lanes = extra + 1;
-    }
-    if (lanes > kMaxLanes) lanes = kMaxLanes;
-    const int64_t units = (j.len + kAlign - 1) / kAlign;
-    if (lanes > units) lanes = (int)units;
-    if (lanes < 1) lanes = 1;
-    j.nlanes = lanes;
-    const int64_t per = (units + lanes - 1) / lanes;
-    for (int l = 0; l <= lanes; ++l) {
-        int64_t e = (int64_t)l * per * kAlign;
-        j.shard[l] = e < j.len ? e : j.len;
-    }
-    for (int l = 0; l < lanes; ++l) { j.rc[l] = 0; j.err[l][0] = 0; }
-    int gpus = lanes < g.ndev ? lanes : g.ndev;
-    g_stats.lanes_last = lanes;
-    g_stats.gpus_last = gpus;
-    for (int l = 0; l < lanes; ++l) {
-        int rc = ensure_lane(l);
-        if (rc) return rc;
-    }
-    return 0;
-}
-
-int first_error(Job& j) {
-    for (int l = 0; l < j.nlanes; ++l)
-        if (j.rc[l]) { set_error("lane %d (GPU %d): %s", l, g.lanes[l].device, j.err[l]); return j.rc[l]; }
-    return 0;
-}
-
-int decline() { g_stats.declined += 1; return NTE_DECLINED; }
-
-bool host_kind(int pk) { return pk == PK_PAGEABLE || pk == PK_PINNED; }
-
-// operands that already live in device / managed memory: run in place on that GPU, no PCIe
-// the GPU a resident pointer belongs to (managed memory: wherever it was last prefetched, else GPU 0)
-int device_of(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.device >= 0 && at.device < g.ndev) return at.device;
-    cudaGetLastError();
-    return 0;
-}
-
-// managed operands: make the pages resident on the GPU before the kernel touches them, otherwise the
-// kernel demand-faults them over PCIe at a fraction of the copy rate.  A no-op once they are there.
-// Prefetching a range that is already resident still costs ~1 ms of driver time per GiB (page-table
-// walk), 5x the kernel it precedes.  So a range is prefetched the FIRST time it is seen on a GPU and
-// trusted afterwards; if host code touched some pages in between, the kernel demand-faults those back
-// (correct, slower, and then they are resident again).  Guarded by g.api_mu (held by every dispatch).
-std::map<const void*, size_t> g_prefetched[kMaxLanes];
-std::mutex g_prefetch_mu;  // the lanes of a sharded resident call prefetch concurrently
-std::map<const void*, size_t> g_managed_allocs;  // blocks handed out by nte_alloc_managed
-
-int prefetch_managed(const void* p, int pk, size_t bytes, Lane& L) {
-    if (pk != PK_MANAGED || !bytes) return 0;
-    std::lock_guard<std::mutex> lk(g_prefetch_mu);
-    std::map<const void*, size_t>& seen = g_prefetched[L.device];
-    auto it = seen.find(p);
-    if (it != seen.end() && it->second >= bytes) return 0;
-    PNCU_CUDA(cudaMemPrefetchAsync(p, bytes, L.device, L.s_k));
-    if (seen.size() > 4096) seen.clear();
-    seen[p] = bytes;
-    // the pages leave whichever GPU had them: drop the other devices' records that overlap the range
-    for (int d = 0; d < kMaxLanes; ++d) {
-        if (d == L.device) continue;
-        std::map<const void*, size_t>& other = g_prefetched[d];
-        for (auto o = other.begin(); o != other.end();) {
-            const char* lo = (const char*)o->first;
-            if (lo < (const char*)p + bytes && (const char*)p < lo + o->second) o = other.erase(o);
-            else ++o;
-        }
-    }
-    return 0;
-}
-
-void forget_prefetched(const void* lo, size_t bytes) {
-    std::lock_guard<std::mutex> lk(g_prefetch_mu);
-    for (int d = 0; d < kMaxLanes; ++d) {
-        std::map<const void*, size_t>& seen = g_prefetched[d];
-        for (auto it = seen.lower_bound(lo); it != seen.end() && (const char*)it->first < (const char*)lo + bytes;) it = seen.erase(it);
-    }
-}
-
-int run_resident(Job& j) {
-    const int dev = device_of(j.out);
-    int rc = ensure_lane(dev);
-    if (rc) return rc;
-    g_stats.lanes_last = 1;
-    g_stats.gpus_last = 1;
-    Lane& L = g.lanes[dev];
-    PNCU_CUDA(cudaSetDevice(L.device));
-    const bool binary = j.kind == JOB_BINARY;
-    const char* in1 = j.in1;
-    const char* in2 = j.in2;
-    // a host scalar (NumPy's `a + 5.0`) next to resident arrays: one 8-byte copy
-    if (j.s1 == 0 && host_kind(j.pk_in1)) {
-        memcpy(L.h_small, j.in1, j.isz_in);
-        PNCU_CUDA(cudaMemcpyAsync(L.d_scalar, L.h_small, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
-        in1 = L.d_scalar;
-    }
-    if (binary && j.s2 == 0 && host_kind(j.pk_in2)) {
-        memcpy(L.h_small + 16, j.in2, j.isz_in);
-        PNCU_CUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
-        in2 = L.d_scalar + 16;
-    }
-    const char* lo;
-    int64_t bytes;
-    if (j.s1) {
-        extent_of(j.in1, j.len, j.s1, j.isz_in, &lo, &bytes);
-        if ((rc = prefetch_managed(lo, j.pk_in1, (size_t)bytes, L))) return rc;
-    }
-    if (binary && j.s2) {
-        extent_of(j.in2, j.len, j.s2, j.isz_in, &lo, &bytes);
-        if ((rc = prefetch_managed(lo, j.pk_in2, (size_t)bytes, L))) return rc;
-    }
-    extent_of(j.out, j.len, j.so, j.isz_out, &lo, &bytes);
-    if ((rc = prefetch_managed(lo, j.pk_out, (size_t)bytes, L))) return rc;
-    if (binary)
-        rc = j.fn2(in1, in2, j.out, j.len, j.s1, j.s2, j.so, (pncu_stream_t)L.s_k);
-    else
-        rc = j.fn1(in1, j.out, j.len, j.s1, j.so, (pncu_stream_t)L.s_k);
-    if (rc) return rc;
-    g_stats.launches += 1;
-    PNCU_CUDA(cudaStreamSynchronize(L.s_k));
-    return 0;
-}
-
-// ---- managed operands spread over all GPUs ----------------------------------------------------------------
-// A managed (cudaMallocManaged) ndarray is addressable from every GPU, so a large one does not have to live
-// on one: shard l of every operand -- the same contiguous split at multiples of 65 536 elements the host path
-// uses -- is prefetched to GPU l the first time it is seen there, and every call then runs one kernel per GPU on
-// its own shard, in place, with no PCIe and no exchange (reductions: block partials gathered on GPU 0 as in the
-// host path).  np.add(a, b, out=c) on managed arrays thus runs at G times one GPU's HBM rate.
+// ---- RESIDENT element-wise work: one launch per GPU, in place -------------------------------------------------
+// Operands in managed / device memory.  Shard l of a large managed array lives on GPU l (placed there the first
+// time it is seen, then remembered); every call runs one kernel per GPU on its own shard and waits once.
 constexpr size_t kShardResidentMinBytes = (size_t)64 << 20;  // smaller arrays stay on one GPU
-
-bool shard_resident(const Job& j, bool binary) {
-    if (g.ndev < 2 || !g.threading) return false;
-    if (j.pk_out != PK_MANAGED || j.so != j.isz_out) return false;
-    if (j.s1 != 0 && (j.pk_in1 != PK_MANAGED || j.s1 != j.isz_in)) return false;
-    if (binary && j.s2 != 0 && (j.pk_in2 != PK_MANAGED || j.s2 != j.isz_in)) return false;
-    return (size_t)j.len * (size_t)(j.isz_in > j.isz_out ? j.isz_in : j.isz_out) >= kShardResidentMinBytes;
-}
-
-int plan_one_lane_per_gpu(Job& j) {
-    const int64_t units = (j.len + kAlign - 1) / kAlign;
-    int lanes = g.ndev < units ? g.ndev : (int)units;
-    if (lanes < 1) lanes = 1;
-    j.nlanes = lanes;
-    const int64_t per = (units + lanes - 1) / lanes;
-    for (int l = 0; l <= lanes; ++l) {
-        const int64_t e = (int64_t)l * per * kAlign;
-        j.shard[l] = e < j.len ? e : j.len;
-    }
-    for (int l = 0; l < lanes; ++l) {
-        j.rc[l] = 0; j.err[l][0] = 0;
-        int rc = ensure_lane(l);
-        if (rc) return rc;
-    }
-    g_stats.lanes_last = lanes;
-    g_stats.gpus_last = lanes;
-    return 0;
-}
 
 void lane_resident(Lane& L, Job& j, int li) {
     if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
     const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
     if (e0 >= e1) return;
     const int64_t n = e1 - e0;
-    const bool binary = j.kind == JOB_BINARY;
-    const char* in1 = j.s1 ? j.in1 + e0 * j.isz_in : j.in1;
-    const char* in2 = binary ? (j.s2 ? j.in2 + e0 * j.isz_in : j.in2) : nullptr;
-    char* out = j.out + e0 * j.isz_out;
     int rc;
-    if (j.s1 == 0 && host_kind(j.pk_in1)) {
-        memcpy(L.h_small, j.in1, j.isz_in);
-        LCUDA(cudaMemcpyAsync(L.d_scalar, L.h_small, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
-        in1 = L.d_scalar;
-    }
-    if (binary && j.s2 == 0 && host_kind(j.pk_in2)) {
-        memcpy(L.h_small + 16, j.in2, j.isz_in);
-        LCUDA(cudaMemcpyAsync(L.d_scalar + 16, L.h_small + 16, j.isz_in, cudaMemcpyHostToDevice, L.s_k));
-        in2 = L.d_scalar + 16;
-    }
-    if (j.s1 && (rc = prefetch_managed(in1, j.pk_in1, (size_t)n * j.isz_in, L))) { fail(j, li, rc); return; }
-    if (binary && j.s2 && (rc = prefetch_managed(in2, j.pk_in2, (size_t)n * j.isz_in, L))) { fail(j, li, rc); return; }
-    if ((rc = prefetch_managed(out, j.pk_out, (size_t)n * j.isz_out, L))) { fail(j, li, rc); return; }
-    if (binary) rc = j.fn2(in1, in2, out, n, j.s1, j.s2, j.so, (pncu_stream_t)L.s_k);
-    else rc = j.fn1(in1, out, n, j.s1, j.so, (pncu_stream_t)L.s_k);
-    if (rc) { fail(j, li, rc); return; }
-    g_stats.launches += 1;
-}
-
-void lane_reduce_resident(Lane& L, Job& j, int li) {
-    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
-    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
-    if (e0 >= e1) return;
-    const int64_t n = e1 - e0;
-    const char* in = j.in1 + e0 * j.isz_in;
-    int rc;
-    if ((rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
-    if ((rc = prefetch_managed(in, j.pk_in1, (size_t)n * j.isz_in, L))) { fail(j, li, rc); return; }
-    if (j.kind == JOB_REDUCE) rc = pncu_reduce_partials(j.func, j.atype, in, n, L.d_partials, (pncu_stream_t)L.s_k);
-    else rc = pncu_argminmax_partials(j.argkind, j.atype, in, n, e0, L.d_partials, (pncu_stream_t)L.s_k);
-    if (rc) { fail(j, li, rc); return; }
-    g_stats.launches += 1;
-}
-
-// fused chain on sharded managed operands: a*b+c in place per GPU, or pass 1 of its sum into the lane's partials
-void lane_fused_resident(Lane& L, Job& j, int li) {
-    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
-    const int64_t e0 = j.shard[li], e1 = j.shard[li + 1];
-    if (e0 >= e1) return;
-    const int64_t n = e1 - e0;
-    const size_t bytes = (size_t)n * j.isz_in;
-    const bool to_sum = j.kind == JOB_MULADD_SUM;
-    const char* a = j.in1 + e0 * j.isz_in;
-    const char* b = j.in2 + e0 * j.isz_in;
-    const char* c = j.in3 + e0 * j.isz_in;
-    int rc;
-    if ((rc = prefetch_managed(a, j.pk_in1, bytes, L)) || (rc = prefetch_managed(b, j.pk_in2, bytes, L)) ||
-        (rc = prefetch_managed(c, j.pk_in3, bytes, L))) { fail(j, li, rc); return; }
-    if (!to_sum) {
-        char* o = j.out + e0 * j.isz_in;
-        if ((rc = prefetch_managed(o, j.pk_out, bytes, L))) { fail(j, li, rc); return; }
-        rc = j.fn3(a, b, c, o, n, (pncu_stream_t)L.s_k);
+    if (j.kind == JOB_MULADD) {
+        rc = j.fn3(j.in1 + e0 * j.isz_in, j.in2 + e0 * j.isz_in, j.in3 + e0 * j.isz_in, j.out + e0 * j.isz_in, n, (pncu_stream_t)L.s_k);
     } else {
-        if ((rc = ensure_partials(L, (size_t)(j.slot0[li + 1] - j.slot0[li]) * j.partial_bytes))) { fail(j, li, rc); return; }
-        rc = pncu_muladd_sum_partials(j.atype, a, b, c, n, L.d_partials, (pncu_stream_t)L.s_k);
+        const bool binary = j.kind == JOB_BINARY;
+        const char* in1 = j.in1 + e0 * j.s1;
+        const char* in2 = binary ? j.in2 + e0 * j.s2 : nullptr;
+        char* out = j.out + e0 * j.so;
+        if (j.s1 == 0 && !j.k1.resident() && (rc = stage_scalar(L, j.in1, j.isz_in, 0, &in1))) { fail(j, li, rc); return; }
+        if (binary && j.s2 == 0 && !j.k2.resident() && (rc = stage_scalar(L, j.in2, j.isz_in, 1, &in2))) { fail(j, li, rc); return; }
+        if (binary) rc = j.fn2(in1, in2, out, n, j.s1, j.s2, j.so, (pncu_stream_t)L.s_k);
+        else rc = j.fn1(in1, out, n, j.s1, j.so, (pncu_stream_t)L.s_k);
     }
     if (rc) { fail(j, li, rc); return; }
     g_stats.launches += 1;
+    cudaError_t e = cudaStreamSynchronize(L.s_k);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize(resident shard)", __FILE__, __LINE__); fail(j, li, (int)e); }
 }
 
-// Resident shards need no host-side copying, so no worker threads either: the calling thread queues the work of
-// every GPU (asynchronous launches, ~5 us each) and then waits for all of them -- a condition-variable wake-up per
-// lane would cost more than a 128 MiB shard takes to stream.
-void run_resident_lanes(Job& j, LaneFn fn) {
-    for (int li = 0; li < j.nlanes; ++li) fn(g.lanes[li], j, li);
-    for (int li = 0; li < j.nlanes; ++li) {
-        if (j.rc[li]) continue;
-        Lane& L = g.lanes[li];
-        cudaError_t e = cudaSetDevice(L.device);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(L.s_k);
-        if (e != cudaSuccess) { cuda_fail(e, "cudaStreamSynchronize(resident shard)", __FILE__, __LINE__); fail(j, li, (int)e); }
+// place every managed array operand of a resident job: sharded over the job's lanes, or whole on its one lane.
+// Runs on the calling thread before the lanes are posted (a hit costs one short list walk per operand).
+int place_operands(Job& j) {
+    struct Arr { const Operand* o; const char* p; int64_t stride; int isz; };
+    Arr arrs[4];
+    int na = 0;
+    if (j.s1 != 0 && j.in1) arrs[na++] = Arr{&j.k1, j.in1, j.s1, j.isz_in};
+    if ((j.kind == JOB_BINARY || j.kind == JOB_MULADD || j.kind == JOB_MULADD_SUM) && j.s2 != 0 && j.in2) arrs[na++] = Arr{&j.k2, j.in2, j.s2, j.isz_in};
+    if ((j.kind == JOB_MULADD || j.kind == JOB_MULADD_SUM) && j.in3) arrs[na++] = Arr{&j.k3, j.in3, j.isz_in, j.isz_in};
+    if (j.out && j.so != 0) arrs[na++] = Arr{&j.ko, j.out, j.so, j.isz_out};
+    for (int a = 0; a < na; ++a) {
+        const Arr& A = arrs[a];
+        if (A.o->kind != MK_MANAGED) continue;
+        if (j.nlanes == 1) {
+            const char* lo;
+            int64_t bytes;
+            extent_of(A.p, j.len, A.stride, A.isz, &lo, &bytes);
+            int rc = place_whole(*A.o, lo, (size_t)bytes, g.lanes[j.lane_id[0]]);
+            if (rc) return rc;
+            continue;
+        }
+        // sharded (contiguous operands only): note = (range, 100 + lanes, bytes of the first shard)
+        const char* lo = A.p;
+        const size_t bytes = (size_t)j.len * A.isz;
+        const size_t piece = (size_t)(j.shard[1] - j.shard[0]) * A.isz;
+        std::lock_guard<std::mutex> lk(g_note_mu);
+        if (note_hit(*A.o, lo, bytes, 100 + j.nlanes, piece)) continue;
+        for (int l = 0; l < j.nlanes; ++l) {
+            Lane& L = g.lanes[j.lane_id[l]];
+            const size_t b = (size_t)(j.shard[l + 1] - j.shard[l]) * A.isz;
+            if (!b) continue;
+            PNCU_CUDA(cudaSetDevice(L.device));
+            PNCU_CUDA(cudaMemPrefetchAsync(A.p + j.shard[l] * A.isz, b, L.device, L.s_k));
+            g_stats.prefetches += 1;
+        }
+        note_set(*A.o, lo, bytes, 100 + j.nlanes, piece);
+    }
+    return 0;
+}
+
+// are all array operands contiguous managed memory, and is the job big enough to spread over the GPUs?
+bool want_sharding(const Job& j, int narrays, const Operand* const* ops, const int64_t* strides, const int* iszs) {
+    if (g.ndev < 2 || !g.threading) return false;
+    for (int a = 0; a < narrays; ++a)
+        if (ops[a]->kind != MK_MANAGED || strides[a] != iszs[a]) return false;
+    const int wide = j.isz_in > j.isz_out ? j.isz_in : j.isz_out;
+    return (size_t)j.len * (size_t)wide >= kShardResidentMinBytes;
+}
+
+// ---- RESIDENT reductions: one kernel per GPU, exchange and fold on the device --------------------------------
+// Each lane launches ONE kernel (pncu_reduce_fused / pncu_argminmax_fused / pncu_muladd_sum_fused): pass 1 on its
+// shard; the last CTA of a non-root GPU stores the shard's block partials into GPU 0's table over NVLink and
+// bumps its arrival counter; GPU 0's last CTA waits for the other shards, folds the whole table in slot order,
+// writes the result into lane 0's MAPPED host scratch and then the completion flag, which the caller polls.
+int launch_fused_shard(Lane& L, Job& j, int li, const pncu_fused_exchange* x, void* out, const void* start) {
+    const int64_t e0 = j.shard[li], n = j.shard[li + 1] - j.shard[li];
+    int rc;
+    if (j.kind == JOB_REDUCE)
+        rc = pncu_reduce_fused(j.func, j.atype, j.in1 + e0 * j.s1, n, x, out, start, (pncu_stream_t)L.s_k);
+    else if (j.kind == JOB_ARG)
+        rc = pncu_argminmax_fused(j.argkind, j.atype, j.in1 + e0 * j.s1, n, e0, x, (int64_t*)out, (pncu_stream_t)L.s_k);
+    else
+        rc = pncu_muladd_sum_fused(j.atype, j.in1 + e0 * j.isz_in, j.in2 + e0 * j.isz_in, j.in3 + e0 * j.isz_in, n, x, out,
+                                   (pncu_stream_t)L.s_k);
+    if (!rc) g_stats.launches += 1;
+    return rc;
+}
+
+pncu_fused_exchange g_x[kMaxLanes];  // per-lane exchange descriptors of the call in flight
+
+void lane_reduce_shard(Lane& L, Job& j, int li) {   // lanes >= 1: launch and return
+    if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); fail(j, li, PNCU_ERR_NO_DEVICE); return; }
+    int rc = launch_fused_shard(L, j, li, &g_x[li], nullptr, nullptr);
+    if (rc) fail(j, li, rc);
+}
+
+// poll lane L's completion flag for `want`; the stream is queried now and then so that a failed launch or a
+// faulted kernel surfaces as an error instead of an endless wait
+int wait_flag(Lane& L, uint64_t want) {
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(L.h_small + kOffFlag);
+    unsigned polls = 0;
+    for (;;) {
+        const unsigned long long v = __atomic_load_n(f, __ATOMIC_ACQUIRE);
+        if ((v & ~PNCU_FUSED_TIMEOUT_BIT) == want) {
+            if (v & PNCU_FUSED_TIMEOUT_BIT) {
+                set_error("a GPU never delivered its block partials to the reduction exchange (waited ~2 s); no result was produced");
+                return PNCU_ERR_TIMEOUT;
+            }
+            return 0;
+        }
+        NTE_PAUSE();
+        if ((++polls & 0x3ff) == 0) {
+            cudaError_t e = cudaStreamQuery(L.s_k);
+            if (e == cudaErrorNotReady) continue;
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamQuery(reduction)", __FILE__, __LINE__);
+            const unsigned long long v2 = __atomic_load_n(f, __ATOMIC_ACQUIRE);
+            if ((v2 & ~PNCU_FUSED_TIMEOUT_BIT) == want) continue;   // published between the two looks
+            set_error("the reduction kernel finished without publishing a result");
+            return PNCU_ERR_ARGUMENT;
+        }
     }
 }
 
-int run_resident_sharded(Job& j) {
-    int rc = plan_one_lane_per_gpu(j);
-    if (rc) return rc;
-    run_resident_lanes(j, lane_resident);
-    return first_error(j);
+// bring the exchange back to a known state after a failure (all lanes idle first)
+void reset_exchange(Job& j) {
+    for (int l = 0; l < j.nlanes; ++l) {
+        Lane& L = g.lanes[j.lane_id[l]];
+        if (cudaSetDevice(L.device) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cudaStreamSynchronize(L.s_k) != cudaSuccess) cudaGetLastError();
+        pncu_fused_reset((pncu_stream_t)L.s_k);
+        if (cudaStreamSynchronize(L.s_k) != cudaSuccess) cudaGetLastError();
+    }
+    Lane& L0 = g.lanes[0];
+    if (L0.ready && cudaSetDevice(L0.device) == cudaSuccess) {
+        if (cudaMemset(L0.d_scalar + kOffArrived, 0, 8) != cudaSuccess) cudaGetLastError();
+    }
+    g.x_expected = 0;
 }
+
+int run_reduce_resident(Job& j, bool sharded) {
+    int rc;
+    if (sharded) {
+        if ((rc = plan_one_lane_per_gpu(j))) return rc;
+    } else {
+        const char* lo;
+        int64_t bytes;
+        extent_of(j.in1, j.len, j.s1, j.isz_in, &lo, &bytes);
+        if ((rc = plan_on_device(j, home_of(j.k1, lo, (size_t)bytes), false))) return rc;
+    }
+    if ((rc = place_operands(j))) return rc;
+    Lane& L0 = g.lanes[j.lane_id[0]];
+    PNCU_CUDA(cudaSetDevice(L0.device));
+    const void* start = nullptr;
+    if (j.host_start) {
+        memcpy(L0.h_small + kOffStart, j.host_start, j.out_bytes);
+        start = L0.h_small + kOffStart;
+    }
+    const uint64_t want = ++L0.seq;
+    if (j.nlanes == 1) {
+        pncu_fused_exchange& x = g_x[0];
+        memset(&x, 0, sizeof(x));
+        x.n = 1;
+        x.done_flag = reinterpret_cast<unsigned long long*>(L0.h_small + kOffFlag);
+        x.done_value = want;
+        if ((rc = launch_fused_shard(L0, j, 0, &x, L0.h_small + kOffResult, start))) return rc;
+        if ((rc = wait_flag(L0, want))) { reset_exchange(j); return rc; }
+    } else {
+        for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
+        const size_t need = (size_t)j.slot0[j.nlanes] * j.partial_bytes;
+        if (g.x_table_bytes < need) {
+            if (g.x_table) cudaFree(g.x_table);
+            g.x_table = nullptr;
+            g.x_table_bytes = 0;
+            const size_t cap = need < ((size_t)1 << 20) ? ((size_t)1 << 20) : need * 2;
+            PNCU_CUDA(cudaMalloc((void**)&g.x_table, cap));
+            g.x_table_bytes = cap;
+        }
+        g.x_expected += (unsigned long long)(j.nlanes - 1);
+        for (int l = 0; l < j.nlanes; ++l) {
+            pncu_fused_exchange& x = g_x[l];
+            memset(&x, 0, sizeof(x));
+            x.n = j.nlanes; x.self = l; x.all = 0; x.root = 0;
+            x.slot_base = j.slot0[l];
+            x.total_count = j.slot0[j.nlanes];
+            x.slots[0] = g.x_table;
+            x.arrived[0] = reinterpret_cast<unsigned long long*>(L0.d_scalar + kOffArrived);
+            x.expected = g.x_expected;
+            if (l == 0) {
+                x.done_flag = reinterpret_cast<unsigned long long*>(L0.h_small + kOffFlag);
+                x.done_value = want;
+            }
+        }
+        // post the other GPUs' launches, launch the root here, wait for the posts (launch status), then for the flag
+        for (int l = 1; l < j.nlanes; ++l) {
+            const int p = j.lane_id[l];
+            nte::Worker*& w = g.pool[p];
+            if (!w) { w = new nte::Worker(); w->start(p, g.spin_ns); }
+            g_post[p].job = &j; g_post[p].fn = lane_reduce_shard; g_post[p].logical = l;
+            w->post(worker_thunk, &g_post[p]);
+        }
+        rc = launch_fused_shard(L0, j, 0, &g_x[0], L0.h_small + kOffResult, start);
+        if (rc) fail(j, 0, rc);
+        for (int l = 1; l < j.nlanes; ++l) g.pool[j.lane_id[l]]->wait();
+        if ((rc = first_error(j))) { reset_exchange(j); return rc; }   // a shard was never launched: do not wait for it
+        if ((rc = wait_flag(L0, want))) { reset_exchange(j); return rc; }
+    }
+    memcpy(j.host_out, L0.h_small + kOffResult, j.out_bytes);
+    g_stats.d2h += j.out_bytes;
+    return 0;
+}
+
+// ---- host-operand reductions: gather every lane's partials on GPU 0, fold there in fixed order ----------------
+int finish_on_gpu0(Job& j) {
+    Lane& L0 = g.lanes[0];
+    PNCU_CUDA(cudaSetDevice(L0.device));
+    const int64_t total = j.slot0[j.nlanes];
+    char* all = L0.d_partials;
+    if (j.nlanes > 1) {
+        // lane 0's buffer holds its own slots at [0, n0); append the others behind them
+        if ((size_t)total * j.partial_bytes > L0.partials_bytes) {
+            // grow, preserving lane 0's partials
+            char* bigger = nullptr;
+            PNCU_CUDA(cudaMalloc((void**)&bigger, (size_t)total * j.partial_bytes * 2));
+            PNCU_CUDA(cudaMemcpyAsync(bigger, L0.d_partials, (size_t)j.slot0[1] * j.partial_bytes, cudaMemcpyDeviceToDevice, L0.s_k));
+            PNCU_CUDA(cudaStreamSynchronize(L0.s_k));
+            cudaFree(L0.d_partials);
+            L0.d_partials = bigger;
+            L0.partials_bytes = (size_t)total * j.partial_bytes * 2;
+            all = bigger;
+        }
+        for (int l = 1; l < j.nlanes; ++l) {
+            const int64_t cnt = j.slot0[l + 1] - j.slot0[l];
+            if (cnt <= 0) continue;
+            Lane& L = g.lanes[j.lane_id[l]];
+            // peer copy (NVLink P2P when enabled, else staged by the driver); same-GPU lanes: plain D2D
+            PNCU_CUDA(cudaMemcpyPeerAsync(all + j.slot0[l] * j.partial_bytes, L0.device, L.d_partials, L.device,
+                                          (size_t)cnt * j.partial_bytes, L0.s_k));
+        }
+    }
+    // the finish kernel reads the start value from, and writes the result into, lane 0's mapped host scratch
+    const void* start = nullptr;
+    if (j.host_start) {
+        memcpy(L0.h_small + kOffStart, j.host_start, j.out_bytes);
+        start = L0.h_small + kOffStart;
+    }
+    int rc;
+    if (j.kind == JOB_ARG) rc = pncu_argminmax_finish(j.argkind, j.atype, all, total, (int64_t*)(L0.h_small + kOffResult), (pncu_stream_t)L0.s_k);
+    else rc = pncu_reduce_finish(j.func, j.atype, all, total, L0.h_small + kOffResult, start, (pncu_stream_t)L0.s_k);
+    if (rc) return rc;
+    g_stats.launches += 1;
+    PNCU_CUDA(cudaStreamSynchronize(L0.s_k));
+    memcpy(j.host_out, L0.h_small + kOffResult, j.out_bytes);
+    g_stats.d2h += j.out_bytes;
+    return 0;
+}
+
+bool usable() { return g.inited && !g.forked.load(std::memory_order_relaxed); }
+
+// fault injection for the error-path tests: the n-th GPU dispatch from now reports a launch failure
+int injected_fault() {
+    if (g.fault_countdown > 0 && --g.fault_countdown == 0) {
+        set_error("injected fault (nte_inject_fault / PNUMPY_CUDA_FAULT_INJECT): simulated cudaErrorLaunchFailure");
+        return (int)cudaErrorLaunchFailure;
+    }
+    return 0;
+}
+
+void atfork_child() { g.forked.store(true); }
 
 }  // namespace
 
@@ -803,42 +1018,55 @@ extern "C" {
 
 int nte_init(void) {
     std::lock_guard<std::mutex> lk(g.api_mu);
+    if (g.forked) { set_error("CUDA cannot be used in a fork()ed child; start workers with the 'spawn' method"); return PNCU_ERR_NO_DEVICE; }
     if (g.inited) return 0;
     int n = 0;
     int rc = pncu_init(&n);
     if (rc) return rc;
+    DeviceGuard guard;
     g.ndev = n > kMaxLanes ? kMaxLanes : n;
+    if (g.ndev > PNCU_MAX_PEERS) g.ndev = PNCU_MAX_PEERS;
     const char* env = getenv("PNUMPY_CUDA_MIN_ELEMS");
     if (env && *env) g.min_elems = atoll(env);
     env = getenv("PNUMPY_CUDA_SLAB_BYTES");
     if (env && *env) g.slab_bytes = (size_t)atoll(env);
     env = getenv("PNUMPY_CUDA_DEVICES");  // use only the first k devices
     if (env && *env && atoi(env) > 0 && atoi(env) < g.ndev) g.ndev = atoi(env);
-    // peer access so that the reduction gather can go GPU -> GPU 0 over NVLink
+    env = getenv("PNUMPY_CUDA_SPIN_US");
+    if (env && *env) g.spin_ns = (uint64_t)atoll(env) * 1000ull;
+    env = getenv("PNUMPY_CUDA_FAULT_INJECT");
+    if (env && *env) g.fault_countdown = atoll(env);
+    // peer access: the reduction exchange stores into GPU 0's table, the host path gathers partials with peer copies
+    g.peer_all = true;
     for (int a = 0; a < g.ndev; ++a)
         for (int b = 0; b < g.ndev; ++b) {
             if (a == b) continue;
             int can = 0;
+            bool ok = false;
             if (cudaDeviceCanAccessPeer(&can, a, b) == cudaSuccess && can) {
                 cudaSetDevice(a);
                 cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+                ok = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
                 if (e != cudaSuccess) cudaGetLastError();
             } else {
                 cudaGetLastError();
             }
+            if (!ok && b == 0) g.peer_all = false;
         }
-    cudaSetDevice(0);
+    static bool atfork_registered = false;
+    if (!atfork_registered) { pthread_atfork(nullptr, nullptr, atfork_child); atfork_registered = true; }
     g.inited = true;
     return 0;
 }
 
 int nte_shutdown(void) {
     std::lock_guard<std::mutex> lk(g.api_mu);
+    if (g.forked) return 0;   // the child owns neither the threads nor the CUDA context
+    DeviceGuard guard;
     for (int l = 1; l < kMaxLanes; ++l) {
-        Worker* w = g.pool[l];
+        nte::Worker* w = g.pool[l];
         if (!w) continue;
-        { std::lock_guard<std::mutex> wl(w->mu); w->quit = true; w->cv.notify_all(); }
-        w->th.join();
+        w->stop();
         delete w;
         g.pool[l] = nullptr;
     }
@@ -859,11 +1087,14 @@ int nte_shutdown(void) {
         cudaStreamDestroy(L.s_h2d); cudaStreamDestroy(L.s_k); cudaStreamDestroy(L.s_d2h);
         L = Lane();
     }
+    if (g.x_table) { cudaSetDevice(0); cudaFree(g.x_table); g.x_table = nullptr; g.x_table_bytes = 0; }
+    g.x_expected = 0;
     g.inited = false;
     return 0;
 }
 
 int nte_device_count(void) { return g.inited ? g.ndev : 0; }
+int nte_is_forked_child(void) { return g.forked ? 1 : 0; }
 
 int nte_max_workers(void) { return kMaxLanes - 1; }
 int nte_set_workers(int workers) {
@@ -887,106 +1118,178 @@ int64_t nte_set_slab_bytes(int64_t bytes) {
     g.slab_bytes = (size_t)((bytes / unit) * unit);
     return p;
 }
+int64_t nte_inject_fault(int64_t nth) {
+    std::lock_guard<std::mutex> lk(g.api_mu);
+    int64_t p = g.fault_countdown;
+    g.fault_countdown = nth < 0 ? 0 : nth;
+    return p;
+}
 
 void* nte_alloc_pinned(size_t bytes) {
-    if (pncu_init(nullptr)) return nullptr;
+    if (g.forked || pncu_init(nullptr)) return nullptr;
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
+    registry_add(p, bytes ? bytes : 1, MK_PINNED, -1);
     return p;
 }
 void nte_free_pinned(void* ptr) {
-    if (ptr && cudaFreeHost(ptr) != cudaSuccess) cudaGetLastError();
+    if (!ptr) return;
+    registry_remove(ptr);
+    if (g.forked) return;   // not ours to free in a fork()ed child
+    if (cudaFreeHost(ptr) != cudaSuccess) cudaGetLastError();
 }
 
 void* nte_alloc_managed(size_t bytes) {
-    if (pncu_init(nullptr)) return nullptr;
+    if (g.forked || pncu_init(nullptr)) return nullptr;
     void* p = nullptr;
     if (cudaMallocManaged(&p, bytes ? bytes : 1, cudaMemAttachGlobal) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
-    std::lock_guard<std::mutex> lk(g.api_mu);
-    g_managed_allocs[p] = bytes ? bytes : 1;
+    registry_add(p, bytes ? bytes : 1, MK_MANAGED, -1);
     return p;
 }
 void nte_free_managed(void* ptr) {
     if (!ptr) return;
     {
+        // a dispatch in flight may hold the block's residency notes: wait for it
         std::lock_guard<std::mutex> lk(g.api_mu);
-        auto it = g_managed_allocs.find(ptr);
-        const size_t bytes = it != g_managed_allocs.end() ? it->second : 1;
-        if (it != g_managed_allocs.end()) g_managed_allocs.erase(it);
-        forget_prefetched(ptr, bytes);  // views into the block are remembered by their own base address
+        std::lock_guard<std::mutex> nk(g_note_mu);
+        registry_remove(ptr);
     }
+    if (g.forked) return;
     if (cudaFree(ptr) != cudaSuccess) cudaGetLastError();
+}
+// zero a managed block ON the GPU (np.zeros under the managed recycler must not drag the pages to the host)
+int nte_zero_managed(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return 0;
+    if (!usable()) return PNCU_ERR_NO_DEVICE;
+    DeviceGuard guard;
+    PNCU_CUDA(cudaSetDevice(0));
+    PNCU_CUDA(cudaMemsetAsync(ptr, 0, bytes, cudaStreamPerThread));
+    PNCU_CUDA(cudaStreamSynchronize(cudaStreamPerThread));
+    Operand o;
+    if (lookup_registry(ptr, &o) && o.notes) {
+        std::lock_guard<std::mutex> nk(g_note_mu);
+        note_set(o, (const char*)ptr, bytes, 0, 0);
+    }
+    return 0;
+}
+// a recycled managed block is about to be handed to a new owner: what we knew about its pages stays valid
+// (they are where the last kernel left them), so nothing to do; exported for symmetry / tests
+void nte_forget_residency(void* ptr) {
+    AllocInfo ai;
+    if (!ptr || !registry_find(ptr, &ai) || !ai.notes) return;
+    std::lock_guard<std::mutex> lk(g.api_mu);
+    std::lock_guard<std::mutex> nk(g_note_mu);
+    ai.notes->clear();
 }
 
 void nte_get_stats(nte_stats* o) {
     if (!o) return;
     o->calls = g_stats.calls; o->declined = g_stats.declined; o->launches = g_stats.launches;
     o->h2d_bytes = g_stats.h2d; o->d2h_bytes = g_stats.d2h; o->staged_bytes = g_stats.staged;
-    o->lanes_last = g_stats.lanes_last; o->gpus_last = g_stats.gpus_last;
+    o->lanes_last = g_stats.lanes_last; o->gpus_last = g_stats.gpus_last; o->prefetches = g_stats.prefetches;
 }
 void nte_reset_stats(void) {
     g_stats.calls = 0; g_stats.declined = 0; g_stats.launches = 0; g_stats.h2d = 0; g_stats.d2h = 0;
-    g_stats.staged = 0; g_stats.lanes_last = 0; g_stats.gpus_last = 0;
+    g_stats.staged = 0; g_stats.lanes_last = 0; g_stats.gpus_last = 0; g_stats.prefetches = 0;
+}
+
+// `out` may alias an input exactly (every element is read before its result is written, by the same thread or
+// through staging); any other overlap needs the sequential semantics of the caller's loop (NumPy's accumulate
+// calls a binary loop as (out, in + s, out + s); reference: src/pnumpy/_pnumpy.cpp:743-745)
+static bool partial_overlap(const Job& j, bool binary) {
+    const char* olo;
+    int64_t ob;
+    extent_of(j.out, j.len, j.so, j.isz_out, &olo, &ob);
+    const char* ins[2] = {j.in1, binary ? j.in2 : nullptr};
+    const int64_t strides[2] = {j.s1, j.s2};
+    for (int k = 0; k < 2; ++k) {
+        if (!ins[k]) continue;
+        const char* ilo;
+        int64_t ib;
+        extent_of(ins[k], strides[k] ? j.len : 1, strides[k], j.isz_in, &ilo, &ib);
+        const bool overlap = ilo < olo + ob && olo < ilo + ib;
+        if (overlap && !(ins[k] == j.out && strides[k] == j.so && j.isz_in == j.isz_out)) return true;
+    }
+    return false;
 }
 
 static int dispatch_elementwise(Job& j, int max_workers) {
-    if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false, 8)) return decline();  // below every class's threshold
+    if (!usable()) {
+        if (g.forked) return decline();   // a fork()ed child runs NumPy's loops
+        set_error("nte_init() has not succeeded");
+        return PNCU_ERR_NO_DEVICE;
+    }
+    if (j.len <= 0) return decline();
+    const bool binary = j.kind == JOB_BINARY;
+    // 1. memory kinds from the registry (no driver call); small calls on memory we did not hand out are declined
+    //    right here -- that is every small NumPy call on ordinary arrays, and it costs three map lookups
+    const bool r1 = lookup_registry(j.in1, &j.k1);
+    const bool r2 = binary ? lookup_registry(j.in2, &j.k2) : true;
+    const bool ro = lookup_registry(j.out, &j.ko);
+    const bool known_resident = j.k1.resident() || (binary && j.k2.resident()) || j.ko.resident();
+    if (!known_resident && j.len < lowest_threshold()) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();  // re-entrant / concurrent caller: run the old loop
-    const bool binary = j.kind == JOB_BINARY;
-    j.pk_in1 = classify(j.in1);
-    j.pk_in2 = binary ? classify(j.in2) : PK_PAGEABLE;
-    j.pk_out = classify(j.out);
-    const bool any_resident = !host_kind(j.pk_out) || (j.s1 != 0 && !host_kind(j.pk_in1)) ||
-                              (binary && j.s2 != 0 && !host_kind(j.pk_in2));
-    if (any_resident) {
-        // every ARRAY operand must be resident (a host array next to a managed one goes to the caller's
-        // loop, which may read managed memory); host scalars are copied by run_resident
-        const bool all_ok = !host_kind(j.pk_out) && (j.s1 == 0 || !host_kind(j.pk_in1)) &&
-                            (!binary || j.s2 == 0 || !host_kind(j.pk_in2));
-        if (!all_ok) return decline();
-        int rc = shard_resident(j, binary) ? run_resident_sharded(j) : run_resident(j);
+    if (!r1) classify_driver(j.in1, &j.k1);
+    if (binary && !r2) classify_driver(j.in2, &j.k2);
+    if (!ro) classify_driver(j.out, &j.ko);
+    if (!binary) j.k2 = Operand();
+    const bool vec1 = j.s1 != 0, vec2 = binary && j.s2 != 0;
+    if (!vec1 && !vec2) return decline();   // scalar op scalar
+    if (!stride_ok(j.in1, j.s1, j.isz_in) || (binary && !stride_ok(j.in2, j.s2, j.isz_in)) || !stride_ok(j.out, j.so, j.isz_out))
+        return decline();
+    if (partial_overlap(j, binary)) return decline();
+    const int narr = 1 + (vec1 ? 1 : 0) + (vec2 ? 1 : 0);
+    const int nres = (j.ko.resident() ? 1 : 0) + (vec1 && j.k1.resident() ? 1 : 0) + (vec2 && j.k2.resident() ? 1 : 0);
+    DeviceGuard guard;
+    int rc;
+    if (nres == narr) {
+        // ---- every array operand is resident: one launch per GPU, in place, whatever the size
+        const Operand* ops[3]; int64_t strides[3]; int iszs[3]; int na = 0;
+        ops[na] = &j.ko; strides[na] = j.so; iszs[na++] = j.isz_out;
+        if (vec1) { ops[na] = &j.k1; strides[na] = j.s1; iszs[na++] = j.isz_in; }
+        if (vec2) { ops[na] = &j.k2; strides[na] = j.s2; iszs[na++] = j.isz_in; }
+        if ((rc = injected_fault())) return rc;
+        if (want_sharding(j, na, ops, strides, iszs)) {
+            if ((rc = plan_one_lane_per_gpu(j))) return rc;
+        } else {
+            const char* lo;
+            int64_t bytes;
+            extent_of(j.out, j.len, j.so, j.isz_out, &lo, &bytes);
+            int dev = home_of(j.ko, lo, (size_t)bytes);
+            if (vec1 && j.k1.kind == MK_DEVICE) dev = home_of(j.k1, j.in1, 1);
+            if (vec2 && j.k2.kind == MK_DEVICE) dev = home_of(j.k2, j.in2, 1);
+            if (j.ko.kind == MK_DEVICE) dev = home_of(j.ko, j.out, 1);
+            if ((rc = plan_on_device(j, dev, false))) return rc;
+        }
+        if ((rc = place_operands(j))) return rc;
+        run_lanes(j, lane_resident);
+        rc = first_error(j);
         if (!rc) g_stats.calls += 1;
         return rc;
     }
-    // an op whose output does not depend on its input (isnan / isinf / isfinite of integers): shipping the input
-    // over PCIe to memset the output would be absurd -- NumPy's own loop is a memset already
-    if (j.op_class == NTE_CLASS_CONST) return decline();
-    {
-        const bool pageable = j.pk_out == PK_PAGEABLE || (j.s1 != 0 && j.pk_in1 == PK_PAGEABLE) ||
-                              (binary && j.s2 != 0 && j.pk_in2 == PK_PAGEABLE);
+    if (nres == 0) {
+        // ---- host operands only: worth a PCIe round trip?
+        // an op whose output does not depend on its input (isnan / isinf / isfinite of integers): shipping the input
+        // over PCIe to memset the output would be absurd -- NumPy's own loop is a memset already
+        if (j.op_class == NTE_CLASS_CONST) return decline();
+        const bool pageable = j.ko.kind == MK_PAGEABLE || (vec1 && j.k1.kind == MK_PAGEABLE) || (vec2 && j.k2.kind == MK_PAGEABLE);
         if (j.len < threshold_for(j.op_class, pageable, j.isz_in > j.isz_out ? j.isz_in : j.isz_out)) return decline();
     }
-    // host operands: contiguous ones are DMA'd (pinned) or memcpy'd (pageable) into the slabs, any
-    // other stride (a multiple of the item size, negative allowed) is gathered / scattered by the lane
-    if (j.s1 == 0 && (!binary || j.s2 == 0)) return decline();
-    if (!stride_ok(j.in1, j.s1, j.isz_in) || (binary && !stride_ok(j.in2, j.s2, j.isz_in)) || !stride_ok(j.out, j.so, j.isz_out))
-        return decline();
-    // exact aliasing of out with an input is fine (every element is staged before its result is written
-    // back); any other overlap needs the sequential semantics of the caller's loop
-    {
-        const char* olo;
-        int64_t ob;
-        extent_of(j.out, j.len, j.so, j.isz_out, &olo, &ob);
-        const char* ins[2] = {j.in1, binary ? j.in2 : nullptr};
-        const int64_t strides[2] = {j.s1, j.s2};
-        for (int k = 0; k < 2; ++k) {
-            if (!ins[k]) continue;
-            const char* ilo;
-            int64_t ib;
-            extent_of(ins[k], strides[k] ? j.len : 1, strides[k], j.isz_in, &ilo, &ib);
-            const bool overlap = ilo < olo + ob && olo < ilo + ib;
-            if (overlap && !(ins[k] == j.out && strides[k] == j.so && j.isz_in == j.isz_out)) return decline();
-        }
-    }
-    int rc = plan(j, max_workers);
+    // ---- at least one host array (possibly next to resident ones): the staging pipeline
+    if ((rc = injected_fault())) return rc;
+    int dev = -1;
+    if (j.ko.kind == MK_DEVICE) dev = home_of(j.ko, j.out, 1);
+    else if (vec1 && j.k1.kind == MK_DEVICE) dev = home_of(j.k1, j.in1, 1);
+    else if (vec2 && j.k2.kind == MK_DEVICE) dev = home_of(j.k2, j.in2, 1);
+    if (dev >= 0) rc = plan_on_device(j, dev, true);   // device memory belongs to one GPU
+    else rc = plan(j, max_workers);
     if (rc) return rc;
     run_lanes(j, lane_elementwise);
     rc = first_error(j);
@@ -1019,107 +1322,36 @@ int nte_unary_class(pncu_unary_fn launcher, int in_itemsize, int out_itemsize, c
     return dispatch_elementwise(j, max_workers);
 }
 
-// gather every lane's partials on GPU 0, fold there in fixed order, bring the scalar back
-static int finish_on_gpu0(Job& j, void* host_out, int out_bytes, const void* host_start) {
-    Lane& L0 = g.lanes[0];
-    PNCU_CUDA(cudaSetDevice(L0.device));
-    const int64_t total = j.slot0[j.nlanes];
-    char* all = L0.d_partials;
-    if (j.nlanes > 1) {
-        // lane 0's buffer holds its own slots at [0, n0); append the others behind them
-        if ((size_t)total * j.partial_bytes > L0.partials_bytes) {
-            // grow, preserving lane 0's partials
-            char* bigger = nullptr;
-            PNCU_CUDA(cudaMalloc((void**)&bigger, (size_t)total * j.partial_bytes * 2));
-            PNCU_CUDA(cudaMemcpyAsync(bigger, L0.d_partials, (size_t)j.slot0[1] * j.partial_bytes, cudaMemcpyDeviceToDevice, L0.s_k));
-            PNCU_CUDA(cudaStreamSynchronize(L0.s_k));
-            cudaFree(L0.d_partials);
-            L0.d_partials = bigger;
-            L0.partials_bytes = (size_t)total * j.partial_bytes * 2;
-            all = bigger;
-        }
-        for (int l = 1; l < j.nlanes; ++l) {
-            const int64_t cnt = j.slot0[l + 1] - j.slot0[l];
-            if (cnt <= 0) continue;
-            Lane& L = g.lanes[l];
-            // peer copy (NVLink P2P when enabled, else staged by the driver); same-GPU lanes: plain D2D
-            PNCU_CUDA(cudaMemcpyPeerAsync(all + j.slot0[l] * j.partial_bytes, L0.device, L.d_partials, L.device,
-                                          (size_t)cnt * j.partial_bytes, L0.s_k));
-        }
+static int dispatch_reduce(Job& j, int max_workers) {
+    if (!usable()) {
+        if (g.forked) return decline();
+        set_error("nte_init() has not succeeded");
+        return PNCU_ERR_NO_DEVICE;
     }
-    char* d_res = L0.d_scalar + 32;
-    int rc;
-    if (j.kind == JOB_REDUCE) {
-        const void* d_start = nullptr;
-        if (host_start) {
-            memcpy(L0.h_small, host_start, out_bytes);
-            PNCU_CUDA(cudaMemcpyAsync(L0.d_scalar, L0.h_small, out_bytes, cudaMemcpyHostToDevice, L0.s_k));
-            d_start = L0.d_scalar;
-        }
-        rc = pncu_reduce_finish(j.func, j.atype, all, total, d_res, d_start, (pncu_stream_t)L0.s_k);
-    } else {
-        rc = pncu_argminmax_finish(j.argkind, j.atype, all, total, (int64_t*)d_res, (pncu_stream_t)L0.s_k);
-    }
-    if (rc) return rc;
-    g_stats.launches += 1;
-    PNCU_CUDA(cudaMemcpyAsync(L0.h_small + 32, d_res, out_bytes, cudaMemcpyDeviceToHost, L0.s_k));
-    PNCU_CUDA(cudaStreamSynchronize(L0.s_k));
-    memcpy(host_out, L0.h_small + 32, out_bytes);
-    g_stats.d2h += out_bytes;
-    return 0;
-}
-
-static int dispatch_reduce(Job& j, void* host_out, int out_bytes, const void* host_start, int max_workers) {
-    if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false, 8)) return decline();
+    if (j.len <= 0) return decline();
+    const bool r1 = lookup_registry(j.in1, &j.k1);
+    if (!j.k1.resident() && j.len < lowest_threshold()) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
-    j.pk_in1 = classify(j.in1);
-    if (host_kind(j.pk_in1) && j.len < threshold_for(NTE_CLASS_REDUCE, j.pk_in1 == PK_PAGEABLE, j.isz_in)) return decline();
+    if (!r1) classify_driver(j.in1, &j.k1);
+    DeviceGuard guard;
     int rc;
-    if (!host_kind(j.pk_in1)) {
-        // resident input: both passes on its GPU (contiguous only: pass 1 streams whole blocks)
-        if (j.s1 != j.isz_in) return decline();
-        if (g.ndev > 1 && g.threading && j.pk_in1 == PK_MANAGED && (size_t)j.len * j.isz_in >= kShardResidentMinBytes) {
-            // a large managed array: one shard per GPU (see run_resident_sharded), partials gathered on GPU 0
-            if ((rc = plan_one_lane_per_gpu(j))) return rc;
-            for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
-            run_resident_lanes(j, lane_reduce_resident);
-            if ((rc = first_error(j))) return rc;
-            rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
-            if (!rc) g_stats.calls += 1;
-            return rc;
-        }
-        const int dev = device_of(j.in1);
-        if ((rc = ensure_lane(dev))) return rc;
-        g_stats.lanes_last = 1;
-        g_stats.gpus_last = 1;
-        Lane& L = g.lanes[dev];
-        PNCU_CUDA(cudaSetDevice(L.device));
-        if ((rc = prefetch_managed(j.in1, j.pk_in1, (size_t)j.len * j.isz_in, L))) return rc;
-        const int64_t slots = pncu_reduce_partial_count(j.atype, j.len);
-        if ((rc = ensure_partials(L, (size_t)slots * j.partial_bytes))) return rc;
-        if (j.kind == JOB_REDUCE) rc = pncu_reduce_partials(j.func, j.atype, j.in1, j.len, L.d_partials, (pncu_stream_t)L.s_k);
-        else rc = pncu_argminmax_partials(j.argkind, j.atype, j.in1, j.len, 0, L.d_partials, (pncu_stream_t)L.s_k);
-        if (rc) return rc;
-        g_stats.launches += 1;
-        j.nlanes = 1; j.slot0[0] = 0; j.slot0[1] = slots;
-        // finish_on_gpu0 works on lanes[0]; alias it when the data lives elsewhere
-        if (&L != &g.lanes[0]) {
-            PNCU_CUDA(cudaStreamSynchronize(L.s_k));
-            if ((rc = ensure_lane(0))) return rc;
-            if ((rc = ensure_partials(g.lanes[0], (size_t)slots * j.partial_bytes))) return rc;
-            PNCU_CUDA(cudaMemcpyPeer(g.lanes[0].d_partials, g.lanes[0].device, L.d_partials, L.device, (size_t)slots * j.partial_bytes));
-        }
-        rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
+    if (j.k1.resident()) {
+        // resident input: one kernel per GPU; a large contiguous managed array is sharded over all of them
+        if ((rc = injected_fault())) return rc;
+        const bool sharded = g.ndev > 1 && g.threading && g.peer_all && j.k1.kind == MK_MANAGED && j.s1 == j.isz_in &&
+                             (size_t)j.len * j.isz_in >= kShardResidentMinBytes;
+        rc = run_reduce_resident(j, sharded);
         if (!rc) g_stats.calls += 1;
         return rc;
     }
+    if (j.len < threshold_for(NTE_CLASS_REDUCE, j.k1.kind == MK_PAGEABLE, j.isz_in)) return decline();
+    if ((rc = injected_fault())) return rc;
     if ((rc = plan(j, max_workers))) return rc;
     for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
     run_lanes(j, lane_reduce);
     if ((rc = first_error(j))) return rc;
-    rc = finish_on_gpu0(j, host_out, out_bytes, host_start);
+    rc = finish_on_gpu0(j);
     if (!rc) g_stats.calls += 1;
     return rc;
 }
@@ -1132,7 +1364,8 @@ int nte_reduce(int func, int atype, const void* in, void* out, int use_out_as_st
     Job j;
     j.kind = JOB_REDUCE; j.func = func; j.atype = atype; j.isz_in = isz; j.isz_out = isz; j.partial_bytes = pb;
     j.in1 = (const char*)in; j.len = len; j.s1 = strideIn;
-    return dispatch_reduce(j, out, isz, use_out_as_start ? out : nullptr, max_workers);
+    j.host_out = out; j.out_bytes = isz; j.host_start = use_out_as_start ? out : nullptr;
+    return dispatch_reduce(j, max_workers);
 }
 
 int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out_index, int max_workers) {
@@ -1141,71 +1374,35 @@ int nte_argminmax(int kind, int atype, const void* in, int64_t len, int64_t* out
     Job j;
     j.kind = JOB_ARG; j.argkind = kind; j.atype = atype; j.isz_in = isz; j.isz_out = 8; j.partial_bytes = 16;
     j.in1 = (const char*)in; j.len = len; j.s1 = isz;
-    return dispatch_reduce(j, out_index, 8, nullptr, max_workers);
+    j.host_out = out_index; j.out_bytes = 8;
+    return dispatch_reduce(j, max_workers);
 }
 
 // fused chain: element-wise (out != NULL) or summed (host_out)
-static int dispatch_fused(Job& j, void* host_out, int max_workers) {
-    if (!g.inited) { set_error("nte_init() has not succeeded"); return PNCU_ERR_NO_DEVICE; }
-    if (j.len <= 0 || j.len < threshold_for(NTE_CLASS_HEAVY, false, 8)) return decline();
+static int dispatch_fused(Job& j, int max_workers) {
+    if (!usable()) {
+        if (g.forked) return decline();
+        set_error("nte_init() has not succeeded");
+        return PNCU_ERR_NO_DEVICE;
+    }
+    if (j.len <= 0) return decline();
+    const bool to_sum = j.kind == JOB_MULADD_SUM;
+    const bool r1 = lookup_registry(j.in1, &j.k1), r2 = lookup_registry(j.in2, &j.k2), r3 = lookup_registry(j.in3, &j.k3);
+    const bool ro = to_sum ? true : lookup_registry(j.out, &j.ko);
+    const bool known_resident = j.k1.resident() || j.k2.resident() || j.k3.resident() || (!to_sum && j.ko.resident());
+    if (!known_resident && j.len < lowest_threshold()) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
-    const bool to_sum = j.kind == JOB_MULADD_SUM;
-    j.pk_in1 = classify(j.in1); j.pk_in2 = classify(j.in2); j.pk_in3 = classify(j.in3);
-    j.pk_out = to_sum ? j.pk_in1 : classify(j.out);
-    const int pks[4] = {j.pk_in1, j.pk_in2, j.pk_in3, j.pk_out};
+    if (!r1) classify_driver(j.in1, &j.k1);
+    if (!r2) classify_driver(j.in2, &j.k2);
+    if (!r3) classify_driver(j.in3, &j.k3);
+    if (!ro) classify_driver(j.out, &j.ko);
+    if (to_sum) j.ko = j.k1;
+    const Operand* ks[4] = {&j.k1, &j.k2, &j.k3, &j.ko};
     int nhost = 0, npageable = 0;
-    for (int k = 0; k < 4; ++k) { nhost += host_kind(pks[k]); npageable += pks[k] == PK_PAGEABLE; }
-    if (nhost != 0 && nhost != 4) return decline();  // host and resident arrays mixed: the caller's loops
-    if (nhost == 4 && j.len < threshold_for(NTE_CLASS_STREAM, npageable != 0, j.isz_in)) return decline();
+    for (int k = 0; k < 4; ++k) { nhost += ks[k]->host(); npageable += ks[k]->kind == MK_PAGEABLE; }
+    if (nhost != 0 && nhost != 4) return decline();  // host and resident arrays mixed: the caller's ufunc chain
     const size_t bytes = (size_t)j.len * j.isz_in;
-    int rc;
-    if (nhost == 0) {
-        // resident operands: in place on their GPU, no PCIe
-        const bool all_managed = j.pk_in1 == PK_MANAGED && j.pk_in2 == PK_MANAGED && j.pk_in3 == PK_MANAGED &&
-                                 (to_sum || j.pk_out == PK_MANAGED);
-        if (g.ndev > 1 && g.threading && all_managed && bytes >= kShardResidentMinBytes) {
-            // large managed operands live sharded over the GPUs (run_resident_sharded): so does the fused chain
-            if ((rc = plan_one_lane_per_gpu(j))) return rc;
-            if (to_sum)
-                for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
-            run_resident_lanes(j, lane_fused_resident);
-            if ((rc = first_error(j))) return rc;
-            if (to_sum) {
-                j.kind = JOB_REDUCE;
-                j.func = PNCU_ADD;
-                if ((rc = finish_on_gpu0(j, host_out, j.isz_in, nullptr))) return rc;
-            }
-            g_stats.calls += 1;
-            return 0;
-        }
-        const int dev = device_of(j.in1);
-        if ((rc = ensure_lane(dev))) return rc;
-        g_stats.lanes_last = 1;
-        g_stats.gpus_last = 1;
-        Lane& L = g.lanes[dev];
-        PNCU_CUDA(cudaSetDevice(L.device));
-        if ((rc = prefetch_managed(j.in1, j.pk_in1, bytes, L))) return rc;
-        if ((rc = prefetch_managed(j.in2, j.pk_in2, bytes, L))) return rc;
-        if ((rc = prefetch_managed(j.in3, j.pk_in3, bytes, L))) return rc;
-        if (!to_sum) {
-            if ((rc = prefetch_managed(j.out, j.pk_out, bytes, L))) return rc;
-            if ((rc = j.fn3(j.in1, j.in2, j.in3, j.out, j.len, (pncu_stream_t)L.s_k))) return rc;
-            g_stats.launches += 1;
-            PNCU_CUDA(cudaStreamSynchronize(L.s_k));
-        } else {
-            pncu_three_reduce_fn full = pncu_GetMulAddSumFast(j.atype);
-            char* d_res = L.d_scalar + 32;
-            if ((rc = full(j.in1, j.in2, j.in3, d_res, j.len, (pncu_stream_t)L.s_k))) return rc;
-            g_stats.launches += 2;
-            PNCU_CUDA(cudaMemcpyAsync(L.h_small + 32, d_res, j.isz_in, cudaMemcpyDeviceToHost, L.s_k));
-            PNCU_CUDA(cudaStreamSynchronize(L.s_k));
-            memcpy(host_out, L.h_small + 32, j.isz_in);
-            g_stats.d2h += j.isz_in;
-        }
-        g_stats.calls += 1;
-        return 0;
-    }
     if (!to_sum) {
         // `out` may alias an input exactly; partial overlap is declined
         const char* ins[3] = {j.in1, j.in2, j.in3};
@@ -1214,6 +1411,27 @@ static int dispatch_fused(Job& j, void* host_out, int max_workers) {
             if (overlap && ins[k] != j.out) return decline();
         }
     }
+    DeviceGuard guard;
+    int rc;
+    if (nhost == 0) {
+        if ((rc = injected_fault())) return rc;
+        const bool all_managed = j.k1.kind == MK_MANAGED && j.k2.kind == MK_MANAGED && j.k3.kind == MK_MANAGED && j.ko.kind == MK_MANAGED;
+        const bool sharded = g.ndev > 1 && g.threading && all_managed && bytes >= kShardResidentMinBytes && (!to_sum || g.peer_all);
+        if (to_sum) {
+            rc = run_reduce_resident(j, sharded);
+        } else {
+            if (sharded) rc = plan_one_lane_per_gpu(j);
+            else rc = plan_on_device(j, home_of(j.ko, j.out, bytes), false);
+            if (rc) return rc;
+            if ((rc = place_operands(j))) return rc;
+            run_lanes(j, lane_resident);
+            rc = first_error(j);
+        }
+        if (!rc) g_stats.calls += 1;
+        return rc;
+    }
+    if (j.len < threshold_for(NTE_CLASS_STREAM, npageable != 0, j.isz_in)) return decline();
+    if ((rc = injected_fault())) return rc;
     if ((rc = plan(j, max_workers))) return rc;
     if (to_sum)
         for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
@@ -1222,8 +1440,7 @@ static int dispatch_fused(Job& j, void* host_out, int max_workers) {
     if (to_sum) {
         j.kind = JOB_REDUCE;  // the partials are those of the ADD reduction: ordinary gather + finish
         j.func = PNCU_ADD;
-        rc = finish_on_gpu0(j, host_out, j.isz_in, nullptr);
-        if (rc) return rc;
+        if ((rc = finish_on_gpu0(j))) return rc;
     }
     g_stats.calls += 1;
     return 0;
@@ -1235,8 +1452,8 @@ int nte_muladd(int atype, const void* in1, const void* in2, const void* in3, voi
     Job j;
     j.kind = JOB_MULADD; j.fn3 = fn; j.atype = atype; j.isz_in = j.isz_out = pncu_itemsize(atype);
     j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.in3 = (const char*)in3; j.out = (char*)out; j.len = len;
-    j.s1 = j.s2 = j.isz_in;
-    return dispatch_fused(j, nullptr, max_workers);
+    j.s1 = j.s2 = j.so = j.isz_in;
+    return dispatch_fused(j, max_workers);
 }
 
 int nte_muladd_sum(int atype, const void* in1, const void* in2, const void* in3, void* out, int64_t len, int max_workers) {
@@ -1246,7 +1463,8 @@ int nte_muladd_sum(int atype, const void* in1, const void* in2, const void* in3,
     j.partial_bytes = pncu_reduce_partial_bytes(PNCU_ADD, atype);
     j.in1 = (const char*)in1; j.in2 = (const char*)in2; j.in3 = (const char*)in3; j.len = len;
     j.s1 = j.s2 = j.isz_in;
-    return dispatch_fused(j, out, max_workers);
+    j.host_out = out; j.out_bytes = j.isz_in;
+    return dispatch_fused(j, max_workers);
 }
 
 }  // extern "C"

@@ -122,16 +122,35 @@ static stSettings g_Settings = {1, 0, 0, 0, 0};
 static PyObject* gpUnaryDict = NULL;  // {(ufunc_name, dtype_num): address of the stUFunc}
 static char g_DeviceString[512] = "";
 
-// ---- ledger: counts per category while enabled (reference: src/pnumpy/ledger.cpp:144-272 keeps a ring
-// of records and printf()s each one; the toggles are kept, the printf is not) ---------------------------
+// ---- ledger: per-category counters and a ring of per-call records while enabled (reference:
+// src/pnumpy/ledger.cpp:144-272 keeps a ring of records -- name, lengths, start/end ticks -- and printf()s each
+// one; the ring and the toggles are kept, the printf is not).  Ticks are timer_gettsc() values. -----------------
 struct LedgerCounters { int64_t gpu_calls, old_calls, elements; };
 static LedgerCounters g_Ledger[5];
 enum { CAT_BINARY, CAT_UNARY, CAT_COMPARE, CAT_TRIG, CAT_ARGMINMAX };
-static inline void ledger(int cat, bool gpu, int64_t n) {
+struct LedgerRecord {
+    uint64_t t0, t1;      // rdtsc at dispatcher entry / exit
+    int64_t n;            // elements
+    int64_t bytes;        // algorithmic bytes moved (inputs + output)
+    int16_t cat, funcop, atype;
+    int8_t gpu, reduce;
+};
+static const int kLedgerRing = 4096;
+static LedgerRecord g_LedgerRing[kLedgerRing];
+static uint64_t g_LedgerHead = 0;     // records ever written
+static std::mutex g_LedgerMu;
+static inline uint64_t rdtsc_now(void);
+static inline void ledger(int cat, bool gpu, int64_t n, uint64_t t0 = 0, int funcop = 0, int atype = 0, int64_t bytes = 0,
+                          bool reduce = false) {
     if (!g_Settings.LedgerEnabled) return;
+    std::lock_guard<std::mutex> lk(g_LedgerMu);
     if (gpu) g_Ledger[cat].gpu_calls++; else g_Ledger[cat].old_calls++;
     g_Ledger[cat].elements += n;
+    LedgerRecord& r = g_LedgerRing[g_LedgerHead++ % kLedgerRing];
+    r.t0 = t0; r.t1 = rdtsc_now(); r.n = n; r.bytes = bytes;
+    r.cat = (int16_t)cat; r.funcop = (int16_t)funcop; r.atype = (int16_t)atype; r.gpu = gpu; r.reduce = reduce;
 }
+static inline uint64_t ledger_t0(void) { return g_Settings.LedgerEnabled ? rdtsc_now() : 0; }
 
 // A CUDA failure inside a loop: NumPy has dropped the GIL around large loops, so take it back first.
 static void raise_cuda_error(const char* where, int rc) {
@@ -149,39 +168,47 @@ static void raise_cuda_error(const char* where, int rc) {
 static void AtopBinaryMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
     stUFunc* p = &g_UFuncLUT[funcop][atype];
     const npy_intp n = dimensions[0];
+    const uint64_t t0 = ledger_t0();
+    const bool reduce = IS_BINARY_REDUCE;
+    const int isz = pncu_itemsize(atype);
+    const int64_t bytes = reduce ? (int64_t)n * isz : (int64_t)n * (2 * isz + pncu_itemsize(p->OutType));
     if (g_Settings.AtopEnabled) {
         int rc = NTE_DECLINED;
-        if (IS_BINARY_REDUCE) {
+        if (reduce) {
             // the middle array is the real input; the accumulator seeds the fold (:646-652)
             if (p->pReduceFunc) rc = nte_reduce(funcop, atype, args[1], args[0], 1, (int64_t)n, (int64_t)steps[1], p->MaxThreads);
         } else if (p->pBinaryFunc) {
-            rc = nte_binary(p->pBinaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], args[2],
+            rc = nte_binary(p->pBinaryFunc, isz, pncu_itemsize(p->OutType), args[0], args[1], args[2],
                             (int64_t)n, (int64_t)steps[0], (int64_t)steps[1], (int64_t)steps[2], p->MaxThreads);
         }
-        if (rc == 0) { ledger(CAT_BINARY, true, n); return; }
+        if (rc == 0) { ledger(CAT_BINARY, true, n, t0, funcop, atype, bytes, reduce); return; }
         if (rc != NTE_DECLINED) { raise_cuda_error("binary ufunc loop", rc); return; }
     }
-    ledger(CAT_BINARY, false, n);
     p->pOldFunc(args, dimensions, steps, innerloop);
+    ledger(CAT_BINARY, false, n, t0, funcop, atype, bytes, reduce);
 }
 
 // reference: AtopCompareMathFunction, src/pnumpy/_pnumpy.cpp:805-866
 static void AtopCompareMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
     stUFunc* p = &g_CompFuncLUT[funcop][atype];
     const npy_intp n = dimensions[0];
+    const uint64_t t0 = ledger_t0();
+    const int64_t bytes = (int64_t)n * (2 * pncu_itemsize(atype) + 1);
     if (g_Settings.AtopEnabled && p->pBinaryFunc) {
         int rc = nte_binary(p->pBinaryFunc, pncu_itemsize(atype), 1, args[0], args[1], args[2], (int64_t)n,
                             (int64_t)steps[0], (int64_t)steps[1], (int64_t)steps[2], p->MaxThreads);
-        if (rc == 0) { ledger(CAT_COMPARE, true, n); return; }
+        if (rc == 0) { ledger(CAT_COMPARE, true, n, t0, funcop, atype, bytes); return; }
         if (rc != NTE_DECLINED) { raise_cuda_error("comparison ufunc loop", rc); return; }
     }
-    ledger(CAT_COMPARE, false, n);
     p->pOldFunc(args, dimensions, steps, innerloop);
+    ledger(CAT_COMPARE, false, n, t0, funcop, atype, bytes);
 }
 
 static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int atype,
-                         bool const_output = false) {
+                         int funcop, bool const_output = false) {
     const npy_intp n = dimensions[0];
+    const uint64_t t0 = ledger_t0();
+    const int64_t bytes = (int64_t)n * (pncu_itemsize(atype) + pncu_itemsize(p->OutType));
     // the reference drops the fast pointer when the output stride is 0 (:882-884, 946-948)
     if (g_Settings.AtopEnabled && p->pUnaryFunc && steps[1] != 0) {
         // integer classifiers (isnan(int) == False everywhere): constant output, see NTE_CLASS_CONST
@@ -190,35 +217,38 @@ static void unary_common(stUFunc* p, int cat, char** args, const npy_intp* dimen
         int rc = nte_unary_class(p->pUnaryFunc, pncu_itemsize(atype), pncu_itemsize(p->OutType), args[0], args[1], (int64_t)n,
                                  (int64_t)steps[0], (int64_t)steps[1], p->MaxThreads,
                                  op_class);
-        if (rc == 0) { ledger(cat, true, n); return; }
+        if (rc == 0) { ledger(cat, true, n, t0, funcop, atype, bytes); return; }
         if (rc != NTE_DECLINED) { raise_cuda_error("unary ufunc loop", rc); return; }
     }
-    ledger(cat, false, n);
     p->pOldFunc(args, dimensions, steps, innerloop);
+    ledger(cat, false, n, t0, funcop, atype, bytes);
 }
 // reference: AtopUnaryMathFunction, src/pnumpy/_pnumpy.cpp:874-932
 static void AtopUnaryMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
     const bool classifier = funcop == PNCU_ISNAN || funcop == PNCU_ISINF || funcop == PNCU_ISFINITE || funcop == PNCU_ISNOTNAN ||
                             funcop == PNCU_ISNOTINF || funcop == PNCU_ISNOTFINITE;
-    unary_common(&g_UnaryFuncLUT[funcop][atype], CAT_UNARY, args, dimensions, steps, innerloop, atype, classifier);
+    unary_common(&g_UnaryFuncLUT[funcop][atype], CAT_UNARY, args, dimensions, steps, innerloop, atype, funcop, classifier);
 }
 // reference: AtopTrigMathFunction, src/pnumpy/_pnumpy.cpp:938-996
 static void AtopTrigMathFunction(char** args, const npy_intp* dimensions, const npy_intp* steps, void* innerloop, int funcop, int atype) {
-    unary_common(&g_TrigFuncLUT[funcop][atype], CAT_TRIG, args, dimensions, steps, innerloop, atype);
+    unary_common(&g_TrigFuncLUT[funcop][atype], CAT_TRIG, args, dimensions, steps, innerloop, atype, funcop);
 }
 
 // reference: AtopArgMinMaxMathFunction, src/pnumpy/_pnumpy.cpp:1105-1118 (an empty `if (AtopEnabled) {}`
 // followed by the old function: the reference never accelerated it; this build does)
 static int AtopArgMinMaxMathFunction(void* data, npy_intp n, npy_intp* out_index, void* arr, int kind, int atype) {
     stArgMinMaxFunc* p = &g_ArgMinMaxFuncLUT[kind][atype];
+    const uint64_t t0 = ledger_t0();
+    const int64_t bytes = (int64_t)n * pncu_itemsize(atype);
     if (g_Settings.AtopEnabled && p->pFunc) {
         int64_t idx = 0;
         int rc = nte_argminmax(kind, atype, data, (int64_t)n, &idx, p->MaxThreads);
-        if (rc == 0) { *out_index = (npy_intp)idx; ledger(CAT_ARGMINMAX, true, n); return 0; }
+        if (rc == 0) { *out_index = (npy_intp)idx; ledger(CAT_ARGMINMAX, true, n, t0, kind, atype, bytes, true); return 0; }
         if (rc != NTE_DECLINED) { raise_cuda_error("arg-reduction", rc); return -1; }
     }
-    ledger(CAT_ARGMINMAX, false, n);
-    return p->pOldFunc(data, n, out_index, arr);
+    const int ret = p->pOldFunc(data, n, out_index, arr);
+    ledger(CAT_ARGMINMAX, false, n, t0, kind, atype, bytes, true);
+    return ret;
 }
 
 // =======================================================================================================
@@ -236,51 +266,57 @@ static int AtopArgMinMaxMathFunction(void* data, npy_intp n, npy_intp* out_index
 // the saved 'dd->d' loop -- no arithmetic of ours runs on the CPU.
 static int g_ExtraLoops = 0;
 
+template <class T>
+static void int_to_double_t(const char* src, npy_intp stride, double* dst, npy_intp n) {
+    for (npy_intp i = 0; i < n; ++i) dst[i] = (double)*reinterpret_cast<const T*>(src + i * stride);
+}
+static void int_to_double(int type_num, const char* src, npy_intp stride, double* dst, npy_intp n) {
+    switch (type_num) {
+        case NPY_UBYTE: int_to_double_t<npy_ubyte>(src, stride, dst, n); break;
+        case NPY_SHORT: int_to_double_t<npy_short>(src, stride, dst, n); break;
+        case NPY_USHORT: int_to_double_t<npy_ushort>(src, stride, dst, n); break;
+        case NPY_INT: int_to_double_t<npy_int>(src, stride, dst, n); break;
+        case NPY_UINT: int_to_double_t<npy_uint>(src, stride, dst, n); break;
+        case NPY_LONG: int_to_double_t<npy_long>(src, stride, dst, n); break;
+        case NPY_ULONG: int_to_double_t<npy_ulong>(src, stride, dst, n); break;
+        case NPY_LONGLONG: int_to_double_t<npy_longlong>(src, stride, dst, n); break;
+        default: int_to_double_t<npy_ulonglong>(src, stride, dst, n); break;
+    }
+}
+
 static int int_true_divide_loop(PyArrayMethod_Context* context, char* const* data, const npy_intp* dimensions,
                                 const npy_intp* strides, NpyAuxData*) {
     const int type_num = context->descriptors[0]->type_num;
     const int atype = convert_dtype_to_atop[type_num];
     const npy_intp n = dimensions[0];
+    const uint64_t t0 = ledger_t0();
+    const int64_t bytes = (int64_t)n * (2 * pncu_itemsize(atype) + 8);
     if (g_Settings.AtopEnabled) {
         pncu_any_two_fn fn = pncu_GetIntTrueDivide(atype);
         int rc = fn ? nte_binary(fn, pncu_itemsize(atype), 8, data[0], data[1], data[2], (int64_t)n, (int64_t)strides[0],
                                  (int64_t)strides[1], (int64_t)strides[2], 3)
                     : NTE_DECLINED;
-        if (rc == 0) { ledger(CAT_BINARY, true, n); return 0; }
+        if (rc == 0) { ledger(CAT_BINARY, true, n, t0, PNCU_DIV, atype, bytes); return 0; }
         if (rc != NTE_DECLINED) { raise_cuda_error("int true_divide loop", rc); return -1; }
     }
-    ledger(CAT_BINARY, false, n);
-    // NumPy's own path, chunk by chunk: cast, cast (PyArray_CopyInto on 1-D views), DOUBLE_true_divide
+    // What NumPy itself does for this call: cast both operands to float64, then its own 'dd->d' loop (which also
+    // raises the IEEE flags NumPy's divide-by-zero / invalid warnings come from).  The casts are plain C
+    // conversions (exact for every integer up to 2^53, round-to-nearest beyond: the hardware's cvtsi2sd, which is
+    // what NumPy's cast loops compile to), done chunk by chunk into two small stack buffers: no Python API, so
+    // the GIL stays wherever NumPy left it, and nothing is allocated.
     PyUFuncGenericFunction dd = g_UFuncLUT[PNCU_DIV][PNCU_DOUBLE].pOldFunc;
-    const npy_intp CHUNK = 65536;
-    double* buf = (double*)malloc(2 * CHUNK * sizeof(double));
-    if (!buf) return -1;
-    PyGILState_STATE st = PyGILState_Ensure();  // creating array views needs the Python C-API
-    int ret = 0;
-    for (npy_intp off = 0; off < n && ret == 0; off += CHUNK) {
-        npy_intp cnt = (n - off) < CHUNK ? (n - off) : CHUNK;
-        for (int k = 0; k < 2 && ret == 0; ++k) {
-            PyArray_Descr* src_descr = (PyArray_Descr*)context->descriptors[k];
-            Py_INCREF(src_descr);  // NewFromDescr steals a reference
-            npy_intp sstride = strides[k];
-            PyObject* src = PyArray_NewFromDescr(&PyArray_Type, src_descr, 1, &cnt, &sstride, data[k] + off * strides[k], 0, NULL);
-            npy_intp dstride = 8;
-            PyObject* dst = PyArray_NewFromDescr(&PyArray_Type, PyArray_DescrFromType(NPY_DOUBLE), 1, &cnt, &dstride,
-                                                 buf + k * CHUNK, NPY_ARRAY_WRITEABLE, NULL);
-            if (!src || !dst || PyArray_CopyInto((PyArrayObject*)dst, (PyArrayObject*)src) < 0) ret = -1;
-            Py_XDECREF(src);
-            Py_XDECREF(dst);
-        }
-        if (ret == 0) {
-            char* a3[3] = {(char*)buf, (char*)(buf + CHUNK), data[2] + off * strides[2]};
-            const npy_intp dims[1] = {cnt};
-            const npy_intp steps[3] = {8, 8, strides[2]};
-            dd(a3, dims, steps, NULL);
-        }
+    const npy_intp CHUNK = 2048;
+    double buf[2][CHUNK];
+    for (npy_intp off = 0; off < n; off += CHUNK) {
+        const npy_intp cnt = (n - off) < CHUNK ? (n - off) : CHUNK;
+        for (int k = 0; k < 2; ++k) int_to_double(type_num, data[k] + off * strides[k], strides[k], buf[k], cnt);
+        char* a3[3] = {(char*)buf[0], (char*)buf[1], data[2] + off * strides[2]};
+        const npy_intp dims[1] = {cnt};
+        const npy_intp steps[3] = {8, 8, strides[2]};
+        dd(a3, dims, steps, NULL);
     }
-    PyGILState_Release(st);
-    free(buf);
-    return ret;
+    ledger(CAT_BINARY, false, n, t0, PNCU_DIV, atype, bytes);
+    return 0;
 }
 
 static int register_int_true_divide(PyObject* numpy_module) {
@@ -578,82 +614,137 @@ static PyObject* cpustring(PyObject*, PyObject*) {
 static PyObject* ledger_enable(PyObject*, PyObject*) { g_Settings.LedgerEnabled = 1; Py_RETURN_NONE; }
 static PyObject* ledger_disable(PyObject*, PyObject*) { g_Settings.LedgerEnabled = 0; Py_RETURN_NONE; }
 static PyObject* ledger_isenabled(PyObject*, PyObject*) { return PyBool_FromLong(g_Settings.LedgerEnabled); }
+static const char* kLedgerCatNames[5] = {"Binary", "Unary", "Compare", "TrigLog", "ArgMinMax"};
 static PyObject* ledger_info(PyObject*, PyObject*) {
-    static const char* names[5] = {"Binary", "Unary", "Compare", "TrigLog", "ArgMinMax"};
     PyObject* d = PyDict_New();
+    std::lock_guard<std::mutex> lk(g_LedgerMu);
     for (int c = 0; c < 5; ++c) {
         PyObject* v = Py_BuildValue("{s:L,s:L,s:L}", "gpu_calls", (long long)g_Ledger[c].gpu_calls, "numpy_calls",
                                     (long long)g_Ledger[c].old_calls, "elements", (long long)g_Ledger[c].elements);
-        PyDict_SetItemString(d, names[c], v);
+        PyDict_SetItemString(d, kLedgerCatNames[c], v);
         Py_DECREF(v);
     }
     return d;
 }
+// ledger_records(last=None) -> the most recent per-call records, oldest first (the reference's ledger ring,
+// src/pnumpy/ledger.cpp:144-272: category, op, type, length, start/end ticks), plus where the call ran
+static PyObject* ledger_records(PyObject*, PyObject* args) {
+    long long last = kLedgerRing;
+    if (!PyArg_ParseTuple(args, "|L:ledger_records", &last)) return NULL;
+    std::vector<LedgerRecord> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_LedgerMu);
+        uint64_t have = g_LedgerHead < (uint64_t)kLedgerRing ? g_LedgerHead : (uint64_t)kLedgerRing;
+        if (last >= 0 && (uint64_t)last < have) have = (uint64_t)last;
+        for (uint64_t i = g_LedgerHead - have; i < g_LedgerHead; ++i) recs.push_back(g_LedgerRing[i % kLedgerRing]);
+    }
+    PyObject* list = PyList_New((Py_ssize_t)recs.size());
+    if (!list) return NULL;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        const LedgerRecord& r = recs[i];
+        PyObject* v = Py_BuildValue("{s:s,s:i,s:i,s:L,s:L,s:K,s:K,s:K,s:O,s:O}", "category", kLedgerCatNames[r.cat], "op", (int)r.funcop,
+                                    "atype", (int)r.atype, "elements", (long long)r.n, "bytes", (long long)r.bytes, "start_tsc",
+                                    (unsigned long long)r.t0, "end_tsc", (unsigned long long)r.t1, "ticks",
+                                    (unsigned long long)(r.t1 - r.t0), "gpu", r.gpu ? Py_True : Py_False, "reduce",
+                                    r.reduce ? Py_True : Py_False);
+        if (!v) { Py_DECREF(list); return NULL; }
+        PyList_SET_ITEM(list, (Py_ssize_t)i, v);
+    }
+    return list;
+}
+static PyObject* ledger_clear(PyObject*, PyObject*) {
+    std::lock_guard<std::mutex> lk(g_LedgerMu);
+    memset(g_Ledger, 0, sizeof(g_Ledger));
+    g_LedgerHead = 0;
+    Py_RETURN_NONE;
+}
 
-// ---- recycler: NEP-49 data allocator that hands out PINNED host memory for large ndarrays and recycles
-// freed blocks (the reference's roadmap for its placeholder recycler, src/pnumpy/__init__.py:18-21,
-// src/pnumpy/recycler.cpp).  Operands that live in pinned memory are DMA'd in place by nte. ---------------
-static const size_t kPinnedThreshold = (size_t)1 << 20;
+// ---- recycler: NEP-49 data allocator that gives large ndarrays memory the GPU can reach, and recycles freed
+// blocks (the reference's roadmap for its placeholder recycler, src/pnumpy/__init__.py:18-21,
+// src/pnumpy/recycler.cpp, doc_src/source/roadmap.rst:27-31).  Two kinds:
+//   "pinned"   page-locked host memory: nte DMAs such operands in place (no staging copy); every call still
+//              crosses PCIe.
+//   "managed"  CUDA managed memory: the arrays NumPy creates -- np.empty, ufunc outputs, temporaries of
+//              a*b+c -- are DEVICE-CAPABLE from birth.  A hooked call whose operands are managed runs in place
+//              on the GPU at any size; intermediates never cross PCIe; pages migrate to the host only when host
+//              code touches them.  This is what makes residency reachable through the unmodified NumPy API.
+// Blocks are recycled by exact size (NumPy asks for the same sizes over and over); a recycled managed block
+// keeps its pages where the last kernel left them. ------------------------------------------------------------
+enum { RK_PINNED = 0, RK_MANAGED = 1 };
+static size_t g_RecyclerThreshold[2] = {(size_t)1 << 20, (size_t)256 << 10};
+static int g_RecyclerKind = RK_PINNED;
 static std::mutex g_PoolMu;
-static std::multimap<size_t, void*> g_Pool;
-static size_t g_PoolBytes = 0, g_PoolCap = (size_t)8 << 30;
-static int64_t g_PoolHits = 0, g_PoolMisses = 0, g_PinnedLive = 0;
+static std::multimap<size_t, void*> g_Pool[2];
+static size_t g_PoolBytes[2] = {0, 0}, g_PoolCap = (size_t)8 << 30;
+static int64_t g_PoolHits = 0, g_PoolMisses = 0, g_BlocksLive = 0;
 
-static std::map<void*, size_t> g_Live;  // pinned blocks currently owned by ndarrays -> their size
+struct LiveBlock { size_t size; int kind; };
+static std::map<void*, LiveBlock> g_Live;  // blocks currently owned by ndarrays
 
-static void* pool_get(size_t size) {
+static void* pool_get(size_t size, int kind) {
     void* p = NULL;
     {
         std::lock_guard<std::mutex> lk(g_PoolMu);
-        auto it = g_Pool.find(size);
-        if (it != g_Pool.end()) {
+        auto it = g_Pool[kind].find(size);
+        if (it != g_Pool[kind].end()) {
             p = it->second;
-            g_Pool.erase(it);
-            g_PoolBytes -= size;
+            g_Pool[kind].erase(it);
+            g_PoolBytes[kind] -= size;
             g_PoolHits++;
         } else {
             g_PoolMisses++;
         }
     }
-    if (!p) p = nte_alloc_pinned(size);
+    if (!p) p = kind == RK_MANAGED ? nte_alloc_managed(size) : nte_alloc_pinned(size);
     if (p) {
         std::lock_guard<std::mutex> lk(g_PoolMu);
-        g_Live[p] = size;
-        g_PinnedLive++;
+        g_Live[p] = LiveBlock{size, kind};
+        g_BlocksLive++;
     }
     return p;
 }
 // true (and the block is retired) if `p` is one of ours
 static bool pool_put(void* p) {
-    size_t size = 0;
+    LiveBlock b;
     {
         std::lock_guard<std::mutex> lk(g_PoolMu);
         auto it = g_Live.find(p);
         if (it == g_Live.end()) return false;
-        size = it->second;
+        b = it->second;
         g_Live.erase(it);
-        g_PinnedLive--;
-        if (g_PoolBytes + size <= g_PoolCap) {
-            g_Pool.insert(std::make_pair(size, p));
-            g_PoolBytes += size;
+        g_BlocksLive--;
+        if (!nte_is_forked_child() && g_PoolBytes[0] + g_PoolBytes[1] + b.size <= g_PoolCap) {
+            g_Pool[b.kind].insert(std::make_pair(b.size, p));
+            g_PoolBytes[b.kind] += b.size;
             return true;
         }
     }
-    nte_free_pinned(p);
+    if (b.kind == RK_MANAGED) nte_free_managed(p); else nte_free_pinned(p);
     return true;
 }
-static size_t pinned_size_of(void* p) {
+static bool live_block_of(void* p, LiveBlock* b) {
     std::lock_guard<std::mutex> lk(g_PoolMu);
     auto it = g_Live.find(p);
-    return it == g_Live.end() ? 0 : it->second;
+    if (it == g_Live.end()) return false;
+    *b = it->second;
+    return true;
 }
 static void* rc_malloc(void*, size_t size) {
-    if (size >= kPinnedThreshold) { void* p = pool_get(size); if (p) return p; }
+    const int kind = g_RecyclerKind;
+    if (size >= g_RecyclerThreshold[kind]) { void* p = pool_get(size, kind); if (p) return p; }
     return malloc(size ? size : 1);
 }
 static void* rc_calloc(void*, size_t nelem, size_t elsize) {
     const size_t size = nelem * elsize;
-    if (size >= kPinnedThreshold) { void* p = pool_get(size); if (p) { memset(p, 0, size); return p; } }
+    const int kind = g_RecyclerKind;
+    if (size >= g_RecyclerThreshold[kind]) {
+        void* p = pool_get(size, kind);
+        if (p) {
+            // managed: zero on the GPU, so np.zeros() does not drag the pages to the host
+            if (kind != RK_MANAGED || nte_zero_managed(p, size) != 0) memset(p, 0, size);
+            return p;
+        }
+    }
     return calloc(nelem ? nelem : 1, elsize ? elsize : 1);
 }
 static void rc_free(void*, void* ptr, size_t) {
@@ -662,25 +753,43 @@ static void rc_free(void*, void* ptr, size_t) {
 }
 static void* rc_realloc(void* ctx, void* ptr, size_t new_size) {
     if (!ptr) return rc_malloc(ctx, new_size);
-    const size_t old_pinned = pinned_size_of(ptr);
-    if (!old_pinned && new_size < kPinnedThreshold) return realloc(ptr, new_size ? new_size : 1);
-    if (!old_pinned) {
-        // growing a malloc'd block past the threshold: plain realloc keeps the data valid; it simply
-        // stays pageable (staged through nte's slabs like any other host array)
-        return realloc(ptr, new_size);
+    LiveBlock b;
+    if (!live_block_of(ptr, &b)) {
+        // a malloc'd block: plain realloc keeps the data valid; grown past the threshold it simply stays
+        // pageable (staged through nte's slabs like any other host array)
+        return realloc(ptr, new_size ? new_size : 1);
     }
     void* q = rc_malloc(ctx, new_size);
     if (!q) return NULL;
-    memcpy(q, ptr, old_pinned < new_size ? old_pinned : new_size);
+    memcpy(q, ptr, b.size < new_size ? b.size : new_size);
     pool_put(ptr);
     return q;
 }
-static PyDataMem_Handler g_RecyclerHandler = {"pnumpy_b200_pinned_recycler", 1, {NULL, rc_malloc, rc_calloc, rc_realloc, rc_free}};
+static PyDataMem_Handler g_RecyclerHandler = {"pnumpy_b200_recycler", 1, {NULL, rc_malloc, rc_calloc, rc_realloc, rc_free}};
 static PyObject* g_OldHandler = NULL;
 
-static PyObject* recycler_enable(PyObject*, PyObject*) {
+// recycler_enable(kind="pinned", threshold=None): the reference's recycler_enable() takes no arguments and so
+// keeps working; kind="managed" makes large ndarrays device-capable (see above).  Env PNUMPY_B200_RECYCLER sets
+// the default kind.
+static PyObject* recycler_enable(PyObject*, PyObject* args, PyObject* kwargs) {
+    static const char* kwlist[] = {"kind", "threshold", NULL};
+    const char* kind = NULL;
+    PyObject* threshold = Py_None;
+    if (!PyArg_ParseTupleAndKeywords(args, kwargs, "|zO:recycler_enable", (char**)kwlist, &kind, &threshold)) return NULL;
+    if (!g_Settings.Initialized) { PyErr_SetString(PyExc_RuntimeError, "call initialize() first"); return NULL; }
+    if (!kind) kind = getenv("PNUMPY_B200_RECYCLER");
+    int k = RK_PINNED;
+    if (kind && *kind) {
+        if (!strcmp(kind, "managed")) k = RK_MANAGED;
+        else if (strcmp(kind, "pinned")) { PyErr_SetString(PyExc_ValueError, "kind must be 'pinned' or 'managed'"); return NULL; }
+    }
+    if (threshold != Py_None) {
+        const long long t = PyLong_AsLongLong(threshold);
+        if (t < 0) { if (!PyErr_Occurred()) PyErr_SetString(PyExc_ValueError, "threshold must be >= 0"); return NULL; }
+        g_RecyclerThreshold[k] = (size_t)(t < 4096 ? 4096 : t);
+    }
+    g_RecyclerKind = k;
     if (!g_Settings.RecyclerEnabled) {
-        if (!g_Settings.Initialized) { PyErr_SetString(PyExc_RuntimeError, "call initialize() first"); return NULL; }
         PyObject* cap = PyCapsule_New(&g_RecyclerHandler, "mem_handler", NULL);
         if (!cap) return NULL;
         PyObject* old = PyDataMem_SetHandler(cap);
@@ -704,9 +813,27 @@ static PyObject* recycler_disable(PyObject*, PyObject*) {
 static PyObject* recycler_isenabled(PyObject*, PyObject*) { return PyBool_FromLong(g_Settings.RecyclerEnabled); }
 static PyObject* recycler_info(PyObject*, PyObject*) {
     std::lock_guard<std::mutex> lk(g_PoolMu);
-    return Py_BuildValue("{s:L,s:L,s:L,s:L,s:L,s:L}", "pooled_blocks", (long long)g_Pool.size(), "pooled_bytes",
-                         (long long)g_PoolBytes, "hits", (long long)g_PoolHits, "misses", (long long)g_PoolMisses,
-                         "live_pinned_blocks", (long long)g_PinnedLive, "threshold_bytes", (long long)kPinnedThreshold);
+    return Py_BuildValue("{s:s,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L}", "kind", g_RecyclerKind == RK_MANAGED ? "managed" : "pinned",
+                         "pooled_blocks", (long long)(g_Pool[0].size() + g_Pool[1].size()), "pooled_bytes",
+                         (long long)(g_PoolBytes[0] + g_PoolBytes[1]), "pooled_managed_bytes", (long long)g_PoolBytes[1],
+                         "hits", (long long)g_PoolHits, "misses", (long long)g_PoolMisses,
+                         "live_blocks", (long long)g_BlocksLive, "live_pinned_blocks", (long long)g_BlocksLive,
+                         "threshold_bytes", (long long)g_RecyclerThreshold[g_RecyclerKind],
+                         "pool_cap_bytes", (long long)g_PoolCap);
+}
+// give pooled (free) blocks back to CUDA; live arrays are untouched
+static PyObject* recycler_trim(PyObject*, PyObject*) {
+    std::vector<std::pair<void*, int>> victims;
+    {
+        std::lock_guard<std::mutex> lk(g_PoolMu);
+        for (int k = 0; k < 2; ++k) {
+            for (auto& kv : g_Pool[k]) victims.push_back(std::make_pair(kv.second, k));
+            g_Pool[k].clear();
+            g_PoolBytes[k] = 0;
+        }
+    }
+    for (auto& v : victims) { if (v.second == RK_MANAGED) nte_free_managed(v.first); else nte_free_pinned(v.first); }
+    return PyLong_FromSize_t(victims.size());
 }
 
 // ---- timers.  reference: src/pnumpy/ledger.cpp:91-114 ---------------------------------------------------
@@ -732,12 +859,19 @@ static PyObject* timer_getutc(PyObject*, PyObject*) {
 static PyObject* cuda_info(PyObject*, PyObject*) {
     nte_stats s;
     nte_get_stats(&s);
-    return Py_BuildValue("{s:i,s:s,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:i,s:i,s:i}", "devices", nte_device_count(), "device_string",
+    return Py_BuildValue("{s:i,s:s,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:L,s:i,s:i,s:i,s:L,s:i}", "devices", nte_device_count(), "device_string",
                          g_DeviceString, "min_elems", (long long)nte_get_min_elems(), "calls", (long long)s.calls, "declined",
                          (long long)s.declined, "launches", (long long)s.launches, "library_launches", (long long)pncu_launch_count(),
                          "h2d_bytes", (long long)s.h2d_bytes, "d2h_bytes", (long long)s.d2h_bytes, "staged_bytes",
                          (long long)s.staged_bytes, "lanes_last", (long long)s.lanes_last, "gpus_last", (long long)s.gpus_last,
-                         "workers", nte_get_workers(), "threading", nte_get_threading(), "extra_loops", g_ExtraLoops);
+                         "workers", nte_get_workers(), "threading", nte_get_threading(), "extra_loops", g_ExtraLoops,
+                         "prefetches", (long long)s.prefetches, "forked_child", nte_is_forked_child());
+}
+// cuda_inject_fault(n): the n-th GPU dispatch from now fails like a bad launch (error-path tests); 0 disarms
+static PyObject* cuda_inject_fault(PyObject*, PyObject* args) {
+    long long n = 0;
+    if (!PyArg_ParseTuple(args, "L:cuda_inject_fault", &n)) return NULL;
+    return PyLong_FromLongLong(nte_inject_fault(n));
 }
 static PyObject* cuda_reset_stats(PyObject*, PyObject*) { nte_reset_stats(); Py_RETURN_NONE; }
 static PyObject* cuda_setthreshold(PyObject*, PyObject* args) {
@@ -874,7 +1008,12 @@ static PyMethodDef module_functions[] = {
     {"ledger_disable", ledger_disable, METH_VARARGS, "disable the ledger"},
     {"ledger_isenabled", ledger_isenabled, METH_VARARGS, "returns True if the ledger is enabled"},
     {"ledger_info", ledger_info, METH_VARARGS, "per-category call counts recorded while the ledger was enabled"},
-    {"recycler_enable", recycler_enable, METH_VARARGS, "large ndarrays are born in recycled pinned host memory"},
+    {"ledger_records", ledger_records, METH_VARARGS, "the most recent per-call records (op, type, elements, bytes, ticks, gpu)"},
+    {"ledger_clear", ledger_clear, METH_VARARGS, "zero the ledger counters and drop the records"},
+    {"recycler_enable", (PyCFunction)(void (*)(void))recycler_enable, METH_VARARGS | METH_KEYWORDS,
+     "recycler_enable(kind='pinned'|'managed', threshold=None): large ndarrays are born in recycled pinned host / CUDA managed memory"},
+    {"recycler_trim", recycler_trim, METH_VARARGS, "free the pooled (unused) blocks; returns how many"},
+    {"cuda_inject_fault", cuda_inject_fault, METH_VARARGS, "fail the n-th GPU dispatch from now (tests); returns the previous countdown"},
     {"recycler_disable", recycler_disable, METH_VARARGS, "restore NumPy's default data allocator"},
     {"recycler_isenabled", recycler_isenabled, METH_VARARGS, "returns True if the recycler is enabled"},
     {"recycler_info", recycler_info, METH_VARARGS, "pinned-block pool statistics"},

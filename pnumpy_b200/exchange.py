@@ -1,9 +1,9 @@
-"""Cross-GPU reductions with the exchange fused into pass 2 (include/pnumpy_cuda.h,
-``pncu_reduce_exchange_finish`` / ``pncu_argminmax_exchange_finish``): after the ordinary pass 1 on its own
-shard, each participant launches ONE kernel that stores its block partials into every participant's slot
-table over NVLink, bumps the arrival counters, waits on the device for everybody else's and folds the
-complete table.  No NCCL call, no host synchronisation between the passes; every participant gets the same
-bits as a single GPU would produce.
+"""Cross-GPU reductions with the exchange done INSIDE the reduction kernel (include/pnumpy_cuda.h,
+``pncu_reduce_fused`` / ``pncu_argminmax_fused``): each participant launches ONE kernel on its own shard.
+Its pass-1 CTAs take tickets; the CTA that draws the last one stores the shard's block partials into every
+participant's slot table over NVLink, bumps the arrival counters, waits on the device for everybody else's
+and folds the complete table.  No NCCL call, no second launch, no host synchronisation; every participant
+gets the same bits as a single GPU would produce.
 
 ``Exchange`` owns one participant's tables (two, used alternately) and the pointers to everybody else's:
 * ``Exchange.in_process(devices, max_slots)`` -- one process driving several GPUs (peer access),
@@ -11,6 +11,11 @@ bits as a single GPU would produce.
   IPC handles exchanged once with ``torch.distributed.all_gather_object`` (control plane only).
 This mirrors what the reference does with its per-chunk partials on the calling thread
 (src/pnumpy/_pnumpy.cpp:666-700), spread over GPUs.
+
+A participant that never arrives (a lost rank) is an ERROR, not a hang and not a wrong number: the kernel
+gives up after ~2 s WITHOUT folding and without writing the result, flags the call in this participant's
+status word, and ``Exchange.wait()`` raises ``PnumpyCudaError``; the Exchange is unusable afterwards (the
+arrival counters of the ranks no longer agree).
 """
 import ctypes
 
@@ -19,6 +24,7 @@ import numpy as np
 from . import cabi
 
 SLOT_BYTES = 16  # the largest partial: {value bits, index} of an arg-reduction
+_HEADER = 512    # counters (2 x 128 B) + status word, in front of the two tables
 
 
 class Exchange:
@@ -27,20 +33,14 @@ class Exchange:
         self._bases, self._counters, self._imported = bases, counters, list(imported)  # [participant][parity] addresses
         self.epoch = 0
         self.expected = [0, 0]
-        self._scratch, self._scratch_bytes, self._retired = None, 0, []
-        self._tables = []
-        for parity in (0, 1):
-            t = cabi.PeerTable()
-            t.n = world
-            for d in range(world):
-                t.slots[d] = bases[d][parity]
-                t.arrived[d] = counters[d][parity]
-            self._tables.append(t)
+        self.broken = None
+        self._status = None      # device address of this participant's status word
+        self._seen_timeouts = None  # pncu_exchange_timeouts() of this device when the first reduction was issued
 
     # ---- construction ---------------------------------------------------------------------------------
     @staticmethod
     def _alloc(lib, max_slots):
-        nbytes = 2 * max_slots * SLOT_BYTES + 256
+        nbytes = 2 * max_slots * SLOT_BYTES + _HEADER
         p = ctypes.c_void_p()
         cabi.check(lib.pncu_malloc(ctypes.byref(p), nbytes), "pncu_malloc")
         cabi.check(lib.pncu_memset(p, 0, nbytes, None), "pncu_memset")
@@ -49,7 +49,7 @@ class Exchange:
 
     @staticmethod
     def _layout(base, max_slots):
-        tab = [base + 256, base + 256 + max_slots * SLOT_BYTES]
+        tab = [base + _HEADER, base + _HEADER + max_slots * SLOT_BYTES]
         return tab, [base, base + 128]
 
     @classmethod
@@ -68,6 +68,7 @@ class Exchange:
         for r, d in enumerate(devices):
             x = cls(r, len(devices), [l[0] for l in lay], [l[1] for l in lay], max_slots, d)
             x._own = raw[r]
+            x._status = raw[r] + 256
             out.append(x)
         return out
 
@@ -99,6 +100,7 @@ class Exchange:
         lay = [cls._layout(b, max_slots) for b in raw]
         x = cls(rank, world, [l[0] for l in lay], [l[1] for l in lay], max_slots, dev.value, imported)
         x._own = own
+        x._status = own + 256
         if sync:
             dist.barrier()
         return x
@@ -110,56 +112,72 @@ class Exchange:
         self._imported = []
         lib.pncu_set_device(self.device)
         lib.pncu_device_sync()
-        for p in self._retired + ([self._scratch] if self._scratch else []):
-            lib.pncu_free(p)
-        self._retired, self._scratch, self._scratch_bytes = [], None, 0
         if getattr(self, "_own", None):
             lib.pncu_free(self._own)
             self._own = None
 
     # ---- one reduction ------------------------------------------------------------------------------------
-    def _begin(self, counts, partial_bytes):
-        """`counts[r]` = block partials participant r contributes.
-        -> (table, slot_base, total, expected, local scratch pointer)"""
-        lib = cabi.load()
+    def _begin(self, counts):
+        """`counts[r]` = block partials participant r contributes -> the pncu_fused_exchange of this call"""
+        if self.broken:
+            raise cabi.PnumpyCudaError(f"this Exchange is unusable: {self.broken}")
+        if self._seen_timeouts is None:
+            lib = cabi.load()
+            cabi.check(lib.pncu_set_device(self.device), "set_device")
+            self._seen_timeouts = int(lib.pncu_exchange_timeouts())
         parity = self.epoch & 1
         self.epoch += 1
         total = int(sum(counts))
         if total > self.max_slots:
             raise cabi.PnumpyCudaError(f"{total} block partials exceed the exchange tables ({self.max_slots} slots)")
-        self.expected[parity] += self.world * lib.pncu_exchange_slices()
-        need = int(counts[self.rank]) * partial_bytes
-        if getattr(self, "_scratch_bytes", 0) < need:
-            p = ctypes.c_void_p()
-            cabi.check(lib.pncu_set_device(self.device), "set_device")
-            cabi.check(lib.pncu_malloc(ctypes.byref(p), max(need, 1 << 20)), "pncu_malloc")
-            if getattr(self, "_scratch", None):
-                self._retired.append(self._scratch)   # may still be read by queued work: freed in close()
-            self._scratch, self._scratch_bytes = p.value, max(need, 1 << 20)
-        return self._tables[parity], int(sum(counts[: self.rank])), total, self.expected[parity], self._scratch
+        self.expected[parity] += self.world - 1
+        x = cabi.FusedExchange()
+        x.n, x.self, x.all, x.root = self.world, self.rank, 1, 0
+        x.slot_base, x.total_count = int(sum(counts[: self.rank])), total
+        for d in range(self.world):
+            x.slots[d] = self._bases[d][parity]
+            x.arrived[d] = self._counters[d][parity]
+        x.expected = self.expected[parity]
+        # the status word doubles as the completion flag: its TIMEOUT bit is what wait() looks at
+        x.done_flag = self._status
+        x.done_value = self.epoch
+        return x
 
     def reduce(self, op, shard, counts, out, start=None, stream=None):
         """all-reduce of `op` ('ADD', 'MIN', 'MAX', 'MUL') over every participant's `shard` (a DeviceArray)
-        into the one-element DeviceArray `out` of this participant.  Asynchronous on `stream`."""
+        into the one-element DeviceArray `out` of this participant.  Asynchronous on `stream`: call wait()
+        before reading `out`."""
         lib = cabi.load()
         f, t = cabi.BINARY_OPS[op], shard.atype
-        table, slot_base, total, expected, scratch = self._begin(counts, lib.pncu_reduce_partial_bytes(f, t))
-        cabi.check(lib.pncu_reduce_partials(f, t, shard.ptr, shard.size, scratch, stream), "partials")
-        cabi.check(lib.pncu_reduce_exchange_finish(f, t, scratch, int(counts[self.rank]), slot_base, ctypes.byref(table), self.rank,
-                                                   total, out.ptr, start.ptr if start is not None else None, expected, stream),
-                   "exchange_finish")
+        x = self._begin(counts)
+        cabi.check(lib.pncu_reduce_fused(f, t, shard.ptr, shard.size, ctypes.byref(x), out.ptr,
+                                         start.ptr if start is not None else None, stream), "reduce_fused")
         return out
 
     def argminmax(self, kind, shard, counts, index_base, out, stream=None):
         """global index (int64 DeviceArray `out`) of the first max (kind 0) / min (kind 1); `index_base` is the
         global offset of this participant's shard."""
         lib = cabi.load()
-        t = shard.atype
-        table, slot_base, total, expected, scratch = self._begin(counts, 16)
-        cabi.check(lib.pncu_argminmax_partials(kind, t, shard.ptr, shard.size, int(index_base), scratch, stream), "arg partials")
-        cabi.check(lib.pncu_argminmax_exchange_finish(kind, t, scratch, int(counts[self.rank]), slot_base, ctypes.byref(table),
-                                                      self.rank, total, out.ptr, expected, stream), "arg exchange_finish")
+        x = self._begin(counts)
+        cabi.check(lib.pncu_argminmax_fused(kind, shard.atype, shard.ptr, shard.size, int(index_base), ctypes.byref(x),
+                                            out.ptr, stream), "argminmax_fused")
         return out
+
+    def wait(self, stream=None):
+        """Synchronise `stream` and raise if any reduction since the last wait() gave up on a participant
+        (nothing was written to its `out`).  Returns the number of reductions issued so far."""
+        lib = cabi.load()
+        cabi.check(lib.pncu_set_device(self.device), "set_device")
+        cabi.check(lib.pncu_stream_sync(stream), "sync")
+        word = ctypes.c_uint64(0)
+        cabi.check(lib.pncu_memcpy_d2h(ctypes.byref(word), self._status, 8, stream), "status")
+        cabi.check(lib.pncu_stream_sync(stream), "sync")
+        timeouts = int(lib.pncu_exchange_timeouts())   # an earlier call's flag may have been overwritten by a later one
+        if word.value & cabi.FUSED_TIMEOUT_BIT or (self._seen_timeouts is not None and timeouts > self._seen_timeouts):
+            self.broken = (f"rank {self.rank}: a participant did not deliver its block partials within the bounded wait "
+                           f"(reduction #{word.value & ~cabi.FUSED_TIMEOUT_BIT}); no result was produced")
+            raise cabi.PnumpyCudaError(self.broken)
+        return self.epoch
 
 
 def block_counts(shard_sizes, dtype):

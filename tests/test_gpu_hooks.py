@@ -321,10 +321,12 @@ def test_managed_arrays_run_in_place(pn, rng):
     m = u.max()
     i = u.argmin()
     np.add(u, np.float32(2.5), out=t)      # host scalar next to resident arrays
-    g = np.greater(t, c)                    # output allocated by NumPy (pageable) -> NumPy's loop reads managed memory
     info = pn.cuda_info()
     assert info["calls"] == 6 and info["h2d_bytes"] == 0 and info["staged_bytes"] == 0, info
     assert info["d2h_bytes"] <= 64          # only the reduction scalars came back
+    g = np.greater(t, c)                    # output allocated by NumPy (pageable): inputs in place, result staged back
+    info = pn.cuda_info()
+    assert info["calls"] == 7 and info["h2d_bytes"] == 0 and info["d2h_bytes"] <= 64 + n, info
     want_u = ha * hb + hc
     assert_bits_equal(np.asarray(u), want_u, "chain on managed arrays")
     assert_bits_equal(np.asarray(t), want_u + np.float32(2.5), "scalar operand")
@@ -682,3 +684,257 @@ def test_other_ways_numpy_calls_a_hooked_loop(pn, rng):
 def _at(z, idx):
     np.add.at(z, idx, 1.0)
     return z
+
+
+# ---- round 2: residency through the unmodified NumPy API, error paths, ledger records -------------------------
+def test_managed_recycler_makes_numpy_arrays_device_capable(pn, rng):
+    """recycler_enable(kind="managed"): the arrays NumPy itself creates -- np.empty, ufunc outputs, the temporaries
+    of a*b+c -- live in CUDA managed memory, so a plain NumPy expression runs on the GPU with no PCIe copies, at
+    every size, and only the reduction scalar comes back (reference roadmap: src/pnumpy/__init__.py:18-21,
+    doc_src/source/roadmap.rst:27-31)."""
+    from pnumpy_b200 import _pnumpy
+    old_thr = pn.cuda_setthreshold(1 << 19)      # the DEFAULT host threshold: residency must not depend on it
+    pn.recycler_enable(kind="managed")
+    try:
+        assert pn.recycler_info()["kind"] == "managed"
+        n = 1_000_000                             # pn.benchmark's size: far below the host-operand threshold
+        a = (np.arange(n, dtype=np.int64) % 253 + 1).astype(np.float32)   # astype output: born managed
+        b = a.copy()
+        assert _pnumpy.pointer_kind(a.ctypes.data) == 3 and _pnumpy.pointer_kind(b.ctypes.data) == 3
+        tiny = np.ones(100, np.float32)
+        assert _pnumpy.pointer_kind(tiny.ctypes.data) == 0      # small arrays stay on malloc
+        pn.cuda_reset_stats()
+        c = a * b + a                             # two ufunc calls, one temporary: all managed, all on the GPU
+        s = c.sum()
+        eq = a == b                               # 1 000 000-byte bool output: above the managed threshold too
+        info = pn.cuda_info()
+        assert info["calls"] == 4 and info["declined"] == 0, info
+        assert info["h2d_bytes"] == 0 and info["staged_bytes"] == 0 and info["d2h_bytes"] <= 64, info
+        assert _pnumpy.pointer_kind(c.ctypes.data) == 3 and _pnumpy.pointer_kind(eq.ctypes.data) == 3
+        ha = (np.arange(n, dtype=np.int64) % 253 + 1).astype(np.float64)
+        assert float(s) == float(np.sum(ha * ha + ha))          # exact: every term is an integer < 2^24
+        assert eq.all()
+        # steady state: nothing is prefetched again, recycled blocks are reused
+        np.add(a, b, out=c)
+        pre = pn.cuda_info()["prefetches"]
+        for _ in range(5):
+            np.add(a, b, out=c)
+            d = a + b
+            del d
+        assert pn.cuda_info()["prefetches"] == pre
+        assert pn.recycler_info()["hits"] >= 4
+        z = np.zeros(n, np.float32)               # zeroed on the GPU
+        assert _pnumpy.pointer_kind(z.ctypes.data) == 3 and not z.any()
+    finally:
+        pn.recycler_disable()
+        pn.cuda_setthreshold(old_thr)
+        pn.cuda_setthreshold(0)
+    assert _pnumpy.pointer_kind(np.ones(n, np.float32).ctypes.data) == 0
+
+
+def test_small_ops_on_managed_memory_stay_on_the_gpu(pn, rng):
+    """A small op on (a slice of) a managed array must not fall to NumPy's CPU loop (which would migrate the pages
+    back to the host): resident operands run on the GPU at EVERY size, whatever the host-operand threshold."""
+    old_thr = pn.cuda_setthreshold(1 << 19)
+    pn.ledger_enable()
+    pn.ledger_clear()
+    try:
+        h = rng.normal(size=1 << 20).astype(np.float32)
+        m = pn.managed_array(h)
+        out = pn.managed_empty(1 << 20, np.float32)
+        np.add(m, m, out=out)                     # places the pages
+        pn.cuda_reset_stats()
+        for cnt in (1, 7, 1000, 4097, 65537):
+            np.multiply(m[5:5 + cnt], m[9:9 + cnt], out=out[3:3 + cnt])
+            assert float(m[100:100 + cnt].sum()) == pytest.approx(float(np.sum(h[100:100 + cnt], dtype=np.float64)), rel=1e-6)
+            assert int(m[:cnt].argmax()) == int(h[:cnt].argmax())
+        info = pn.cuda_info()
+        assert info["calls"] == 15 and info["declined"] == 0 and info["h2d_bytes"] == 0, info
+        li = pn.ledger_info()
+        assert li["Binary"]["numpy_calls"] == 0 and li["ArgMinMax"]["numpy_calls"] == 0, li   # no CPU loop touched the pages
+        assert_bits_equal(np.asarray(out[3:3 + 65537]), h[5:5 + 65537] * h[9:9 + 65537], "small slices")
+        # strided managed views run on the GPU too (strided kernels), reductions included
+        pn.cuda_reset_stats()
+        np.add(m[::3], m[1::3][: m[::3].size], out=out[: m[::3].size])
+        r = float(m[::2].max())
+        assert pn.cuda_info()["calls"] == 2 and pn.cuda_info()["declined"] == 0
+        assert r == float(h[::2].max())
+        k = h[::3].size
+        assert_bits_equal(np.asarray(out[:k]), h[::3] + h[1::3][:k], "strided managed views")
+    finally:
+        pn.ledger_disable()
+        pn.cuda_setthreshold(old_thr)
+        pn.cuda_setthreshold(0)
+
+
+def test_accumulate_and_partial_overlap_on_managed_arrays(pn, rng):
+    """NumPy's accumulate calls a binary loop as (out, in + s, out + s): partially overlapping operands need the
+    sequential semantics of NumPy's own loop.  The dispatcher must DECLINE that for resident operands exactly as
+    it does for host ones -- not raise."""
+    n = 300_000
+    h = rng.integers(-50, 50, n).astype(np.int64)
+    m, m2 = pn.managed_array(h), pn.managed_empty(n, np.int64)
+    np.cumsum(m, out=m2)
+    assert np.array_equal(np.asarray(m2), np.cumsum(h))
+    np.add.accumulate(m, out=m)
+    assert np.array_equal(np.asarray(m), np.cumsum(h))
+    f = pn.managed_array(rng.normal(size=n))
+    want = np.maximum.accumulate(np.asarray(f).copy())
+    np.maximum.accumulate(f, out=f)
+    assert np.array_equal(np.asarray(f), want)
+    g = pn.managed_array(h.astype(np.float64))
+    hg = h.astype(np.float64)
+    np.add(g[1:], g[:-1], out=g[1:])             # exact aliasing of out with in1: allowed, parallel-safe
+    hg[1:] = hg[1:] + hg[:-1].copy()
+    assert np.array_equal(np.asarray(g), hg)
+
+
+def test_mixed_resident_and_host_operands(pn, rng):
+    """A call that mixes a managed array with ordinary host arrays: the resident operand is used in place, the host
+    ones are staged; nothing falls back to the CPU loop and the bytes moved are those of the host operands only."""
+    n = (1 << 21) + 77
+    ha, hb = rng.normal(size=n), rng.normal(size=n)
+    ma = pn.managed_array(ha)
+    out = np.empty(n)
+    pn.cuda_reset_stats()
+    np.subtract(ma, hb, out=out)                  # managed - pageable -> pageable
+    info = pn.cuda_info()
+    assert info["calls"] == 1 and info["declined"] == 0 and info["h2d_bytes"] == 8 * n and info["d2h_bytes"] == 8 * n, info
+    assert_bits_equal(out, ha - hb, "managed - host")
+    mo = pn.managed_empty(n, np.float64)
+    pn.cuda_reset_stats()
+    np.multiply(hb, ha, out=mo)                   # host * host -> managed: no D2H
+    info = pn.cuda_info()
+    assert info["calls"] == 1 and info["h2d_bytes"] == 16 * n and info["d2h_bytes"] == 0, info
+    assert_bits_equal(np.asarray(mo), hb * ha, "host * host -> managed")
+    g = np.greater(ma, 0.25)                      # managed vs host scalar -> pageable bool
+    assert np.array_equal(g, ha > 0.25)
+
+
+def test_same_operand_is_uploaded_once(pn, rng):
+    """np.multiply(a, a): the reference loads the operand once when in1 == in2
+    (src/atop/ops_binary.cpp:631-658); over PCIe that halves the H2D bytes."""
+    n = 1 << 22
+    a = pn.pinned_array(rng.normal(size=n).astype(np.float32))
+    out = pn.pinned_empty(n, np.float32)
+    pn.cuda_reset_stats()
+    np.multiply(a, a, out=out)
+    info = pn.cuda_info()
+    assert info["calls"] == 1 and info["h2d_bytes"] == 4 * n and info["d2h_bytes"] == 4 * n, info
+    assert_bits_equal(np.asarray(out), np.asarray(a) * np.asarray(a), "a*a")
+    pn.cuda_reset_stats()
+    np.add(a, a[::-1], out=out)                   # same buffer, different view: two uploads
+    assert pn.cuda_info()["h2d_bytes"] == 8 * n
+    assert_bits_equal(np.asarray(out), np.asarray(a) + np.asarray(a)[::-1], "a + a[::-1]")
+    r = pn.muladd(a, a, a)                        # the fused chain uploads a repeated operand once as well
+    assert_bits_equal(np.asarray(r), np.asarray(a) * np.asarray(a) + np.asarray(a), "muladd(a, a, a)")
+
+
+def test_cuda_failure_raises_runtime_error_and_the_process_stays_usable(pn, rng):
+    """SURVEY.md 8(b) error convention, verified on this NumPy: a CUDA failure inside a hooked loop (injected here:
+    the dispatcher reports cudaErrorLaunchFailure without touching the device) surfaces as RuntimeError from the
+    NumPy call itself -- never a silently wrong array, never NumPy's CPU loop -- and the next call works."""
+    n = 1 << 20
+    a, b = rng.normal(size=n), rng.normal(size=n)
+    m = pn.managed_array(a)
+    for what, call in (("binary, host operands", lambda: np.add(a, b)),
+                       ("unary", lambda: np.sqrt(np.abs(a))),
+                       ("compare", lambda: np.less(a, b)),
+                       ("reduction", lambda: a.sum()),
+                       ("arg-reduction", lambda: a.argmax()),
+                       ("binary, resident operands", lambda: np.add(m, m)),
+                       ("resident reduction", lambda: m.max()),
+                       ("int true_divide", lambda: np.true_divide(np.arange(1, n + 1), np.arange(2, n + 2)))):
+        assert pn.cuda_inject_fault(1) == 0
+        with pytest.raises(RuntimeError, match="failed on the GPU"):
+            call()
+        assert pn.cuda_inject_fault(0) == 0     # consumed
+        got, want, calls = _both(pn, call)      # the very next call runs on the GPU and is right
+        assert calls >= 1, what
+        if isinstance(got, np.ndarray):
+            assert np.array_equal(got, want), what
+        else:
+            assert got == pytest.approx(want, rel=1e-12), what
+    # the fused entry points report through their own return path
+    pn.cuda_inject_fault(1)
+    with pytest.raises(RuntimeError, match="failed on the GPU"):
+        pn.muladd_sum(a, b, a)
+    assert float(pn.muladd_sum(a, b, a)) == pytest.approx(float(np.sum(a * b + a)), rel=1e-9)
+
+
+def test_forked_child_runs_numpy_loops(pn, rng):
+    """CUDA cannot be used in a fork()ed child.  The child must not hang on worker threads that do not exist there
+    nor raise from dead CUDA calls: every hooked call is declined and NumPy's own loop runs (fork-start
+    multiprocessing workers that use NumPy keep working, on the CPU)."""
+    n = 1 << 21
+    a, b = rng.normal(size=n), rng.normal(size=n)
+    want = a + b
+    (a + b)                                     # make sure the parent has lanes and worker threads
+    r, w = os.pipe()
+    pid = os.fork()
+    if pid == 0:
+        code = 1
+        try:
+            import signal
+            signal.alarm(60)                    # a hang is a failure, not a stuck test run
+            ok = np.array_equal(a + b, want) and float(a.sum()) == pytest.approx(float(want.sum() - b.sum()), rel=1e-9)
+            ok = ok and int(a.argmax()) == int(np.argmax(a)) and pn.cuda_info()["forked_child"] == 1
+            big = np.empty(1 << 22)             # allocation paths must not touch CUDA either
+            big[:] = 1.0
+            ok = ok and float(big.sum()) == float(1 << 22)
+            code = 0 if ok else 2
+        except BaseException:
+            code = 3
+        os.write(w, bytes([code]))
+        os._exit(code)
+    os.close(w)
+    _, status = os.waitpid(pid, 0)
+    got = os.read(r, 1)
+    os.close(r)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0 and got == b"\x00", (status, got)
+    got, want2, calls = _both(pn, lambda: a + b)  # the parent is unaffected
+    assert calls == 1 and np.array_equal(got, want2)
+
+
+def test_ledger_records_each_call(pn, rng):
+    """reference: the ledger ring of per-call records (src/pnumpy/ledger.cpp:144-272)."""
+    a = rng.normal(size=1 << 18).astype(np.float32)
+    pn.ledger_enable()
+    pn.ledger_clear()
+    try:
+        np.add(a, a)
+        np.sin(a)
+        a.sum()
+        a.argmax()
+        pn.disable()
+        np.add(a, a)
+        pn.enable()
+    finally:
+        pn.ledger_disable()
+    recs = pn.ledger_records()
+    assert [r["category"] for r in recs] == ["Binary", "TrigLog", "Binary", "ArgMinMax", "Binary"], recs
+    assert [r["gpu"] for r in recs] == [True, True, True, True, False]
+    assert recs[0]["elements"] == a.size and recs[0]["bytes"] == 12 * a.size and recs[0]["reduce"] is False
+    assert recs[2]["reduce"] is True and recs[2]["bytes"] == 4 * (a.size - 1) or recs[2]["bytes"] == 4 * a.size
+    assert all(r["end_tsc"] > r["start_tsc"] > 0 and r["ticks"] == r["end_tsc"] - r["start_tsc"] for r in recs)
+    assert len(pn.ledger_records(2)) == 2 and pn.ledger_records(2)[-1] == recs[-1]
+
+
+def test_calling_threads_device_is_left_alone(pn, rng):
+    """The dispatcher drives every GPU from the calling thread; afterwards the thread's current CUDA device must be
+    what it was (torch / cupy code in the same thread relies on it)."""
+    from pnumpy_b200 import cabi
+    lib = cabi.load()
+    import ctypes
+    if pn.cuda_info()["devices"] < 2:
+        pytest.skip("needs two GPUs to be meaningful")
+    cabi.check(lib.pncu_set_device(1), "set_device")
+    try:
+        a = pn.managed_array(rng.normal(size=1 << 25).astype(np.float32))
+        (a + a).sum()
+        np.add(rng.normal(size=1 << 21), 1.0)
+        d = ctypes.c_int(-1)
+        cabi.check(lib.pncu_get_device(ctypes.byref(d)), "get_device")
+        assert d.value == 1
+    finally:
+        cabi.check(lib.pncu_set_device(0), "set_device")

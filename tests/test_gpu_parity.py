@@ -458,6 +458,63 @@ def test_full_size_properties(dev, dt):
         assert dev.reduce("MIN", q).to_host()[0] == 2.0 and dev.reduce("MAX", q).to_host()[0] == 2.0
 
 
+@pytest.mark.parametrize("dt", ["float32", "int64"])
+def test_full_size_against_the_oracle(dev, O, dt):
+    """BASELINE.json configs[1], [2] and [3] at their stated size, 2^28 elements, compared with the CPU ORACLE on
+    the same seeded random inputs -- not with the GPU's own reductions: every element of add / multiply / divide /
+    greater (and float32 sqrt / sin / log / exp) must have the oracle's bits, min / max / argmin / argmax (with a NaN
+    planted for float32) must be the oracle's, and the sum must be within the stated tolerance of a float64 sum."""
+    n = 1 << 28
+    rng = np.random.default_rng(1234)
+    if dt == "float32":
+        a = rng.random(n, dtype=np.float32) * np.float32(253.0) + np.float32(1.0)
+        b = rng.random(n, dtype=np.float32) * np.float32(253.0) + np.float32(1.0)
+    else:
+        a = rng.integers(1, 254, n, dtype=np.int64)
+        b = rng.integers(1, 254, n, dtype=np.int64)
+    da, db = dev.to_device(a), dev.to_device(b)
+    do = dev.empty(n, dt)
+    for op in ("ADD", "MUL") + (("DIV",) if dt == "float32" else ()):
+        dev.binary(op, da, db, out=do)
+        assert_bits_equal(do.to_host(), O.binary(op, a, b), f"{op} {dt} at 2^28")
+    if dt == "int64":
+        dq = dev.int_true_divide(da, db)
+        assert_bits_equal(dq.to_host(), O.int_true_divide(a, b), "int64 true_divide at 2^28")
+        dq.free()
+    dg = dev.compare("GT", da, db)
+    assert_bits_equal(dg.to_host(), O.compare("GT", a, b), f"greater {dt} at 2^28")
+    dg.free()
+    if dt == "float32":
+        for op, src in (("SQRT", a), ("SIN", None), ("LOG", None), ("EXP", None)):
+            if src is None:   # the input ranges of SURVEY.md 8d
+                lo, hi = {"SIN": (-8192.0, 8192.0), "LOG": (1e-6, 1e6), "EXP": (-80.0, 80.0)}[op]
+                src = (rng.random(n, dtype=np.float32) * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+                db.copy_from_host(src)
+                dev.unary(op, db, out=do)
+            else:
+                dev.unary(op, da, out=do)
+            assert_bits_equal(do.to_host(), O.unary(op, src), f"{op} float32 at 2^28")
+    # reductions: the oracle's value for min / max / arg*, the float64 reference for the sum
+    if dt == "float32":
+        s64 = float(np.sum(a, dtype=np.float64))
+        got = float(dev.reduce("ADD", da).to_host()[0])
+        assert abs(got - s64) <= 2.0 ** -23 * abs(s64) + 2.0 ** -50 * float(np.sum(np.abs(a), dtype=np.float64))
+    else:
+        assert int(dev.reduce("ADD", da).to_host()[0]) == int(O.reduce("ADD", a))
+    for kind in (0, 1):
+        assert int(dev.argminmax(kind, da).to_host()[0]) == O.argminmax(kind, a)
+    assert dev.reduce("MIN", da).to_host()[0] == O.reduce("MIN", a) == a.min()
+    assert dev.reduce("MAX", da).to_host()[0] == O.reduce("MAX", a) == a.max()
+    if dt == "float32":
+        a[123456789] = np.nan
+        da.copy_from_host(a)
+        assert np.isnan(dev.reduce("MIN", da).to_host()[0]) and np.isnan(dev.reduce("MAX", da).to_host()[0])
+        assert int(dev.argminmax(0, da).to_host()[0]) == O.argminmax(0, a) == 123456789
+        assert int(dev.argminmax(1, da).to_host()[0]) == O.argminmax(1, a) == 123456789
+    for x in (da, db, do):
+        x.free()
+
+
 # ---- fused chain a*b + c and sum(a*b + c) (SURVEY.md 8f row f-2) -------------------------------------------
 FUSED_DTYPES = ["int32", "uint32", "int64", "uint64", "float32", "float64"]
 
@@ -684,7 +741,7 @@ def _exchange_case(dev, devices, rng):
                     xs[r].reduce(op, shards[r], counts, outs[r])
                 for r, d in enumerate(devices):
                     cabi.check(lib.pncu_set_device(d), "set_device")
-                    dev.sync()
+                    xs[r].wait()
                     got = outs[r].to_host()
                     if op != "ADD" and dt != "int32":
                         assert np.isnan(got[0])
@@ -696,7 +753,7 @@ def _exchange_case(dev, devices, rng):
                     xs[r].argminmax(kind, shards[r], counts, bounds[r], idxs[r])
                 for r, d in enumerate(devices):
                     cabi.check(lib.pncu_set_device(d), "set_device")
-                    dev.sync()
+                    xs[r].wait()
                     assert int(idxs[r].to_host()[0]) == want_arg[kind], (dt, kind, r, rep)
         for r, d in enumerate(devices):
             cabi.check(lib.pncu_set_device(d), "set_device")
@@ -706,8 +763,73 @@ def _exchange_case(dev, devices, rng):
 
 
 def test_fused_exchange_one_gpu(dev, rng):
-    """world = 1: the exchange path (stores + arrival counter + waiting finish) equals the plain two passes"""
+    """world = 1: the one-launch path (ticket, last CTA folds) equals the plain two passes"""
     _exchange_case(dev, [0], rng)
+
+
+def test_fused_exchange_two_participants_on_one_gpu(dev, rng):
+    """two participants that happen to share GPU 0: the whole exchange protocol (stores into the other
+    participant's table, system fences, arrival counters, device-side wait, alternating tables) runs on a
+    single-GPU box too"""
+    _exchange_case(dev, [0, 0], rng)
+
+
+def test_exchange_timeout_is_loud(dev, rng):
+    """A participant that never shows up must be an ERROR: the waiting kernel gives up after its bounded wait
+    WITHOUT folding the incomplete table and without writing `out`; Exchange.wait() raises and the Exchange
+    refuses further use."""
+    from pnumpy_b200 import cabi, exchange
+    lib = cabi.load()
+    n = 4 * int(lib.pncu_reduce_block_elems())
+    a = rng.normal(0, 1, n).astype(np.float32)
+    xs = exchange.Exchange.in_process([0, 0], max_slots=4096)   # participant 1 never launches anything
+    shard = dev.to_device(a)
+    out = dev.to_device(np.array([-777.0], dtype=np.float32))
+    counts = exchange.block_counts([n, n], np.float32)
+    before = int(lib.pncu_exchange_timeouts())
+    xs[0].reduce("ADD", shard, counts, out)
+    with pytest.raises(cabi.PnumpyCudaError, match="did not deliver"):
+        xs[0].wait()
+    assert int(lib.pncu_exchange_timeouts()) == before + 1
+    assert out.to_host()[0] == np.float32(-777.0)               # never written: no partial fold leaked out
+    with pytest.raises(cabi.PnumpyCudaError, match="unusable"):
+        xs[0].reduce("ADD", shard, counts, out)
+    # the stream's ticket was re-armed by the kernel itself: ordinary reductions keep working
+    assert_bits_equal(dev.reduce("ADD", shard).to_host(), dev.reduce("ADD", shard).to_host())
+    cabi.check(lib.pncu_fused_reset(None), "fused_reset")
+    for x in xs:
+        x.close()
+
+
+def test_one_launch_reductions_match_the_two_pass_building_blocks(dev, rng):
+    """pncu_GetReduceMathOpFast / pncu_GetArgMinMaxOpFast launchers are ONE kernel (last CTA folds); the result
+    must have the bits of pncu_reduce_partials + pncu_reduce_finish for every type, at sizes that give 1 block,
+    a ragged block, fewer and more partials than the 1024 virtual finish threads."""
+    from pnumpy_b200 import cabi
+    lib = cabi.load()
+    for dt in ("int8", "uint16", "int32", "int64", "float32", "float64"):
+        isz = np.dtype(dt).itemsize
+        be = 65536 // isz
+        for n in (1, be - 1, be, 3 * be + 17, 1500 * be + 5, 9000 * be):
+            if n * isz > (1 << 30):
+                continue
+            a = fill_random(n, dt, rng) if np.dtype(dt).kind != "f" else rng.normal(0, 1e3, n).astype(dt)
+            d = dev.to_device(a)
+            nb = int(lib.pncu_reduce_partial_count(cabi.atop_of(dt), n))
+            for op in ("ADD", "MIN", "MAX"):
+                f, t = cabi.BINARY_OPS[op], cabi.atop_of(dt)
+                parts = dev.empty(nb * lib.pncu_reduce_partial_bytes(f, t), np.uint8)
+                two = dev.empty(1, dt)
+                cabi.check(lib.pncu_reduce_partials(f, t, d.ptr, n, parts.ptr, None), "partials")
+                cabi.check(lib.pncu_reduce_finish(f, t, parts.ptr, nb, two.ptr, None, None), "finish")
+                assert dev.reduce(op, d).to_host().tobytes() == two.to_host().tobytes(), (dt, n, op)
+            for kind in (0, 1):
+                parts = dev.empty(nb * 16, np.uint8)
+                two = dev.empty(1, np.int64)
+                cabi.check(lib.pncu_argminmax_partials(kind, cabi.atop_of(dt), d.ptr, n, 0, parts.ptr, None), "arg partials")
+                cabi.check(lib.pncu_argminmax_finish(kind, cabi.atop_of(dt), parts.ptr, nb, two.ptr, None), "arg finish")
+                assert int(dev.argminmax(kind, d).to_host()[0]) == int(two.to_host()[0]), (dt, n, kind)
+            d.free()
 
 
 def test_fused_exchange_two_gpus(dev, rng):

@@ -127,3 +127,39 @@ def test_multirank_combine_protocol_gloo():
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert "OK" in outs[0][0]
+
+
+def test_numpy_propagates_an_exception_set_inside_a_replaced_legacy_loop(tmp_path):
+    """"the L3 stub converts failure into PyErr_SetString(RuntimeError) ... verify on NumPy 2.3.5
+    before relying on it".  This is that verification, on whatever NumPy runs the tests: a loop installed with
+    PyUFunc_ReplaceLoopBySignature that sets RuntimeError (taking the GIL first, as _pnumpy.cpp does) makes the
+    NumPy call raise that very RuntimeError -- for small calls (GIL held) and large ones (GIL released), for
+    element-wise calls and reductions -- and the ufunc keeps working afterwards.  tests/host/legacy_loop_error_probe.c
+    is a 40-line extension compiled here with gcc; it runs in a subprocess because it patches np.add."""
+    import subprocess
+    import sys
+    import sysconfig
+    src = os.path.join(ROOT, "tests", "host", "legacy_loop_error_probe.c")
+    so = tmp_path / ("probe" + sysconfig.get_config_var("EXT_SUFFIX"))
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-I" + sysconfig.get_paths()["include"], "-I" + np.get_include(),
+                           src, "-o", str(so)])
+    code = r'''
+import sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, probe
+assert probe.install() == 0
+for n in (10, 300000):
+    a = np.ones(n, np.float32)
+    for call in (lambda: np.add(a, a), lambda: a.sum()):
+        probe.setmode(1)
+        try:
+            call()
+            raise SystemExit("no exception for n=%d" % n)
+        except RuntimeError as e:
+            assert "injected failure" in str(e), e
+        probe.setmode(0)
+        assert float(np.add(a, a)[0]) == 2.0 and float(a.sum()) == n
+print("ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.stdout, r.stderr)
