@@ -461,11 +461,51 @@ template <> struct WordOps<MaxR<uint8_t>> : MinMaxWord<uint8_t, true> {};
 template <> struct WordOps<MaxR<int16_t>> : MinMaxWord<int16_t, true> {};
 template <> struct WordOps<MaxR<uint16_t>> : MinMaxWord<uint16_t, true> {};
 
+// ---- a thread's share of one FULL logical block, for any element-aligned block start -----------------------
+// Aligned start: pack j of thread t is vector j*256 + t of the block, one 256-bit load each.
+// Misaligned start -- NumPy reduces a.min() / a.max() over a[1:], and views like a[1:].sum() -- : the block is
+// re-cut at the next 32-byte boundary: `head` = elements before it (0 < head < EPV); the NV-1 aligned vectors
+// from there are dealt out exactly as before (still one 256-bit load each, fully coalesced; the very last slot,
+// pack 7 of thread 255, stays empty) and the EPV elements left over at the two ends of the block -- the `head`
+// leading ones and the EPV - head trailing ones -- are picked up one each by threads 0 .. EPV-1 with an element
+// load issued alongside the vector loads.  Same bytes from HBM, same instruction mix.  The fold order is a
+// function of (n, type, alignment) only, so determinism and shard-invariance are untouched.
+template <class In, int EPV>
+__device__ __forceinline__ int block_head(const void* block_start) {
+    return (int)(((32u - (unsigned)((uintptr_t)block_start & 31u)) & 31u) / (unsigned)sizeof(In));
+}
+// position (element offset in the block) of leftover element e
+template <int EPV>
+__device__ __forceinline__ int leftover_pos(int e, int head) { return e < head ? e : (RED_NV * RED_THREADS - 1) * EPV + e; }
+
+template <class In, int EPV, bool SHIFTED>
+__device__ __forceinline__ void load_block(const In* p, int head, Pack<In, EPV> (&r)[RED_NV], In& extra) {
+    if constexpr (!SHIFTED) {
+#pragma unroll
+        for (int j = 0; j < RED_NV; ++j) r[j] = ld_pack<In, EPV>(p + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
+    } else {
+        const In* pa = p + head;
+#pragma unroll
+        for (int j = 0; j < RED_NV - 1; ++j) r[j] = ld_pack<In, EPV>(pa + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
+        // the last slot does not exist for thread 255: it re-reads its previous vector so that every lane issues
+        // the same instruction; the fold skips it (see last_slot_empty)
+        const int jl = threadIdx.x == RED_THREADS - 1 ? RED_NV - 2 : RED_NV - 1;
+        r[RED_NV - 1] = ld_pack<In, EPV>(pa + ((int64_t)jl * RED_THREADS + threadIdx.x) * EPV);
+        if (threadIdx.x < EPV) extra = p[leftover_pos<EPV>((int)threadIdx.x, head)];
+    }
+}
+// how a pass-1 kernel reads a full block: element loads (strided input), aligned vectors, or the re-cut above
+enum { RD_ELEMS = 0, RD_VEC = 1, RD_SHIFTED = 2 };
+inline int read_mode(const void* in, bool contiguous) {
+    if (!contiguous) return RD_ELEMS;
+    return ((uintptr_t)in % 32) == 0 ? RD_VEC : RD_SHIFTED;
+}
+
 // ---- pass 1 --------------------------------------------------------------------------------------
 #ifndef PNCU_RED_MINB
 #define PNCU_RED_MINB 4
 #endif
-template <class R, bool VEC, bool FUSED>
+template <class R, int VEC, bool FUSED>
 __global__ void __launch_bounds__(RED_THREADS, PNCU_RED_MINB)
 reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_base,
                      typename R::Acc* partials, const __grid_constant__ FusedArgs fa) {
@@ -493,29 +533,37 @@ reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_ba
     }
 
     if (VEC && cnt == BE) {
+        constexpr bool SHIFTED = VEC == RD_SHIFTED;
         const In* p = reinterpret_cast<const In*>(base);
         Pack<In, EPV> r[RED_NV];
-#pragma unroll
-        for (int j = 0; j < RED_NV; ++j) r[j] = ld_pack<In, EPV>(p + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
+        In extra = In();
+        const int head = SHIFTED ? block_head<In, EPV>(p) : 0;
+        load_block<In, EPV, SHIFTED>(p, head, r, extra);
+        const bool last_slot_empty = SHIFTED && threadIdx.x == RED_THREADS - 1;
         if constexpr (WordOps<R>::enabled) {
             // 1- and 2-byte types: fold whole 32-bit words (4 or 2 elements per instruction)
             typename WordOps<R>::W wacc[RED_CHAINS];
 #pragma unroll
             for (int c = 0; c < RED_CHAINS; ++c) wacc[c] = WordOps<R>::seed(*reinterpret_cast<const In*>(base));
 #pragma unroll
-            for (int j = 0; j < RED_NV; ++j)
+            for (int j = 0; j < RED_NV; ++j) {
+                if (SHIFTED && j == RED_NV - 1 && last_slot_empty) continue;
 #pragma unroll
                 for (int wi = 0; wi < 8; ++wi) wacc[j % RED_CHAINS] = WordOps<R>::step(wacc[j % RED_CHAINS], r[j].w[wi]);
+            }
 #pragma unroll
             for (int c = 0; c < RED_CHAINS; ++c) acc[c] = R::combine(acc[c], WordOps<R>::finish(wacc[c]));
         } else {
 #pragma unroll
             for (int j = 0; j < RED_NV; ++j) {
-                const int64_t e0 = gidx0 + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV;
+                if (SHIFTED && j == RED_NV - 1 && last_slot_empty) continue;
+                const int64_t e0 = gidx0 + head + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV;
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) acc[j % RED_CHAINS] = R::step(acc[j % RED_CHAINS], r[j].get(e), e0 + e);
             }
         }
+        if (SHIFTED && threadIdx.x < EPV)
+            acc[0] = R::step(acc[0], extra, gidx0 + leftover_pos<EPV>((int)threadIdx.x, head));
     } else {
         // ragged last block, strided or misaligned input: element loads, same fixed order
         for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS)
@@ -610,7 +658,7 @@ struct IdxMinR {  // block fold of phase B
 };
 
 // arg-reduction pass 1: partial[k] = {extreme of block k, global index of its first occurrence}
-template <class T, bool IS_MAX, bool VEC, bool FUSED>
+template <class T, bool IS_MAX, int VEC, bool FUSED>
 __global__ void __launch_bounds__(RED_THREADS, 3)
 arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partials, const __grid_constant__ FusedArgs fa) {
     typedef typename Widen<T>::type W;
@@ -624,17 +672,22 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
     const int64_t start = k * BE;
     const int64_t cnt = (n - start) < BE ? (n - start) : BE;
     const T* p = in + start;
-    const bool full = VEC && cnt == BE;
+    const bool full = VEC != RD_ELEMS && cnt == BE;
 
     Pack<T, EPV> r[RED_NV];
     W m = (W)p[0];
+    constexpr bool SHIFTED = VEC == RD_SHIFTED;
+    const int head = SHIFTED ? block_head<T, EPV>(p) : 0;   // see load_block
+    const bool has_extra = SHIFTED && full && threadIdx.x < EPV;  // this thread also holds one leftover element
+    T extra = T();
     if (full) {
-#pragma unroll
-        for (int j = 0; j < RED_NV; ++j) r[j] = ld_pack<T, EPV>(p + ((int64_t)j * RED_THREADS + threadIdx.x) * EPV);
+        load_block<T, EPV, SHIFTED>(p, head, r, extra);
+        // (thread 255's duplicated last pack is harmless here: phase A is idempotent, phase B skips it)
 #pragma unroll
         for (int j = 0; j < RED_NV; ++j)
 #pragma unroll
             for (int e = 0; e < EPV; ++e) m = ext_nan<W, IS_MAX>(m, (W)r[j].get(e));
+        if (has_extra) m = ext_nan<W, IS_MAX>(m, (W)extra);
     } else {
         for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) m = ext_nan<W, IS_MAX>(m, (W)p[i]);
     }
@@ -666,7 +719,8 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
 #pragma unroll
                         for (int e = EPV - 1; e >= 0; --e) {
                             const W x = (W)r[j].get(e);
-                            c = (x != x) ? (j * RED_THREADS * EPV + e) : c;
+                            const bool real = j < RED_NV - 1 || !(SHIFTED && threadIdx.x == RED_THREADS - 1);
+                            c = (x != x && real) ? (j * RED_THREADS * EPV + e) : c;
                         }
                 }
             } else {
@@ -675,10 +729,18 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
 #pragma unroll
                     for (int e = EPV - 1; e >= 0; --e) {
                         const W x = (W)r[j].get(e);
-                        c = (x == mb) ? (j * RED_THREADS * EPV + e) : c;
+                        const bool real = j < RED_NV - 1 || !(SHIFTED && threadIdx.x == RED_THREADS - 1);
+                        c = (x == mb && real) ? (j * RED_THREADS * EPV + e) : c;
                     }
             }
-            if (c != NONE) local = c + (int)threadIdx.x * EPV;
+            if (c != NONE) local = c + (int)threadIdx.x * EPV + head;
+            if (has_extra) {   // the leftover elements sit at the two ends of the block
+                const W x = (W)extra;
+                bool hit = x == mb;
+                if constexpr (is_fp<T>::value) hit = want_nan ? (x != x) : hit;
+                const int pos = leftover_pos<EPV>((int)threadIdx.x, head);
+                if (hit && pos < local) local = pos;
+            }
         } else {
             for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) {
                 const W x = (W)p[i];
@@ -770,6 +832,8 @@ exchange_finish_kernel(const typename R::Acc* local, int64_t local_count, const 
 template <class In> inline int64_t nblocks_for(int64_t len) { return (len + block_elems<In>() - 1) / block_elems<In>(); }
 
 static const FusedArgs kNoFuse = {};
+// does this participant of a one-launch reduction fold (and therefore need `out`)?
+inline bool consumes(const pncu_fused_exchange* x) { return !x || x->n <= 1 || x->all || x->self == x->root; }
 
 // FusedArgs and the place pass 1 writes its partials for a ONE-LAUNCH reduction of `nb` blocks.
 // x == NULL (or x->n == 1): single GPU, partials in the stream's scratch.  x->n > 1: see pncu_fused_exchange.
@@ -817,16 +881,21 @@ int launch_partials(const void* in, int64_t len, int64_t stride, int64_t index_b
     typedef typename R::Acc Acc;
     const int64_t nb = nblocks_for<In>(len);
     if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
-    const bool vec = stride == (int64_t)sizeof(In) && ((uintptr_t)in % 32) == 0;
+    const int mode = read_mode(in, stride == (int64_t)sizeof(In));
     const char* p = (const char*)in;
     const unsigned g = (unsigned)nb;
+#define PNCU_LAUNCH_RED(MODE, FUSEDFLAG, ARGS) \
+    reduce_blocks_kernel<R, MODE, FUSEDFLAG><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, ARGS)
     if (fa) {
-        if (vec) reduce_blocks_kernel<R, true, true><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, *fa);
-        else reduce_blocks_kernel<R, false, true><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, *fa);
+        if (mode == RD_VEC) PNCU_LAUNCH_RED(RD_VEC, true, *fa);
+        else if (mode == RD_SHIFTED) PNCU_LAUNCH_RED(RD_SHIFTED, true, *fa);
+        else PNCU_LAUNCH_RED(RD_ELEMS, true, *fa);
     } else {
-        if (vec) reduce_blocks_kernel<R, true, false><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, kNoFuse);
-        else reduce_blocks_kernel<R, false, false><<<g, RED_THREADS, 0, st>>>(p, len, stride, index_base, (Acc*)partials, kNoFuse);
+        if (mode == RD_VEC) PNCU_LAUNCH_RED(RD_VEC, false, kNoFuse);
+        else if (mode == RD_SHIFTED) PNCU_LAUNCH_RED(RD_SHIFTED, false, kNoFuse);
+        else PNCU_LAUNCH_RED(RD_ELEMS, false, kNoFuse);
     }
+#undef PNCU_LAUNCH_RED
     return after_launch("reduce_blocks_kernel");
 }
 
@@ -835,16 +904,19 @@ int launch_arg_partials(const void* in, int64_t len, int64_t /*stride*/, int64_t
                         cudaStream_t st, const FusedArgs* fa = nullptr) {
     const int64_t nb = nblocks_for<T>(len);
     if (nb > 0x7fffffff) { set_error("length %lld exceeds the grid limit", (long long)len); return PNCU_ERR_ARGUMENT; }
-    const bool vec = ((uintptr_t)in % 32) == 0;
+    const int mode = read_mode(in, true);   // contiguous by contract
     const unsigned g = (unsigned)nb;
     ArgPair<T>* pp = (ArgPair<T>*)partials;
+#define PNCU_LAUNCH_ARG(MODE, FUSEDFLAG, ARGS) \
+    arg_blocks_kernel<T, IS_MAX, MODE, FUSEDFLAG><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, ARGS)
     if (fa) {
-        if (vec) arg_blocks_kernel<T, IS_MAX, true, true><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, *fa);
-        else arg_blocks_kernel<T, IS_MAX, false, true><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, *fa);
+        if (mode == RD_VEC) PNCU_LAUNCH_ARG(RD_VEC, true, *fa);
+        else PNCU_LAUNCH_ARG(RD_SHIFTED, true, *fa);
     } else {
-        if (vec) arg_blocks_kernel<T, IS_MAX, true, false><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, kNoFuse);
-        else arg_blocks_kernel<T, IS_MAX, false, false><<<g, RED_THREADS, 0, st>>>((const T*)in, len, index_base, pp, kNoFuse);
+        if (mode == RD_VEC) PNCU_LAUNCH_ARG(RD_VEC, false, kNoFuse);
+        else PNCU_LAUNCH_ARG(RD_SHIFTED, false, kNoFuse);
     }
+#undef PNCU_LAUNCH_ARG
     return after_launch("arg_blocks_kernel");
 }
 
@@ -866,7 +938,7 @@ int launch_reduce_fused(const void* in, int64_t len, int64_t stride, int64_t /*i
                         void* out, const void* startVal, cudaStream_t st) {
     typedef typename R::In In;
     int rc;
-    if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (!out && consumes(x)) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
     if (len <= 0) { set_error("one-launch reduction of an empty shard"); return PNCU_ERR_ARGUMENT; }
     if ((rc = check_reduce_args<R>(in, stride))) return rc;
     FusedArgs fa;
@@ -922,7 +994,7 @@ int launch_muladd_sum_fused(const void* a, const void* b, const void* c, int64_t
                             cudaStream_t st) {
     typedef typename R::In In;
     int rc;
-    if (!out) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (!out && consumes(x)) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
     if (len <= 0) { set_error("one-launch reduction of an empty shard"); return PNCU_ERR_ARGUMENT; }
     FusedArgs fa;
     void* partials = NULL;
@@ -969,7 +1041,7 @@ template <class R>
 int launch_arg_fused(const void* in, int64_t len, int64_t /*stride*/, int64_t index_base, const pncu_fused_exchange* x,
                      void* out_index, const void* /*startVal*/, cudaStream_t st) {
     int rc;
-    if (!out_index) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
+    if (!out_index && consumes(x)) { set_error("null output"); return PNCU_ERR_ARGUMENT; }
     if (len <= 0) { set_error("arg-reduction of an empty sequence"); return PNCU_ERR_ARGUMENT; }
     if ((rc = check_reduce_args<R>(in, sizeof(typename R::In)))) return rc;
     FusedArgs fa;

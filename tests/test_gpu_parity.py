@@ -704,9 +704,11 @@ def test_more_transcendentals_do_not_depend_on_neighbours(dev, rng, op):
 def _exchange_case(dev, devices, rng):
     """sum / min / max / argmax of one array cut into len(devices) shards, every shard on its own GPU, through
     Exchange: every participant must end with the bits a single GPU produces."""
+    import ctypes
     from pnumpy_b200 import cabi, exchange
     lib = cabi.load()
     world = len(devices)
+    timeouts0 = {}
     align = int(lib.pncu_reduce_block_elems())
     n = 5 * align * world + 12345
     for dt in ("float32", "float64", "int32"):
@@ -727,21 +729,26 @@ def _exchange_case(dev, devices, rng):
         want = {op: dev.reduce(op, whole).to_host().tobytes() for op in ("ADD", "MIN", "MAX")}
         want_arg = [int(dev.argminmax(k, whole).to_host()[0]) for k in (0, 1)]
         xs = exchange.Exchange.in_process(devices, max_slots=8192)
-        shards, outs, idxs = [], [], []
+        shards, outs, idxs, streams = [], [], [], []
         for r, d in enumerate(devices):
             cabi.check(lib.pncu_set_device(d), "set_device")
             shards.append(dev.to_device(a[bounds[r]:bounds[r + 1]]))
             outs.append(dev.empty(1, dt))
             idxs.append(dev.empty(1, np.int64))
+            # participants wait for each other ON THE DEVICE: two that share a GPU need a stream each
+            st = ctypes.c_void_p()
+            cabi.check(lib.pncu_stream_create(ctypes.byref(st)), "stream")
+            streams.append(st)
+            timeouts0[d] = int(lib.pncu_exchange_timeouts())
         counts = exchange.block_counts([s.size for s in shards], dt)
         for rep in range(3):  # several calls: both tables, growing counters
             for op in ("ADD", "MIN", "MAX"):
                 for r, d in enumerate(devices):
                     cabi.check(lib.pncu_set_device(d), "set_device")
-                    xs[r].reduce(op, shards[r], counts, outs[r])
+                    xs[r].reduce(op, shards[r], counts, outs[r], stream=streams[r])
                 for r, d in enumerate(devices):
                     cabi.check(lib.pncu_set_device(d), "set_device")
-                    xs[r].wait()
+                    xs[r].wait(streams[r])
                     got = outs[r].to_host()
                     if op != "ADD" and dt != "int32":
                         assert np.isnan(got[0])
@@ -750,15 +757,16 @@ def _exchange_case(dev, devices, rng):
             for kind in (0, 1):
                 for r, d in enumerate(devices):
                     cabi.check(lib.pncu_set_device(d), "set_device")
-                    xs[r].argminmax(kind, shards[r], counts, bounds[r], idxs[r])
+                    xs[r].argminmax(kind, shards[r], counts, bounds[r], idxs[r], stream=streams[r])
                 for r, d in enumerate(devices):
                     cabi.check(lib.pncu_set_device(d), "set_device")
-                    xs[r].wait()
+                    xs[r].wait(streams[r])
                     assert int(idxs[r].to_host()[0]) == want_arg[kind], (dt, kind, r, rep)
         for r, d in enumerate(devices):
             cabi.check(lib.pncu_set_device(d), "set_device")
-            assert lib.pncu_exchange_timeouts() == 0
+            assert lib.pncu_exchange_timeouts() == timeouts0[d]
             xs[r].close()
+            cabi.check(lib.pncu_stream_destroy(streams[r]), "stream")
     cabi.check(lib.pncu_set_device(devices[0]), "set_device")
 
 
