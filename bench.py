@@ -11,9 +11,17 @@ launches, 272 algorithmic bytes per element).  With N GPUs every r
 on its own 2^28-element shard (weak scaling; element-wise work needs no exchange).
 `value` is the whole-job algorithmic GB/s with inputs resident in HBM; `e2e` is the same sweep
 through the NumPy ufunc hooks on pinned HOST ndarrays (PCIe copies inside the timed region).
-`detail` (outside the timed steps) adds the other covered ufuncs -- sin/log/exp/sqrt (configs[2]),
-sum/min/max/argmin/argmax (configs[3], with the cross-rank partial combine when N > 1) and the
-a*b+c -> sum chain (configs[4]) -- each with GB/s and the fraction of both HBM peaks.
+Beside the contract's keys the line carries, at top level:
+  `resident`        -- STRONG scaling of the product path: ONE process (rank 0) drives all N GPUs through the NumPy
+                       hooks on managed ndarrays (np.add / np.sin / ndarray.sum / argmax at 2^28 and 2^30 elements):
+                       the nte dispatcher shards every call over the GPUs; results must equal the one-GPU bits;
+  `reductions_2p30` -- configs[3]: sum/min/max/argmin/argmax of 2^30 float32 IN TOTAL with NaNs planted, sharded over
+                       the N ranks, one kernel per rank with the NVLink exchange inside (pncu_*_fused), timed beside the
+                       NCCL all_gather variant; results must be the one-GPU / NumPy answers;
+  `parity`          -- every check above as a boolean.  ANY false (or an exchange timeout) makes the process exit 3,
+                       so the driver's multi-GPU runs are parity tests too.
+`detail` (outside the timed steps) adds the other covered ufuncs -- sin/log/exp/sqrt (configs[2]), the per-GPU
+reductions and the a*b+c -> sum chain (configs[4]) -- each with GB/s and the fraction of both HBM peaks.
 Every timing is CUDA events on the launching stream, after warm-up; inputs (>= 1 GiB per operand)
 are far larger than the 126 MB L2, so no separate flush is needed.
 """
@@ -298,6 +306,14 @@ def run_cuda(args):
     for x in keep:
         x.free()
 
+    # ---- parity gates: every rank checks its own results; any failure anywhere fails the whole job -------------
+    parity = {}
+    red = detail.pop("reductions_2p30", None) if isinstance(detail, dict) else None
+    if red is not None:
+        parity.update({"reductions_2p30." + k: bool(v) for k, v in red.get("checks", {}).items()})
+    for key in ("chain_fused_device_resident",):
+        if key in detail:
+            parity[key + ".bit_identical_to_unfused"] = bool(detail[key].get("bit_identical_to_unfused"))
     line = None
     if rank == 0:
         e2e = run_e2e(args) if not args.no_e2e else None
@@ -307,18 +323,193 @@ def run_cuda(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "i32/i64/f32/f64 (native width, FMA contraction off)",
                 "data": "synthetic", "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
                 "frac_of_measured_peak": round(value / world / peak, 4), "frac_of_8tbs": round(value / world / 8000.0, 4),
-                "roofline": roofline, "per_kernel": per_kernel, "detail": detail}
+                "roofline": roofline}
         if e2e is not None:
+            resident = e2e.pop("resident", None)
             line["e2e"] = e2e
+            if resident is not None:
+                line["resident"] = resident
+                parity.update({"resident." + k: bool(v) for k, v in resident.get("checks", {}).items()})
+            ch = e2e.get("chain") or {}
+            if isinstance(ch.get("fused"), dict):
+                parity["e2e.chain.fused_bit_identical_to_unfused"] = bool(ch["fused"].get("bit_identical_to_unfused"))
+            if isinstance(e2e.get("config0"), dict) and "result_equal" in e2e["config0"]:
+                parity["e2e.config0.result_equal"] = bool(e2e["config0"]["result_equal"])
+        if red is not None:
+            line["reductions_2p30"] = red
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        line["parity"] = parity
+        line["parity_ok"] = all(parity.values())
+        line["per_kernel"] = per_kernel
+        line["detail"] = detail
+    ok = all(parity.values())
     if dist:
         if rank != 0:
             torch.cuda.synchronize()
-        dist.barrier(group=cpu_group)   # blocks on the CPU: the other ranks' GPUs stay idle during rank 0's e2e phase
+        # blocks on the CPU: the other ranks' GPUs stay idle during rank 0's end-to-end / resident phase
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=cpu_group)
+        ok = bool(int(flag.item()))
         dist.destroy_process_group()
     if line is not None:
+        line["parity_ok"] = bool(ok and line["parity_ok"])
         print(json.dumps(line), flush=True)
+    if not ok:
+        sys.stderr.write("bench.py: PARITY FAILURE: " + json.dumps({k: v for k, v in parity.items() if not v}) + "\n")
+        sys.exit(3)
+
+
+def run_reductions_2p30(args, dev, cabi, lib, stream, rank, world, dist):
+    """configs[3]: sum / min / max / argmin / argmax over 2^30 float32 IN TOTAL, sharded over the `world` ranks at
+    multiples of 65536 elements, every shard with one NaN planted for the min/max/arg* runs (SURVEY.md 8d case iv).
+    Each rank launches ONE kernel per reduction: pass 1 on its shard, the shard's block partials pushed into every
+    rank's slot table over NVLink by the last CTA, which then waits on the device for the other shards and folds the
+    whole table (pncu_reduce_fused / pncu_argminmax_fused through pnumpy_b200.exchange.Exchange) -- no NCCL call, no
+    host synchronisation.  The plain variant (pass 1, NCCL all_gather of the partials, finish kernel) is timed beside
+    it and must give the same bits.  Timing: host wall clock around `reps` calls incl. the exchange, max over ranks."""
+    import ctypes
+    total = 1 << args.red_lg
+    lo, hi = shard_bounds(total, rank, world)
+    n = hi - lo
+    t = cabi.atop_of(np.float32)
+    counts = partial_counts(total, 4, world)
+    cnt = counts[rank]
+    x = dev.empty(n, np.float32)
+    piece = (np.random.default_rng(4321).random(1 << 22, dtype=np.float32) * np.float32(253.0) + np.float32(1.0))
+    dp = dev.to_device(piece)
+    for off in range(0, n, piece.size):
+        cabi.check(lib.pncu_memcpy_d2d(x.ptr + off * 4, dp.ptr, min(piece.size, n - off) * 4, None), "fill")
+    dev.sync()
+    dp.free()
+    res, ri = dev.empty(1, np.float32), dev.empty(1, np.int64)
+    reps = 10
+    out = {"elements_total": total, "elements_per_rank": n, "ranks": world,
+           "timing": f"host wall clock around {reps} calls incl. the exchange, max over ranks"}
+
+    def timed_ms(fn):
+        for _ in range(3):
+            fn()
+        cabi.check(lib.pncu_device_sync(), "sync")
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        cabi.check(lib.pncu_device_sync(), "sync")
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        if dist:
+            import torch
+            tt_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            ms = float(tt_.item())
+        return ms
+
+    xch, xch_error = None, None
+    if world > 1:
+        import torch
+        from pnumpy_b200 import exchange
+        try:
+            xch = exchange.Exchange.from_torch_distributed(max_slots=sum(counts), sync=False)
+        except Exception as e:  # e.g. CUDA IPC not permitted in this container: every rank must agree to fall back
+            xch_error = str(e)
+        okflag = torch.tensor([0 if xch_error else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(okflag, op=dist.ReduceOp.MIN)
+        if int(okflag.item()) == 0:
+            if xch is not None:
+                xch.close()
+            xch, xch_error = None, xch_error or "another rank could not map the peer tables"
+        dist.barrier()
+    out["exchange"] = ("none (1 GPU): one kernel, the last CTA folds" if world == 1 else
+                       ("inside the reduction kernel: the last CTA of every rank stores its shard's block partials into every "
+                        "rank's slot table over NVLink (CUDA IPC mappings), waits on the device for the others and folds; "
+                        "no NCCL call, no host sync" if xch is not None else
+                        f"NCCL all_gather between the passes (fused exchange unavailable: {xch_error})"))
+
+    def two_pass_nccl(kind, fop, target):
+        """pass 1, NCCL all_gather of the block partials, finish kernel: the plain way"""
+        import torch
+        pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
+        m = max(counts)
+        mine_t = torch.zeros(m * pbytes, dtype=torch.uint8, device="cuda")
+        all_t = torch.empty(world * m * pbytes, dtype=torch.uint8, device="cuda")
+        packed = torch.empty(sum(counts) * pbytes, dtype=torch.uint8, device="cuda")
+
+        def run():
+            if kind is None:
+                cabi.check(lib.pncu_reduce_partials(fop, t, x.ptr, n, mine_t.data_ptr(), stream), "partials")
+            else:
+                cabi.check(lib.pncu_argminmax_partials(kind, t, x.ptr, n, ctypes.c_int64(lo), mine_t.data_ptr(), stream), "arg partials")
+            cabi.check(lib.pncu_stream_sync(stream), "sync")
+            dist.all_gather_into_tensor(all_t, mine_t)
+            off = 0
+            for r in range(world):   # compact the padded gather into global slot order
+                packed[off: off + counts[r] * pbytes] = all_t[r * m * pbytes: r * m * pbytes + counts[r] * pbytes]
+                off += counts[r] * pbytes
+            torch.cuda.current_stream().synchronize()
+            if kind is None:
+                cabi.check(lib.pncu_reduce_finish(fop, t, packed.data_ptr(), sum(counts), target.ptr, None, stream), "finish")
+            else:
+                cabi.check(lib.pncu_argminmax_finish(kind, t, packed.data_ptr(), sum(counts), target.ptr, stream), "arg finish")
+        return run
+
+    def one_launch(kind, name):
+        if world == 1 or xch is None:
+            if kind is None:
+                op = {"sum": "ADD", "min": "MIN", "max": "MAX"}[name]
+                return lambda: dev.reduce(op, x, out=res, stream=stream)
+            return lambda: dev.argminmax(kind, x, out=ri, stream=stream)
+        if kind is None:
+            op = {"sum": "ADD", "min": "MIN", "max": "MAX"}[name]
+            return lambda: xch.reduce(op, x, counts, res, stream=stream)
+        return lambda: xch.argminmax(kind, x, counts, lo, ri, stream=stream)
+
+    # the float64 reference of the sum: the piece repeats, so it is a few float64 sums on the host
+    full, rem = divmod(total, piece.size)
+    s64 = full * float(np.sum(piece, dtype=np.float64)) + float(np.sum(piece[:rem], dtype=np.float64))
+    checks = {}
+    for name, kind in (("sum", None), ("min", None), ("max", None), ("argmin", 1), ("argmax", 0)):
+        if name == "min":   # from here on: one NaN per shard; rank 0's is the first of the whole job
+            nan_at = (1234567 * (rank + 1)) % n
+            nanv = np.array([np.nan], dtype=np.float32)
+            cabi.check(lib.pncu_memcpy_h2d(x.ptr + 4 * nan_at, nanv.ctypes.data, 4, stream), "plant NaN")
+            cabi.check(lib.pncu_stream_sync(stream), "sync")
+        fop = cabi.BINARY_OPS[{"sum": "ADD", "min": "MIN", "max": "MAX"}.get(name, "MAX")]
+        fn = one_launch(kind, name)
+        if world > 1 and xch is None:
+            fn = two_pass_nccl(kind, fop, res if kind is None else ri)
+        ms = timed_ms(fn)
+        if xch is not None:
+            xch.wait(stream)
+        got = res.to_host() if kind is None else ri.to_host()
+        row = {"ms": round(ms, 4), "gbs": round(4.0 * total / (ms * 1e-3) / 1e9, 1), "melem_per_s": round(total / (ms * 1e-3) / 1e6, 0)}
+        if name == "sum":
+            row["result"] = float(got[0])
+            row["within_tolerance"] = bool(abs(float(got[0]) - s64) <= 2.0 ** -23 * abs(s64) + 2.0 ** -50 * s64)
+            checks["sum_within_tolerance"] = row["within_tolerance"]
+        elif kind is None:
+            row["nan_semantics_ok"] = bool(np.isnan(got[0]))
+            checks[name + "_nan_ok"] = row["nan_semantics_ok"]
+        else:
+            row["nan_semantics_ok"] = int(got[0]) == 1234567 % (shard_bounds(total, 0, world)[1])  # global index of rank 0's NaN
+            checks[name + "_nan_ok"] = row["nan_semantics_ok"]
+        if world > 1 and xch is not None:
+            plain_target = dev.empty(1, np.float32 if kind is None else np.int64)
+            plain = two_pass_nccl(kind, fop, plain_target)
+            row["nccl_all_gather_variant_ms"] = round(timed_ms(plain), 4)
+            same = plain_target.to_host().tobytes() == got.tobytes()
+            if kind is None and name != "sum":
+                same = bool(np.isnan(plain_target.to_host()[0]) and np.isnan(got[0]))   # NaN payloads are unspecified
+            row["same_bits_as_nccl_variant"] = bool(same)
+            checks[name + "_same_as_nccl"] = bool(same)
+        out[name] = row
+    if xch is not None:
+        out["exchange_timeouts"] = int(lib.pncu_exchange_timeouts())
+        checks["no_exchange_timeouts"] = out["exchange_timeouts"] == 0
+        xch.close()
+    out["checks"] = checks
+    x.free()
+    return out
 
 
 def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
@@ -375,150 +566,8 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
          "frac_of_8tbs": round(bytes_per_elem(name, dt) * n / (ms * 1e-3) / 1e9 / 8000.0, 4),
          "melem_per_s": round(n / (ms * 1e-3) / 1e6, 0)} for name, dt, ms in rows]
 
-    # configs[3]: float32 sum over the WHOLE job (world x 2^28 elements) with the cross-rank combine:
-    # pass 1 on every rank's shard, ONE NCCL all_gather of the block partials, one finish kernel.
-    a = byname["float32"][0]
-    f, t = cabi.BINARY_OPS["ADD"], cabi.atop_of(np.float32)
-    pb = lib.pncu_reduce_partial_bytes(f, t)
-    cnt = lib.pncu_reduce_partial_count(t, n)
     res = dev.empty(1, np.float32)
-    xch = None
-    counts = [cnt] * world
-
-    def timed_ms(fn):
-        """host wall clock around `reps` calls (the collective included), max over ranks"""
-        for _ in range(3):
-            fn()
-        cabi.check(lib.pncu_device_sync(), "sync")
-        if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            fn()
-        cabi.check(lib.pncu_device_sync(), "sync")
-        ms = (time.perf_counter() - t0) * 1e3 / reps
-        if dist:
-            import torch
-            tt_ = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
-            ms = float(tt_.item())
-        return ms
-
-    reps = 10
-    nccl_ms = None
-    if world == 1:
-        parts = dev.empty(cnt * pb, np.uint8)
-
-        def sharded_sum():
-            cabi.check(lib.pncu_reduce_partials(f, t, a.ptr, n, parts.ptr, stream), "partials")
-            cabi.check(lib.pncu_reduce_finish(f, t, parts.ptr, cnt, res.ptr, None, stream), "finish")
-    else:
-        import torch
-        from pnumpy_b200 import exchange
-        mine = torch.empty(cnt, dtype=torch.float64, device="cuda")
-        allp = torch.empty(world * cnt, dtype=torch.float64, device="cuda")
-
-        def sharded_sum_nccl():  # the plain way, timed beside the fused exchange
-            cabi.check(lib.pncu_reduce_partials(f, t, a.ptr, n, mine.data_ptr(), stream), "partials")
-            cabi.check(lib.pncu_stream_sync(stream), "sync")
-            dist.all_gather_into_tensor(allp, mine)
-            torch.cuda.current_stream().synchronize()
-            cabi.check(lib.pncu_reduce_finish(f, t, allp.data_ptr(), world * cnt, res.ptr, None, stream), "finish")
-        nccl_ms = timed_ms(sharded_sum_nccl)
-        nccl_bits = res.to_host().tobytes()
-        # the product path: pass 2 is one kernel that stores this rank's block partials into every rank's slot
-        # table over NVLink (CUDA IPC mappings), waits on the device for the others' and folds -- no collective
-        # call, no host synchronisation in between
-        xch_error = None
-        try:
-            xch = exchange.Exchange.from_torch_distributed(max_slots=world * cnt, sync=False)
-        except Exception as e:  # e.g. CUDA IPC not permitted in this container: every rank must agree to fall back
-            xch_error = str(e)
-        okflag = torch.tensor([0 if xch_error else 1], dtype=torch.int32, device="cuda")
-        dist.all_reduce(okflag, op=dist.ReduceOp.MIN)
-        if int(okflag.item()) == 0:
-            if xch is not None:
-                xch.close()
-            xch = None
-            xch_error = xch_error or "another rank could not map the peer tables"
-            sharded_sum = sharded_sum_nccl
-        else:
-            def sharded_sum():
-                xch.reduce("ADD", a, counts, res, stream=stream)
-    ms = timed_ms(sharded_sum)
-    out["sharded_sum_f32"] = {"elements_total": n * world, "ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1),
-                              "collective": "none (1 GPU)" if world == 1 else
-                              ("fused into pass 2: one kernel per rank stores its block partials into every rank's slot table over "
-                               "NVLink (CUDA IPC mappings), waits on the device for the others' and folds; no NCCL call, no host sync"
-                               if xch is not None else f"NCCL all_gather between the passes (fused exchange unavailable: {xch_error})"),
-                              "result": float(res.to_host()[0])}
-    if nccl_ms is not None:
-        out["sharded_sum_f32"].update({"nccl_all_gather_variant_ms": round(nccl_ms, 4),
-                                       "nccl_all_gather_variant_gbs": round(4.0 * n * world / (nccl_ms * 1e-3) / 1e9, 1),
-                                       "same_bits_as_nccl_variant": res.to_host().tobytes() == nccl_bits})
-
-    # configs[3], the other reductions, with NaN inputs: every rank's float32 shard gets ONE NaN at a
-    # pseudo-random index (SURVEY.md 8d case iv).  min/max must come back NaN and argmin/argmax the GLOBAL
-    # index of the first NaN (rank 0's).  Same two passes with the exchange fused in (4 B partials for min/max,
-    # 16 B {value, index} for the arg-reductions) -- timed like the sum.
-    xn = byname["float32"][2]  # the float32 output buffer, free at this point
-    cabi.check(lib.pncu_memcpy_d2d(xn.ptr, a.ptr, n * 4, stream), "copy")
-    nan_at = (1234567 * (rank + 1)) % n
-    nanv = np.array([np.nan], dtype=np.float32)
-    cabi.check(lib.pncu_memcpy_h2d(xn.ptr + 4 * nan_at, nanv.ctypes.data, 4, stream), "plant NaN")
-    cabi.check(lib.pncu_stream_sync(stream), "sync")
-    ri = dev.empty(1, np.int64)
-    nan_rows = {}
-    for name, kind in (("min", None), ("max", None), ("argmin", 1), ("argmax", 0)):
-        fop = cabi.BINARY_OPS["MIN" if name == "min" else "MAX"]
-        if world == 1:
-            pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
-            buf = dev.empty(cnt * pbytes, np.uint8)
-
-            def sharded(kind=kind, fop=fop, buf=buf):
-                if kind is None:
-                    cabi.check(lib.pncu_reduce_partials(fop, t, xn.ptr, n, buf.ptr, stream), "partials")
-                    cabi.check(lib.pncu_reduce_finish(fop, t, buf.ptr, cnt, res.ptr, None, stream), "finish")
-                else:
-                    cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(0), buf.ptr, stream), "arg partials")
-                    cabi.check(lib.pncu_argminmax_finish(kind, t, buf.ptr, cnt, ri.ptr, stream), "arg finish")
-        elif xch is not None:
-            def sharded(kind=kind, name=name):
-                if kind is None:
-                    xch.reduce("MIN" if name == "min" else "MAX", xn, counts, res, stream=stream)
-                else:
-                    xch.argminmax(kind, xn, counts, rank * n, ri, stream=stream)
-        else:  # fused exchange unavailable: NCCL all_gather of the block partials between the passes
-            import torch
-            pbytes = 16 if kind is not None else lib.pncu_reduce_partial_bytes(fop, t)
-            mine_t = torch.empty(cnt * pbytes, dtype=torch.uint8, device="cuda")
-            all_t = torch.empty(world * cnt * pbytes, dtype=torch.uint8, device="cuda")
-
-            def sharded(kind=kind, fop=fop, mine_t=mine_t, all_t=all_t):
-                if kind is None:
-                    cabi.check(lib.pncu_reduce_partials(fop, t, xn.ptr, n, mine_t.data_ptr(), stream), "partials")
-                else:
-                    cabi.check(lib.pncu_argminmax_partials(kind, t, xn.ptr, n, ctypes.c_int64(rank * n), mine_t.data_ptr(), stream), "arg partials")
-                cabi.check(lib.pncu_stream_sync(stream), "sync")
-                dist.all_gather_into_tensor(all_t, mine_t)
-                torch.cuda.current_stream().synchronize()
-                if kind is None:
-                    cabi.check(lib.pncu_reduce_finish(fop, t, all_t.data_ptr(), world * cnt, res.ptr, None, stream), "finish")
-                else:
-                    cabi.check(lib.pncu_argminmax_finish(kind, t, all_t.data_ptr(), world * cnt, ri.ptr, stream), "arg finish")
-        ms = timed_ms(sharded)
-        if kind is None:
-            ok = bool(np.isnan(res.to_host()[0]))
-        else:
-            ok = int(ri.to_host()[0]) == 1234567 % n  # rank 0's NaN is the first of the whole job
-        nan_rows[name] = {"ms": round(ms, 4), "gbs": round(4.0 * n * world / (ms * 1e-3) / 1e9, 1), "nan_semantics_ok": ok}
-    if xch is not None:
-        nan_rows["exchange_timeouts"] = int(lib.pncu_exchange_timeouts())
-    out["sharded_nan_reductions_f32"] = {
-        "elements_total": n * world, "nan_per_shard": 1,
-        "collective": "none (1 GPU)" if world == 1 else ("fused exchange over NVLink peer memory (see sharded_sum_f32)"
-                                                        if xch is not None else "NCCL all_gather between the passes"),
-        "timing": "host wall clock around 10 calls incl. the collective, max over ranks", **nan_rows}
+    out["reductions_2p30"] = run_reductions_2p30(args, dev, cabi, lib, stream, rank, world, dist)
 
     # configs[4], device-resident leg: t = a*b; u = t+c; r = u.sum() as three kernels (28 B/element)
     a, b, o = byname["float32"][0], byname["float32"][1], byname["float32"][2]
@@ -548,6 +597,72 @@ def run_detail(args, dev, cabi, lib, stream, keep, n, peak, rank, world, dist):
     ms = timeit(lambda: dev.muladd(a, b, c, out=o, stream=stream))
     out["muladd_f32"] = {"expr": "o=a*b+c float32 in one pass (muladd_vec_kernel)", "elements": n, "ms": round(ms, 4),
                          "gbs": round(16.0 * n / (ms * 1e-3) / 1e9, 1), "frac_of_8tbs": round(16.0 * n / (ms * 1e-3) / 1e9 / 8000.0, 4)}
+    return out
+
+
+def run_resident(pn, args):
+    """STRONG scaling of the product path (north_star: "splits large 1-D arrays evenly across up to 8 B200s"): this ONE
+    process drives all N GPUs through plain NumPy calls on managed ndarrays -- np.add / np.sin / ndarray.sum / max /
+    argmax.  The nte dispatcher keeps shard l of every operand on GPU l and runs one kernel per GPU per call (reductions:
+    the block partials meet in GPU 0's table over NVLink inside the same kernels); nothing crosses PCIe.  Wall clock per
+    call (median of 20), algorithmic GB/s.  Every result is compared with the SAME call restricted to one GPU
+    (thread_disable): the bits must not depend on the number of GPUs."""
+    out = {"what": "np.add / np.sin / ndarray.sum / max / argmax through the hooks on managed float32 ndarrays; one process, "
+                   "all GPUs; wall clock per call (median of 20)", "gpus": int(pn.cuda_info()["devices"]), "sizes": {}}
+    checks = {}
+
+    def med(fn, k=20):
+        fn()
+        fn()
+        ts = []
+        for _ in range(k):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    try:
+        for lg in args.resident_lg:
+            m = 1 << lg
+            ma, mb, mo, m1 = (pn.managed_empty(m, np.float32) for _ in range(4))
+            piece = np.random.default_rng(7).random(1 << 22, dtype=np.float32) * np.float32(253.0) + np.float32(1.0)
+            ma.reshape(-1, piece.size)[:] = piece
+            mb.reshape(-1, piece.size)[:] = piece[::-1]
+            ma[(3 * m) // 5 + 11] = np.float32(1e6)      # a unique maximum, away from any shard boundary
+            rows = {}
+            pn.thread_enable()
+            pn.cuda_reset_stats()
+            for name, bpe, fn in (("add", 12, lambda: np.add(ma, mb, out=mo)), ("sin", 8, lambda: np.sin(ma, out=mo)),
+                                  ("sum", 4, lambda: ma.sum()), ("max", 4, lambda: ma.max()), ("argmax", 4, lambda: ma.argmax())):
+                s_ = med(fn)
+                rows[name] = {"ms": round(s_ * 1e3, 4), "gbs": round(bpe * m / s_ / 1e9, 1), "melem_per_s": round(m / s_ / 1e6, 0),
+                              "gpus_used": int(pn.cuda_info()["gpus_last"])}
+            rows["h2d_bytes"] = int(pn.cuda_info()["h2d_bytes"])
+            # N GPUs vs one GPU: same bits
+            np.add(ma, mb, out=mo)
+            rN = (ma.sum(), ma.max(), int(ma.argmax()))
+            pn.thread_disable()
+            np.add(ma, mb, out=m1)
+            r1 = (ma.sum(), ma.max(), int(ma.argmax()))
+            same_add = bool(np.array_equal(mo, m1))
+            np.sin(ma, out=m1)
+            pn.thread_enable()
+            np.sin(ma, out=mo)
+            same_sin = bool(np.array_equal(mo, m1))
+            rows["bit_identical_to_one_gpu"] = {"add": same_add, "sin": same_sin, "sum": bool(np.float32(rN[0]).tobytes() == np.float32(r1[0]).tobytes()),
+                                                "max": bool(rN[1] == r1[1] == np.float32(1e6)), "argmax": bool(rN[2] == r1[2] == (3 * m) // 5 + 11)}
+            for k_, v_ in rows["bit_identical_to_one_gpu"].items():
+                checks[f"2p{lg}_{k_}_same_as_one_gpu"] = v_
+            checks[f"2p{lg}_no_pcie"] = rows["h2d_bytes"] == 0
+            rows["sum_result"] = float(rN[0])
+            out["sizes"][f"2p{lg}"] = rows
+            del ma, mb, mo, m1
+    except Exception as e:  # pragma: no cover
+        out["error"] = str(e)
+        checks["resident_ran"] = False
+    finally:
+        pn.thread_enable()
+    out["checks"] = checks
     return out
 
 
@@ -664,37 +779,9 @@ def run_e2e(args):
             del big, a, b, c, t, o
         except Exception as e:  # pragma: no cover
             chain["at_2p%d" % args.chain_lg] = {"error": str(e)}
-    # the same hooks on DEVICE-RESIDENT ndarrays (CUDA managed memory): no PCIe in steady state
-    resident = None
-    try:
-        m = 1 << 28
-        ma, mb, mo = pn.managed_empty(m, np.float32), pn.managed_empty(m, np.float32), pn.managed_empty(m, np.float32)
-        piece = rng.random(1 << 22, dtype=np.float32) * 253 + 1
-        ma.reshape(-1, piece.size)[:] = piece
-        mb.reshape(-1, piece.size)[:] = piece[::-1]
-        np.add(ma, mb, out=mo)  # first call migrates the pages to the GPU
-        np.add(ma, mb, out=mo)
-        pn.cuda_reset_stats()
-        t0 = time.perf_counter()
-        for _ in range(10):
-            np.add(ma, mb, out=mo)
-        add_s = (time.perf_counter() - t0) / 10
-        t0 = time.perf_counter()
-        for _ in range(10):
-            np.sin(ma, out=mo)
-        sin_s = (time.perf_counter() - t0) / 10
-        t0 = time.perf_counter()
-        for _ in range(10):
-            ssum = ma.sum()
-        sum_s = (time.perf_counter() - t0) / 10
-        ri = pn.cuda_info()
-        resident = {"what": "np.add / np.sin / ndarray.sum on managed (device-resident) float32 ndarrays, wall clock per call",
-                    "elements": m, "add_gbs": round(12.0 * m / add_s / 1e9, 1), "sin_gbs": round(8.0 * m / sin_s / 1e9, 1),
-                    "sum_gbs": round(4.0 * m / sum_s / 1e9, 1), "h2d_bytes": int(ri["h2d_bytes"]), "gpu_calls": int(ri["calls"]),
-                    "sum": float(ssum)}
-        del ma, mb, mo
-    except Exception as e:  # pragma: no cover
-        resident = {"error": str(e)}
+    # the same hooks on DEVICE-RESIDENT ndarrays (CUDA managed memory), spread over all N GPUs by the dispatcher
+    arrs.clear()
+    resident = run_resident(pn, args)
     # configs[0]: np.add float32 on 1 000 000 contiguous elements (pn.benchmark's size), hooks off vs on.
     # 12 MB of PCIe traffic per call: latency-bound, the GPU path has to beat ~0.5 ms of NumPy loop.
     config0 = None
@@ -824,7 +911,7 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
-    cpu = run_cpu_baseline(sample_lg=args.cpu_lg, reps=max(1, args.steps))
+    cpu = run_cpu_baseline(sample_lg=args.cpu_lg, reps=max(1, min(args.steps, 20)))
     line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "i32/i64/f32/f64", "data": "synthetic", "config": workload_config(world),
@@ -845,7 +932,9 @@ def main():
     ap.add_argument("--e2e-lg", type=int, default=28, help="log2 elements per operand of the end-to-end sweep")
     ap.add_argument("--chain-lg", type=int, default=30, help="log2 elements of the end-to-end a*b+c -> sum chain (configs[4]: 2^30)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-lg", type=int, default=27, help="log2 elements per operand of the CPU sample")
+    ap.add_argument("--cpu-lg", type=int, default=28, help="log2 elements per operand of the CPU sample (configs[1]: 2^28)")
+    ap.add_argument("--red-lg", type=int, default=30, help="log2 TOTAL elements of the sharded reductions (configs[3]: 2^30)")
+    ap.add_argument("--resident-lg", type=int, nargs="*", default=[28, 30], help="log2 elements of the strong-scaling resident leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

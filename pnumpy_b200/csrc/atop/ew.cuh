@@ -118,6 +118,60 @@ __device__ __forceinline__ void st_pack(T* p, const Pack<T, N>& v) {
     st_words<Pack<T, N>::BYTES>(p, v.w);
 }
 
+// ---- operands whose alignment disagrees with the output's ----------------------------------------------
+// The vector kernels store aligned wide vectors of `out`.  A contiguous input that sits `m` bytes past its own
+// vector alignment at the same element (a[1:] next to a[:-1], any view cut at an odd element) would need a
+// misaligned 256-bit load.  Instead every lane loads the ALIGNED vector that contains its first byte, takes the
+// next aligned vector from the NEXT LANE's registers (one shuffle per word; lane 31 and the last active lane
+// load theirs directly) and extracts bytes [m, m + BYTES) of the pair with funnel shifts.  Same bytes from HBM,
+// still one fully coalesced 256-bit load per lane, and the arithmetic sees exactly the elements it would have
+// seen -- results cannot differ.  (The reference's AVX2 loops simply use unaligned loads, loadu,
+// src/atop/ops_binary.cpp:600-616.)  The launcher guarantees that both aligned vectors of every active lane lie
+// inside the operand (it widens the scalar head / tail by one vector), so nothing outside the array is read.
+template <int W, int WS>
+struct FunnelExtract {
+    static __device__ __forceinline__ void run(const uint32_t (&A)[W], const uint32_t (&N)[W], unsigned ws, unsigned bs, uint32_t* out) {
+        if (ws == WS) {
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                const uint32_t lo = (i + WS < W) ? A[(i + WS) % W] : N[(i + WS) % W];
+                const uint32_t hi = (i + WS + 1 < W) ? A[(i + WS + 1) % W] : N[(i + WS + 1) % W];
+                out[i] = __funnelshift_r(lo, hi, bs);
+            }
+        } else {
+            FunnelExtract<W, WS + 1>::run(A, N, ws, bs, out);
+        }
+    }
+};
+template <int W>
+struct FunnelExtract<W, W> {
+    static __device__ __forceinline__ void run(const uint32_t (&)[W], const uint32_t (&)[W], unsigned, unsigned, uint32_t*) {}
+};
+
+// `p`: this lane's first element (element-aligned); `m` = (address of p) mod BYTES, warp-uniform; `active`: this
+// lane has a vector; `next_active`: so has the next lane.  Must be called by all 32 lanes of the warp.
+template <class T, int N>
+__device__ __forceinline__ Pack<T, N> ld_pack_realigned(const T* p, unsigned m, bool active, bool next_active) {
+    constexpr int BYTES = Pack<T, N>::BYTES;
+    static_assert(BYTES % 4 == 0, "vectors are whole words");
+    constexpr int W = BYTES / 4;
+    Pack<T, N> r;
+    if (m == 0) {   // this operand agrees with the output after all (uniform branch)
+        if (active) r = ld_pack<T, N>(p); else r.zero();
+        return r;
+    }
+    const char* base = reinterpret_cast<const char*>(p) - m;
+    uint32_t A[W], Nx[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) A[w] = 0u;
+    if (active) ld_words<BYTES>(base, A);
+#pragma unroll
+    for (int w = 0; w < W; ++w) Nx[w] = __shfl_down_sync(0xffffffffu, A[w], 1);
+    if (active && ((threadIdx.x & 31) == 31 || !next_active)) ld_words<BYTES>(base + BYTES, Nx);
+    FunnelExtract<W, 0>::run(A, Nx, m >> 2, (m & 3u) * 8u, r.w);
+    return r;
+}
+
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 enum Layout { LAY_VV = 0, LAY_SV = 1, LAY_VS = 2 };
@@ -132,10 +186,10 @@ struct Epv { static constexpr int value = EW_VEC_BYTES / cmax((int)sizeof(In), (
 
 // ---- binary ----------------------------------------------------------------------
 // F: struct { typedef In; typedef Out; static __device__ Out apply(In, In); }
-template <class F, int LAYOUT>
+template <class F, int LAYOUT, bool REALIGN>
 __global__ void __launch_bounds__(EW_BLOCK)
 ew2_vec_kernel(const typename F::In* a, const typename F::In* b, typename F::Out* o,
-               int64_t head, int64_t nvec, int64_t n) {
+               int64_t head, int64_t nvec, int64_t n, unsigned ma, unsigned mb) {
     typedef typename F::In In;
     typedef typename F::Out Out;
     constexpr int EPV = Epv<In, Out>::value;
@@ -145,25 +199,33 @@ ew2_vec_kernel(const typename F::In* a, const typename F::In* b, typename F::Out
     if (LAYOUT == LAY_VS) sb = b[0];
 
     const int64_t v = (int64_t)blockIdx.x * EW_BLOCK + threadIdx.x;
-    if (v < nvec) {
+    const bool active = v < nvec;
+    if (REALIGN || active) {
         const int64_t e0 = head + v * EPV;
         Pack<In, EPV> ra, rb;
-        if (LAYOUT != LAY_SV) ra = ld_pack<In, EPV>(a + e0);
-        if (LAYOUT != LAY_VS) rb = ld_pack<In, EPV>(b + e0);
-        Pack<Out, EPV> r;
-        if constexpr (WordOp<F>::enabled && sizeof(In) == sizeof(Out)) {
-            // 1- and 2-byte types: whole words through the SIMD-in-a-word form (functors.cuh)
-            const unsigned wa = splat_word<In>(sa), wb = splat_word<In>(sb);
-#pragma unroll
-            for (int w = 0; w < Pack<Out, EPV>::WORDS; ++w)
-                r.w[w] = WordOp<F>::word(LAYOUT == LAY_SV ? wa : ra.w[w], LAYOUT == LAY_VS ? wb : rb.w[w]);
+        if constexpr (REALIGN) {   // every lane takes part in the shuffles, active or not
+            if (LAYOUT != LAY_SV) ra = ld_pack_realigned<In, EPV>(a + e0, ma, active, v + 1 < nvec);
+            if (LAYOUT != LAY_VS) rb = ld_pack_realigned<In, EPV>(b + e0, mb, active, v + 1 < nvec);
         } else {
-            r.zero();
-#pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra.get(e), LAYOUT == LAY_VS ? sb : rb.get(e)));
+            if (LAYOUT != LAY_SV) ra = ld_pack<In, EPV>(a + e0);
+            if (LAYOUT != LAY_VS) rb = ld_pack<In, EPV>(b + e0);
         }
-        st_pack<Out, EPV>(o + e0, r);
+        if (active) {
+            Pack<Out, EPV> r;
+            if constexpr (WordOp<F>::enabled && sizeof(In) == sizeof(Out)) {
+                // 1- and 2-byte types: whole words through the SIMD-in-a-word form (functors.cuh)
+                const unsigned wa = splat_word<In>(sa), wb = splat_word<In>(sb);
+#pragma unroll
+                for (int w = 0; w < Pack<Out, EPV>::WORDS; ++w)
+                    r.w[w] = WordOp<F>::word(LAYOUT == LAY_SV ? wa : ra.w[w], LAYOUT == LAY_VS ? wb : rb.w[w]);
+            } else {
+                r.zero();
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    r.set(e, F::apply(LAYOUT == LAY_SV ? sa : ra.get(e), LAYOUT == LAY_VS ? sb : rb.get(e)));
+            }
+            st_pack<Out, EPV>(o + e0, r);
+        }
     }
     // head + tail scalars: elements before the first / after the last aligned wide vector
     if (blockIdx.x == 0) {
@@ -252,25 +314,37 @@ __device__ __forceinline__ Pack<typename F::Out, EPV> apply_pack(const Pack<type
     return r;
 }
 
-template <class F>
+template <class F, bool REALIGN>
 __global__ void __launch_bounds__(EW_BLOCK)
-ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n) {
+ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n, unsigned ma) {
     typedef typename F::In In;
     typedef typename F::Out Out;
     constexpr int EPV = Epv<In, Out>::value;
     constexpr int U = unroll_of<F>::value;
+    // the branch-free fast body (table functors keep theirs for ew1_table_kernel: no table here)
+    constexpr bool FAST = has_fast<F>::value && smem_of<F>::value == 0;
     const int64_t v0 = (int64_t)blockIdx.x * (EW_BLOCK * U) + threadIdx.x;
-    if (v0 + (int64_t)(U - 1) * EW_BLOCK < nvec) {
-        Pack<In, EPV> ra[U];
+    const bool full = v0 + (int64_t)(U - 1) * EW_BLOCK < nvec;
+    Pack<In, EPV> ra[U];
+    if constexpr (REALIGN) {
+        // input misaligned relative to the output (see ld_pack_realigned): every lane runs the loads and shuffles
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t v = v0 + (int64_t)u * EW_BLOCK;
+            ra[u] = ld_pack_realigned<In, EPV>(a + head + v * EPV, ma, v < nvec, v + 1 < nvec);
+        }
+    } else if (full) {
 #pragma unroll
         for (int u = 0; u < U; ++u) ra[u] = ld_pack<In, EPV>(a + head + (v0 + (int64_t)u * EW_BLOCK) * EPV);
-        bool all_fast = has_fast<F>::value;
-        if constexpr (has_fast<F>::value) {
+    }
+    if (full) {
+        bool all_fast = FAST;
+        if constexpr (FAST) {
 #pragma unroll
             for (int u = 0; u < U; ++u) all_fast = all_fast && pack_ok<F, EPV>(ra[u]);
         }
         if (all_fast) {
-            if constexpr (has_fast<F>::value) {
+            if constexpr (FAST) {
 #pragma unroll
                 for (int u = 0; u < U; ++u)
                     st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, fast_pack<F, EPV>(ra[u], nullptr));
@@ -285,8 +359,9 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
         for (int u = 0; u < U; ++u) {
             const int64_t v = v0 + (int64_t)u * EW_BLOCK;
             if (v < nvec) {
-                const Pack<In, EPV> ra = ld_pack<In, EPV>(a + head + v * EPV);
-                st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra));
+                Pack<In, EPV> rx;
+                if constexpr (REALIGN) rx = ra[u]; else rx = ld_pack<In, EPV>(a + head + v * EPV);
+                st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(rx));
             }
         }
     }
@@ -447,23 +522,40 @@ int launch_binary(const void* in1, const void* in2, void* out, int64_t len, int6
     const bool c1 = s1 == (int64_t)sizeof(In), c2 = s2 == (int64_t)sizeof(In);
     const bool z1 = s1 == 0, z2 = s2 == 0;
     if (so == (int64_t)sizeof(Out) && ((c1 && c2) || (z1 && c2) || (c1 && z2))) {
-        // elements to peel so that `out` reaches its vector alignment; inputs must agree
+        // elements to peel so that `out` reaches its vector alignment
         int64_t head = ((OUT_VB - (int64_t)((uintptr_t)out % OUT_VB)) % OUT_VB) / (int64_t)sizeof(Out);
         if (head > len) head = len;
-        const bool a_ok = z1 || ((uintptr_t)in1 + head * sizeof(In)) % IN_VB == 0;
-        const bool b_ok = z2 || ((uintptr_t)in2 + head * sizeof(In)) % IN_VB == 0;
-        if (a_ok && b_ok) {
-            const int64_t nvec = (len - head) / EPV;
+        // where does each input stand at that element?  0 = agrees with `out` (plain aligned vector loads)
+        unsigned ma = z1 ? 0u : (unsigned)(((uintptr_t)in1 + head * sizeof(In)) % IN_VB);
+        unsigned mb = z2 ? 0u : (unsigned)(((uintptr_t)in2 + head * sizeof(In)) % IN_VB);
+        int64_t nvec = (len - head) / EPV;
+        const bool realign = (ma | mb) != 0 && IN_VB % 4 == 0;
+        if (realign) {
+            // a realigning lane reads the aligned vector that contains its first byte and the one after it: keep
+            // both inside the operand by leaving one more vector to the scalar head (if the first aligned vector
+            // would start before the array) and one to the scalar tail
+            if ((int64_t)(head * sizeof(In)) < (int64_t)(ma > mb ? ma : mb)) head += EPV;
+            if (head > len) head = len;
+            nvec = (len - head) / EPV - 1;
+            if (nvec < 0) nvec = 0;
+        }
+        if (realign || (ma | mb) == 0) {
             const unsigned grid = full_grid(nvec, EW_BLOCK);
             const In* a = (const In*)in1;
             const In* b = (const In*)in2;
             Out* o = (Out*)out;
-            if (c1 && c2)
-                ew2_vec_kernel<F, LAY_VV><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+            if (realign) {
+                if constexpr (IN_VB % 4 == 0) {
+                    if (c1 && c2) ew2_vec_kernel<F, LAY_VV, true><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len, ma, mb);
+                    else if (z1) ew2_vec_kernel<F, LAY_SV, true><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len, ma, mb);
+                    else ew2_vec_kernel<F, LAY_VS, true><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len, ma, mb);
+                }
+            } else if (c1 && c2)
+                ew2_vec_kernel<F, LAY_VV, false><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len, 0u, 0u);
             else if (z1)
-                ew2_vec_kernel<F, LAY_SV><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+                ew2_vec_kernel<F, LAY_SV, false><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len, 0u, 0u);
             else
-                ew2_vec_kernel<F, LAY_VS><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len);
+                ew2_vec_kernel<F, LAY_VS, false><<<grid, EW_BLOCK, 0, st>>>(a, b, o, head, nvec, len, 0u, 0u);
             return after_launch("ew2_vec_kernel");
         }
     }
@@ -494,16 +586,27 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
     if (so == (int64_t)sizeof(Out) && s1 == (int64_t)sizeof(In)) {
         int64_t head = ((OUT_VB - (int64_t)((uintptr_t)out % OUT_VB)) % OUT_VB) / (int64_t)sizeof(Out);
         if (head > len) head = len;
-        if (((uintptr_t)in + head * sizeof(In)) % IN_VB == 0) {
+        const unsigned ma = (unsigned)(((uintptr_t)in + head * sizeof(In)) % IN_VB);
+        if (ma == 0) {
             const int64_t nvec = (len - head) / EPV;
             if constexpr (smem_of<F>::value != 0) {
                 ew1_table_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value * EW_TABLE_TILES), EW_BLOCK, 0, st>>>(
                     (const In*)in, (Out*)out, head, nvec, len);
                 return after_launch("ew1_table_kernel");
             } else {
-                ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
+                ew1_vec_kernel<F, false><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len, 0u);
                 return after_launch("ew1_vec_kernel");
             }
+        }
+        if constexpr (IN_VB % 4 == 0) {
+            // input misaligned relative to the output: realigning vector kernel (see ld_pack_realigned); one more
+            // vector goes to the scalar head / tail so that no lane reads outside the array
+            if ((int64_t)(head * sizeof(In)) < (int64_t)ma) head += EPV;
+            if (head > len) head = len;
+            int64_t nvec = (len - head) / EPV - 1;
+            if (nvec < 0) nvec = 0;
+            ew1_vec_kernel<F, true><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len, ma);
+            return after_launch("ew1_vec_kernel");
         }
     }
     ew1_strided_kernel<F><<<full_grid(len, EW_BLOCK), EW_BLOCK, 0, st>>>((const char*)in, (char*)out, len, s1, so);
