@@ -333,10 +333,24 @@ __device__ __noinline__ void fused_finish(const typename R::Acc* local, int64_t 
     int64_t count = local_count;
     if (fa.n > 1) {
         const bool consumer = fa.all || fa.self == fa.root;
-        for (int d = 0; d < fa.n; ++d) {
-            if (d == fa.self || !(fa.all || d == fa.root)) continue;
-            Acc* dst = reinterpret_cast<Acc*>(fa.slots[d]) + fa.slot_base;
-            for (int64_t i = threadIdx.x; i < local_count; i += RED_THREADS) dst[i] = ld_cg(local + i);
+        // push: PUSH_MLP loads in flight per thread, then the stores to every consumer (posted writes over NVLink)
+        constexpr int PUSH_MLP = 8;
+        for (int64_t i0 = threadIdx.x; i0 < local_count; i0 += (int64_t)RED_THREADS * PUSH_MLP) {
+            Acc x[PUSH_MLP];
+#pragma unroll
+            for (int m = 0; m < PUSH_MLP; ++m) {
+                const int64_t i = i0 + (int64_t)m * RED_THREADS;
+                if (i < local_count) x[m] = ld_cg(local + i);
+            }
+            for (int d = 0; d < fa.n; ++d) {
+                if (d == fa.self || !(fa.all || d == fa.root)) continue;
+                Acc* dst = reinterpret_cast<Acc*>(fa.slots[d]) + fa.slot_base;
+#pragma unroll
+                for (int m = 0; m < PUSH_MLP; ++m) {
+                    const int64_t i = i0 + (int64_t)m * RED_THREADS;
+                    if (i < local_count) dst[i] = x[m];
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {

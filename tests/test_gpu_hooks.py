@@ -745,11 +745,16 @@ def test_small_ops_on_managed_memory_stay_on_the_gpu(pn, rng):
         m = pn.managed_array(h)
         out = pn.managed_empty(1 << 20, np.float32)
         np.add(m, m, out=out)                     # places the pages
+        cnts = (2, 7, 1000, 4097, 65537)
+        pn.disable()                              # expectations from NumPy's own loops, on the host copy
+        want = [(float(np.sum(h[100:100 + cnt], dtype=np.float64)), int(h[:cnt].argmax())) for cnt in cnts]
+        pn.enable()
         pn.cuda_reset_stats()
-        for cnt in (2, 7, 1000, 4097, 65537):
+        pn.ledger_clear()
+        for cnt, (wsum, warg) in zip(cnts, want):
             np.multiply(m[5:5 + cnt], m[9:9 + cnt], out=out[3:3 + cnt])
-            assert float(m[100:100 + cnt].sum()) == pytest.approx(float(np.sum(h[100:100 + cnt], dtype=np.float64)), rel=1e-6)
-            assert int(m[:cnt].argmax()) == int(h[:cnt].argmax())
+            assert float(m[100:100 + cnt].sum()) == pytest.approx(wsum, rel=1e-6)
+            assert int(m[:cnt].argmax()) == warg
         info = pn.cuda_info()
         assert info["calls"] == 15 and info["declined"] == 0 and info["h2d_bytes"] == 0, info
         li = pn.ledger_info()
@@ -757,13 +762,15 @@ def test_small_ops_on_managed_memory_stay_on_the_gpu(pn, rng):
         assert_bits_equal(np.asarray(out[3:3 + 65537]), h[5:5 + 65537] * h[9:9 + 65537], "small slices")
         # strided managed views run on the GPU too (strided kernels), reductions included
         pn.cuda_reset_stats()
-        np.add(m[::3], m[1::3][: m[::3].size], out=out[: m[::3].size])
+        k = h[::3].size
+        np.add(m[::3], m[1::3][:k], out=out[:k])
         r = float(m[::2].max())
         assert pn.cuda_info()["calls"] == 2 and pn.cuda_info()["declined"] == 0
+        pn.disable()
         assert r == float(h[::2].max())
-        k = h[::3].size
         assert_bits_equal(np.asarray(out[:k]), h[::3] + h[1::3][:k], "strided managed views")
     finally:
+        pn.enable()
         pn.ledger_disable()
         pn.cuda_setthreshold(old_thr)
         pn.cuda_setthreshold(0)
