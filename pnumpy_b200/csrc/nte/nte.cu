@@ -105,6 +105,7 @@ enum JobKind { JOB_BINARY, JOB_UNARY, JOB_REDUCE, JOB_ARG, JOB_MULADD, JOB_MULAD
 struct Operand {
     int kind = MK_UNKNOWN;
     int device = -1;
+    const char* base = nullptr;     // start of the registered allocation (managed blocks: its head page is special)
     std::vector<ResidencyNote>* notes = nullptr;
     bool resident() const { return kind == MK_DEVICE || kind == MK_MANAGED; }
     bool host() const { return kind == MK_PAGEABLE || kind == MK_PINNED; }
@@ -164,6 +165,7 @@ bool lookup_registry(const void* p, Operand* o) {
     if (!registry_find(p, &ai)) return false;
     o->kind = ai.kind;
     o->device = ai.device;
+    o->base = ai.base;
     o->notes = ai.notes;
     return true;
 }
@@ -338,14 +340,32 @@ int home_of(const Operand& o, const char* lo, size_t bytes) {
     }
     return 0;
 }
+// The HEAD PAGE of every managed block we hand out stays in host memory and is mapped into every GPU
+// (cudaMemAdviseSetPreferredLocation = CPU + SetAccessedBy each GPU, see nte_alloc_managed): NumPy reads element 0
+// of an array ON THE HOST before every min / max reduction (it seeds the accumulator with a[0] and passes a[1:] to
+// the loop).  If that page lived on the GPU, every a.max() would fault it to the host and the kernel would fault it
+// back (~50 us per call, measured); as it is, the host reads it locally and the kernels read / write its 4 KiB
+// over PCIe.  Prefetches therefore skip it.
+constexpr size_t kHeadBytes = 4096;
+int prefetch_clipped(const Operand& o, const char* lo, size_t bytes, Lane& L) {
+    if (o.base && lo < o.base + kHeadBytes) {
+        const size_t skip = (size_t)(o.base + kHeadBytes - lo);
+        if (skip >= bytes) return 0;
+        lo += skip;
+        bytes -= skip;
+    }
+    PNCU_CUDA(cudaMemPrefetchAsync(lo, bytes, L.device, L.s_k));
+    g_stats.prefetches += 1;
+    return 0;
+}
 // make [lo, lo + bytes) of a managed operand resident on lane L's GPU (no-op for device memory / known placement)
 int place_whole(const Operand& o, const char* lo, size_t bytes, Lane& L) {
     if (o.kind != MK_MANAGED || !bytes) return 0;
     std::lock_guard<std::mutex> lk(g_note_mu);
     if (note_hit(o, lo, bytes, L.device, 0)) return 0;
     PNCU_CUDA(cudaSetDevice(L.device));
-    PNCU_CUDA(cudaMemPrefetchAsync(lo, bytes, L.device, L.s_k));
-    g_stats.prefetches += 1;
+    int rc = prefetch_clipped(o, lo, bytes, L);
+    if (rc) return rc;
     note_set(o, lo, bytes, L.device, 0);
     return 0;
 }
@@ -794,8 +814,8 @@ int place_operands(Job& j) {
             const size_t b = (size_t)(j.shard[l + 1] - j.shard[l]) * A.isz;
             if (!b) continue;
             PNCU_CUDA(cudaSetDevice(L.device));
-            PNCU_CUDA(cudaMemPrefetchAsync(A.p + j.shard[l] * A.isz, b, L.device, L.s_k));
-            g_stats.prefetches += 1;
+            int rc = prefetch_clipped(*A.o, A.p + j.shard[l] * A.isz, b, L);
+            if (rc) return rc;
         }
         note_set(*A.o, lo, bytes, 100 + j.nlanes, piece);
     }
@@ -1148,6 +1168,13 @@ void* nte_alloc_managed(size_t bytes) {
     if (cudaMallocManaged(&p, bytes ? bytes : 1, cudaMemAttachGlobal) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
+    }
+    // head page: host-resident, mapped into every GPU (see kHeadBytes); failures only cost speed
+    if (bytes >= 2 * kHeadBytes) {
+        bool ok = cudaMemAdvise(p, kHeadBytes, cudaMemAdviseSetPreferredLocation, cudaCpuDeviceId) == cudaSuccess;
+        for (int d = 0; ok && d < (g.ndev > 0 ? g.ndev : 1); ++d)
+            ok = cudaMemAdvise(p, kHeadBytes, cudaMemAdviseSetAccessedBy, d) == cudaSuccess;
+        if (!ok) cudaGetLastError();
     }
     registry_add(p, bytes ? bytes : 1, MK_MANAGED, -1);
     return p;

@@ -762,13 +762,13 @@ def test_small_ops_on_managed_memory_stay_on_the_gpu(pn, rng):
         assert_bits_equal(np.asarray(out[3:3 + 65537]), h[5:5 + 65537] * h[9:9 + 65537], "small slices")
         # strided managed views run on the GPU too (strided kernels), reductions included
         pn.cuda_reset_stats()
-        k = h[::3].size
-        np.add(m[::3], m[1::3][:k], out=out[:k])
+        k = h[1::3].size
+        np.add(m[::3][:k], m[1::3], out=out[:k])
         r = float(m[::2].max())
         assert pn.cuda_info()["calls"] == 2 and pn.cuda_info()["declined"] == 0
         pn.disable()
         assert r == float(h[::2].max())
-        assert_bits_equal(np.asarray(out[:k]), h[::3] + h[1::3][:k], "strided managed views")
+        assert_bits_equal(np.asarray(out[:k]), h[::3][:k] + h[1::3], "strided managed views")
     finally:
         pn.enable()
         pn.ledger_disable()
