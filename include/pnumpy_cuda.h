@@ -219,6 +219,12 @@ PNCU_API pncu_any_two_fn pncu_GetIntTrueDivide(int atopInType1);
 /* fused a*b+c and sum(a*b+c) for int32/uint32/int64/uint64/float32/float64; NULL otherwise */
 PNCU_API pncu_any_three_fn pncu_GetMulAddFast(int atopInType1);
 PNCU_API pncu_three_reduce_fn pncu_GetMulAddSumFast(int atopInType1);
+/* dtype conversion (`astype`), the first item of the reference's roadmap (doc_src/source/roadmap.rst:11-15;
+ * SURVEY.md 8f row f-4): out[i] = (OutType)in[i] with NumPy's cast semantics -- int -> int wraps, anything -> bool
+ * is x != 0, int -> float and float64 -> float32 round to nearest even, float -> int truncates toward zero and
+ * returns what x86's cvttss2si / cvttsd2si return when the value does not fit (NumPy does the same and warns).
+ * A pncu_unary_fn over (inType, outType) for bool, the eight integer types, float32 and float64; NULL otherwise. */
+PNCU_API pncu_unary_fn pncu_GetConvertFast(int atopInType, int atopOutType);
 /* itemsize of an atop type, 0 if unsupported (src/pnumpy/_pnumpy.cpp:43-54) */
 PNCU_API int pncu_itemsize(int atype);
 

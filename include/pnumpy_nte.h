@@ -157,6 +157,12 @@ typedef struct nte_stats {
     int64_t prefetches;     /* cudaMemPrefetchAsync calls issued for managed operands */
 } nte_stats;
 PNCU_API void nte_get_stats(nte_stats* out);
+/* per-call trace for latency work: when on, the dispatcher records CLOCK_MONOTONIC ns at eight stations of every
+ * RESIDENT dispatch -- enter, lock taken, shards planned, operands placed, workers posted, own launch done (or own
+ * shard finished, element-wise), workers joined, result in place -- and nte_get_trace copies the last call's eight
+ * values (tools/resident_probe.py --trace prints the differences). */
+PNCU_API void nte_set_trace(int on);
+PNCU_API void nte_get_trace(int64_t* out8);
 PNCU_API void nte_reset_stats(void);
 
 #ifdef __cplusplus

@@ -621,3 +621,54 @@ int oracle_argminmax(int kind, int t, const void* in, int64_t n, int64_t* idx) {
     }
     return -1;
 }
+
+/* ---- dtype conversion (`astype`) ------------------------------------------------------------------
+ * Not in the reference yet (first item of its roadmap, doc_src/source/roadmap.rst:11-15); the
+ * semantics to match are NumPy's cast loops, which are plain C casts.  This function IS those casts,
+ * compiled by the same family of compiler for the same ISA, so values a C cast leaves undefined
+ * (float -> int out of range / NaN) come out as x86's cvttss2si / cvttsd2si produce them -- as they do
+ * in NumPy.  `volatile` keeps gcc from folding an out-of-range conversion at compile time or
+ * vectorising it into an instruction with different saturation.  tests/test_oracle.py pins this
+ * against NumPy's astype on random bit patterns for all 121 type pairs. */
+/* float -> uint32 as NumPy's (SSE-vectorised) loop does it, observed on NumPy 2.3.5 / x86-64: values below 2^31
+ * (and NaN) go through the 32-bit conversion, larger ones through (int32)(x - 2^31) ^ 2^31; what does not fit
+ * comes out as 0x80000000 resp. 0.  Integers take the plain cast. */
+static inline uint32_t f_to_u32(double x) {
+    volatile double v = x;
+    if (v >= 2147483648.0) { volatile double w = v - 2147483648.0; return (uint32_t)(int32_t)w ^ 0x80000000u; }
+    return (uint32_t)(int32_t)v;
+}
+#define TO_U32(v) _Generic((v), float: f_to_u32((double)(v)), double: f_to_u32((double)(v)), default: (uint32_t)(v))
+#define CONV_ROW(TI, in_is_bool)                                                          \
+    switch (to) {                                                                         \
+        case T_BOOL: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((uint8_t*)out)[i] = (uint8_t)(v != 0); } return 0; \
+        case T_I8:  for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((int8_t*)out)[i] = in_is_bool ? (int8_t)(v != 0) : (int8_t)v; } return 0; \
+        case T_U8:  for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((uint8_t*)out)[i] = in_is_bool ? (uint8_t)(v != 0) : (uint8_t)v; } return 0; \
+        case T_I16: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((int16_t*)out)[i] = in_is_bool ? (int16_t)(v != 0) : (int16_t)v; } return 0; \
+        case T_U16: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((uint16_t*)out)[i] = in_is_bool ? (uint16_t)(v != 0) : (uint16_t)v; } return 0; \
+        case T_I32: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((int32_t*)out)[i] = in_is_bool ? (int32_t)(v != 0) : (int32_t)v; } return 0; \
+        case T_U32: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((uint32_t*)out)[i] = in_is_bool ? (uint32_t)(v != 0) : TO_U32(v); } return 0; \
+        case T_I64: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((int64_t*)out)[i] = in_is_bool ? (int64_t)(v != 0) : (int64_t)v; } return 0; \
+        case T_U64: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((uint64_t*)out)[i] = in_is_bool ? (uint64_t)(v != 0) : (uint64_t)v; } return 0; \
+        case T_F32: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((float*)out)[i] = in_is_bool ? (float)(v != 0) : (float)v; } return 0; \
+        case T_F64: for (i = 0; i < n; ++i) { volatile TI v = ((const TI*)in)[i]; ((double*)out)[i] = in_is_bool ? (double)(v != 0) : (double)v; } return 0; \
+    }                                                                                     \
+    return -1;
+
+int oracle_convert(int from, int to, const void* in, void* out, int64_t n) {
+    int64_t i;
+    switch (from) {
+        case T_BOOL: CONV_ROW(uint8_t, 1)
+        case T_I8: CONV_ROW(int8_t, 0)
+        case T_U8: CONV_ROW(uint8_t, 0)
+        case T_I16: CONV_ROW(int16_t, 0)
+        case T_U16: CONV_ROW(uint16_t, 0)
+        case T_I32: CONV_ROW(int32_t, 0)
+        case T_U32: CONV_ROW(uint32_t, 0)
+        case T_I64: CONV_ROW(int64_t, 0)
+        case T_U64: CONV_ROW(uint64_t, 0)
+        case T_F32: CONV_ROW(float, 0)
+        case T_F64: CONV_ROW(double, 0)
+    }
+    return -1;
+}

@@ -55,6 +55,7 @@ def lib():
         L.oracle_trig.argtypes = L.oracle_unary.argtypes
         L.oracle_reduce.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _i64, _i64]
         L.oracle_argminmax.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _i64, ctypes.POINTER(_i64)]
+        L.oracle_convert.argtypes = [ctypes.c_int, ctypes.c_int, _vp, _vp, _i64]
         _olib = L
     return _olib
 
@@ -123,6 +124,16 @@ def unary(op, a):
                                 a.strides[0], out.strides[0])
     if rc:
         raise NotImplementedError(f"oracle: {op} {a.dtype}")
+    return out
+
+
+def astype(a, dtype):
+    """a.astype(dtype) as plain C casts (oracle_convert)"""
+    a = np.ascontiguousarray(a).reshape(-1)
+    out = np.empty(a.size, dtype=np.dtype(dtype))
+    rc = lib().oracle_convert(atop_of(a.dtype), atop_of(out.dtype), a.ctypes.data, out.ctypes.data, a.size)
+    if rc:
+        raise NotImplementedError(f"oracle: convert {a.dtype} -> {out.dtype}")
     return out
 
 

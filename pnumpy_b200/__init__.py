@@ -47,7 +47,7 @@ __all__ = [
     'argmin', 'argmax',
     # additions of this build (nothing above changes meaning)
     'cuda_info', 'cuda_reset_stats', 'cuda_setthreshold', 'cuda_getthreshold', 'cuda_setslab', 'cuda_inject_fault',
-    'pinned_empty', 'pinned_array', 'managed_empty', 'managed_array', 'muladd', 'muladd_sum',
+    'pinned_empty', 'pinned_array', 'managed_empty', 'managed_array', 'muladd', 'muladd_sum', 'astype',
 ]
 
 import numpy as np  # noqa: E402
@@ -106,6 +106,33 @@ def muladd(a, b, c, out=None):
     if isinstance(res, np.ndarray) and _pnumpy.fused_muladd(a, b, c, res):
         return res
     return np.add(np.multiply(a, b), c, out=out)
+
+
+def astype(a, dtype, out=None):
+    """``a.astype(dtype)`` on the GPU -- dtype conversion is the first item of pnumpy's roadmap
+    (``doc_src/source/roadmap.rst:11-15``); NumPy has no public hook for its cast loops, hence a function.
+
+    Same values as NumPy's cast for bool, the integer types, float32 and float64: integers wrap, float -> int
+    truncates toward zero (and yields what x86's conversion instructions yield when the value does not fit,
+    which is what NumPy returns, with a warning), int -> float and float64 -> float32 round to nearest even.
+    The result lives in the same kind of memory as ``a`` (managed stays managed, pinned stays pinned);
+    anything the GPU path does not take (other dtypes, non-contiguous arrays, small host arrays) is NumPy's
+    own ``astype``."""
+    a = np.asanyarray(a)
+    dtype = np.dtype(dtype)
+    if out is None:
+        k = _pnumpy.pointer_kind(a.ctypes.data) if a.size else 0
+        res = managed_empty(a.shape, dtype) if k >= 2 else (pinned_empty(a.shape, dtype) if k == 1 else np.empty(a.shape, dtype))
+    else:
+        res = out
+        if res.dtype != dtype or res.shape != a.shape:
+            raise ValueError("out must have the requested dtype and the shape of a")
+    if _pnumpy.convert(a, res):
+        return res
+    if out is None:
+        return a.astype(dtype)
+    np.copyto(out, a, casting="unsafe")
+    return out
 
 
 def muladd_sum(a, b, c):

@@ -80,6 +80,7 @@ SIGNATURES = {
     "pncu_GetIntTrueDivide": (_vp, [ctypes.c_int]),
     "pncu_GetMulAddFast": (_vp, [ctypes.c_int]),
     "pncu_GetMulAddSumFast": (_vp, [ctypes.c_int]),
+    "pncu_GetConvertFast": (_vp, [ctypes.c_int, ctypes.c_int]),
     "pncu_muladd_sum_partials": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _c_i64, _vp, _vp]),
     "pncu_itemsize": (ctypes.c_int, [ctypes.c_int]),
     "pncu_reduce_block_elems": (_c_i64, []),
@@ -221,6 +222,10 @@ def get_int_true_divide(atype):
 
 def get_muladd(atype):
     return _getter("pncu_GetMulAddFast", ANY_THREE_FN, atype, with_out=False)
+
+
+def get_convert(in_atype, out_atype):
+    return _getter("pncu_GetConvertFast", UNARY_FN, in_atype, out_atype, with_out=False)
 
 
 def get_muladd_sum(atype):

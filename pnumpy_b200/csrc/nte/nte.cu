@@ -41,6 +41,12 @@ constexpr int kRing = 3;          // staging slots per lane
 constexpr int kMaxLanes = 16;     // the reference's hard maximum: 15 workers + caller (threads.h:56-66)
 constexpr int64_t kAlign = 65536; // == pncu_reduce_block_elems()
 
+// optional per-call trace (nte_set_trace): monotonic ns at the stations of the last dispatch
+enum { TR_ENTER, TR_LOCKED, TR_PLANNED, TR_PLACED, TR_POSTED, TR_LAUNCHED, TR_JOINED, TR_DONE, TR_N };
+int64_t g_trace[TR_N];
+bool g_trace_on = false;
+#define TRACE(i) do { if (g_trace_on) g_trace[i] = (int64_t)nte::now_ns(); } while (0)
+
 struct Stats {
     std::atomic<int64_t> calls{0}, declined{0}, launches{0}, h2d{0}, d2h{0}, staged{0}, lanes_last{0}, gpus_last{0},
         prefetches{0};
@@ -749,8 +755,11 @@ void run_lanes(Job& j, LaneFn fn) {
         g_post[p].job = &j; g_post[p].fn = fn; g_post[p].logical = l;
         w->post(worker_thunk, &g_post[p]);
     }
+    TRACE(TR_POSTED);
     fn(g.lanes[j.lane_id[0]], j, 0);  // the caller is lane 0
+    TRACE(TR_LAUNCHED);
     for (int l = 1; l < j.nlanes; ++l) g.pool[j.lane_id[l]]->wait();
+    TRACE(TR_JOINED);
 }
 
 // ---- RESIDENT element-wise work: one launch per GPU, in place -------------------------------------------------
@@ -911,7 +920,9 @@ int run_reduce_resident(Job& j, bool sharded) {
         extent_of(j.in1, j.len, j.s1, j.isz_in, &lo, &bytes);
         if ((rc = plan_on_device(j, home_of(j.k1, lo, (size_t)bytes), false))) return rc;
     }
+    TRACE(TR_PLANNED);
     if ((rc = place_operands(j))) return rc;
+    TRACE(TR_PLACED);
     Lane& L0 = g.lanes[j.lane_id[0]];
     PNCU_CUDA(cudaSetDevice(L0.device));
     const void* start = nullptr;
@@ -962,14 +973,18 @@ int run_reduce_resident(Job& j, bool sharded) {
             g_post[p].job = &j; g_post[p].fn = lane_reduce_shard; g_post[p].logical = l;
             w->post(worker_thunk, &g_post[p]);
         }
+        TRACE(TR_POSTED);
         rc = launch_fused_shard(L0, j, 0, &g_x[0], L0.h_small + kOffResult, start);
         if (rc) fail(j, 0, rc);
+        TRACE(TR_LAUNCHED);
         for (int l = 1; l < j.nlanes; ++l) g.pool[j.lane_id[l]]->wait();
+        TRACE(TR_JOINED);
         if ((rc = first_error(j))) { reset_exchange(j); return rc; }   // a shard was never launched: do not wait for it
         if ((rc = wait_flag(L0, want))) { reset_exchange(j); return rc; }
     }
     memcpy(j.host_out, L0.h_small + kOffResult, j.out_bytes);
     g_stats.d2h += j.out_bytes;
+    TRACE(TR_DONE);
     return 0;
 }
 
@@ -1138,6 +1153,11 @@ int64_t nte_set_slab_bytes(int64_t bytes) {
     g.slab_bytes = (size_t)((bytes / unit) * unit);
     return p;
 }
+void nte_set_trace(int on) { g_trace_on = on != 0; }
+void nte_get_trace(int64_t* out8) {
+    if (!out8) return;
+    for (int i = 0; i < TR_N; ++i) out8[i] = g_trace[i];
+}
 int64_t nte_inject_fault(int64_t nth) {
     std::lock_guard<std::mutex> lk(g.api_mu);
     int64_t p = g.fault_countdown;
@@ -1253,6 +1273,7 @@ static int dispatch_elementwise(Job& j, int max_workers) {
         return PNCU_ERR_NO_DEVICE;
     }
     if (j.len <= 0) return decline();
+    TRACE(TR_ENTER);
     const bool binary = j.kind == JOB_BINARY;
     // 1. memory kinds from the registry (no driver call); small calls on memory we did not hand out are declined
     //    right here -- that is every small NumPy call on ordinary arrays, and it costs three map lookups
@@ -1263,6 +1284,7 @@ static int dispatch_elementwise(Job& j, int max_workers) {
     if (!known_resident && j.len < lowest_threshold()) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();  // re-entrant / concurrent caller: run the old loop
+    TRACE(TR_LOCKED);
     if (!r1) classify_driver(j.in1, &j.k1);
     if (binary && !r2) classify_driver(j.in2, &j.k2);
     if (!ro) classify_driver(j.out, &j.ko);
@@ -1295,10 +1317,13 @@ static int dispatch_elementwise(Job& j, int max_workers) {
             if (j.ko.kind == MK_DEVICE) dev = home_of(j.ko, j.out, 1);
             if ((rc = plan_on_device(j, dev, false))) return rc;
         }
+        TRACE(TR_PLANNED);
         if ((rc = place_operands(j))) return rc;
+        TRACE(TR_PLACED);
         run_lanes(j, lane_resident);
         rc = first_error(j);
         if (!rc) g_stats.calls += 1;
+        TRACE(TR_DONE);
         return rc;
     }
     if (nres == 0) {
@@ -1356,10 +1381,12 @@ static int dispatch_reduce(Job& j, int max_workers) {
         return PNCU_ERR_NO_DEVICE;
     }
     if (j.len <= 0) return decline();
+    TRACE(TR_ENTER);
     const bool r1 = lookup_registry(j.in1, &j.k1);
     if (!j.k1.resident() && j.len < lowest_threshold()) return decline();
     std::unique_lock<std::mutex> lk(g.api_mu, std::try_to_lock);
     if (!lk.owns_lock()) return decline();
+    TRACE(TR_LOCKED);
     if (!r1) classify_driver(j.in1, &j.k1);
     DeviceGuard guard;
     int rc;

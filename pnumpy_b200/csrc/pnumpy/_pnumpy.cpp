@@ -867,6 +867,16 @@ static PyObject* cuda_info(PyObject*, PyObject*) {
                          "workers", nte_get_workers(), "threading", nte_get_threading(), "extra_loops", g_ExtraLoops,
                          "prefetches", (long long)s.prefetches, "forked_child", nte_is_forked_child());
 }
+// cuda_trace(on=None): switch the dispatcher's per-call trace on / off; returns the last call's eight stations (ns)
+static PyObject* cuda_trace(PyObject*, PyObject* args) {
+    PyObject* on = Py_None;
+    if (!PyArg_ParseTuple(args, "|O:cuda_trace", &on)) return NULL;
+    if (on != Py_None) nte_set_trace(PyObject_IsTrue(on));
+    int64_t t[8];
+    nte_get_trace(t);
+    return Py_BuildValue("(LLLLLLLL)", (long long)t[0], (long long)t[1], (long long)t[2], (long long)t[3], (long long)t[4],
+                         (long long)t[5], (long long)t[6], (long long)t[7]);
+}
 // cuda_inject_fault(n): the n-th GPU dispatch from now fails like a bad launch (error-path tests); 0 disarms
 static PyObject* cuda_inject_fault(PyObject*, PyObject* args) {
     long long n = 0;
@@ -975,6 +985,39 @@ static PyObject* fused_muladd_sum(PyObject*, PyObject* args) {
     return PyArray_Scalar(result, descr, NULL);
 }
 
+// =======================================================================================================
+// dtype conversion (the first item of the reference's roadmap,
+// doc_src/source/roadmap.rst:11-15; an ADDITION: NumPy offers no public hook for its cast loops).
+// convert(src, dst) -> True when dst[...] = src.astype(dst.dtype) ran on the GPU; False when the caller must use
+// NumPy's astype (dtype without a kernel, non-contiguous or mismatched operands, below the dispatch threshold).
+static PyObject* convert(PyObject*, PyObject* args) {
+    PyObject *so = NULL, *dobj = NULL;
+    if (!PyArg_ParseTuple(args, "OO:convert", &so, &dobj)) return NULL;
+    if (!g_Settings.AtopEnabled || !PyArray_Check(so) || !PyArray_Check(dobj)) Py_RETURN_FALSE;
+    PyArrayObject* src = (PyArrayObject*)so;
+    PyArrayObject* dst = (PyArrayObject*)dobj;
+    const int need = NPY_ARRAY_C_CONTIGUOUS | NPY_ARRAY_ALIGNED;
+    if ((PyArray_FLAGS(src) & need) != need || (PyArray_FLAGS(dst) & (need | NPY_ARRAY_WRITEABLE)) != (need | NPY_ARRAY_WRITEABLE)) Py_RETURN_FALSE;
+    if (!PyArray_ISNOTSWAPPED(src) || !PyArray_ISNOTSWAPPED(dst) || PyArray_SIZE(src) != PyArray_SIZE(dst)) Py_RETURN_FALSE;
+    const int st = PyArray_TYPE(src), dt = PyArray_TYPE(dst);
+    if (st < 0 || st >= COUNT_OF(convert_dtype_to_atop) || dt < 0 || dt >= COUNT_OF(convert_dtype_to_atop)) Py_RETURN_FALSE;
+    const int sa = convert_dtype_to_atop[st], da = convert_dtype_to_atop[dt];
+    if (sa < 0 || da < 0) Py_RETURN_FALSE;
+    pncu_unary_fn fn = pncu_GetConvertFast(sa, da);
+    if (!fn) Py_RETURN_FALSE;
+    const npy_intp n = PyArray_SIZE(src);
+    const uint64_t t0 = ledger_t0();
+    int rc;
+    Py_BEGIN_ALLOW_THREADS
+    rc = nte_unary_class(fn, pncu_itemsize(sa), pncu_itemsize(da), PyArray_DATA(src), PyArray_DATA(dst), (int64_t)n,
+                         pncu_itemsize(sa), pncu_itemsize(da), 3, NTE_CLASS_STREAM);
+    Py_END_ALLOW_THREADS
+    if (rc == NTE_DECLINED) Py_RETURN_FALSE;
+    if (rc) return PyErr_Format(PyExc_RuntimeError, "pnumpy_b200: dtype conversion failed on the GPU (status %d): %s", rc, pncu_last_error());
+    ledger(CAT_UNARY, true, n, t0, 0, sa, (int64_t)n * (pncu_itemsize(sa) + pncu_itemsize(da)));
+    Py_RETURN_TRUE;
+}
+
 // pointer_kind(address) -> 0 pageable host, 1 pinned host, 2 device, 3 managed
 static PyObject* pointer_kind(PyObject*, PyObject* args) {
     unsigned long long addr = 0;
@@ -985,6 +1028,7 @@ static PyObject* pointer_kind(PyObject*, PyObject* args) {
 
 static PyMethodDef module_functions[] = {
     {"pointer_kind", pointer_kind, METH_VARARGS, "0 pageable host, 1 pinned host, 2 device, 3 managed"},
+    {"convert", convert, METH_VARARGS, "dst[...] = src.astype(dst.dtype) on the GPU; False when the caller must use NumPy's astype"},
     {"fused_muladd", fused_muladd, METH_VARARGS, "a*b+c into out in one GPU pass; False when the caller must run the ufunc chain"},
     {"fused_muladd_sum", fused_muladd_sum, METH_VARARGS, "sum(a*b+c) in one GPU pass; None when the caller must run the ufunc chain"},
     {"managed_alloc", managed_alloc, METH_VARARGS, "(capsule, address) of a CUDA managed block"},
@@ -1013,6 +1057,7 @@ static PyMethodDef module_functions[] = {
     {"recycler_enable", (PyCFunction)(void (*)(void))recycler_enable, METH_VARARGS | METH_KEYWORDS,
      "recycler_enable(kind='pinned'|'managed', threshold=None): large ndarrays are born in recycled pinned host / CUDA managed memory"},
     {"recycler_trim", recycler_trim, METH_VARARGS, "free the pooled (unused) blocks; returns how many"},
+    {"cuda_trace", cuda_trace, METH_VARARGS, "cuda_trace(on=None): toggle the per-call trace; returns the last resident call's eight stations in ns"},
     {"cuda_inject_fault", cuda_inject_fault, METH_VARARGS, "fail the n-th GPU dispatch from now (tests); returns the previous countdown"},
     {"recycler_disable", recycler_disable, METH_VARARGS, "restore NumPy's default data allocator"},
     {"recycler_isenabled", recycler_isenabled, METH_VARARGS, "returns True if the recycler is enabled"},

@@ -169,6 +169,18 @@ def unary(op, a, out=None, stream=None):
     return out
 
 
+def astype(a, dtype, out=None, stream=None):
+    """out = a converted to `dtype` with NumPy's cast semantics (pncu_GetConvertFast)."""
+    dtype = np.dtype(dtype)
+    fn = cabi.get_convert(a.atype, cabi.atop_of(dtype))
+    if fn is None:
+        raise cabi.PnumpyCudaError(f"no conversion kernel {a.dtype} -> {dtype}")
+    if out is None:
+        out = DeviceArray(a.size, dtype, a.device)
+    cabi.check(fn(a.ptr, out.ptr, a.size, a.dtype.itemsize, out.dtype.itemsize, stream), "astype")
+    return out
+
+
 def reduce(op, a, out=None, start=None, stream=None):
     """*out = fold(op, a) [op *start]; returns the 1-element DeviceArray `out`."""
     fn = cabi.get_reduce(cabi.BINARY_OPS[op], a.atype)

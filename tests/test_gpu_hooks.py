@@ -947,3 +947,33 @@ def test_calling_threads_device_is_left_alone(pn, rng):
         assert d.value == 1
     finally:
         cabi.check(lib.pncu_set_device(0), "set_device")
+
+
+def test_astype_through_the_dispatcher(pn, rng):
+    """pn.astype: dtype conversion (the reference's roadmap item) through nte -- host arrays staged, managed arrays in
+    place -- equal to NumPy's astype; what the GPU path does not take falls back to NumPy's own cast."""
+    n = (1 << 20) + 5
+    h = rng.normal(0, 1000, n)
+    for src_dt, dst_dt in (("float64", "float32"), ("float64", "int32"), ("int64", "float64"), ("float32", "int8"), ("int16", "bool"),
+                           ("uint8", "float32"), ("bool", "int64")):
+        a = h.astype(src_dt)
+        pn.cuda_reset_stats()
+        got = pn.astype(a, dst_dt)
+        assert pn.cuda_info()["calls"] == 1, (src_dt, dst_dt)
+        with np.errstate(all="ignore"):
+            assert_bits_equal(got, a.astype(dst_dt), f"{src_dt} -> {dst_dt}")
+    m = pn.managed_array(h.astype(np.float32))
+    pn.cuda_reset_stats()
+    r = pn.astype(m, np.float64)
+    info = pn.cuda_info()
+    from pnumpy_b200 import _pnumpy
+    assert info["calls"] == 1 and info["h2d_bytes"] == 0 and info["d2h_bytes"] == 0 and _pnumpy.pointer_kind(r.ctypes.data) == 3
+    assert_bits_equal(np.asarray(r), h.astype(np.float32).astype(np.float64), "managed float32 -> float64")
+    out = np.empty(n, np.int16)
+    assert pn.astype(h, np.int16, out=out) is out
+    with np.errstate(all="ignore"):
+        assert_bits_equal(out, h.astype(np.int16), "out=")
+    c = np.arange(12.0).reshape(3, 4)[:, ::2]           # non-contiguous: NumPy's cast
+    assert np.array_equal(pn.astype(c, np.int32), c.astype(np.int32))
+    z = np.arange(5.0).astype(np.complex128)             # no kernel: NumPy's cast
+    assert np.array_equal(pn.astype(z, np.complex64), z.astype(np.complex64))

@@ -1048,3 +1048,30 @@ def test_every_op_on_misaligned_views(dev, rng, dt):
                 assert_bits_equal(dev.compare(name, va, vb).to_host(), f(a, b), f"{name} {dt} off={off} n={n}")
                 tested += 1
     assert tested >= 4 * 8
+
+
+# ---- dtype conversion --------------------------------------------------------------
+@pytest.mark.parametrize("di", DTYPES)
+def test_convert_vs_oracle_and_numpy(dev, O, rng, di):
+    """pncu_GetConvertFast: every (from, to) pair on random bit patterns plus edge values, at a length that is not
+    a multiple of any vector width and from a misaligned start: bit-exact against the oracle (= NumPy's astype,
+    tests/test_oracle.py::test_oracle_convert_is_numpy_astype)."""
+    import warnings
+    n = N_SMALL
+    a = fill_random(n + 3, di, rng)
+    if np.dtype(di).kind == "f":
+        a[::3] = rng.normal(0, 1e5, a[::3].size).astype(di)
+        edge = np.array([2**31, -2**31, 2**31 - 1, 2**63, -2**63, 2**64, 255.9, -0.9, 65536.5, -32769.0, 3e9, 4294967295.0,
+                         4294967296.0, -1.0, 0.0, -0.0, np.inf, -np.inf, np.nan, -2147483649.0, 2147483647.5], dtype=di)
+        a[1::7] = edge[np.arange(a[1::7].size) % edge.size]
+    da = dev.to_device(a)
+    for do in DTYPES:
+        for off in (0, 3):
+            src = a[off: off + n]
+            got = dev.astype(da.view(off, n), do).to_host()
+            want = O.astype(src, do)
+            assert_bits_equal(got, want, f"{di} -> {do} (offset {off})")
+            if not (np.dtype(di).kind == "f" and do == "uint32"):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    assert_bits_equal(got, src.astype(do), f"{di} -> {do} vs NumPy (offset {off})")

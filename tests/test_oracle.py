@@ -153,3 +153,28 @@ def test_oracle_trig_vs_live_reference(rng, op, lo, hi):
 
 def test_reduction_input_size():
     assert RED_N > 3 * 65536
+
+
+def test_oracle_convert_is_numpy_astype(rng):
+    """dtype conversion: the oracle's casts against NumPy's `astype` on random BIT PATTERNS
+    (NaN, inf, denormals, values far outside every integer range) for all 121 (from, to) pairs -- bit-exact, NaN to
+    NaN.  One documented exception: float -> uint32 of values outside (-2^31, 2^32) (and NaN), where NumPy's own
+    answer depends on whether the element falls in the vectorised body or the scalar tail of its loop (both are
+    undefined behaviour in C); there the test keeps to the representable range."""
+    import warnings
+    from oracle import oracle as O
+    for di in DTYPES:
+        a = fill_random(50021, di, rng)
+        if np.dtype(di).kind == "f":
+            a[::3] = rng.normal(0, 1e5, a[::3].size).astype(di)
+            edge = np.array([2**31, -2**31, 2**31 - 1, 2**63, -2**63, 2**64, 255.9, -0.9, 65536.5, -32769.0, 3e9,
+                             4294967295.0, 4294967296.0, -1.0, 0.0, -0.0, np.inf, -np.inf, np.nan], dtype=di)
+            a[1::7] = edge[np.arange(a[1::7].size) % edge.size]
+        for do in DTYPES:
+            x = a
+            if np.dtype(di).kind == "f" and do == "uint32":
+                x = a[(a > -2147483648.0) & (a < 4294967296.0)]
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = x.astype(do)
+            assert_bits_equal(O.astype(x, do), want, f"{di} -> {do}")

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("PNUMPY_B200_AUTOINIT", "0")
 import pnumpy_b200 as pn  # noqa: E402
 
-lgs = [int(x) for x in sys.argv[1:]] or [28, 30]
+lgs = [int(x) for x in sys.argv[1:] if not x.startswith('-')] or [28, 30]
 pn.init()
 pn.enable()
 ndev = pn.cuda_info()["devices"]
@@ -54,6 +54,23 @@ for lg in lgs:
         print(f"  {name:12s} {s * 1e3:8.4f} ms (best {best * 1e3:8.4f})  {bpe * m / s / 1e9:9.1f} GB/s  gpus={res[name]['gpus']}  {bits or ''}", flush=True)
     # element-wise results: a 64-bit digest computed on the GPU side of things would be self-referential; use the host
     np.add(ma, mb, out=mo)
+    if "--trace" in sys.argv or os.environ.get("PROBE_TRACE"):
+        from pnumpy_b200 import _pnumpy
+        _pnumpy.cuda_trace(True)
+        names = ("lock", "plan", "place", "post", "own launch/shard", "join", "result")
+        for name, fn in (("add", lambda: np.add(ma, mb, out=mo)), ("sum", lambda: ma.sum()), ("argmax", lambda: ma.argmax())):
+            acc, wall = np.zeros(7), []
+            for _ in range(20):
+                t0 = time.perf_counter_ns()
+                fn()
+                t1 = time.perf_counter_ns()
+                tr = np.array(_pnumpy.cuda_trace(), dtype=np.int64)
+                acc += np.diff(tr)[:7]
+                wall.append((t1 - t0, tr[0] - t0, t1 - tr[7]))
+            w = np.median(np.array(wall), axis=0)
+            print(f"  trace {name:7s} wall {w[0] / 1e3:7.1f} us = numpy-in {w[1] / 1e3:5.1f} + " +
+                  " + ".join(f"{n_} {v / 20 / 1e3:5.1f}" for n_, v in zip(names, acc)) + f" + numpy-out {w[2] / 1e3:5.1f}", flush=True)
+        _pnumpy.cuda_trace(False)
     res["add_crc"] = int(np.bitwise_xor.reduce(np.asarray(mo[: 1 << 24]).view(np.uint32).astype(np.uint64) * np.arange(1, (1 << 24) + 1, dtype=np.uint64)))
     out["sizes"][str(lg)] = res
     del ma, mb, mo
