@@ -333,8 +333,14 @@ def run_cuda(args):
             ch = e2e.get("chain") or {}
             if isinstance(ch.get("fused"), dict):
                 parity["e2e.chain.fused_bit_identical_to_unfused"] = bool(ch["fused"].get("bit_identical_to_unfused"))
+            for k_, v_ in ch.items():
+                if k_.startswith("managed_recycler_2p") and isinstance(v_, dict):
+                    parity["e2e.chain." + k_ + ".bit_identical_to_fused"] = bool(v_.get("bit_identical_to_fused"))
+                    parity["e2e.chain." + k_ + ".no_pcie"] = v_.get("h2d_bytes") == 0
             if isinstance(e2e.get("config0"), dict) and "result_equal" in e2e["config0"]:
                 parity["e2e.config0.result_equal"] = bool(e2e["config0"]["result_equal"])
+                if "managed_recycler_result_equal" in e2e["config0"]:
+                    parity["e2e.config0.managed_recycler_result_equal"] = bool(e2e["config0"]["managed_recycler_result_equal"])
         if red is not None:
             line["reductions_2p30"] = red
         if cpu is not None:
@@ -779,8 +785,40 @@ def run_e2e(args):
             del big, a, b, c, t, o
         except Exception as e:  # pragma: no cover
             chain["at_2p%d" % args.chain_lg] = {"error": str(e)}
-    # the same hooks on DEVICE-RESIDENT ndarrays (CUDA managed memory), spread over all N GPUs by the dispatcher
+    # configs[4] once more, through the UNMODIFIED NumPy API with the managed recycler on: the operands and the
+    # temporaries of `a*b + c` are born in CUDA managed memory (NEP-49 allocator), so after the first touch nothing
+    # crosses PCIe -- what the reference's recycler roadmap asks for (src/pnumpy/__init__.py:18-21)
     arrs.clear()
+    if isinstance(chain, dict) and "error" not in chain:
+        try:
+            pn.recycler_enable(kind="managed")
+            for lg in sorted({args.e2e_lg, args.chain_lg}):
+                m = 1 << lg
+                piece = np.random.default_rng(99).random(1 << 22, dtype=np.float32) * 253 + 1
+                a, b, c = np.empty(m, np.float32), np.empty(m, np.float32), np.empty(m, np.float32)
+                for x in (a, b, c):
+                    x.reshape(-1, piece.size)[:] = piece
+                h0 = pn.cuda_info()["h2d_bytes"]
+                r = (a * b + c).sum()          # first call: pages move to the GPU(s)
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    r = (a * b + c).sum()
+                    ts.append(time.perf_counter() - t0)
+                s_ = float(np.median(ts))
+                rf = pn.muladd_sum(a, b, c)
+                chain["managed_recycler_2p%d" % lg] = {
+                    "expr": "(a*b + c).sum() in plain NumPy, arrays and temporaries born managed (recycler_enable(kind='managed'))",
+                    "elements": m, "ms": round(s_ * 1e3, 3), "equivalent_gbs_at_28B_per_elem": round(28.0 * m / s_ / 1e9, 1),
+                    "h2d_bytes": int(pn.cuda_info()["h2d_bytes"] - h0), "gpus_used": int(pn.cuda_info()["gpus_last"]),
+                    "bit_identical_to_fused": bool(np.asarray(rf).tobytes() == np.asarray(r).tobytes()), "result": float(r)}
+                del a, b, c
+        except Exception as e:  # pragma: no cover
+            chain["managed_recycler_error"] = str(e)
+        finally:
+            pn.recycler_disable()
+            pn.recycler_trim()
+    # the same hooks on DEVICE-RESIDENT ndarrays (CUDA managed memory), spread over all N GPUs by the dispatcher
     resident = run_resident(pn, args)
     # configs[0]: np.add float32 on 1 000 000 contiguous elements (pn.benchmark's size), hooks off vs on.
     # 12 MB of PCIe traffic per call: latency-bound, the GPU path has to beat ~0.5 ms of NumPy loop.
@@ -810,6 +848,20 @@ def run_e2e(args):
                    "gpu_pageable_operands_us": t_pageable, "gpu_pinned_operands_us": t_pinned,
                    "speedup_pinned_vs_numpy": round(t_numpy / t_pinned, 2), "result_equal": same}
         del qa, qb, qo
+        # the same call on arrays NumPy itself allocated while the managed recycler was on (default thresholds)
+        pn.recycler_enable(kind="managed")
+        try:
+            ra = (np.arange(m, dtype=np.float32) % 253) + 1
+            rb, ro = ra.copy(), np.empty(m, np.float32)
+            np.add(ra, rb, out=ro)
+            config0["managed_recycler_us"] = med_us(lambda: np.add(ra, rb, out=ro))
+            config0["managed_recycler_temporaries_us"] = med_us(lambda: ra + rb)
+            config0["managed_recycler_result_equal"] = bool(np.array_equal(ro, pa + pb))
+            config0["speedup_managed_vs_numpy"] = round(t_numpy / config0["managed_recycler_us"], 2)
+            del ra, rb, ro
+        finally:
+            pn.recycler_disable()
+            pn.recycler_trim()
     except Exception as e:  # pragma: no cover
         config0 = {"error": str(e)}
     pn.disable()

@@ -3,16 +3,19 @@
 // (GetTrigOpFast returns NULL for them, src/atop/ops_trig.cpp:599-777, and the dispatcher threads
 // NumPy's own loop over 16K chunks, src/pnumpy/_pnumpy.cpp:973-993).  SURVEY.md 8(f) row f-4.
 //
-// Here they get a GPU body.  This file holds the ones that are CUDA's math library inside the same
-// streaming kernel as sin/log/exp (ew1_vec_kernel, several 256-bit loads in flight per thread): all
-// float32 ones and float64 exp2, cosh, cbrt.  The other thirteen float64 ones have lean bodies in
-// f64_math.cuh and are picked in ops_trig.cu before this getter is asked.  There is no reference arithmetic
+// Here they get a GPU body.  This file holds the float32 ones and float64 exp2, cosh, cbrt, inside the same
+// streaming kernel as sin/log/exp (ew1_vec_kernel, several 256-bit loads in flight per thread).  Where CUDA's
+// math library streams at the HBM rate it is used as is (6.8 TB/s: profiles/r01_transcendentals.md); float32
+// asinh / acosh / atanh did not (4.2 / 5.6 / 6.3 TB/s, issue-bound) and have lean branch-free bodies in
+// f32_math.cuh.  The other thirteen float64 ones have lean bodies in f64_math.cuh and are picked in ops_trig.cu
+// before this getter is asked.  There is no reference arithmetic
 // to be bit-identical to -- NumPy's loops call the platform libm / SVML, whose results differ from
 // one libm to the next in the last place -- so the parity bar is stated in ULP against the
 // correctly rounded value: <= 4 ULP (tests/test_gpu_parity.py; CUDA documents 1-4 ULP for these),
 // with the IEEE special cases (NaN, +-inf, +-0, domain errors -> NaN, poles -> +-inf) exact.
 #include "ew.cuh"
 #include "functors.cuh"
+#include "f32_math.cuh"
 
 using namespace pncu;
 
@@ -32,9 +35,6 @@ PNCU_LIBM_F32(Atan, atanf)
 PNCU_LIBM_F32(Sinh, sinhf)
 PNCU_LIBM_F32(Cosh, coshf)
 PNCU_LIBM_F32(Tanh, tanhf)
-PNCU_LIBM_F32(Asinh, asinhf)
-PNCU_LIBM_F32(Acosh, acoshf)
-PNCU_LIBM_F32(Atanh, atanhf)
 PNCU_LIBM_F32(Log2, log2f)
 PNCU_LIBM_F32(Log10, log10f)
 PNCU_LIBM_F32(Exp2, exp2f)
@@ -46,6 +46,23 @@ PNCU_LIBM_F64(Exp2, exp2)
 PNCU_LIBM_F64(Cbrt, cbrt)
 #undef PNCU_LIBM_F32
 #undef PNCU_LIBM_F64
+
+// fast body on the fast domain (tested once per thread, ew.cuh), CUDA's function out of line elsewhere
+__device__ __noinline__ float asinhf_elem(float a) { return f32_asinh_ok(a) ? f32_asinh_fast(a) : asinhf(a); }
+__device__ __noinline__ float acoshf_elem(float a) { return f32_acosh_ok(a) ? f32_acosh_fast(a) : acoshf(a); }
+__device__ __noinline__ float atanhf_elem(float a) { return f32_atanh_ok(a) ? f32_atanh_fast(a) : atanhf(a); }
+#define PNCU_F32_FAST_FUNCTOR(NAME, OK, FAST, ELEM)                                                \
+    struct NAME {                                                                                  \
+        typedef float In; typedef float Out;                                                       \
+        static constexpr int kUnroll = 4; static constexpr bool kHasFast = true;                   \
+        static __device__ __forceinline__ bool ok(float a) { return OK(a); }                       \
+        static __device__ __forceinline__ float fast(float a) { return FAST(a); }                  \
+        static __device__ __forceinline__ float apply(float a) { return ELEM(a); }                 \
+    };
+PNCU_F32_FAST_FUNCTOR(AsinhF32, f32_asinh_ok, f32_asinh_fast, asinhf_elem)
+PNCU_F32_FAST_FUNCTOR(AcoshF32, f32_acosh_ok, f32_acosh_fast, acoshf_elem)
+PNCU_F32_FAST_FUNCTOR(AtanhF32, f32_atanh_ok, f32_atanh_fast, atanhf_elem)
+#undef PNCU_F32_FAST_FUNCTOR
 
 }  // namespace
 

@@ -643,8 +643,18 @@ def test_more_transcendentals_within_4ulp(dev, O, rng, op, dt):
         small = 1.0 + np.abs(small)
     elif op in ("LOG2", "LOG10"):
         small = 1.0 + small
-    edge = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 2.0, -2.0, 0.5, 1e-40, -1e-40, 1e38, -1e38])
-    x = np.concatenate([x, small, edge]).astype(dt)
+    # magnitudes from 1e-30 up (log-uniform): where asinh/atanh/sinh/... are x (1 + O(x^2)) and a sloppy reciprocal
+    # or a cancelling sum shows; acosh gets 1 + tiny, the logs 1 +- tiny
+    tiny = np.exp(rng.uniform(np.log(1e-30), 0.0, 1 << 12)) * rng.choice([-1.0, 1.0], 1 << 12)
+    if op == "ACOSH":
+        tiny = 1.0 + np.abs(tiny)
+    elif op in ("LOG2", "LOG10"):
+        tiny = 1.0 + tiny * 0.5
+    elif op == "LOG1P":
+        tiny = np.where(tiny < -0.5, -tiny, tiny)
+    edge = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 2.0, -2.0, 0.5, 1e-40, -1e-40, 1e38, -1e38,
+                     1.0 - 2.0 ** -24, -1.0 + 2.0 ** -24, 1.0 + 2.0 ** -23, 2.0 ** 59, 2.0 ** 60, 2.0 ** 61, -2.0 ** 60])
+    x = np.concatenate([x, small, tiny, edge]).astype(dt)
     launches0 = _launches()
     got = dev.unary(op, dev.to_device(x)).to_host()
     assert _launches() > launches0 and got.dtype == x.dtype
@@ -671,28 +681,35 @@ def test_more_transcendentals_within_4ulp(dev, O, rng, op, dt):
     del tf
 
 
-@pytest.mark.parametrize("op", sorted(MORE_TRIG))
-def test_more_transcendentals_do_not_depend_on_neighbours(dev, rng, op):
-    """float64: the lean bodies run when a thread's whole set of inputs is in the fast domain, the general
-    function otherwise -- a value must get the same bits either way, and from the strided kernel."""
+NEIGHBOUR_CASES = [(op, "float64") for op in sorted(MORE_TRIG)] + [(op, "float32") for op in ("ASINH", "ACOSH", "ATANH")]
+
+
+@pytest.mark.parametrize("op,dt", NEIGHBOUR_CASES)
+def test_more_transcendentals_do_not_depend_on_neighbours(dev, rng, op, dt):
+    """float64 (all) and the hand-written float32 bodies: the lean body runs when a thread's whole set of inputs
+    is in the fast domain, the general function otherwise -- a value must get the same bits either way, and from
+    the strided kernel."""
     from pnumpy_b200 import cabi
     fn, lo, hi = MORE_TRIG[op]
     n = (1 << 15) + 3
-    x = rng.uniform(lo, hi, n)
+    isz = np.dtype(dt).itemsize
+    x = rng.uniform(lo, hi, n).astype(dt)
     clean = dev.unary(op, dev.to_device(x)).to_host()
     y = x.copy()
     pos = rng.choice(n, 300, replace=False)
-    edges = np.array([np.nan, np.inf, -np.inf, 1e300, -1e300, 0.0, -0.0, 1.0, -1.0, 5e-324, 2.0 ** 80, -3.0])
+    big = 1e300 if dt == "float64" else 1e38
+    edges = np.array([np.nan, np.inf, -np.inf, big, -big, 0.0, -0.0, 1.0, -1.0, float(np.finfo(dt).smallest_subnormal),
+                      2.0 ** 80, -3.0]).astype(dt)
     y[pos] = edges[np.arange(pos.size) % edges.size]
     mixed = dev.unary(op, dev.to_device(y)).to_host()
     keep = np.ones(n, bool)
     keep[pos] = False
     assert np.array_equal(mixed[keep].view(np.uint8), clean[keep].view(np.uint8)), op
-    wide = np.zeros(2 * n)
+    wide = np.zeros(2 * n, dt)
     wide[::2] = y
-    dw, do = dev.to_device(wide), dev.empty(n, np.float64)
+    dw, do = dev.to_device(wide), dev.empty(n, dt)
     fnp = cabi.get_trig(cabi.TRIG_OPS[op], do.atype)[0]
-    cabi.check(fnp(dw.ptr, do.ptr, n, 16, 8, None), "strided")
+    cabi.check(fnp(dw.ptr, do.ptr, n, 2 * isz, isz, None), "strided")
     dev.sync()
     strided = do.to_host()
     assert np.array_equal(np.isnan(strided), np.isnan(mixed))
