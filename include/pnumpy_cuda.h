@@ -242,6 +242,8 @@ PNCU_API int pncu_itemsize(int atype);
  * ------------------------------------------------------------------------- */
 /* alignment (in elements) that shard boundaries must have */
 PNCU_API int64_t pncu_reduce_block_elems(void);
+/* pass 2 folds the slots (block partials) in groups of this many consecutive slots first, then the group partials */
+PNCU_API int pncu_reduce_group_slots(void);
 /* number of partial slots pass 1 writes for `len` elements of `atype` (= ceil(len / B)) */
 PNCU_API int64_t pncu_reduce_partial_count(int atype, int64_t len);
 /* bytes of one block partial for (func, type); 0 if no kernel */
@@ -329,6 +331,11 @@ PNCU_API int64_t pncu_exchange_timeouts(void);
  * can poll it instead of synchronising the stream.  If a shard never arrives (~2 s) the consumer does not fold
  * and does not write `out`; it publishes `done_value | PNCU_FUSED_TIMEOUT_BIT` and counts the event
  * (pncu_exchange_timeouts).  After such a failure call pncu_fused_reset(stream) before reusing the stream.
+ * Pass 2 folds the slots in two levels (groups of pncu_reduce_group_slots() = 64 consecutive slots, then the group
+ * partials).  When EVERY participant's `slot_base` is a multiple of 64 and `group_offset` is set (every consumer's
+ * allocation `slots[d]` then holds a second table of (total_count + 63) / 64 partials at that byte offset, behind
+ * the slots), each participant folds its own groups and stores only those: 1/64 of the exchange traffic and no
+ * level-A work left for the consumer.  Same bits either way.
  * x == NULL: a single GPU with no completion flag.
  * replaces: the per-chunk partials + second pass on the caller, src/pnumpy/_pnumpy.cpp:666-700.
  * ------------------------------------------------------------------------- */
@@ -345,6 +352,7 @@ typedef struct pncu_fused_exchange {
     unsigned long long expected;                  /* running total a consumer's counter reaches with this call */
     unsigned long long* done_flag;                /* optional */
     unsigned long long done_value;
+    int64_t group_offset;                         /* optional (0 = none): byte offset of the GROUP table in every consumer's `slots[d]` */
 } pncu_fused_exchange;
 PNCU_API int pncu_reduce_fused(int func, int atype, const void* in, int64_t len, const pncu_fused_exchange* x,
                                void* out, const void* startVal, pncu_stream_t stream);
@@ -352,6 +360,9 @@ PNCU_API int pncu_argminmax_fused(int kind, int atype, const void* in, int64_t l
                                   const pncu_fused_exchange* x, int64_t* out_index, pncu_stream_t stream);
 PNCU_API int pncu_muladd_sum_fused(int atype, const void* in1, const void* in2, const void* in3, int64_t len,
                                    const pncu_fused_exchange* x, void* out, pncu_stream_t stream);
+/* profiling aid: nanoseconds the most recent one-launch reduction on the current device spent in its tail (the last
+ * CTA: ticket drawn -> exchange -> pass 2 -> result published); synchronises the device */
+PNCU_API int64_t pncu_last_tail_ns(void);
 /* re-arm the stream's ticket counter after a failed or timed-out one-launch reduction */
 PNCU_API int pncu_fused_reset(pncu_stream_t stream);
 /* peer memory plumbing: same-process peer access, and CUDA IPC handles (64 bytes) for one-process-per-GPU jobs */

@@ -84,6 +84,8 @@ SIGNATURES = {
     "pncu_muladd_sum_partials": (ctypes.c_int, [ctypes.c_int, _vp, _vp, _vp, _c_i64, _vp, _vp]),
     "pncu_itemsize": (ctypes.c_int, [ctypes.c_int]),
     "pncu_reduce_block_elems": (_c_i64, []),
+    "pncu_reduce_group_slots": (ctypes.c_int, []),
+    "pncu_last_tail_ns": (_c_i64, []),
     "pncu_reduce_partial_count": (_c_i64, [ctypes.c_int, _c_i64]),
     "pncu_reduce_partial_bytes": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "pncu_reduce_partials": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _vp, _c_i64, _vp, _vp]),
@@ -142,7 +144,8 @@ class FusedExchange(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int), ("self", ctypes.c_int), ("all", ctypes.c_int), ("root", ctypes.c_int),
                 ("slot_base", _c_i64), ("total_count", _c_i64),
                 ("slots", _vp * PNCU_MAX_PEERS), ("arrived", _vp * PNCU_MAX_PEERS),
-                ("expected", ctypes.c_uint64), ("done_flag", _vp), ("done_value", ctypes.c_uint64)]
+                ("expected", ctypes.c_uint64), ("done_flag", _vp), ("done_value", ctypes.c_uint64),
+                ("group_offset", _c_i64)]
 
 
 FUSED_TIMEOUT_BIT = 1 << 63

@@ -16,20 +16,23 @@
 //           Arg-reductions keep the block in registers: phase A finds the block extreme
 //           (NaN-propagating), phase B scans the registers for its first occurrence; HBM is read
 //           once and there is no per-element index arithmetic.
-//   pass 2: ONE CTA folds the partials: (virtual) thread t of 1024 takes slots t, t+1024, ... in order,
-//           then the same warp/shared tree, then applies the start value and writes the result.
+//   pass 2: ONE CTA folds the partials in two levels.  Level A: every GROUP of 64 consecutive slots (4 MiB of
+//           input) is folded by eight lanes -- lane j takes slots 64g + j, + 8, ... in order, then a three-level
+//           shuffle-down tree -- into group partial g.  Level B: (virtual) thread t of 1024 takes group partials t, t+1024,
+//           ... in order, then the same warp/shared tree, then the start value is applied and the result written.
 //   ONE LAUNCH: the complete reductions (pncu_GetReduceMathOpFast launchers, pncu_*_fused) do not launch
 //           pass 2 at all.  Every pass-1 CTA takes a ticket after storing its partial (one atomicAdd, used
 //           for NOTHING but the ticket); the CTA that draws the last ticket runs pass 2 itself, its 256
 //           threads standing in for the 1024 of the finish kernel (thread t plays t, t+256, t+512, t+768),
 //           so the fold order -- and every bit of the result -- is that of the two-launch building blocks.
-//           With several GPUs the last CTA of each first stores its shard's partials into the consumers'
-//           slot tables over NVLink (one system fence, one arrival count per destination) and the
-//           consumer's last CTA waits on the device for the other shards before it folds the whole table.
-// Every choice above is a function of (n, type) only -- not of the grid, the SM count or the
+//           With several GPUs the last CTA of each first hands its shard to the consumers over NVLink (one system
+//           fence, one arrival count per destination) and the consumer's last CTA waits on the device for the other
+//           shards before it finishes.  What is handed over: when every shard starts at a multiple of 64 slots,
+//           its GROUP partials (level A done by the owner: 1/64 of the bytes, and the consumer only runs level B);
+//           otherwise the raw slots (the consumer runs both levels over the whole table).  Same tree either way.
+// Every choice above is a function of (n, type) only -- not of the grid, the SM count, the shard boundaries or the
 // arrival order of CTAs -- so results are bit-reproducible run to run, and a multi-GPU split
-// at multiples of 65536 elements that gathers all partials before pass 2 is bit-identical to
-// the single-GPU result.  No atomics anywhere.
+// at multiples of 65536 elements is bit-identical to the single-GPU result.  No atomics anywhere.
 //
 // Semantics (8c):
 //   sum/prod of float32 accumulate in float64 (the reference's intent, ops_binary.cpp:1069-70),
@@ -52,6 +55,8 @@ constexpr int RED_THREADS = 256;
 constexpr int RED_NV = RED_BLOCK_BYTES / (RED_THREADS * 32);  // 256-bit vectors per thread (8)
 constexpr int RED_CHAINS = 4;            // independent accumulators per thread
 constexpr int FIN_THREADS = 1024;
+constexpr int FOLD_GROUP = 64;           // slots per level-A group of pass 2
+inline __host__ __device__ int64_t groups_for(int64_t slots) { return (slots + FOLD_GROUP - 1) / FOLD_GROUP; }
 template <class In> __host__ __device__ constexpr int64_t block_elems() { return RED_BLOCK_BYTES / (int64_t)sizeof(In); }
 
 // ---- reducer policies ------------------------------------------------------------------------
@@ -278,6 +283,87 @@ __device__ __forceinline__ typename R::Acc fold_table(const typename R::Acc* par
     return r;
 }
 
+// Level A of pass 2: group g = slots [64g, 64g + 64) of `slots[0, count)` -> store(g, partial).  EIGHT LANES fold one
+// group: lane j of the eight takes slots 64g + j, + 8, ... + 56 in ascending order (seven combines in registers),
+// then a three-level shuffle-down tree over the eight lanes.  A warp therefore folds four groups per step with three
+// shuffle levels in all -- pass 2 runs on ONE SM, whose shuffle unit is the bottleneck of a full-warp tree per group
+// (measured: 2x the time of the flat fold it replaced) -- and every load instruction still reads four runs of
+// 8 consecutive slots (whole 32-byte sectors for every partial size).  Slots past `count` (last group only) are
+// skipped; a lane with none holds the identity, or a copy of the group's first slot for the idempotent ops that have
+// none.  STEPS steps are loaded before the first combine (8 STEPS loads in flight per lane); any number of warps may
+// share the work (a group's tree does not depend on who runs it).  The destination may be peer memory.
+constexpr int FOLD_LANES = 8;                        // lanes per group
+constexpr int FOLD_SEQ = FOLD_GROUP / FOLD_LANES;    // slots a lane folds in registers
+template <class R, int THREADS, class Store>
+__device__ __forceinline__ void fold_groups(const typename R::Acc* slots, int64_t count, Store store) {
+    typedef typename R::Acc Acc;
+    constexpr int NW = THREADS / 32;
+    constexpr int GPW = 32 / FOLD_LANES;             // groups per warp step (4)
+    constexpr int STEPS = sizeof(Acc) >= 16 ? 1 : (sizeof(Acc) == 8 ? 2 : 4);   // 32 registers of loads in flight per lane
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / FOLD_LANES, j = lane % FOLD_LANES;
+    const int64_t ngroups = groups_for(count);
+    const int64_t full = count / FOLD_GROUP;          // groups with all 64 slots
+    for (int64_t g0 = (int64_t)warp * (GPW * STEPS); g0 < ngroups; g0 += (int64_t)NW * (GPW * STEPS)) {
+        if (g0 + GPW * STEPS <= full) {
+            // unconditional loads first, all of them (predicated loads get interleaved with their uses and serialise;
+            // the slots were evicted from L2 by the stream, so every round trip is HBM's)
+            Acc x[STEPS][FOLD_SEQ];
+#pragma unroll
+            for (int st = 0; st < STEPS; ++st)
+#pragma unroll
+                for (int k = 0; k < FOLD_SEQ; ++k) x[st][k] = ld_cg(slots + (g0 + st * GPW + sub) * FOLD_GROUP + k * FOLD_LANES + j);
+#pragma unroll
+            for (int st = 0; st < STEPS; ++st) {
+                Acc a = x[st][0];
+#pragma unroll
+                for (int k = 1; k < FOLD_SEQ; ++k) a = R::combine(a, x[st][k]);
+#pragma unroll
+                for (int o = FOLD_LANES / 2; o > 0; o >>= 1) a = R::combine(a, Shfl<Acc>::down(a, o));
+                if (j == 0) store(g0 + st * GPW + sub, a);
+            }
+        } else {
+            // the last batch of a warp: step by step, the ragged last group with its fill-ins
+            for (int st = 0; st < STEPS; ++st) {
+                const int64_t g = g0 + st * GPW + sub;
+                const int64_t base = g * FOLD_GROUP;
+                const bool live = base < count;          // (all lanes run the shuffles)
+                Acc a = R::identity();
+                if (live) {
+                    const Acc fill = R::kHasIdentity ? R::identity() : ld_cg(slots + base);
+                    a = base + j < count ? ld_cg(slots + base + j) : fill;
+                    for (int k = 1; k < FOLD_SEQ; ++k) {
+                        const int64_t i = base + k * FOLD_LANES + j;
+                        if (i < count) a = R::combine(a, ld_cg(slots + i));
+                    }
+                }
+#pragma unroll
+                for (int o = FOLD_LANES / 2; o > 0; o >>= 1) a = R::combine(a, Shfl<Acc>::down(a, o));
+                if (live && j == 0) store(g, a);
+            }
+        }
+    }
+}
+
+// Only floating-point sums and products depend on the fold ORDER (integers wrap, min / max / arg-reductions are
+// associative and commutative bit for bit), so only they must take the two-level tree wherever the table is folded.
+// Everything else folds a whole table FLAT when one CTA has it all in front of it anyway (one level less: ~2-4 us on a
+// 2^28-element reduction) and in two levels when that spreads the work over the GPUs -- same bits by associativity.
+template <class R> struct OrderSensitive { static constexpr bool value = false; };
+template <class T> struct OrderSensitive<SumR<T, double>> { static constexpr bool value = true; };
+template <class T> struct OrderSensitive<ProdR<T, double>> { static constexpr bool value = true; };
+
+// both levels by one CTA: level A into `gscratch` (global memory of this GPU, groups_for(count) entries), level B
+// over it.  Result valid in thread 0.
+template <class R, int THREADS>
+__device__ __forceinline__ typename R::Acc fold_two_level(const typename R::Acc* slots, int64_t count, typename R::Acc* gscratch,
+                                                          typename R::Acc* smem) {
+    if constexpr (!OrderSensitive<R>::value) return fold_table<R, THREADS>(slots, count, smem);
+    fold_groups<R, THREADS>(slots, count, [gscratch](int64_t g, typename R::Acc a) { gscratch[g] = a; });
+    __syncthreads();   // the CTA's own global stores are visible to all of its threads (read back through L2)
+    return fold_table<R, THREADS>(gscratch, groups_for(count), smem);
+}
+
 template <class R, bool VALUE>
 __device__ __forceinline__ void store_result(typename R::Acc a, void* out, const void* startVal) {
     if constexpr (VALUE) {
@@ -298,12 +384,19 @@ struct FusedArgs {
                                       // consuming participant's own pass 1 writes directly
     unsigned long long* arrived[PNCU_MAX_PEERS];
     unsigned long long expected;      // arrivals a consumer's counter shows once every other shard is in
+    long long group_off;              // > 0: hierarchical -- every shard starts at a multiple of FOLD_GROUP slots and
+                                      // consumer d's GROUP table (groups_for(total_count) entries) is slots[d] + group_off bytes
+    void* gscratch;                   // this GPU's level-A output when it folds a whole slot table itself
     void* out;
     const void* startVal;
     unsigned long long* done_flag;    // optional (may be mapped host memory): receives done_value after `out`,
     unsigned long long done_value;    //   or done_value | PNCU_FUSED_TIMEOUT_BIT when a shard never arrived
 };
 __device__ unsigned long long g_exchange_timeouts = 0;
+// duration of the most recent one-launch tail on this device (last CTA: ticket drawn -> result published), for
+// tools/reduce_breakdown.py: two %globaltimer reads and one store per KERNEL
+__device__ unsigned long long g_tail_ns = 0;
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 constexpr unsigned long long EXCH_WAIT_NS = 2000000000ULL;
 
 // thread 0: wait until *counter >= expected; false after EXCH_WAIT_NS (a lost participant is reported, not hung on)
@@ -322,18 +415,44 @@ __device__ __forceinline__ void publish(unsigned long long* flag, unsigned long 
     if (flag) asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(value) : "memory");
 }
 
+// The tail runs ONCE per kernel, on one CTA, with its code cold (the stream has evicted it from every cache): its
+// instructions are fetched from HBM, so its size is part of its latency (measured: a tail with three inlined copies of
+// each level cost ~7 us more than the same arithmetic in one copy).  Hence: one out-of-line instance of level A
+// (destinations passed as a list) and one of level B, shared by the single-GPU, hierarchical and flat paths.
+// where level A's group partials go: this GPU's scratch, or (hierarchical exchange) every consumer's group table
+template <class R>
+__device__ __forceinline__ void fused_level_a(const typename R::Acc* slots, int64_t count, const FusedArgs& fa, bool hier) {
+    typedef typename R::Acc Acc;
+    const int64_t gbase = fa.slot_base / FOLD_GROUP;
+    fold_groups<R, RED_THREADS>(slots, count, [&fa, hier, gbase](int64_t g, Acc a) {
+        if (!hier) { reinterpret_cast<Acc*>(fa.gscratch)[g] = a; return; }
+        for (int d = 0; d < fa.n; ++d)
+            if (fa.all || d == fa.root) reinterpret_cast<Acc*>(reinterpret_cast<char*>(fa.slots[d]) + fa.group_off)[gbase + g] = a;
+    });
+}
+template <class R>
+__device__ __forceinline__ typename R::Acc fused_level_b(const typename R::Acc* groups, int64_t ngroups, typename R::Acc* smem) {
+    return fold_table<R, RED_THREADS>(groups, ngroups, smem);
+}
+
 template <class R, bool VALUE>
 __device__ __noinline__ void fused_finish(const typename R::Acc* local, int64_t local_count, const FusedArgs& fa) {
     typedef typename R::Acc Acc;
     __shared__ Acc fin_smem[FIN_THREADS / 32];
     __shared__ int s_ok;
+    const unsigned long long t_begin = global_ns();
     __threadfence();                         // the other CTAs' partials (acquire side of their tickets)
     if (threadIdx.x == 0) *fa.ticket = 0u;   // re-arm for the next launch on this stream
-    const Acc* table = local;
+    const bool multi = fa.n > 1;
+    const bool consumer = !multi || fa.all || fa.self == fa.root;
+    const bool hier = multi && fa.group_off > 0;
+    // does this CTA fold a whole slot table by itself (single GPU, or the consumer of a flat exchange)?  Then only the
+    // order-sensitive reductions need level A; the others fold the slots flat (see OrderSensitive)
+    const bool two_level = hier || OrderSensitive<R>::value;
+    const Acc* table = local;                // what level A runs over on this GPU, and how many slots
     int64_t count = local_count;
-    if (fa.n > 1) {
-        const bool consumer = fa.all || fa.self == fa.root;
-        // push: PUSH_MLP loads in flight per thread, then the stores to every consumer (posted writes over NVLink)
+    if (multi && !hier) {
+        // flat: push the raw slots, PUSH_MLP loads in flight per thread, then the stores to every consumer
         constexpr int PUSH_MLP = 8;
         for (int64_t i0 = threadIdx.x; i0 < local_count; i0 += (int64_t)RED_THREADS * PUSH_MLP) {
             Acc x[PUSH_MLP];
@@ -344,14 +463,20 @@ __device__ __noinline__ void fused_finish(const typename R::Acc* local, int64_t 
             }
             for (int d = 0; d < fa.n; ++d) {
                 if (d == fa.self || !(fa.all || d == fa.root)) continue;
-                Acc* dst = reinterpret_cast<Acc*>(fa.slots[d]) + fa.slot_base;
+                Acc* to = reinterpret_cast<Acc*>(fa.slots[d]) + fa.slot_base;
 #pragma unroll
                 for (int m = 0; m < PUSH_MLP; ++m) {
                     const int64_t i = i0 + (int64_t)m * RED_THREADS;
-                    if (i < local_count) dst[i] = x[m];
+                    if (i < local_count) to[i] = x[m];
                 }
             }
         }
+        table = reinterpret_cast<const Acc*>(fa.slots[fa.self]);   // a consumer runs level A over the WHOLE table later
+        count = fa.total_count;
+    } else if (two_level) {
+        fused_level_a<R>(table, count, fa, hier);
+    }
+    if (multi) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();
@@ -366,13 +491,17 @@ __device__ __noinline__ void fused_finish(const typename R::Acc* local, int64_t 
             if (threadIdx.x == 0) publish(fa.done_flag, fa.done_value | PNCU_FUSED_TIMEOUT_BIT);
             return;
         }
-        table = reinterpret_cast<const Acc*>(fa.slots[fa.self]);
-        count = fa.total_count;
+        if (!hier && two_level) fused_level_a<R>(table, count, fa, hier);
     }
-    Acc a = fold_table<R, RED_THREADS>(table, count, fin_smem);
+    __syncthreads();   // level A's stores (this CTA's own, or the peers' behind the arrival counter) before level B's loads
+    const Acc* groups = hier ? reinterpret_cast<const Acc*>(reinterpret_cast<const char*>(fa.slots[fa.self]) + fa.group_off)
+                             : reinterpret_cast<const Acc*>(fa.gscratch);
+    const Acc a = two_level ? fused_level_b<R>(groups, groups_for(multi ? fa.total_count : local_count), fin_smem)
+                            : fused_level_b<R>(table, count, fin_smem);
     if (threadIdx.x == 0) {
         store_result<R, VALUE>(a, fa.out, fa.startVal);
         publish(fa.done_flag, fa.done_value);
+        g_tail_ns = global_ns() - t_begin;
     }
 }
 
@@ -600,7 +729,7 @@ reduce_blocks_kernel(const char* in, int64_t n, int64_t stride, int64_t index_ba
 // while HBM is read once (12 B per float32 element instead of 28).  The three operands are
 // loaded four vectors at a time (384 B in flight per thread).
 template <class R, bool VEC, bool FUSED>
-__global__ void __launch_bounds__(RED_THREADS)
+__global__ void __launch_bounds__(RED_THREADS, FUSED ? 3 : 1)   // one-launch form: room for the tail's call frame (at 64 registers the main loop spills)
 muladd_sum_blocks_kernel(const typename R::In* a, const typename R::In* b, const typename R::In* c,
                          int64_t n, typename R::Acc* partials, const __grid_constant__ FusedArgs fa) {
     typedef typename R::In In;
@@ -779,10 +908,10 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
 // else write the index (arg-reductions).
 template <class R, bool VALUE>
 __global__ void __launch_bounds__(FIN_THREADS)
-reduce_finish_kernel(const typename R::Acc* partials, int64_t count, void* out, const void* startVal) {
+reduce_finish_kernel(const typename R::Acc* partials, int64_t count, typename R::Acc* gscratch, void* out, const void* startVal) {
     typedef typename R::Acc Acc;
     __shared__ Acc smem[FIN_THREADS / 32];
-    Acc a = fold_table<R, FIN_THREADS>(partials, count, smem);
+    Acc a = fold_two_level<R, FIN_THREADS>(partials, count, gscratch, smem);
     if (threadIdx.x == 0) store_result<R, VALUE>(a, out, startVal);
 }
 
@@ -812,7 +941,8 @@ struct PeerOut {
 template <class R, bool VALUE>
 __global__ void __launch_bounds__(FIN_THREADS)
 exchange_finish_kernel(const typename R::Acc* local, int64_t local_count, const PeerOut po, int64_t total_count,
-                       void* out, const void* startVal, unsigned long long expected, unsigned long long* status) {
+                       typename R::Acc* gscratch, void* out, const void* startVal, unsigned long long expected,
+                       unsigned long long* status) {
     typedef typename R::Acc Acc;
     __shared__ Acc smem[FIN_THREADS / 32];
     __shared__ int s_ok;
@@ -838,7 +968,7 @@ exchange_finish_kernel(const typename R::Acc* local, int64_t local_count, const 
         if (threadIdx.x == 0 && status) atomicOr(status, PNCU_FUSED_TIMEOUT_BIT);
         return;
     }
-    Acc a = fold_table<R, FIN_THREADS>(reinterpret_cast<const Acc*>(po.slots[po.self]), total_count, smem);
+    Acc a = fold_two_level<R, FIN_THREADS>(reinterpret_cast<const Acc*>(po.slots[po.self]), total_count, gscratch, smem);
     if (threadIdx.x == 0) store_result<R, VALUE>(a, out, startVal);
 }
 
@@ -855,13 +985,16 @@ int prepare_fused(const pncu_fused_exchange* x, size_t acc_bytes, int64_t nb, vo
                   cudaStream_t st, FusedArgs* fa, void** partials) {
     void* ws = NULL;
     unsigned* ticket = NULL;
-    int rc = get_workspace(st, (size_t)nb * acc_bytes, &ws, &ticket);
+    // scratch layout: [nb slots of this launch][group partials of the largest table this GPU may fold itself]
+    const int64_t fold_slots = x && x->n > 1 && x->total_count > nb ? x->total_count : nb;
+    int rc = get_workspace(st, (size_t)(nb + groups_for(fold_slots)) * acc_bytes, &ws, &ticket);
     if (rc) return rc;
     *fa = FusedArgs();
     fa->ticket = ticket;
     fa->n = 1;
     fa->out = out;
     fa->startVal = startVal;
+    fa->gscratch = (char*)ws + (size_t)nb * acc_bytes;
     *partials = ws;
     if (!x) return 0;
     fa->done_flag = x->done_flag;
@@ -883,6 +1016,14 @@ int prepare_fused(const pncu_fused_exchange* x, size_t acc_bytes, int64_t nb, vo
         if (used && (!x->slots[d] || !x->arrived[d])) { set_error("fused exchange: null table for participant %d", d); return PNCU_ERR_ARGUMENT; }
         fa->slots[d] = x->slots[d];
         fa->arrived[d] = x->arrived[d];
+    }
+    if (x->group_offset > 0) {
+        if (x->slot_base % FOLD_GROUP || x->group_offset % 16 || (size_t)x->group_offset < (size_t)x->total_count * acc_bytes) {
+            set_error("fused exchange: group_offset %lld needs slot_base %lld to be a multiple of %d and the group table to lie behind "
+                      "the %lld slots, 16-byte aligned", (long long)x->group_offset, (long long)x->slot_base, FOLD_GROUP, (long long)x->total_count);
+            return PNCU_ERR_ARGUMENT;
+        }
+        fa->group_off = x->group_offset;
     }
     if (x->all || x->self == x->root) *partials = (char*)x->slots[x->self] + (size_t)x->slot_base * acc_bytes;
     return 0;
@@ -1083,14 +1224,20 @@ struct ReduceOps {
 };
 template <class R, bool VALUE>
 int finish_thunk(const void* partials, int64_t count, void* out, const void* startVal, cudaStream_t st) {
-    reduce_finish_kernel<R, VALUE><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)partials, count, out, startVal);
+    void* gs = NULL;   // level-A output: this stream's scratch (the caller's partials live elsewhere)
+    int rc = get_workspace(st, (size_t)groups_for(count) * sizeof(typename R::Acc), &gs);
+    if (rc) return rc;
+    reduce_finish_kernel<R, VALUE><<<1, FIN_THREADS, 0, st>>>((const typename R::Acc*)partials, count, (typename R::Acc*)gs, out, startVal);
     return after_launch("reduce_finish_kernel");
 }
 template <class R, bool VALUE>
 int exchange_finish_thunk(const void* local, int64_t local_count, const PeerOut* po, int64_t total_count, void* out,
                           const void* startVal, unsigned long long expected, unsigned long long* status, cudaStream_t st) {
+    void* gs = NULL;
+    int rc = get_workspace(st, (size_t)groups_for(total_count) * sizeof(typename R::Acc), &gs);
+    if (rc) return rc;
     exchange_finish_kernel<R, VALUE><<<dim3(EXCH_SLICES, po->n), FIN_THREADS, 0, st>>>(
-        (const typename R::Acc*)local, local_count, *po, total_count, out, startVal, expected, status);
+        (const typename R::Acc*)local, local_count, *po, total_count, (typename R::Acc*)gs, out, startVal, expected, status);
     return after_launch("exchange_finish_kernel");
 }
 template <class R>
@@ -1230,6 +1377,7 @@ extern "C" pncu_argminmax_fn pncu_GetArgMinMaxOpFast(int kind, int t) {
 }
 
 extern "C" int64_t pncu_reduce_block_elems(void) { return RED_ALIGN_ELEMS; }
+extern "C" int pncu_reduce_group_slots(void) { return FOLD_GROUP; }
 
 extern "C" int64_t pncu_reduce_partial_count(int t, int64_t len) {
     const int isz = pncu_itemsize(t);
@@ -1335,6 +1483,13 @@ extern "C" int pncu_argminmax_exchange_finish(int kind, int t, const void* local
     PeerOut po;
     if ((rc = fill_peers(peers, self, slot_base, &po))) return rc;
     return o.exchange_finish(local_partials, local_count, &po, total_count, out_index, NULL, expected, status, as_stream(stream));
+}
+
+extern "C" int64_t pncu_last_tail_ns(void) {
+    unsigned long long v = 0;
+    if (ensure_init()) return -1;
+    if (cudaMemcpyFromSymbol(&v, g_tail_ns, sizeof(v)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int64_t)v;
 }
 
 extern "C" int64_t pncu_exchange_timeouts(void) {

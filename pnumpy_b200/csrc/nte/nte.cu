@@ -40,6 +40,7 @@ namespace {
 constexpr int kRing = 3;          // staging slots per lane
 constexpr int kMaxLanes = 16;     // the reference's hard maximum: 15 workers + caller (threads.h:56-66)
 constexpr int64_t kAlign = 65536; // == pncu_reduce_block_elems()
+constexpr int64_t kBlockBytes = 65536;  // bytes of input per reduction slot (checked against pncu_reduce_partial_count in nte_init)
 
 // optional per-call trace (nte_set_trace): monotonic ns at the stations of the last dispatch
 enum { TR_ENTER, TR_LOCKED, TR_PLANNED, TR_PLACED, TR_POSTED, TR_LAUNCHED, TR_JOINED, TR_DONE, TR_N };
@@ -378,7 +379,8 @@ int place_whole(const Operand& o, const char* lo, size_t bytes, Lane& L) {
 
 // ---- shard plans ----------------------------------------------------------------------------------------
 // `lanes` contiguous shards at multiples of 65536 elements, as even as the unit allows (no empty shard)
-void cut_shards(Job& j, int lanes) {
+void cut_shards(Job& j, int lanes, int64_t align = kAlign) {
+    const int64_t kAlign = align;   // (shadows the default unit: reductions over several GPUs cut at whole fold groups)
     const int64_t units = (j.len + kAlign - 1) / kAlign;
     if (lanes > units) lanes = (int)units;
     if (lanes < 1) lanes = 1;
@@ -421,8 +423,8 @@ int plan_on_device(Job& j, int dev, bool slabs) {
     return slabs ? ensure_slabs(dev) : ensure_lane(dev);
 }
 // resident operands: one lane per GPU
-int plan_one_lane_per_gpu(Job& j) {
-    cut_shards(j, g.ndev);
+int plan_one_lane_per_gpu(Job& j, int64_t align = kAlign) {
+    cut_shards(j, g.ndev, align);
     for (int l = 0; l < j.nlanes; ++l) {
         int rc = ensure_lane(l);
         if (rc) return rc;
@@ -913,7 +915,10 @@ void reset_exchange(Job& j) {
 int run_reduce_resident(Job& j, bool sharded) {
     int rc;
     if (sharded) {
-        if ((rc = plan_one_lane_per_gpu(j))) return rc;
+        // shards start at whole fold groups (64 slots = 4 MiB of input): every GPU folds its own groups and only the
+        // group partials cross NVLink (pncu_fused_exchange::groups); any split gives the single-GPU bits
+        const int64_t group_elems = (int64_t)pncu_reduce_group_slots() * (kBlockBytes / j.isz_in);
+        if ((rc = plan_one_lane_per_gpu(j, group_elems > kAlign ? group_elems : kAlign))) return rc;
     } else {
         const char* lo;
         int64_t bytes;
@@ -941,7 +946,11 @@ int run_reduce_resident(Job& j, bool sharded) {
         if ((rc = wait_flag(L0, want))) { reset_exchange(j); return rc; }
     } else {
         for (int l = 0; l <= j.nlanes; ++l) j.slot0[l] = pncu_reduce_partial_count(j.atype, j.shard[l]);
-        const size_t need = (size_t)j.slot0[j.nlanes] * j.partial_bytes;
+        const size_t slots_bytes = (((size_t)j.slot0[j.nlanes] * j.partial_bytes + 255) / 256) * 256;
+        const int group = pncu_reduce_group_slots();
+        const size_t need = slots_bytes + (size_t)((j.slot0[j.nlanes] + group - 1) / group) * j.partial_bytes;
+        bool aligned = true;
+        for (int l = 0; l < j.nlanes; ++l) aligned = aligned && j.slot0[l] % group == 0;
         if (g.x_table_bytes < need) {
             if (g.x_table) cudaFree(g.x_table);
             g.x_table = nullptr;
@@ -958,6 +967,7 @@ int run_reduce_resident(Job& j, bool sharded) {
             x.slot_base = j.slot0[l];
             x.total_count = j.slot0[j.nlanes];
             x.slots[0] = g.x_table;
+            x.group_offset = aligned ? (int64_t)slots_bytes : 0;
             x.arrived[0] = reinterpret_cast<unsigned long long*>(L0.d_scalar + kOffArrived);
             x.expected = g.x_expected;
             if (l == 0) {
@@ -1088,6 +1098,11 @@ int nte_init(void) {
             }
             if (!ok && b == 0) g.peer_all = false;
         }
+    if (pncu_reduce_partial_count(PNCU_DOUBLE, kBlockBytes / 8) != 1 || pncu_reduce_partial_count(PNCU_DOUBLE, kBlockBytes / 8 + 1) != 2 ||
+        pncu_reduce_block_elems() != kAlign) {
+        set_error("nte: reduction block geometry differs from libpnumpy_cuda's");
+        return PNCU_ERR_ARGUMENT;
+    }
     static bool atfork_registered = false;
     if (!atfork_registered) { pthread_atfork(nullptr, nullptr, atfork_child); atfork_registered = true; }
     g.inited = true;

@@ -28,9 +28,11 @@ _HEADER = 512    # counters (2 x 128 B) + status word, in front of the two table
 
 
 class Exchange:
-    def __init__(self, rank, world, bases, counters, max_slots, device, imported=()):
+    def __init__(self, rank, world, bases, counters, groups, max_slots, device, imported=()):
         self.rank, self.world, self.max_slots, self.device = rank, world, int(max_slots), device
         self._bases, self._counters, self._imported = bases, counters, list(imported)  # [participant][parity] addresses
+        self._groups = groups    # [participant][parity]: group tables (level A of pass 2 done by the shard's owner)
+        self.hierarchical = 0    # calls whose shards were group-aligned (group partials travelled, not slots)
         self.epoch = 0
         self.expected = [0, 0]
         self.broken = None
@@ -39,18 +41,23 @@ class Exchange:
 
     # ---- construction ---------------------------------------------------------------------------------
     @staticmethod
-    def _alloc(lib, max_slots):
-        nbytes = 2 * max_slots * SLOT_BYTES + _HEADER
+    def _group_cap(max_slots):
+        return (max_slots + 63) // 64 + 1
+
+    @classmethod
+    def _alloc(cls, lib, max_slots):
+        nbytes = 2 * (max_slots + cls._group_cap(max_slots)) * SLOT_BYTES + _HEADER
         p = ctypes.c_void_p()
         cabi.check(lib.pncu_malloc(ctypes.byref(p), nbytes), "pncu_malloc")
         cabi.check(lib.pncu_memset(p, 0, nbytes, None), "pncu_memset")
         cabi.check(lib.pncu_stream_sync(None), "sync")
         return p.value
 
-    @staticmethod
-    def _layout(base, max_slots):
-        tab = [base + _HEADER, base + _HEADER + max_slots * SLOT_BYTES]
-        return tab, [base, base + 128]
+    @classmethod
+    def _layout(cls, base, max_slots):
+        per = (max_slots + cls._group_cap(max_slots)) * SLOT_BYTES   # one parity: slot table, then group table
+        tab = [base + _HEADER, base + _HEADER + per]
+        return tab, [base, base + 128], [t + max_slots * SLOT_BYTES for t in tab]
 
     @classmethod
     def in_process(cls, devices, max_slots):
@@ -66,7 +73,7 @@ class Exchange:
         lay = [cls._layout(b, max_slots) for b in raw]
         out = []
         for r, d in enumerate(devices):
-            x = cls(r, len(devices), [l[0] for l in lay], [l[1] for l in lay], max_slots, d)
+            x = cls(r, len(devices), [l[0] for l in lay], [l[1] for l in lay], [l[2] for l in lay], max_slots, d)
             x._own = raw[r]
             x._status = raw[r] + 256
             out.append(x)
@@ -98,7 +105,7 @@ class Exchange:
             raw.append(p.value)
             imported.append(p.value)
         lay = [cls._layout(b, max_slots) for b in raw]
-        x = cls(rank, world, [l[0] for l in lay], [l[1] for l in lay], max_slots, dev.value, imported)
+        x = cls(rank, world, [l[0] for l in lay], [l[1] for l in lay], [l[2] for l in lay], max_slots, dev.value, imported)
         x._own = own
         x._status = own + 256
         if sync:
@@ -134,9 +141,15 @@ class Exchange:
         x = cabi.FusedExchange()
         x.n, x.self, x.all, x.root = self.world, self.rank, 1, 0
         x.slot_base, x.total_count = int(sum(counts[: self.rank])), total
+        # every shard starts at a multiple of the fold group (64 slots = 4 MiB of input): each participant folds its
+        # own groups and only the group partials cross NVLink (same bits: pncu_fused_exchange in the header)
+        group = int(cabi.load().pncu_reduce_group_slots())
+        aligned = all(int(sum(counts[:r])) % group == 0 for r in range(self.world))
+        self.hierarchical += int(aligned)
         for d in range(self.world):
             x.slots[d] = self._bases[d][parity]
             x.arrived[d] = self._counters[d][parity]
+        x.group_offset = self.max_slots * SLOT_BYTES if aligned else 0   # _layout: the group table follows the slot table
         x.expected = self.expected[parity]
         # the status word doubles as the completion flag: its TIMEOUT bit is what wait() looks at
         x.done_flag = self._status

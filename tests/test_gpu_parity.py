@@ -718,9 +718,11 @@ def test_more_transcendentals_do_not_depend_on_neighbours(dev, rng, op, dt):
 
 
 # ---- the cross-GPU exchange fused into the two passes -------------------------------------------------
-def _exchange_case(dev, devices, rng):
+def _exchange_case(dev, devices, rng, group_aligned=False):
     """sum / min / max / argmax of one array cut into len(devices) shards, every shard on its own GPU, through
-    Exchange: every participant must end with the bits a single GPU produces."""
+    Exchange: every participant must end with the bits a single GPU produces.  group_aligned: the shards start at
+    multiples of the fold group (64 slots), so each participant folds its own groups and only group partials travel
+    (pncu_fused_exchange::groups) -- same bits again."""
     import ctypes
     from pnumpy_b200 import cabi, exchange
     lib = cabi.load()
@@ -729,6 +731,9 @@ def _exchange_case(dev, devices, rng):
     align = int(lib.pncu_reduce_block_elems())
     n = 5 * align * world + 12345
     for dt in ("float32", "float64", "int32"):
+        if group_aligned:
+            align = int(lib.pncu_reduce_group_slots()) * (65536 // np.dtype(dt).itemsize)
+            n = 2 * align * world + 12345
         a = (rng.normal(0, 100, n)).astype(dt)
         units = -(-n // align)
         per = -(-units // world)
@@ -782,6 +787,7 @@ def _exchange_case(dev, devices, rng):
         for r, d in enumerate(devices):
             cabi.check(lib.pncu_set_device(d), "set_device")
             assert lib.pncu_exchange_timeouts() == timeouts0[d]
+            assert (xs[r].hierarchical > 0) == (group_aligned or world == 1), (xs[r].hierarchical, group_aligned)
             xs[r].close()
             cabi.check(lib.pncu_stream_destroy(streams[r]), "stream")
     cabi.check(lib.pncu_set_device(devices[0]), "set_device")
@@ -797,6 +803,19 @@ def test_fused_exchange_two_participants_on_one_gpu(dev, rng):
     participant's table, system fences, arrival counters, device-side wait, alternating tables) runs on a
     single-GPU box too"""
     _exchange_case(dev, [0, 0], rng)
+
+
+def test_fused_exchange_group_partials_on_one_gpu(dev, rng):
+    """shards that start at whole fold groups: level A of pass 2 is done by each shard's owner and only the group
+    partials are stored into the consumers' tables"""
+    _exchange_case(dev, [0, 0], rng, group_aligned=True)
+
+
+def test_fused_exchange_group_partials_two_gpus(dev, rng):
+    from pnumpy_b200 import cabi
+    if cabi.load().pncu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _exchange_case(dev, [0, 1], rng, group_aligned=True)
 
 
 def test_exchange_timeout_is_loud(dev, rng):

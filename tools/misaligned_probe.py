@@ -78,6 +78,7 @@ for dt in ("float32", "float64", "int8", "int16", "int64"):
                            ("max(a) aligned (reference point)", lambda: dev.reduce("MAX", a.view(0, n), out=r1), None)):
         ms = timed(fn)
         gbs = s * n / (ms * 1e-3) / 1e9
-        print(f"| {name} | {dt} | {ms:.4f} | {gbs:.0f} | {100 * gbs / 8000:.1f} | - |", flush=True)
+        tail = lib.pncu_last_tail_ns() / 1e3 if hasattr(lib, "pncu_last_tail_ns") else float("nan")
+        print(f"| {name} | {dt} | {ms:.4f} | {gbs:.0f} | {100 * gbs / 8000:.1f} | tail {tail:.1f} us |", flush=True)
     for x in (a, b, o):
         x.free()

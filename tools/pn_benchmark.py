@@ -18,3 +18,13 @@ print("## 16 777 216 elements, pinned operands")
 pn.benchmark(ctypes=ct, pinned=True, sizes=[1 << 24], loop_size=10)
 print("## 16 777 216 elements, pageable operands")
 pn.benchmark(ctypes=ct, pinned=False, sizes=[1 << 24], loop_size=10)
+# the reference's own call, nothing added: pn.benchmark() with the managed recycler on -- the arrays benchmark() builds
+# with np.arange(...).astype(...) and the outputs NumPy allocates are born in CUDA managed memory
+print("## 1 000 000 elements, recycler_enable(kind='managed'), default thresholds (plain pn.benchmark())")
+pn.recycler_enable(kind="managed")
+try:
+    pn.benchmark(ctypes=ct, loop_size=30)
+    print("## 16 777 216 elements, recycler_enable(kind='managed')")
+    pn.benchmark(ctypes=ct, sizes=[1 << 24], loop_size=10)
+finally:
+    pn.recycler_disable()
