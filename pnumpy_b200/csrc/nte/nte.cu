@@ -1341,11 +1341,13 @@ static int dispatch_elementwise(Job& j, int max_workers) {
         TRACE(TR_DONE);
         return rc;
     }
-    if (nres == 0) {
-        // ---- host operands only: worth a PCIe round trip?
+    {
+        // ---- at least one HOST array operand: worth a PCIe round trip?  (Also when another operand is resident: NumPy
+        // calls the loops of np.sin(int16_array) with 8192-element cast buffers as input and the managed result array as
+        // output -- 120 staged launches per million elements would be 4x slower than its own loop.)
         // an op whose output does not depend on its input (isnan / isinf / isfinite of integers): shipping the input
         // over PCIe to memset the output would be absurd -- NumPy's own loop is a memset already
-        if (j.op_class == NTE_CLASS_CONST) return decline();
+        if (nres == 0 && j.op_class == NTE_CLASS_CONST) return decline();
         const bool pageable = j.ko.kind == MK_PAGEABLE || (vec1 && j.k1.kind == MK_PAGEABLE) || (vec2 && j.k2.kind == MK_PAGEABLE);
         if (j.len < threshold_for(j.op_class, pageable, j.isz_in > j.isz_out ? j.isz_in : j.isz_out)) return decline();
     }

@@ -255,7 +255,7 @@ static int AtopArgMinMaxMathFunction(void* data, npy_intp n, npy_intp* out_index
 // int / int -> float64 true_divide without NumPy's casts (an ADDITION; the 359 reference hooks are
 // untouched and these loops are not listed in atop_info()).
 //
-// np.true_divide has no integer loops beyond 'bb->d': for int16..int64 operands NumPy casts both
+// np.true_divide has no integer loops (NumPy 2.3: not even 'bb->d'): for int8..int64 operands NumPy casts both
 // inputs to float64 in 8 Mi-element buffers on one CPU thread and then runs 'dd->d' -- the only
 // thing a replace-loop hook (the reference's, src/atop/ops_binary.cpp:926, or ours) ever sees.  On a
 // GPU those casts cost 20x the divide itself.  NumPy 2's public PyUFunc_AddLoopFromSpec lets us add
@@ -272,6 +272,7 @@ static void int_to_double_t(const char* src, npy_intp stride, double* dst, npy_i
 }
 static void int_to_double(int type_num, const char* src, npy_intp stride, double* dst, npy_intp n) {
     switch (type_num) {
+        case NPY_BYTE: int_to_double_t<npy_byte>(src, stride, dst, n); break;
         case NPY_UBYTE: int_to_double_t<npy_ubyte>(src, stride, dst, n); break;
         case NPY_SHORT: int_to_double_t<npy_short>(src, stride, dst, n); break;
         case NPY_USHORT: int_to_double_t<npy_ushort>(src, stride, dst, n); break;
@@ -323,7 +324,8 @@ static int register_int_true_divide(PyObject* numpy_module) {
     if (!g_UFuncLUT[PNCU_DIV][PNCU_DOUBLE].pOldFunc) return 0;
     PyObject* ufunc = PyObject_GetAttrString(numpy_module, "true_divide");
     if (!ufunc) return -1;
-    PyArray_DTypeMeta* ints[] = {&PyArray_UByteDType, &PyArray_ShortDType, &PyArray_UShortDType, &PyArray_IntDType,
+    // (NumPy 2 has no 'bb->d' loop any more: int8 is cast to float64 like the others)
+    PyArray_DTypeMeta* ints[] = {&PyArray_ByteDType, &PyArray_UByteDType, &PyArray_ShortDType, &PyArray_UShortDType, &PyArray_IntDType,
                                  &PyArray_UIntDType, &PyArray_LongDType, &PyArray_ULongDType, &PyArray_LongLongDType,
                                  &PyArray_ULongLongDType};
     for (PyArray_DTypeMeta* dt : ints) {
@@ -674,8 +676,13 @@ enum { RK_PINNED = 0, RK_MANAGED = 1 };
 static size_t g_RecyclerThreshold[2] = {(size_t)1 << 20, (size_t)256 << 10};
 static int g_RecyclerKind = RK_PINNED;
 static std::mutex g_PoolMu;
-static std::multimap<size_t, void*> g_Pool[2];
-static size_t g_PoolBytes[2] = {0, 0}, g_PoolCap = (size_t)8 << 30;
+struct PoolBlock { void* p; uint64_t seq; };
+static std::multimap<size_t, PoolBlock> g_Pool[2];
+// idle bytes kept per kind: pinned blocks are host RAM (8 GiB); managed blocks are HBM the next temporary of the same
+// size will reuse (64 GiB of 180 per GPU; a 2^30-element float32 chain alone cycles through 8 GiB).  When a freed block
+// does not fit, the OLDEST idle blocks make room for it (the sizes a program asks for change over time).
+static size_t g_PoolBytes[2] = {0, 0}, g_PoolCap[2] = {(size_t)8 << 30, (size_t)64 << 30};
+static uint64_t g_PoolSeq = 0;
 static int64_t g_PoolHits = 0, g_PoolMisses = 0, g_BlocksLive = 0;
 
 struct LiveBlock { size_t size; int kind; };
@@ -687,7 +694,7 @@ static void* pool_get(size_t size, int kind) {
         std::lock_guard<std::mutex> lk(g_PoolMu);
         auto it = g_Pool[kind].find(size);
         if (it != g_Pool[kind].end()) {
-            p = it->second;
+            p = it->second.p;
             g_Pool[kind].erase(it);
             g_PoolBytes[kind] -= size;
             g_PoolHits++;
@@ -706,6 +713,8 @@ static void* pool_get(size_t size, int kind) {
 // true (and the block is retired) if `p` is one of ours
 static bool pool_put(void* p) {
     LiveBlock b;
+    std::vector<void*> evicted;
+    bool pooled = false;
     {
         std::lock_guard<std::mutex> lk(g_PoolMu);
         auto it = g_Live.find(p);
@@ -713,12 +722,22 @@ static bool pool_put(void* p) {
         b = it->second;
         g_Live.erase(it);
         g_BlocksLive--;
-        if (!nte_is_forked_child() && g_PoolBytes[0] + g_PoolBytes[1] + b.size <= g_PoolCap) {
-            g_Pool[b.kind].insert(std::make_pair(b.size, p));
+        if (!nte_is_forked_child() && b.size <= g_PoolCap[b.kind]) {
+            while (g_PoolBytes[b.kind] + b.size > g_PoolCap[b.kind] && !g_Pool[b.kind].empty()) {
+                auto oldest = g_Pool[b.kind].begin();
+                for (auto it = g_Pool[b.kind].begin(); it != g_Pool[b.kind].end(); ++it)
+                    if (it->second.seq < oldest->second.seq) oldest = it;
+                evicted.push_back(oldest->second.p);
+                g_PoolBytes[b.kind] -= oldest->first;
+                g_Pool[b.kind].erase(oldest);
+            }
+            g_Pool[b.kind].insert(std::make_pair(b.size, PoolBlock{p, ++g_PoolSeq}));
             g_PoolBytes[b.kind] += b.size;
-            return true;
+            pooled = true;
         }
     }
+    for (void* q : evicted) { if (b.kind == RK_MANAGED) nte_free_managed(q); else nte_free_pinned(q); }
+    if (pooled) return true;
     if (b.kind == RK_MANAGED) nte_free_managed(p); else nte_free_pinned(p);
     return true;
 }
@@ -789,6 +808,8 @@ static PyObject* recycler_enable(PyObject*, PyObject* args, PyObject* kwargs) {
         g_RecyclerThreshold[k] = (size_t)(t < 4096 ? 4096 : t);
     }
     g_RecyclerKind = k;
+    const char* cap_gib = getenv("PNUMPY_B200_POOL_GIB");   // idle bytes the pool of this kind may keep
+    if (cap_gib && *cap_gib && atoll(cap_gib) >= 0) g_PoolCap[k] = (size_t)atoll(cap_gib) << 30;
     if (!g_Settings.RecyclerEnabled) {
         PyObject* cap = PyCapsule_New(&g_RecyclerHandler, "mem_handler", NULL);
         if (!cap) return NULL;
@@ -819,7 +840,7 @@ static PyObject* recycler_info(PyObject*, PyObject*) {
                          "hits", (long long)g_PoolHits, "misses", (long long)g_PoolMisses,
                          "live_blocks", (long long)g_BlocksLive, "live_pinned_blocks", (long long)g_BlocksLive,
                          "threshold_bytes", (long long)g_RecyclerThreshold[g_RecyclerKind],
-                         "pool_cap_bytes", (long long)g_PoolCap);
+                         "pool_cap_bytes", (long long)g_PoolCap[g_RecyclerKind]);
 }
 // give pooled (free) blocks back to CUDA; live arrays are untouched
 static PyObject* recycler_trim(PyObject*, PyObject*) {
@@ -827,7 +848,7 @@ static PyObject* recycler_trim(PyObject*, PyObject*) {
     {
         std::lock_guard<std::mutex> lk(g_PoolMu);
         for (int k = 0; k < 2; ++k) {
-            for (auto& kv : g_Pool[k]) victims.push_back(std::make_pair(kv.second, k));
+            for (auto& kv : g_Pool[k]) victims.push_back(std::make_pair(kv.second.p, k));
             g_Pool[k].clear();
             g_PoolBytes[k] = 0;
         }
