@@ -354,15 +354,19 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
             for (int u = 0; u < U; ++u)
                 st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
         }
+    } else if constexpr (REALIGN) {
+        // (unrolled: a dynamic index into ra[] would put the whole array -- also on the fast path above -- in local
+        // memory: sin(a[1:]) ran at 61 % of the aligned rate with the 128-byte stack frame that cost)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t v = v0 + (int64_t)u * EW_BLOCK;
+            if (v < nvec) st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra[u]));
+        }
     } else {
 #pragma unroll 1
         for (int u = 0; u < U; ++u) {
             const int64_t v = v0 + (int64_t)u * EW_BLOCK;
-            if (v < nvec) {
-                Pack<In, EPV> rx;
-                if constexpr (REALIGN) rx = ra[u]; else rx = ld_pack<In, EPV>(a + head + v * EPV);
-                st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(rx));
-            }
+            if (v < nvec) st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ld_pack<In, EPV>(a + head + v * EPV)));
         }
     }
     if (blockIdx.x == 0) {

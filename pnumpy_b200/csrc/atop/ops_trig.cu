@@ -434,6 +434,14 @@ PNCU_F64_FAST_FUNCTOR(SinhF64, f64_exp_ok, f64_sinh_fast, sinh64_elem)
 PNCU_F64_FAST_FUNCTOR(TanF64, f64_sincos_ok, f64_tan_fast, tan64_elem)
 #undef PNCU_F64_FAST_FUNCTOR
 #undef PNCU_F64_FAST_FUNCTOR_U
+__device__ __noinline__ double exp2_64_elem(double a) { return f64_exp2_ok(a) ? f64_exp2_fast(a) : exp2(a); }
+struct Exp2F64 {
+    typedef double In; typedef double Out;
+    static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
+    static __device__ __forceinline__ bool ok(double a) { return f64_exp2_ok(a); }
+    static __device__ __forceinline__ double fast(double a) { return f64_exp2_fast(a); }
+    static __device__ __forceinline__ double apply(double a) { return exp2_64_elem(a); }
+};
 struct Expm1F64 {
     typedef double In; typedef double Out;
     static constexpr int kUnroll = 2; static constexpr bool kHasFast = true;
@@ -479,6 +487,9 @@ extern "C" pncu_unary_fn pncu_GetTrigOpFast(int func, int t, int* wantedOutType)
             return trig_more(func, t);
         case PNCU_EXPM1:
             if (t == PNCU_DOUBLE) return launch_unary<Expm1F64>;
+            return trig_more(func, t);
+        case PNCU_EXP2:
+            if (t == PNCU_DOUBLE) return launch_unary<Exp2F64>;
             return trig_more(func, t);
         case PNCU_ATAN:
             if (t == PNCU_DOUBLE) return launch_unary<AtanF64>;

@@ -3,11 +3,11 @@
 // (GetTrigOpFast returns NULL for them, src/atop/ops_trig.cpp:599-777, and the dispatcher threads
 // NumPy's own loop over 16K chunks, src/pnumpy/_pnumpy.cpp:973-993).  SURVEY.md 8(f) row f-4.
 //
-// Here they get a GPU body.  This file holds the float32 ones and float64 exp2, cosh, cbrt, inside the same
+// Here they get a GPU body.  This file holds the float32 ones and float64 cosh, cbrt, inside the same
 // streaming kernel as sin/log/exp (ew1_vec_kernel, several 256-bit loads in flight per thread).  Where CUDA's
 // math library streams at the HBM rate it is used as is (6.8 TB/s: profiles/r01_transcendentals.md); float32
 // asinh / acosh / atanh did not (4.2 / 5.6 / 6.3 TB/s, issue-bound) and have lean branch-free bodies in
-// f32_math.cuh.  The other thirteen float64 ones have lean bodies in f64_math.cuh and are picked in ops_trig.cu
+// f32_math.cuh.  The other fourteen float64 ones have lean bodies in f64_math.cuh and are picked in ops_trig.cu
 // before this getter is asked.  There is no reference arithmetic
 // to be bit-identical to -- NumPy's loops call the platform libm / SVML, whose results differ from
 // one libm to the next in the last place -- so the parity bar is stated in ULP against the
@@ -42,7 +42,6 @@ PNCU_LIBM_F32(Expm1, expm1f)
 PNCU_LIBM_F32(Log1p, log1pf)
 PNCU_LIBM_F32(Cbrt, cbrtf)
 PNCU_LIBM_F64(Cosh, cosh)
-PNCU_LIBM_F64(Exp2, exp2)
 PNCU_LIBM_F64(Cbrt, cbrt)
 #undef PNCU_LIBM_F32
 #undef PNCU_LIBM_F64
@@ -91,7 +90,7 @@ pncu_unary_fn trig_more(int func, int t) {
         PNCU_PICK(PNCU_ATANH, Atanh)
         PNCU_PICK(PNCU_LOG2, Log2)
         PNCU_PICK(PNCU_LOG10, Log10)
-        PNCU_PICK2(PNCU_EXP2, Exp2)
+        PNCU_PICK(PNCU_EXP2, Exp2)
         PNCU_PICK(PNCU_EXPM1, Expm1)
         PNCU_PICK(PNCU_LOG1P, Log1p)
         PNCU_PICK2(PNCU_CBRT, Cbrt)

@@ -73,6 +73,19 @@ int main(int argc, char** argv) {
             upd(sexp, x, f64_exp_fast(x), expl((long double)x));
         }
     if (f64_exp_fast(0.0) != 1.0 || f64_exp_fast(-0.0) != 1.0) { printf("exp(0) != 1\n"); bad = 1; }
+    // exp2: the same ranges scaled, exact at integers, domain
+    Stat sexp2;
+    const double e2ranges[][2] = {{-1, 1}, {-100, 100}, {-1019.9, 1019.9}, {-1e-5, 1e-5}, {-0.5, 0.5}};
+    for (auto& rg : e2ranges)
+        for (long i = 0; i < N; ++i) {
+            double x = uni(rg[0], rg[1]);
+            if (!f64_exp2_ok(x)) continue;
+            upd(sexp2, x, f64_exp2_fast(x), exp2l((long double)x));
+        }
+    for (int k = -1019; k <= 1019; ++k)
+        if (f64_exp2_fast((double)k) != ldexp(1.0, k)) { printf("exp2(%d) not exact\n", k); bad = 1; break; }
+    if (f64_exp2_fast(-0.0) != 1.0 || f64_exp2_ok(1020.0) || f64_exp2_ok(-1020.0) || f64_exp2_ok(NAN) || f64_exp2_ok(INFINITY) || !f64_exp2_ok(1019.99) ||
+        !f64_exp2_ok(-1019.99) || !f64_exp2_ok(5e-324)) { printf("exp2 domain / exp2(-0) wrong\n"); bad = 1; }
     // log: uniform, near 1, random bit patterns of positive normals
     const double lranges[][2] = {{0.5, 2}, {1e-3, 1e6}, {0.99, 1.01}, {1 - 1e-9, 1 + 1e-9}, {0.6, 0.8}, {1.3, 1.5}};
     for (auto& rg : lranges)
@@ -217,6 +230,7 @@ int main(int argc, char** argv) {
     printf("sin %ld %.4f %.17g\n", ssin.n, ssin.worst, ssin.at);
     printf("cos %ld %.4f %.17g\n", scos.n, scos.worst, scos.at);
     printf("exp %ld %.4f %.17g\n", sexp.n, sexp.worst, sexp.at);
+    printf("exp2 %ld %.4f %.17g\n", sexp2.n, sexp2.worst, sexp2.at);
     printf("log %ld %.4f %.17g\n", slog.n, slog.worst, slog.at);
     return bad;
 }
