@@ -174,10 +174,11 @@ __device__ __forceinline__ Pack<T, N> ld_pack_realigned(const T* p, unsigned m, 
 
 __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
+constexpr int EW_BLOCK = 256;   // threads per CTA == vectors per tile
+
 enum Layout { LAY_VV = 0, LAY_SV = 1, LAY_VS = 2 };
 
 
-constexpr int EW_BLOCK = 256;   // threads per CTA == vectors per tile
 constexpr int EW_VEC_BYTES = 32;
 
 // elements per wide vector for an (In, Out) pair
@@ -314,9 +315,9 @@ __device__ __forceinline__ Pack<typename F::Out, EPV> apply_pack(const Pack<type
     return r;
 }
 
-template <class F, bool REALIGN>
+template <class F>
 __global__ void __launch_bounds__(EW_BLOCK)
-ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n, unsigned ma) {
+ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n) {
     typedef typename F::In In;
     typedef typename F::Out Out;
     constexpr int EPV = Epv<In, Out>::value;
@@ -325,19 +326,10 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
     constexpr bool FAST = has_fast<F>::value && smem_of<F>::value == 0;
     const int64_t v0 = (int64_t)blockIdx.x * (EW_BLOCK * U) + threadIdx.x;
     const bool full = v0 + (int64_t)(U - 1) * EW_BLOCK < nvec;
-    Pack<In, EPV> ra[U];
-    if constexpr (REALIGN) {
-        // input misaligned relative to the output (see ld_pack_realigned): every lane runs the loads and shuffles
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t v = v0 + (int64_t)u * EW_BLOCK;
-            ra[u] = ld_pack_realigned<In, EPV>(a + head + v * EPV, ma, v < nvec, v + 1 < nvec);
-        }
-    } else if (full) {
+    if (full) {
+        Pack<In, EPV> ra[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) ra[u] = ld_pack<In, EPV>(a + head + (v0 + (int64_t)u * EW_BLOCK) * EPV);
-    }
-    if (full) {
         bool all_fast = FAST;
         if constexpr (FAST) {
 #pragma unroll
@@ -354,19 +346,89 @@ ew1_vec_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_
             for (int u = 0; u < U; ++u)
                 st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_BLOCK) * EPV, apply_pack<F, EPV>(ra[u]));
         }
-    } else if constexpr (REALIGN) {
-        // (unrolled: a dynamic index into ra[] would put the whole array -- also on the fast path above -- in local
-        // memory: sin(a[1:]) ran at 61 % of the aligned rate with the 128-byte stack frame that cost)
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t v = v0 + (int64_t)u * EW_BLOCK;
-            if (v < nvec) st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra[u]));
-        }
     } else {
 #pragma unroll 1
         for (int u = 0; u < U; ++u) {
             const int64_t v = v0 + (int64_t)u * EW_BLOCK;
             if (v < nvec) st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ld_pack<In, EPV>(a + head + v * EPV)));
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tail0 = head + nvec * EPV;
+        const int64_t nscalar = head + (n - tail0);
+        for (int64_t i = threadIdx.x; i < nscalar; i += EW_BLOCK) {
+            const int64_t idx = i < head ? i : tail0 + (i - head);
+            o[idx] = F::apply(a[idx]);
+        }
+    }
+}
+
+// The same for an input whose 32-byte alignment disagrees with the output's (np.sin(a[1:])).  Every lane loads the
+// ALIGNED input vector that holds the first byte of its output vector and takes the following one from the NEXT LANE
+// (one shuffle per word) -- and so that no lane ever needs another warp's registers, a warp produces only 31 output
+// vectors: lane 31 loads and hands over, nothing else.  Costs 3 % of the lanes and nothing else (the overlapping
+// vector is an L1/L2 hit); a first version that gave lane 31 the next warp's vector through an extra divergent load,
+// and a second one through shared memory, added ~10 instructions per element to bodies that are issue-bound
+// (sin(a[1:]): 59-62 % of 8 TB/s; ncu: +29 % instructions, 3 CTAs per SM).  All U vectors of a thread are loaded
+// before the first shuffle.  The launcher guarantees that aligned vectors 0 .. nvec lie inside the operand.
+constexpr int EW_RL_VPW = 31;                              // output vectors per warp
+constexpr int EW_RL_VPB = (EW_BLOCK / 32) * EW_RL_VPW;     // per CTA and unroll step
+
+template <class F>
+__global__ void __launch_bounds__(EW_BLOCK)
+ew1_realign_kernel(const typename F::In* a, typename F::Out* o, int64_t head, int64_t nvec, int64_t n, unsigned ma) {
+    typedef typename F::In In;
+    typedef typename F::Out Out;
+    constexpr int EPV = Epv<In, Out>::value;
+    constexpr int U = unroll_of<F>::value;
+    constexpr bool FAST = has_fast<F>::value && smem_of<F>::value == 0;
+    constexpr int BYTES = Pack<In, EPV>::BYTES;
+    static_assert(BYTES % 4 == 0, "vectors are whole words");
+    constexpr int W = BYTES / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t v0 = (int64_t)blockIdx.x * (EW_RL_VPB * U) + warp * EW_RL_VPW + lane;   // lane 31: the next warp's first
+    const bool out_lane = lane < EW_RL_VPW;
+    const char* base = reinterpret_cast<const char*>(a + head) - ma;   // aligned input vector v starts at base + v BYTES
+    uint32_t A[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t v = v0 + (int64_t)u * EW_RL_VPB;
+#pragma unroll
+        for (int w = 0; w < W; ++w) A[u][w] = 0u;
+        if (v <= nvec && nvec > 0) ld_words<BYTES>(base + v * BYTES, A[u]);   // (nvec == 0: all scalars, `base` means nothing)
+    }
+    Pack<In, EPV> ra[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        uint32_t Nx[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) Nx[w] = __shfl_down_sync(0xffffffffu, A[u][w], 1);
+        FunnelExtract<W, 0>::run(A[u], Nx, ma >> 2, (ma & 3u) * 8u, ra[u].w);
+    }
+    const bool full = out_lane && v0 + (int64_t)(U - 1) * EW_RL_VPB < nvec;
+    if (full) {
+        bool all_fast = FAST;
+        if constexpr (FAST) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) all_fast = all_fast && pack_ok<F, EPV>(ra[u]);
+        }
+        if (all_fast) {
+            if constexpr (FAST) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_RL_VPB) * EPV, fast_pack<F, EPV>(ra[u], nullptr));
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                st_pack<Out, EPV>(o + head + (v0 + (int64_t)u * EW_RL_VPB) * EPV, apply_pack<F, EPV>(ra[u]));
+        }
+    } else if (out_lane) {
+        // (unrolled: a dynamic index would put ra[] in local memory for the whole kernel)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t v = v0 + (int64_t)u * EW_RL_VPB;
+            if (v < nvec) st_pack<Out, EPV>(o + head + v * EPV, apply_pack<F, EPV>(ra[u]));
         }
     }
     if (blockIdx.x == 0) {
@@ -598,7 +660,7 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
                     (const In*)in, (Out*)out, head, nvec, len);
                 return after_launch("ew1_table_kernel");
             } else {
-                ew1_vec_kernel<F, false><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len, 0u);
+                ew1_vec_kernel<F><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len);
                 return after_launch("ew1_vec_kernel");
             }
         }
@@ -609,8 +671,8 @@ int launch_unary(const void* in, void* out, int64_t len, int64_t s1, int64_t so,
             if (head > len) head = len;
             int64_t nvec = (len - head) / EPV - 1;
             if (nvec < 0) nvec = 0;
-            ew1_vec_kernel<F, true><<<full_grid(nvec, EW_BLOCK * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len, ma);
-            return after_launch("ew1_vec_kernel");
+            ew1_realign_kernel<F><<<full_grid(nvec, EW_RL_VPB * unroll_of<F>::value), EW_BLOCK, 0, st>>>((const In*)in, (Out*)out, head, nvec, len, ma);
+            return after_launch("ew1_realign_kernel");
         }
     }
     ew1_strided_kernel<F><<<full_grid(len, EW_BLOCK), EW_BLOCK, 0, st>>>((const char*)in, (char*)out, len, s1, so);
