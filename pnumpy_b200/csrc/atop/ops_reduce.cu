@@ -823,13 +823,27 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
     const int head = SHIFTED ? block_head<T, EPV>(p) : 0;   // see load_block
     const bool has_extra = SHIFTED && full && threadIdx.x < EPV;  // this thread also holds one leftover element
     T extra = T();
+    // 1- and 2-byte integers: both phases a WORD at a time.  A 64 KiB block of int8 holds at most 256 different
+    // values, so the block extreme sits in almost every thread's registers and phase B -- "usually one thread" for
+    // the wide types -- runs everywhere: at three instructions per byte the kernel was compute-bound (31 % of 8 TB/s).
+    constexpr bool WORDWISE = !is_fp<T>::value && sizeof(T) <= 2;
     if (full) {
         load_block<T, EPV, SHIFTED>(p, head, r, extra);
         // (thread 255's duplicated last pack is harmless here: phase A is idempotent, phase B skips it)
+        if constexpr (WORDWISE) {
+            typedef MinMaxWord<T, IS_MAX> MW;
+            typename MW::W acc = MW::seed(p[0]);
 #pragma unroll
-        for (int j = 0; j < RED_NV; ++j)
+            for (int j = 0; j < RED_NV; ++j)
 #pragma unroll
-            for (int e = 0; e < EPV; ++e) m = ext_nan<W, IS_MAX>(m, (W)r[j].get(e));
+                for (int w = 0; w < Pack<T, EPV>::WORDS; ++w) acc = MW::step(acc, r[j].w[w]);
+            m = ext_nan<W, IS_MAX>(m, (W)MW::finish(acc));
+        } else {
+#pragma unroll
+            for (int j = 0; j < RED_NV; ++j)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) m = ext_nan<W, IS_MAX>(m, (W)r[j].get(e));
+        }
         if (has_extra) m = ext_nan<W, IS_MAX>(m, (W)extra);
     } else {
         for (int64_t i = threadIdx.x; i < cnt; i += RED_THREADS) m = ext_nan<W, IS_MAX>(m, (W)p[i]);
@@ -866,6 +880,25 @@ arg_blocks_kernel(const T* in, int64_t n, int64_t index_base, ArgPair<T>* partia
                             c = (x != x && real) ? (j * RED_THREADS * EPV + e) : c;
                         }
                 }
+            } else if constexpr (WORDWISE) {
+                // zero-lane detector on word ^ splat(extreme): the LOWEST flagged lane of a word is exact (a borrow can
+                // only flag lanes above a true match), and the lowest lane is the first element (little endian)
+                constexpr int WORDS = Pack<T, EPV>::WORDS, EPW = 4 / (int)sizeof(T);
+                constexpr uint32_t ONES = sizeof(T) == 1 ? 0x01010101u : 0x00010001u;
+                constexpr uint32_t HIGH = sizeof(T) == 1 ? 0x80808080u : 0x80008000u;
+                const uint32_t splat = splat_word<T>((T)mb);
+                uint32_t cz = 0u;
+                int cw = 0;
+#pragma unroll
+                for (int j = RED_NV - 1; j >= 0; --j)
+#pragma unroll
+                    for (int w = WORDS - 1; w >= 0; --w) {
+                        const uint32_t t = r[j].w[w] ^ splat;
+                        uint32_t z = (t - ONES) & ~t & HIGH;
+                        if (j == RED_NV - 1 && SHIFTED && threadIdx.x == RED_THREADS - 1) z = 0u;
+                        if (z) { cz = z; cw = j * WORDS + w; }
+                    }
+                if (cz) c = (cw / WORDS) * (RED_THREADS * EPV) + (cw % WORDS) * EPW + ((__ffs((int)cz) - 1) >> (sizeof(T) == 1 ? 3 : 4));
             } else {
 #pragma unroll
                 for (int j = RED_NV - 1; j >= 0; --j)
