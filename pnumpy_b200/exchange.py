@@ -3,7 +3,9 @@
 Its pass-1 CTAs take tickets; the CTA that draws the last one stores the shard's block partials into every
 participant's slot table over NVLink, bumps the arrival counters, waits on the device for everybody else's
 and folds the complete table.  No NCCL call, no second launch, no host synchronisation; every participant
-gets the same bits as a single GPU would produce.
+gets the same bits as a single GPU would produce.  When every shard starts at a multiple of 64 slots (4 MiB of
+input) the owner folds its own 64-slot groups first and only the group partials travel (``hierarchical`` counts
+such calls; ``pncu_fused_exchange::group_offset``).
 
 ``Exchange`` owns one participant's tables (two, used alternately) and the pointers to everybody else's:
 * ``Exchange.in_process(devices, max_slots)`` -- one process driving several GPUs (peer access),
@@ -28,10 +30,9 @@ _HEADER = 512    # counters (2 x 128 B) + status word, in front of the two table
 
 
 class Exchange:
-    def __init__(self, rank, world, bases, counters, groups, max_slots, device, imported=()):
+    def __init__(self, rank, world, bases, counters, max_slots, device, imported=()):
         self.rank, self.world, self.max_slots, self.device = rank, world, int(max_slots), device
         self._bases, self._counters, self._imported = bases, counters, list(imported)  # [participant][parity] addresses
-        self._groups = groups    # [participant][parity]: group tables (level A of pass 2 done by the shard's owner)
         self.hierarchical = 0    # calls whose shards were group-aligned (group partials travelled, not slots)
         self.epoch = 0
         self.expected = [0, 0]
@@ -57,7 +58,7 @@ class Exchange:
     def _layout(cls, base, max_slots):
         per = (max_slots + cls._group_cap(max_slots)) * SLOT_BYTES   # one parity: slot table, then group table
         tab = [base + _HEADER, base + _HEADER + per]
-        return tab, [base, base + 128], [t + max_slots * SLOT_BYTES for t in tab]
+        return tab, [base, base + 128]
 
     @classmethod
     def in_process(cls, devices, max_slots):
@@ -73,7 +74,7 @@ class Exchange:
         lay = [cls._layout(b, max_slots) for b in raw]
         out = []
         for r, d in enumerate(devices):
-            x = cls(r, len(devices), [l[0] for l in lay], [l[1] for l in lay], [l[2] for l in lay], max_slots, d)
+            x = cls(r, len(devices), [l[0] for l in lay], [l[1] for l in lay], max_slots, d)
             x._own = raw[r]
             x._status = raw[r] + 256
             out.append(x)
@@ -105,7 +106,7 @@ class Exchange:
             raw.append(p.value)
             imported.append(p.value)
         lay = [cls._layout(b, max_slots) for b in raw]
-        x = cls(rank, world, [l[0] for l in lay], [l[1] for l in lay], [l[2] for l in lay], max_slots, dev.value, imported)
+        x = cls(rank, world, [l[0] for l in lay], [l[1] for l in lay], max_slots, dev.value, imported)
         x._own = own
         x._status = own + 256
         if sync:

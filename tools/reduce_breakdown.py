@@ -24,7 +24,8 @@ for dt in ("int8", "int16", "float32", "float64"):
     p1 = time_call(lambda: cabi.check(lib.pncu_reduce_partials(f, t, a.ptr, n, parts.ptr, None), "p1"))
     p2 = time_call(lambda: cabi.check(lib.pncu_reduce_finish(f, t, parts.ptr, nb, out.ptr, None, None), "p2"))
     both = time_call(lambda: dev.reduce(OP, a, out=out))
-    ka = time_call(lambda: dev.argminmax(0, a))
+    ri = dev.empty(1, np.int64)
+    ka = time_call(lambda: dev.argminmax(0, a, out=ri))
     ideal = s * n / 7.2e9
     print(f"{dt:8s} partials={nb:6d} ideal@7.2TB/s {ideal:.4f} ms | pass1 {p1[0]:.4f} pass2 {p2[0]:.4f} {OP} {both[0]:.4f} ({s*n/both[0]/1e6:.0f} GB/s) argmax {ka[0]:.4f}", flush=True)
     a.free()
