@@ -53,7 +53,8 @@ int ensure_init();                    // 0 or PNCU_ERR_NO_DEVICE
 
 // Per-(device, stream) scratch for reduction partials; grows on demand, never shrinks.
 // `ticket` (optional): the (device, stream)'s zeroed 32-bit counter for one-launch reductions.
-int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** ticket = nullptr);
+int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** ticket = nullptr, size_t ngtickets = 0,
+                  unsigned** gtickets = nullptr);
 int reset_ticket(cudaStream_t stream);
 
 // ---- allocation registry ---------------------------------------------------------------------------

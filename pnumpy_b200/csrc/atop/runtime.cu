@@ -78,10 +78,10 @@ const DevProps* dev_props() {
 // ---- reduction scratch, keyed by (device, stream) --------------------------------------------
 // `ticket`: one 32-bit counter per (device, stream), zero between launches (the last CTA of a one-launch
 // reduction re-arms it); lives in its own allocation so that growing the scratch never disturbs it.
-struct Scratch { void* ptr; size_t bytes; unsigned* ticket; };
+struct Scratch { void* ptr; size_t bytes; unsigned* ticket; unsigned* gtickets; size_t ngtickets; };
 static std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
 
-int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** ticket) {
+int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** ticket, size_t ngtickets, unsigned** gtickets) {
     int d = 0;
     PNCU_CUDA(cudaGetDevice(&d));
     std::lock_guard<std::mutex> lk(g_mu);
@@ -106,8 +106,23 @@ int get_workspace(cudaStream_t stream, size_t bytes, void** out, unsigned** tick
         s.ptr = p;
         s.bytes = want;
     }
+    if (gtickets && s.ngtickets < ngtickets) {
+        // group tickets (one 32-bit counter per 64 slots): zero between launches, so a larger array starts zeroed
+        size_t want = ngtickets < 4096 ? 4096 : ngtickets * 2;
+        void* p = NULL;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(unsigned));
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu) for group tickets failed: %s", want * sizeof(unsigned), cudaGetErrorString(e)); return PNCU_ERR_NOMEM; }
+        PNCU_CUDA(cudaMemset(p, 0, want * sizeof(unsigned)));
+        if (s.gtickets) {
+            cudaStreamSynchronize(stream);   // a kernel queued on this stream may still count in the old array
+            cudaFree(s.gtickets);
+        }
+        s.gtickets = (unsigned*)p;
+        s.ngtickets = want;
+    }
     if (out) *out = s.ptr;
     if (ticket) *ticket = s.ticket;
+    if (gtickets) *gtickets = s.gtickets;
     return 0;
 }
 
@@ -118,6 +133,8 @@ int reset_ticket(cudaStream_t stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_scratch.find(std::make_pair(d, stream));
     if (it != g_scratch.end() && it->second.ticket) PNCU_CUDA(cudaMemsetAsync(it->second.ticket, 0, 256, stream));
+    if (it != g_scratch.end() && it->second.gtickets)
+        PNCU_CUDA(cudaMemsetAsync(it->second.gtickets, 0, it->second.ngtickets * sizeof(unsigned), stream));
     return 0;
 }
 
