@@ -718,7 +718,7 @@ def test_more_transcendentals_do_not_depend_on_neighbours(dev, rng, op, dt):
 
 
 # ---- the cross-GPU exchange fused into the two passes -------------------------------------------------
-def _exchange_case(dev, devices, rng, group_aligned=False):
+def _exchange_case(dev, devices, rng, group_aligned=False, groups_per_shard=2):
     """sum / min / max / argmax of one array cut into len(devices) shards, every shard on its own GPU, through
     Exchange: every participant must end with the bits a single GPU produces.  group_aligned: the shards start at
     multiples of the fold group (64 slots), so each participant folds its own groups and only group partials travel
@@ -733,7 +733,7 @@ def _exchange_case(dev, devices, rng, group_aligned=False):
     for dt in ("float32", "float64", "int32"):
         if group_aligned:
             align = int(lib.pncu_reduce_group_slots()) * (65536 // np.dtype(dt).itemsize)
-            n = 2 * align * world + 12345
+            n = groups_per_shard * align * world + 12345
         a = (rng.normal(0, 100, n)).astype(dt)
         units = -(-n // align)
         per = -(-units // world)
@@ -750,7 +750,7 @@ def _exchange_case(dev, devices, rng, group_aligned=False):
         whole = dev.to_device(a)
         want = {op: dev.reduce(op, whole).to_host().tobytes() for op in ("ADD", "MIN", "MAX")}
         want_arg = [int(dev.argminmax(k, whole).to_host()[0]) for k in (0, 1)]
-        xs = exchange.Exchange.in_process(devices, max_slots=8192)
+        xs = exchange.Exchange.in_process(devices, max_slots=max(8192, 2 * groups_per_shard * 64 * world + 64))
         shards, outs, idxs, streams = [], [], [], []
         for r, d in enumerate(devices):
             cabi.check(lib.pncu_set_device(d), "set_device")
@@ -809,6 +809,19 @@ def test_fused_exchange_group_partials_on_one_gpu(dev, rng):
     """shards that start at whole fold groups: level A of pass 2 is done by each shard's owner and only the group
     partials are stored into the consumers' tables"""
     _exchange_case(dev, [0, 0], rng, group_aligned=True)
+
+
+def test_fused_exchange_group_tickets_on_one_gpu(dev, rng):
+    """shards of >= 256 slots that start at whole groups: the GROUP-TICKET form of the one-launch kernels (every group is
+    folded during pass 1 by the CTA that completes it) together with the exchange of group partials, all-reduce form"""
+    _exchange_case(dev, [0, 0], rng, group_aligned=True, groups_per_shard=5)
+
+
+def test_fused_exchange_group_tickets_two_gpus(dev, rng):
+    from pnumpy_b200 import cabi
+    if cabi.load().pncu_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _exchange_case(dev, [0, 1], rng, group_aligned=True, groups_per_shard=5)
 
 
 def test_fused_exchange_group_partials_two_gpus(dev, rng):
