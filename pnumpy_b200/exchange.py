@@ -144,8 +144,7 @@ class Exchange:
         x.slot_base, x.total_count = int(sum(counts[: self.rank])), total
         # every shard starts at a multiple of the fold group (64 slots = 4 MiB of input): each participant folds its
         # own groups and only the group partials cross NVLink (same bits: pncu_fused_exchange in the header)
-        group = int(cabi.load().pncu_reduce_group_slots())
-        aligned = all(int(sum(counts[:r])) % group == 0 for r in range(self.world))
+        aligned = shards_start_at_whole_groups(counts)
         self.hierarchical += int(aligned)
         for d in range(self.world):
             x.slots[d] = self._bases[d][parity]
@@ -192,6 +191,18 @@ class Exchange:
                            f"(reduction #{word.value & ~cabi.FUSED_TIMEOUT_BIT}); no result was produced")
             raise cabi.PnumpyCudaError(self.broken)
         return self.epoch
+
+
+def shards_start_at_whole_groups(counts):
+    """True when every participant's first slot (the running sum of `counts`) is a multiple of the fold group
+    (pncu_reduce_group_slots() = 64 slots): level A of pass 2 can then be done by each shard's owner."""
+    group = int(cabi.load().pncu_reduce_group_slots())
+    base = 0
+    for c in counts:
+        if base % group:
+            return False
+        base += int(c)
+    return True
 
 
 def block_counts(shard_sizes, dtype):

@@ -112,3 +112,38 @@ def test_fails_loudly_without_gpu():
     assert b"no CPU fallback" in lib.pncu_last_error()
     assert np.all(a == 1)  # untouched
     assert lib.pncu_launch_count() == 0
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirrors in pnumpy_b200/cabi.py (pncu_peer_table, pncu_fused_exchange) must have the size and the field
+    offsets the C compiler gives the structs of include/pnumpy_cuda.h -- a field added on one side only would shift
+    every pointer the kernels read."""
+    import ctypes
+    import subprocess
+    from pnumpy_b200 import cabi
+    fields = {"pncu_peer_table": (cabi.PeerTable, ["n", "slots", "arrived"]),
+              "pncu_fused_exchange": (cabi.FusedExchange, ["n", "self", "all", "root", "slot_base", "total_count", "slots",
+                                                           "arrived", "expected", "done_flag", "done_value", "group_offset"])}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "pnumpy_cuda.h"', 'int main(void) {']
+    for name, (_, fs) in fields.items():
+        src.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in fs:
+            src.append(f'  printf(" %zu", offsetof({name}, {f}));')
+        src.append('  printf("\\n");')
+    src += ['  return 0;', '}']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(c)])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    seen = 0
+    for line in out:
+        tok = line.split()
+        if not tok:
+            continue
+        cls, fs = fields[tok[0]]
+        assert ctypes.sizeof(cls) == int(tok[1]), (tok[0], ctypes.sizeof(cls), tok[1])
+        assert [getattr(cls, f).offset for f in fs] == [int(x) for x in tok[2:]], tok[0]
+        assert [f for f, _ in cls._fields_] == fs, "a field is missing from the test's list"
+        seen += 1
+    assert seen == len(fields)

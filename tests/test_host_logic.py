@@ -163,3 +163,18 @@ print("ok")
 '''
     r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == "ok", (r.stdout, r.stderr)
+
+
+def test_exchange_group_alignment_rule():
+    """pncu_fused_exchange::group_offset may only be set when EVERY shard starts at a whole fold group (64 slots);
+    the last shard may be ragged."""
+    from pnumpy_b200 import cabi, exchange
+    assert cabi.load().pncu_reduce_group_slots() == 64
+    assert exchange.shards_start_at_whole_groups([64, 128, 7])
+    assert exchange.shards_start_at_whole_groups([320, 320, 320, 1])
+    assert exchange.shards_start_at_whole_groups([5])
+    assert not exchange.shards_start_at_whole_groups([24, 24])
+    assert not exchange.shards_start_at_whole_groups([64, 65, 64])
+    # block_counts needs no GPU either: slots per shard = ceil(elements / (64 KiB / itemsize))
+    assert exchange.block_counts([1 << 20, (1 << 20) + 1], "float32") == [64, 65]
+    assert exchange.block_counts([1 << 20], "float64") == [128]
