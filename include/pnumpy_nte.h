@@ -73,8 +73,10 @@ PNCU_API int nte_get_threading(void);
 /* Size threshold.  `n` is the base: streaming element-wise ops on pinned operands decline below it; the
  * effective value is x4 when an operand is pageable, /2 for NTE_CLASS_HEAVY ops (transcendentals), x2 for
  * reductions, and it is applied to BYTES (n x 4 bytes of the widest operand; x3 for 1-byte types) -- the measured
- * crossovers against NumPy's own loops (tools/threshold_probe.py, tools/pn_benchmark.py).  Resident
- * (device / managed) operands always run on the GPU.  Default 2^19; 0 sends everything to the GPU. */
+ * crossovers against NumPy's own loops (tools/threshold_probe.py, tools/pn_benchmark.py).  A call whose
+ * array operands are ALL resident (device / managed memory) always runs on the GPU, whatever its size; a call that
+ * mixes host and resident arrays is held to the threshold like a host call (NumPy feeds np.sin(int16_array) through
+ * 8192-element cast buffers).  Default 2^19; 0 sends everything to the GPU. */
 #define NTE_CLASS_STREAM 0
 #define NTE_CLASS_HEAVY 1
 #define NTE_CLASS_REDUCE 2
